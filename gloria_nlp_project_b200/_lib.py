@@ -1,0 +1,66 @@
+"""ctypes binding of libgloria_b200.so (the C ABI declared in include/gloria_b200.h).
+
+There is deliberately no CPU or PyTorch fallback: if the library is missing or a call fails, a RuntimeError is
+raised (the reference surfaces faults as RuntimeError too).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+from .build import LIB_PATH
+
+_lock = threading.Lock()
+_lib = None
+
+_i, _f, _p, _z = C.c_int, C.c_float, C.c_void_p, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/gloria_b200.h one to one
+PROTOTYPES = {
+    "gloria_b200_version": (_i, []),
+    "gloria_b200_last_error": (C.c_char_p, []),
+    "gloria_b200_launch_count": (C.c_longlong, [_i]),
+    "gloria_b200_local_f32_workspace": (_z, [_i, _i, _i, _i, _i, _i, _z]),
+    "gloria_b200_local_sim_fwd_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p, _z,
+                                           _p]),
+    "gloria_b200_local_sim_bwd_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p, _p,
+                                           _p, _z, _p]),
+    "gloria_b200_tc_spad": (_i, [_i]),
+    "gloria_b200_tc_lpad": (_i, [_i]),
+    "gloria_b200_tc_supported": (_i, [_i, _i, _i]),
+    "gloria_b200_tc_prepack": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "gloria_b200_tc_workspace": (_z, [_i, _i, _i, _i, _i]),
+    "gloria_b200_tc_local_sim_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p, _z,
+                                          _p]),
+    "gloria_b200_tc_local_sim_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p,
+                                          _p, _p, _p, _z, _p]),
+    "gloria_b200_global_sim_fwd": (_i, [_p, _p, _i, _i, _i, _f, _p, _p, _p, _p]),
+    "gloria_b200_global_sim_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p]),
+    "gloria_b200_ce_bidir_fwd": (_i, [_p, _i, _f, _p, _p, _p, _p]),
+    "gloria_b200_ce_bidir_bwd": (_i, [_p, _i, _f, _p, _p, _p, _p, _p]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a). There is no CPU fallback for this path.")
+                h = C.CDLL(LIB_PATH)
+                for name, (res, args) in PROTOTYPES.items():
+                    fn = getattr(h, name)      # AttributeError if a declared symbol is not exported
+                    fn.restype, fn.argtypes = res, args
+                _lib = h
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().gloria_b200_last_error().decode(errors="replace")
+        raise RuntimeError(f"libgloria_b200: {what} failed with status {rc}: {msg}")

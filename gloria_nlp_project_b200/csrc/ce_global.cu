@@ -1,0 +1,189 @@
+// Small warp-level kernels: global cosine similarity (gloria_loss.py:75-80) and the bidirectional
+// cross entropy with arange labels (gloria_loss.py:86-87, 164-170), forward and closed-form backward.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace gloria {
+namespace {
+
+__global__ void vec_norms(const float* __restrict__ x, float* __restrict__ n, int rows, int D) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + (long long)row * D;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) s = fmaf(xr[d], xr[d], s);
+  s = warp_sum(s);
+  if (lane == 0) n[row] = sqrtf(s);
+}
+
+// one CTA per row a of x; warps sweep the rows b of y.  dynamic smem: D floats (x_a)
+__global__ void __launch_bounds__(256) global_cos_fwd(const float* __restrict__ x, const float* __restrict__ y,
+                                                      const float* __restrict__ xn, const float* __restrict__ yn,
+                                                      int Bc, int D, float eps, float* __restrict__ cosm) {
+  extern __shared__ float xs[];
+  const int a = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = x[(long long)a * D + d];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const float na = xn[a];
+  for (int b = warp; b < Bc; b += nwarps) {
+    const float* yr = y + (long long)b * D;
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32) dot = fmaf(xs[d], yr[d], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) cosm[(long long)a * Bc + b] = dot / fmaxf(na * yn[b], eps);
+  }
+}
+
+// Gradient w.r.t. the "row side" of cos[a,b] = <x_a, y_b> / max(|x_a||y_b|, eps); dcos is addressed through
+// (rs, cs) so the same kernel serves both sides.  dynamic smem: (D + Bc) floats.
+__global__ void __launch_bounds__(256) global_cos_bwd_side(const float* __restrict__ x, const float* __restrict__ y,
+                                                           const float* __restrict__ xn,
+                                                           const float* __restrict__ yn,
+                                                           const float* __restrict__ dcos, long long rs,
+                                                           long long cs, int Bc, int D, float eps,
+                                                           float* __restrict__ dx) {
+  extern __shared__ float smem[];
+  float* xs = smem;
+  float* dd = smem + D;
+  __shared__ float red[8];
+  const int a = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = x[(long long)a * D + d];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const float na = xn[a];
+  float esum = 0.f;   // sum_b (dL/d(|x_a||y_b|)) * |y_b|   (lane 0 of each warp)
+  for (int b = warp; b < Bc; b += nwarps) {
+    const float* yr = y + (long long)b * D;
+    float dot = 0.f;
+    for (int d = lane; d < D; d += 32) dot = fmaf(xs[d], yr[d], dot);
+    dot = warp_sum(dot);
+    if (lane == 0) {
+      const float g = dcos[a * rs + b * cs];
+      const float prod = na * yn[b];
+      const float den = fmaxf(prod, eps);
+      dd[b] = g / den;
+      if (prod >= eps) esum += -g * dot / (den * den) * yn[b];
+    }
+  }
+  if (lane == 0) red[warp] = esum;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < nwarps; ++w) tot += red[w];
+  const float coef = na > 0.f ? tot / na : 0.f;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float acc = coef * xs[d];
+    for (int b = 0; b < Bc; ++b) acc = fmaf(dd[b], y[(long long)b * D + d], acc);
+    dx[(long long)a * D + d] = acc;
+  }
+}
+
+// lse over rows (blockIdx.y == 0) and columns (blockIdx.y == 1) of scale * m; one warp per row/column
+__global__ void ce_lse(const float* __restrict__ m, int B, float scale, float* __restrict__ row_lse,
+                       float* __restrict__ col_lse) {
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (idx >= B) return;
+  const int lane = threadIdx.x & 31;
+  const bool col = blockIdx.y == 1;
+  const long long base = col ? idx : (long long)idx * B;
+  const long long step = col ? B : 1;
+  float mx = -INFINITY;
+  for (int k = lane; k < B; k += 32) mx = fmaxf(mx, scale * m[base + k * step]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int k = lane; k < B; k += 32) s += expf(scale * m[base + k * step] - mx);
+  s = warp_sum(s);
+  if (lane == 0) (col ? col_lse : row_lse)[idx] = mx + logf(s);
+}
+
+__global__ void __launch_bounds__(256) ce_losses(const float* __restrict__ m, int B, float scale,
+                                                 const float* __restrict__ row_lse,
+                                                 const float* __restrict__ col_lse, float* __restrict__ losses) {
+  __shared__ float r0[8], r1[8];
+  float a0 = 0.f, a1 = 0.f;
+  for (int k = threadIdx.x; k < B; k += blockDim.x) {
+    const float d = scale * m[(long long)k * B + k];
+    a0 += row_lse[k] - d;
+    a1 += col_lse[k] - d;
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  if ((threadIdx.x & 31) == 0) { r0[threadIdx.x >> 5] = a0; r1[threadIdx.x >> 5] = a1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { s0 += r0[w]; s1 += r1[w]; }
+    losses[0] = s0 / (float)B;
+    losses[1] = s1 / (float)B;
+  }
+}
+
+__global__ void ce_bwd(const float* __restrict__ m, int B, float scale, const float* __restrict__ row_lse,
+                       const float* __restrict__ col_lse, const float* __restrict__ g, float* __restrict__ dm) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * B) return;
+  const int a = (int)(idx / B), b = (int)(idx % B);
+  const float z = scale * m[idx];
+  const float delta = (a == b) ? 1.f : 0.f;
+  const float v = g[0] * (expf(z - row_lse[a]) - delta) + g[1] * (expf(z - col_lse[b]) - delta);
+  dm[idx] = v * scale / (float)B;
+}
+
+}  // namespace
+}  // namespace gloria
+
+using namespace gloria;
+
+extern "C" int gloria_b200_global_sim_fwd(const float* x, const float* y, int Bi, int Bc, int D, float eps,
+                                          float* cosm, float* xn, float* yn, void* stream) {
+  GLORIA_CHECK_ARG(x && y && cosm && xn && yn, "null pointer");
+  GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && D > 0 && D <= 12000, "bad sizes Bi=%d Bc=%d D=%d", Bi, Bc, D);
+  cudaStream_t st = (cudaStream_t)stream;
+  vec_norms<<<(Bi + 7) / 8, 256, 0, st>>>(x, xn, Bi, D);
+  GLORIA_LAUNCHED("vec_norms");
+  vec_norms<<<(Bc + 7) / 8, 256, 0, st>>>(y, yn, Bc, D);
+  GLORIA_LAUNCHED("vec_norms");
+  global_cos_fwd<<<Bi, 256, D * sizeof(float), st>>>(x, y, xn, yn, Bc, D, eps, cosm);
+  GLORIA_LAUNCHED("global_cos_fwd");
+  return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_global_sim_bwd(const float* x, const float* y, const float* xn, const float* yn,
+                                          const float* dcos, int Bi, int Bc, int D, float eps, float* dx, float* dy,
+                                          void* stream) {
+  GLORIA_CHECK_ARG(x && y && xn && yn && dcos && dx && dy, "null pointer");
+  GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && D > 0, "bad sizes Bi=%d Bc=%d D=%d", Bi, Bc, D);
+  GLORIA_CHECK_ARG((size_t)(D + (Bi > Bc ? Bi : Bc)) * sizeof(float) <= 48 * 1024,
+                   "global_sim_bwd: D + B = %d exceeds the 48 KB shared-memory tile", D + (Bi > Bc ? Bi : Bc));
+  cudaStream_t st = (cudaStream_t)stream;
+  global_cos_bwd_side<<<Bi, 256, (D + Bc) * sizeof(float), st>>>(x, y, xn, yn, dcos, Bc, 1, Bc, D, eps, dx);
+  GLORIA_LAUNCHED("global_cos_bwd_side(x)");
+  global_cos_bwd_side<<<Bc, 256, (D + Bi) * sizeof(float), st>>>(y, x, yn, xn, dcos, 1, Bc, Bi, D, eps, dy);
+  GLORIA_LAUNCHED("global_cos_bwd_side(y)");
+  return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_ce_bidir_fwd(const float* m, int B, float scale, float* losses, float* row_lse,
+                                        float* col_lse, void* stream) {
+  GLORIA_CHECK_ARG(m && losses && row_lse && col_lse, "null pointer");
+  GLORIA_CHECK_ARG(B > 0, "bad B=%d", B);
+  cudaStream_t st = (cudaStream_t)stream;
+  ce_lse<<<dim3((B + 7) / 8, 2), 256, 0, st>>>(m, B, scale, row_lse, col_lse);
+  GLORIA_LAUNCHED("ce_lse");
+  ce_losses<<<1, 256, 0, st>>>(m, B, scale, row_lse, col_lse, losses);
+  GLORIA_LAUNCHED("ce_losses");
+  return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_ce_bidir_bwd(const float* m, int B, float scale, const float* row_lse,
+                                        const float* col_lse, const float* g, float* dm, void* stream) {
+  GLORIA_CHECK_ARG(m && row_lse && col_lse && g && dm, "null pointer");
+  GLORIA_CHECK_ARG(B > 0, "bad B=%d", B);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)B * B;
+  ce_bwd<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, B, scale, row_lse, col_lse, g, dm);
+  GLORIA_LAUNCHED("ce_bwd");
+  return GLORIA_OK;
+}

@@ -1,0 +1,50 @@
+// Shared host/device helpers for libgloria_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gloria_b200.h"
+
+namespace gloria {
+
+// thread-local error text + launch counter (no mutable process-global state: entry points stay re-entrant)
+char* err_buf();
+long long& launch_counter();
+
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define GLORIA_CHECK_ARG(cond, ...)                                   \
+  do {                                                                \
+    if (!(cond)) return ::gloria::fail(GLORIA_ERR_BAD_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define GLORIA_CUDA(expr)                                             \
+  do {                                                                \
+    cudaError_t _e = (expr);                                          \
+    if (_e != cudaSuccess) return ::gloria::cuda_fail(_e, #expr);     \
+  } while (0)
+
+// call after every kernel launch
+#define GLORIA_LAUNCHED(name)                                         \
+  do {                                                                \
+    ++::gloria::launch_counter();                                     \
+    cudaError_t _e = cudaPeekAtLastError();                           \
+    if (_e != cudaSuccess) return ::gloria::cuda_fail(_e, name);      \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace gloria

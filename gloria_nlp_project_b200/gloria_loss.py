@@ -1,0 +1,141 @@
+"""Drop-in replacement for the reference module gloria/loss/gloria_loss.py.
+
+Same function names, positional/keyword signatures, defaults and return arities as the reference
+(cosine_similarity :11, attention_fn :19, global_loss :66, kl_divergence :91, entropy :95, local_loss :99);
+the arithmetic runs in the sm_100a kernels of libgloria_b200.so through the custom ops in `ops.py`.
+CUDA tensors only -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _config, ops
+
+__all__ = ["cosine_similarity", "attention_fn", "global_loss", "kl_divergence", "entropy", "local_loss",
+           "local_similarities"]
+
+
+def _mode(*tensors: torch.Tensor) -> int:
+    p = _config.get_precision()
+    if p == "auto":
+        low = any(t is not None and t.dtype in (torch.float16, torch.bfloat16) for t in tensors)
+        p = "bf16" if (low or torch.is_autocast_enabled()) else "fp32"
+    return ops.MODE_BF16 if p == "bf16" else ops.MODE_FP32
+
+
+def _cap_lens(cap_lens: Union[Sequence[int], torch.Tensor], n: int, word_off: int, Lw: int,
+              device: torch.device) -> Tuple[torch.Tensor, List[int]]:
+    """The reference indexes cap_lens[i] as Python ints (list, or tensor -> implicit sync); do the same once."""
+    if isinstance(cap_lens, torch.Tensor):
+        lens = [int(v) for v in cap_lens.reshape(-1).tolist()]
+    else:
+        lens = [int(v) for v in cap_lens]
+    if len(lens) < n:
+        raise RuntimeError(f"cap_lens has {len(lens)} entries for {n} captions")
+    lens = lens[:n]
+    if min(lens) < 1 or max(lens) + word_off > Lw:
+        raise RuntimeError(f"cap_lens out of range: need 1 <= len and len + {word_off} <= {Lw}, got "
+                           f"[{min(lens)}, {max(lens)}]")
+    dev_lens = torch.tensor(lens, dtype=torch.int32).to(device, non_blocking=True)
+    return dev_lens, lens
+
+
+def _context(img_features: torch.Tensor, no_attn_vec: Optional[torch.Tensor]) -> torch.Tensor:
+    """[B, D, H, W] -> [B, D, S] fp32, with the learned no-attention column prepended (gloria_loss.py:30-34)."""
+    B, D = img_features.shape[0], img_features.shape[1]
+    ctx = img_features.reshape(B, D, -1).float()
+    if no_attn_vec is not None:
+        v = no_attn_vec.float().expand(B, no_attn_vec.shape[0]).unsqueeze(-1)
+        ctx = torch.cat([v, ctx], 2)
+    return ctx
+
+
+def local_similarities(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, agg="sum", no_attn_vec=None,
+                       word_offset=0, eps=1e-8, want_attn_maps=False, want_mean_attn=False):
+    """The [B_img, B_cap] matrix the caption loop of gloria_loss.py:116-162 builds (before the temp3 scale).
+
+    Returns (sim, attn_diag or None, attn_mean or None, lens):
+      attn_diag [B_cap, Lcap, S(+1)]  attention of the diagonal pairs (zero rows beyond each caption's length),
+      attn_mean [B_img, B_cap, S(+1)] word-mean attention of every pair.
+    """
+    if not img_features.is_cuda:
+        raise RuntimeError("gloria_b200 runs on CUDA tensors only (sm_100a); there is no CPU fallback")
+    Bc, _, Lw = words_emb.shape
+    dev_lens, lens = _cap_lens(cap_lens, Bc, word_offset, Lw, img_features.device)
+    ctx = _context(img_features, no_attn_vec)
+    words = words_emb.float()
+    mode = _mode(img_features, words_emb)
+    sim, diag, mean = ops.local_sim_fwd(ctx, words, dev_lens, max(lens), word_offset, float(temp1), float(temp2),
+                                        ops.AGG[agg], float(eps), bool(want_attn_maps), bool(want_mean_attn), mode)
+    return sim, (diag if want_attn_maps else None), (mean if want_mean_attn else None), lens
+
+
+# --------------------------------------------------------------------------------------------------------------
+def cosine_similarity(x1, x2, dim=1, eps=1e-8):
+    """gloria_loss.py:11-16 -- row-wise cosine of two [N, D] tensors."""
+    raise NotImplementedError("TODO: row-wise cosine entry point")
+
+
+def attention_fn(query, context, temp1, no_attn_vec=None):
+    """gloria_loss.py:19-63."""
+    raise NotImplementedError("TODO: paired attention entry point")
+
+
+def global_loss(cnn_code, rnn_code, eps=1e-8, temp3=10.0):
+    """gloria_loss.py:66-88 -> (loss0, loss1)."""
+    cosm, _, _ = ops.global_sim_fwd(cnn_code.float(), rnn_code.float(), float(eps))
+    losses, _, _ = ops.ce_bidir_fwd(cosm, float(temp3))
+    return losses[0], losses[1]
+
+
+def kl_divergence(attn1, attn2):
+    """gloria_loss.py:91-92"""
+    return (attn1 * torch.log(attn1 / attn2)).sum(-1)
+
+
+def entropy(attn):
+    """gloria_loss.py:95-96"""
+    return -(attn * torch.log(attn)).sum(-1)
+
+
+def local_loss(
+    img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, temp3=10.0, agg="sum", no_attn_vec=None,
+    no_attn_loss_weight=None, attention_divergence_loss_weight=None, attention_entropy_loss_weight=None
+):
+    """gloria_loss.py:99-201 -> (loss0, loss1, no_attn_loss, kl_loss, entropy_loss, att_maps).
+
+    att_maps[i] is the [1, L_i, H, W] attention map of pair (i, i), differentiable (the supervised-attention
+    loss of GLoRIA.calc_loss back-propagates through it).
+    """
+    batch_size = img_features.shape[0]
+    ih, iw = img_features.shape[2], img_features.shape[3]
+    has_v = no_attn_vec is not None
+    want_mean = (no_attn_loss_weight is not None or attention_divergence_loss_weight is not None
+                 or attention_entropy_loss_weight is not None)
+    sim, diag, mean, lens = local_similarities(img_features, words_emb, cap_lens, temp1, temp2, agg, no_attn_vec,
+                                               word_offset=0, want_attn_maps=True, want_mean_attn=want_mean)
+    s0 = 1 if has_v else 0                                          # returned maps drop the no-attn column (:60-61)
+    att_maps = [diag[i:i + 1, :lens[i], s0:].reshape(1, lens[i], ih, iw) for i in range(words_emb.shape[0])]
+
+    losses, _, _ = ops.ce_bidir_fwd(sim, float(temp3))              # :164-170
+    loss0, loss1 = losses[0], losses[1]
+
+    no_attn_loss, kl_loss, entropy_loss = 0, 0, 0
+    if want_mean:
+        flat = mean[:, :, s0:]                                      # [B_img, B_cap, S]  (:132)
+        ar = torch.arange(batch_size, device=sim.device)
+        if no_attn_loss_weight is not None:                         # :129-130, 173-177 (diagonal pairs only)
+            no_attn_scores = torch.log(1 - flat[ar, ar].sum(-1))
+            no_attn_loss = no_attn_loss_weight * no_attn_scores.mean()
+        if has_v:                                                   # :133-135
+            flat = torch.cat([1 - flat.sum(-1, keepdim=True), flat], -1)
+        if attention_entropy_loss_weight is not None:               # :136-137, 195-197 (weight not applied in ref)
+            entropy_loss = entropy(flat).mean()
+        if attention_divergence_loss_weight is not None:            # :138-139, 180-192
+            cur = flat[ar, ar].unsqueeze(1)                         # attention of pair (i, i)
+            sym = (kl_divergence(cur, flat) + kl_divergence(flat, cur)) / 2      # [B_img, B_cap]
+            off_diag = ~torch.eye(batch_size, dtype=torch.bool, device=sim.device)
+            kl_loss = attention_divergence_loss_weight * (-sym[off_diag].mean())
+    return loss0, loss1, no_attn_loss, kl_loss, entropy_loss, att_maps

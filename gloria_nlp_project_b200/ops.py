@@ -1,0 +1,270 @@
+"""torch custom ops (with autograd) over the C ABI of libgloria_b200.so.
+
+PyTorch is plumbing here: it owns device memory and streams and records the autograd graph; every number is
+computed by the CUDA kernels behind `include/gloria_b200.h`.  The ops are opaque to torch.compile / CUDA graphs
+(`torch.library.custom_op` + `register_fake` + `register_autograd`).  There is no CPU implementation: calling an
+op with CPU tensors raises RuntimeError.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+AGG = {"sum": 0, "mean": 1, "max": 2}
+MODE_FP32, MODE_BF16 = 0, 1
+
+_WS_BUDGET = int(os.environ.get("GLORIA_B200_WS_BYTES", str(4 << 30)))
+
+
+def _need_cuda(*ts: Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gloria_b200 ops run on CUDA tensors only (sm_100a); there is no CPU fallback")
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _stream(t: Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _f32c(t: Tensor) -> Tensor:
+    return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# local similarity
+# ----------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("gloria_b200::local_sim_fwd", mutates_args=())
+def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int, temp1: float,
+                  temp2: float, agg: int, eps: float, want_diag: bool, want_mean: bool,
+                  mode: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """sim [Bi, Bc], attn_diag [Bc, lcap, S] (or empty), attn_mean [Bi, Bc, S] (or empty).
+
+    ctx [Bi, D, S] fp32, words [Bc, D, Lw] fp32, cap_lens int32 [Bc] on the same device.
+    Replaces the caption loop of gloria_loss.py:116-162 (attention_fn + cosine_similarity + aggregation).
+    """
+    _need_cuda(ctx, words, cap_lens)
+    L = _lib.lib()
+    Bi, D, S = ctx.shape
+    Bc, D2, Lw = words.shape
+    if D2 != D:
+        raise RuntimeError(f"feature dims differ: context {D} vs words {D2}")
+    if cap_lens.dtype != torch.int32 or cap_lens.numel() != Bc:
+        raise RuntimeError("cap_lens must be an int32 tensor with one entry per caption")
+    ctx, words, cap_lens = ctx.contiguous(), words.contiguous(), cap_lens.contiguous()
+    dev = ctx.device
+    sim = torch.empty((Bi, Bc), dtype=torch.float32, device=dev)
+    diag = torch.empty((Bc, lcap, S) if want_diag else (0,), dtype=torch.float32, device=dev)
+    mean = torch.empty((Bi, Bc, S) if want_mean else (0,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        if mode == MODE_FP32:
+            nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            rc = L.gloria_b200_local_sim_fwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S,
+                                                 Lw, lcap, word_off, temp1, temp2, agg, eps, sim.data_ptr(),
+                                                 _ptr(diag), _ptr(mean), ws.data_ptr(), nbytes, _stream(ctx))
+            _lib.check(rc, "local_sim_fwd_f32")
+        else:
+            raise RuntimeError("bf16 tensor-core mode is not built in this revision")
+    return sim, diag, mean
+
+
+@local_sim_fwd.register_fake
+def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, want_mean, mode):
+    Bi, D, S = ctx.shape
+    Bc = words.shape[0]
+    return (ctx.new_empty((Bi, Bc)), ctx.new_empty((Bc, lcap, S) if want_diag else (0,)),
+            ctx.new_empty((Bi, Bc, S) if want_mean else (0,)))
+
+
+@torch.library.custom_op("gloria_b200::local_sim_bwd", mutates_args=())
+def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int, temp1: float,
+                  temp2: float, agg: int, eps: float, dsim: Tensor, d_diag: Optional[Tensor],
+                  d_mean: Optional[Tensor], mode: int) -> Tuple[Tensor, Tensor]:
+    """Closed-form backward by recomputation: returns d_ctx [Bi, D, S], d_words [Bc, D, Lw]."""
+    _need_cuda(ctx, words, cap_lens, dsim)
+    L = _lib.lib()
+    Bi, D, S = ctx.shape
+    Bc, _, Lw = words.shape
+    ctx, words, cap_lens, dsim = ctx.contiguous(), words.contiguous(), cap_lens.contiguous(), _f32c(dsim)
+    d_diag = None if d_diag is None else _f32c(d_diag)
+    d_mean = None if d_mean is None else _f32c(d_mean)
+    dev = ctx.device
+    d_ctx = torch.empty_like(ctx)
+    d_words = torch.empty_like(words)
+    with torch.cuda.device(dev):
+        if mode == MODE_FP32:
+            nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            rc = L.gloria_b200_local_sim_bwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S,
+                                                 Lw, lcap, word_off, temp1, temp2, agg, eps, dsim.data_ptr(),
+                                                 _ptr(d_diag), _ptr(d_mean), d_ctx.data_ptr(), d_words.data_ptr(),
+                                                 ws.data_ptr(), nbytes, _stream(ctx))
+            _lib.check(rc, "local_sim_bwd_f32")
+        else:
+            raise RuntimeError("bf16 tensor-core mode is not built in this revision")
+    return d_ctx, d_words
+
+
+@local_sim_bwd.register_fake
+def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim, d_diag, d_mean, mode):
+    return torch.empty_like(ctx), torch.empty_like(words)
+
+
+def _local_setup(c, inputs, output):
+    ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, want_mean, mode = inputs
+    c.save_for_backward(ctx, words, cap_lens)
+    c.args = (lcap, word_off, temp1, temp2, agg, eps, mode)
+    c.set_materialize_grads(False)
+
+
+def _local_backward(c, dsim, d_diag, d_mean):
+    ctx, words, cap_lens = c.saved_tensors
+    lcap, word_off, temp1, temp2, agg, eps, mode = c.args
+    if dsim is None:
+        dsim = torch.zeros((ctx.shape[0], words.shape[0]), dtype=torch.float32, device=ctx.device)
+    if d_diag is not None and d_diag.numel() == 0:
+        d_diag = None
+    if d_mean is not None and d_mean.numel() == 0:
+        d_mean = None
+    d_ctx, d_words = local_sim_bwd(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim, d_diag,
+                                   d_mean, mode)
+    return d_ctx, d_words, None, None, None, None, None, None, None, None, None, None
+
+
+local_sim_fwd.register_autograd(_local_backward, setup_context=_local_setup)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# global cosine similarity  (gloria_loss.py:75-80, gloria_model.py:164-169)
+# ----------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("gloria_b200::global_sim_fwd", mutates_args=())
+def global_sim_fwd(x: Tensor, y: Tensor, eps: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """cos [Bi, Bc] = <x_a, y_b> / max(|x_a||y_b|, eps), plus the saved norms."""
+    _need_cuda(x, y)
+    L = _lib.lib()
+    x, y = x.contiguous(), y.contiguous()
+    Bi, D = x.shape
+    Bc = y.shape[0]
+    if y.shape[1] != D:
+        raise RuntimeError("global feature dims differ")
+    cosm = torch.empty((Bi, Bc), dtype=torch.float32, device=x.device)
+    xn = torch.empty((Bi,), dtype=torch.float32, device=x.device)
+    yn = torch.empty((Bc,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(L.gloria_b200_global_sim_fwd(x.data_ptr(), y.data_ptr(), Bi, Bc, D, eps, cosm.data_ptr(),
+                                                xn.data_ptr(), yn.data_ptr(), _stream(x)), "global_sim_fwd")
+    return cosm, xn, yn
+
+
+@global_sim_fwd.register_fake
+def _(x, y, eps):
+    return x.new_empty((x.shape[0], y.shape[0])), x.new_empty((x.shape[0],)), x.new_empty((y.shape[0],))
+
+
+@torch.library.custom_op("gloria_b200::global_sim_bwd", mutates_args=())
+def global_sim_bwd(x: Tensor, y: Tensor, xn: Tensor, yn: Tensor, dcos: Tensor, eps: float) -> Tuple[Tensor, Tensor]:
+    _need_cuda(x, y, dcos)
+    L = _lib.lib()
+    x, y, dcos = x.contiguous(), y.contiguous(), _f32c(dcos)
+    Bi, D = x.shape
+    Bc = y.shape[0]
+    dx, dy = torch.empty_like(x), torch.empty_like(y)
+    with torch.cuda.device(x.device):
+        _lib.check(L.gloria_b200_global_sim_bwd(x.data_ptr(), y.data_ptr(), xn.data_ptr(), yn.data_ptr(),
+                                                dcos.data_ptr(), Bi, Bc, D, eps, dx.data_ptr(), dy.data_ptr(),
+                                                _stream(x)), "global_sim_bwd")
+    return dx, dy
+
+
+@global_sim_bwd.register_fake
+def _(x, y, xn, yn, dcos, eps):
+    return torch.empty_like(x), torch.empty_like(y)
+
+
+def _global_setup(c, inputs, output):
+    x, y, eps = inputs
+    _, xn, yn = output
+    c.save_for_backward(x, y, xn, yn)
+    c.eps = eps
+    c.set_materialize_grads(False)
+
+
+def _global_backward(c, dcos, dxn, dyn):
+    x, y, xn, yn = c.saved_tensors
+    if dcos is None:
+        return torch.zeros_like(x), torch.zeros_like(y), None
+    dx, dy = global_sim_bwd(x, y, xn, yn, dcos, c.eps)
+    return dx, dy, None
+
+
+global_sim_fwd.register_autograd(_global_backward, setup_context=_global_setup)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# bidirectional cross entropy with arange labels  (gloria_loss.py:86-87, 164-170)
+# ----------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("gloria_b200::ce_bidir_fwd", mutates_args=())
+def ce_bidir_fwd(m: Tensor, scale: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """losses [2] = (CE(scale*m, arange), CE(scale*m^T, arange)); also the row/column log-sum-exps."""
+    _need_cuda(m)
+    L = _lib.lib()
+    m = m.contiguous()
+    if m.dim() != 2 or m.shape[0] != m.shape[1]:
+        raise RuntimeError(f"cross entropy with arange labels needs a square logit matrix, got {tuple(m.shape)}")
+    B = m.shape[0]
+    losses = torch.empty((2,), dtype=torch.float32, device=m.device)
+    row = torch.empty((B,), dtype=torch.float32, device=m.device)
+    col = torch.empty((B,), dtype=torch.float32, device=m.device)
+    with torch.cuda.device(m.device):
+        _lib.check(L.gloria_b200_ce_bidir_fwd(m.data_ptr(), B, scale, losses.data_ptr(), row.data_ptr(),
+                                              col.data_ptr(), _stream(m)), "ce_bidir_fwd")
+    return losses, row, col
+
+
+@ce_bidir_fwd.register_fake
+def _(m, scale):
+    return m.new_empty((2,)), m.new_empty((m.shape[0],)), m.new_empty((m.shape[0],))
+
+
+@torch.library.custom_op("gloria_b200::ce_bidir_bwd", mutates_args=())
+def ce_bidir_bwd(m: Tensor, scale: float, row: Tensor, col: Tensor, g: Tensor) -> Tensor:
+    _need_cuda(m, g)
+    L = _lib.lib()
+    m, g = m.contiguous(), _f32c(g)
+    dm = torch.empty_like(m)
+    with torch.cuda.device(m.device):
+        _lib.check(L.gloria_b200_ce_bidir_bwd(m.data_ptr(), m.shape[0], scale, row.data_ptr(), col.data_ptr(),
+                                              g.data_ptr(), dm.data_ptr(), _stream(m)), "ce_bidir_bwd")
+    return dm
+
+
+@ce_bidir_bwd.register_fake
+def _(m, scale, row, col, g):
+    return torch.empty_like(m)
+
+
+def _ce_setup(c, inputs, output):
+    m, scale = inputs
+    _, row, col = output
+    c.save_for_backward(m, row, col)
+    c.scale = scale
+    c.set_materialize_grads(False)
+
+
+def _ce_backward(c, g, drow, dcol):
+    m, row, col = c.saved_tensors
+    if g is None:
+        return torch.zeros_like(m), None
+    return ce_bidir_bwd(m, c.scale, row, col, g), None
+
+
+ce_bidir_fwd.register_autograd(_ce_backward, setup_context=_ce_setup)

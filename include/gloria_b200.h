@@ -1,0 +1,145 @@
+/*
+ * gloria_b200.h -- C ABI of libgloria_b200.so: GLoRIA local/global contrastive similarity on B200 (sm_100a).
+ *
+ * The reference (strongbeamsprout/gloria-nlp-project) is pure Python/PyTorch and has NO FFI or plugin interface;
+ * its boundary for this path is the set of Python functions in gloria/loss/gloria_loss.py and the loss methods of
+ * gloria/models/gloria_model.py.  Each entry point below names the reference code it
+ * replaces (file:line relative to the reference root).  INTEGRATION.md shows the ctypes binding and the
+ * reference-side monkey patch.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's caching allocator); the library never
+ *     allocates, frees or retains memory, and keeps no mutable global state (re-entrant, device-explicit);
+ *   - `stream` is the caller's cudaStream_t passed as void*; all work is enqueued there, nothing synchronises;
+ *   - return value 0 = success, otherwise a gloria_status (or 1000 + cudaError_t); gloria_b200_last_error()
+ *     gives a thread-local human-readable message.  No exceptions, no exit().
+ *   - layouts are the reference's native ones: region features ctx [Bi, D, S] (S = H*W regions contiguous,
+ *     gloria_loss.py:30), word features words [Bc, D, Lw] (word axis contiguous, text_model.py:126-131),
+ *     cap_lens int32 [Bc].  The caption's words are columns [word_off, word_off + cap_len) of `words`
+ *     (word_off 0: local_loss, gloria_loss.py:122; word_off 1: get_local_similarities, gloria_model.py:179).
+ *   - sim is [Bi, Bc] row-major: sim[j, i] = pair (image j, caption i), the layout of `similarities`
+ *     (gloria_loss.py:160-164) BEFORE the temp3 scale.
+ */
+#ifndef GLORIA_B200_H_
+#define GLORIA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum gloria_status {
+  GLORIA_OK = 0,
+  GLORIA_ERR_BAD_ARG = 1,       /* null pointer, non-positive size, unsupported shape */
+  GLORIA_ERR_WORKSPACE = 2,     /* workspace too small */
+  GLORIA_ERR_UNSUPPORTED = 3,   /* e.g. backward of agg = max */
+  GLORIA_ERR_DRIVER = 4,        /* a driver entry point (tensor-map encode) is unavailable */
+  GLORIA_ERR_CUDA_BASE = 1000   /* 1000 + cudaError_t */
+} gloria_status;
+
+/* aggregation over the caption's words of exp(temp2 * cos): gloria_loss.py:153-158 / gloria_model.py:198-201 */
+#define GLORIA_AGG_SUM 0
+#define GLORIA_AGG_MEAN 1
+#define GLORIA_AGG_MAX 2
+
+int gloria_b200_version(void);
+const char* gloria_b200_last_error(void);
+/* number of kernels launched by this thread's calls since the last reset (bench.py's gpu_launches) */
+long long gloria_b200_launch_count(int reset);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * fp32 mode (CUDA-core FFMA, fp32 accumulate): replaces attention_fn + cosine_similarity + the caption loop of
+ * local_loss (gloria_loss.py:11-63, 116-162) for the un-autocast reference, logits within 1e-5 relative.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Bytes of workspace wanted for Bi images x Bc captions; `budget` caps it (captions are then processed in
+ * chunks).  Always >= the minimum for one caption per chunk. */
+size_t gloria_b200_local_f32_workspace(int Bi, int Bc, int D, int S, int Lw, int Lcap, size_t budget);
+
+/* Forward.  Optional outputs (may be NULL):
+ *   attn_diag [Bc, Lcap, S]  attention map A of the diagonal pair (i, i)   (att_maps, gloria_loss.py:141-143);
+ *                            rows l >= cap_len are zero-filled.  Requires Bi == Bc.
+ *   attn_mean [Bi, Bc, S]    word-mean attention of every pair (flattened_attn, gloria_loss.py:132).
+ * Lcap is an upper bound on cap_lens (<= Lw - word_off).  */
+int gloria_b200_local_sim_fwd_f32(const float* ctx, const float* words, const int32_t* cap_lens,
+                                  int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                  float temp1, float temp2, int agg, float eps,
+                                  float* sim, float* attn_diag, float* attn_mean,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of the above by recomputation (no activations are kept between forward and backward).
+ *   dsim [Bi, Bc]; d_attn_diag [Bc, Lcap, S] or NULL; d_attn_mean [Bi, Bc, S] or NULL.
+ *   d_ctx [Bi, D, S] and d_words [Bc, D, Lw] are fully overwritten (padded word columns get exactly 0). */
+int gloria_b200_local_sim_bwd_f32(const float* ctx, const float* words, const int32_t* cap_lens,
+                                  int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                  float temp1, float temp2, int agg, float eps,
+                                  const float* dsim, const float* d_attn_diag, const float* d_attn_mean,
+                                  float* d_ctx, float* d_words,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * bf16 tensor-core mode (tcgen05 / TMEM / TMA): the fused hot path.  Same math as above with bf16 operands and
+ * fp32 accumulation and softmax (the analogue of the reference under Lightning AMP).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Padded sizes used by the packed bf16 layouts (S -> multiple of 128, L -> multiple of 16). */
+int gloria_b200_tc_spad(int S);
+int gloria_b200_tc_lpad(int Lcap);
+/* 0 if this (D, S, Lcap) is supported by the tensor-core kernels, else GLORIA_ERR_UNSUPPORTED. */
+int gloria_b200_tc_supported(int D, int S, int Lcap);
+
+/* Cast + transpose into TMA-legal bf16 layouts (native row pitches 722 B / 194 B are not 16 B multiples):
+ *   ctx_t  [Bi, Spad, D]  region-major copy (d contiguous), rows s >= S zero
+ *   ctx_n  [Bi, D, Spad]  channel-major copy (s contiguous), cols s >= S zero
+ *   words_t[Bc, Lpad, D]  word-major copy of columns [word_off, word_off+cap_len), other rows zero
+ *   wnorm  [Bc, Lpad]     fp32 |W_l| computed from the fp32 input (gloria_loss.py:14)                         */
+int gloria_b200_tc_prepack(const float* ctx, const float* words, const int32_t* cap_lens,
+                           int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                           void* ctx_t, void* ctx_n, void* words_t, float* wnorm, void* stream);
+
+size_t gloria_b200_tc_workspace(int Bi, int Bc, int D, int S, int Lcap);
+
+/* Fused forward over all Bi x Bc pairs: scores on tcgen05 (K = D), both softmaxes, attention-weighted context
+ * on tcgen05 (K = S), per-word cosine and the temp2 log-sum-exp; only sim[Bi, Bc] (and the optional maps)
+ * reach HBM.  Inputs are the prepacked buffers. */
+int gloria_b200_tc_local_sim_fwd(const void* ctx_t, const void* ctx_n, const void* words_t, const float* wnorm,
+                                 const int32_t* cap_lens, int Bi, int Bc, int D, int S, int Lcap,
+                                 float temp1, float temp2, int agg, float eps,
+                                 float* sim, float* attn_diag, float* attn_mean,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused backward by recomputation; d_ctx [Bi, D, S] fp32 and d_words [Bc, D, Lw] fp32 in the callers' native
+ * layouts are fully overwritten. */
+int gloria_b200_tc_local_sim_bwd(const void* ctx_t, const void* ctx_n, const void* words_t, const float* wnorm,
+                                 const int32_t* cap_lens, int Bi, int Bc, int D, int S, int Lw, int Lcap,
+                                 int word_off, float temp1, float temp2, int agg, float eps,
+                                 const float* dsim, const float* d_attn_diag, const float* d_attn_mean,
+                                 float* d_ctx, float* d_words,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Global similarity (global_loss, gloria_loss.py:75-80; get_global_similarities, gloria_model.py:164-169):
+ *   cosm[a, b] = <x_a, y_b> / max(|x_a| |y_b|, eps),  x [Bi, D], y [Bc, D];  xn [Bi], yn [Bc] are saved norms.
+ * ---------------------------------------------------------------------------------------------------------- */
+int gloria_b200_global_sim_fwd(const float* x, const float* y, int Bi, int Bc, int D, float eps,
+                               float* cosm, float* xn, float* yn, void* stream);
+int gloria_b200_global_sim_bwd(const float* x, const float* y, const float* xn, const float* yn,
+                               const float* dcos, int Bi, int Bc, int D, float eps,
+                               float* dx, float* dy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Bidirectional cross entropy with labels = arange(B) (gloria_loss.py:86-87 and :164-170):
+ *   logits = scale * m (m [B, B]);  losses[0] = CE(logits), losses[1] = CE(logits^T), mean reduction.
+ *   row_lse / col_lse [B] are saved for the backward.  g [2] = upstream gradients of the two losses (device).
+ * ---------------------------------------------------------------------------------------------------------- */
+int gloria_b200_ce_bidir_fwd(const float* m, int B, float scale, float* losses, float* row_lse, float* col_lse,
+                             void* stream);
+int gloria_b200_ce_bidir_bwd(const float* m, int B, float scale, const float* row_lse, const float* col_lse,
+                             const float* g, float* dm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLORIA_B200_H_ */

@@ -154,11 +154,11 @@ def _pair_block(ctx, w, temp1):
     ctx [B, D, S] (no-attn column already prepended), w [D, L].
     Returns dict of per-image intermediates.
     """
-    scores = np.einsum("bds,dl->bsl", ctx, w)               # S_[s,l]
+    scores = np.matmul(np.swapaxes(ctx, 1, 2), w)            # S_[s,l] = sum_d ctx[d,s] w[d,l]
     p = _softmax(scores, axis=2)                            # softmax over words
     a = _softmax(np.swapaxes(p, 1, 2) * temp1, axis=2)      # [B, L, S]
-    c = np.einsum("bds,bls->bdl", ctx, a)                   # weightedContext
-    dot = np.einsum("dl,bdl->bl", w, c)
+    c = np.matmul(ctx, np.swapaxes(a, 1, 2))                 # weightedContext [B, D, L]
+    dot = np.sum(w[None] * c, axis=1)
     nw = np.sqrt(np.sum(w * w, axis=0))[None, :]            # [1, L]
     nc = np.sqrt(np.sum(c * c, axis=1))                     # [B, L]
     return dict(scores=scores, p=p, a=a, c=c, dot=dot, nw=nw, nc=nc)
@@ -282,15 +282,15 @@ def local_sim_pair_bwd(ctx, w, temp1, temp2, g, agg="sum", d_attn_ext=None, eps=
         gamma = np.where(nw > 0, dnw / nw, 0.0)
     dC = ddot[:, None, :] * w[None] + beta[:, None, :] * c        # [B, D, L]
     dw = np.sum(ddot[:, None, :] * c + gamma[:, None, :] * w[None], axis=0)
-    dA = np.einsum("bdl,bds->bls", dC, ctx)
+    dA = np.matmul(np.swapaxes(dC, 1, 2), ctx)                   # [B, L, S]
     if d_attn_ext is not None:
         dA = dA + d_attn_ext
-    dctx = np.einsum("bdl,bls->bds", dC, a)
+    dctx = np.matmul(dC, a)                                      # [B, D, S]
     dZ = a * (dA - np.sum(a * dA, axis=2, keepdims=True))         # softmax #2 backward (logits temp1*P)
     dP = temp1 * np.swapaxes(dZ, 1, 2)                            # [B, S, L]
     dS = p * (dP - np.sum(p * dP, axis=2, keepdims=True))         # softmax #1 backward
-    dctx += np.einsum("dl,bsl->bds", w, dS)
-    dw += np.einsum("bds,bsl->dl", ctx, dS)
+    dctx += np.matmul(w[None], np.swapaxes(dS, 1, 2))
+    dw += np.sum(np.matmul(ctx, dS), axis=0)
     return dctx, dw
 
 

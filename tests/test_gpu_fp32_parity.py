@@ -1,0 +1,229 @@
+"""fp32-mode CUDA path vs golden vectors of the real reference and vs the numpy oracle (B200, `-m gpu`).
+
+Gates (BASELINE.json north_star): logits / loss within 1e-5 relative, gradients within 1e-2 relative (max-norm).
+Everything goes through the drop-in Python surface -> torch custom ops -> C ABI of libgloria_b200.so.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gloria_oracle as O
+from oracle.make_golden import gen_inputs
+from tests.util import Holder, cu, relerr
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-5
+GRAD_TOL = 1e-2      # the stated gate; fp32 mode is expected to sit near 1e-5
+
+
+@pytest.fixture(scope="module")
+def gl():
+    import gloria_nlp_project_b200 as g
+    from gloria_nlp_project_b200 import gloria_loss
+    g.set_precision("fp32")
+    return gloria_loss
+
+
+@pytest.fixture(scope="module")
+def small(golden_dir):
+    return dict(np.load(os.path.join(golden_dir, "small_fp64.npz")))
+
+
+VARIANTS = [
+    ("sum", dict()),
+    ("mean", dict(agg="mean", temp1=3.0, temp2=6.0, temp3=7.0)),
+    ("reg", dict(no_attn_loss_weight=0.3, attention_divergence_loss_weight=0.2, attention_entropy_loss_weight=0.1)),
+    ("ent_only", dict(attention_entropy_loss_weight=1.0, attention_divergence_loss_weight=0.5)),
+]
+
+
+@pytest.mark.parametrize("tag,kw", VARIANTS)
+def test_local_loss_small_golden(gl, small, tag, kw):
+    """local_loss forward + autograd vs the reference's outputs (gloria_loss.py:99-201)."""
+    img, txt = cu(small["img_l"], True), cu(small["txt_l"], True)
+    nav = cu(small["nav"], True) if tag == "reg" else None
+    cl = small["cap_lens"].tolist()
+    l0, l1, na, kl, ent, maps = gl.local_loss(img, txt, cl, no_attn_vec=nav, **kw)
+    assert relerr(l0, small[f"local_{tag}_loss0"]) < LOGIT_TOL
+    assert relerr(l1, small[f"local_{tag}_loss1"]) < LOGIT_TOL
+    for name, v in (("no_attn_loss", na), ("kl_loss", kl), ("entropy_loss", ent)):
+        ref = small[f"local_{tag}_{name}"]
+        if isinstance(v, torch.Tensor):
+            assert abs(float(v) - float(ref)) <= 2e-5 * max(1.0, abs(float(ref))), (name, float(v), float(ref))
+        else:
+            assert v == 0 and float(ref) == 0
+    for i, m in enumerate(maps):
+        ref = small[f"local_{tag}_att_{i}"]
+        assert tuple(m.shape) == ref.shape
+        assert relerr(m, ref) < 1e-5
+    (l0 + 0.7 * l1 + na + kl + ent).backward()
+    assert relerr(img.grad, small[f"local_{tag}_d_img"]) < 1e-4
+    assert relerr(txt.grad, small[f"local_{tag}_d_txt"]) < 1e-4
+    if nav is not None:
+        assert relerr(nav.grad, small[f"local_{tag}_d_nav"]) < 1e-4
+    for i, L in enumerate(cl):                       # padded word columns: exactly zero gradient
+        assert torch.all(txt.grad[i, :, L:] == 0)
+
+
+def test_logits_small_golden(gl, small):
+    sim, _, _, _ = gl.local_similarities(cu(small["img_l"]), cu(small["txt_l"]), small["cap_lens"].tolist())
+    assert relerr(sim * 10.0, small["local_sum_logits"]) < LOGIT_TOL
+
+
+def test_zero_word_vector(gl, small):
+    """cos = 0 through the eps clamp (gloria_loss.py:16); gradients stay finite and match."""
+    txt_np = small["txt_l"].copy()
+    txt_np[2, :, 3] = 0.0
+    img, txt = cu(small["img_l"], True), cu(txt_np, True)
+    l0, l1, *_ = gl.local_loss(img, txt, small["cap_lens"].tolist())
+    assert relerr(l0, small["zero_word_loss0"]) < LOGIT_TOL
+    assert relerr(l1, small["zero_word_loss1"]) < LOGIT_TOL
+    (l0 + l1).backward()
+    assert relerr(img.grad, small["zero_word_d_img"]) < 1e-4
+    assert relerr(txt.grad, small["zero_word_d_txt"]) < 1e-4
+
+
+def test_global_loss_golden(gl, small):
+    x, y = cu(small["img_g"], True), cu(small["txt_g"], True)
+    g0, g1 = gl.global_loss(x, y)
+    assert relerr(g0, small["global_loss0"]) < LOGIT_TOL
+    assert relerr(g1, small["global_loss1"]) < LOGIT_TOL
+    (g0 + 0.7 * g1).backward()
+    assert relerr(x.grad, small["d_img_g"]) < 1e-4
+    assert relerr(y.grad, small["d_txt_g"]) < 1e-4
+
+
+def _sents(cap_lens, Lmax):
+    return [["[CLS]"] + ["w"] * (L - 1) + ["[SEP]"] + ["[PAD]"] * (Lmax - L - 1) for L in cap_lens]
+
+
+def test_calc_loss_with_segmentation_golden(gl, small):
+    """GLoRIA.calc_loss incl. the supervised-attention term (gloria_model.py:132-150)."""
+    from gloria_nlp_project_b200.gloria_model import patch_gloria
+    cl = small["cap_lens"].tolist()
+    model = patch_gloria(Holder(segmentation_loss_weight=0.5))
+    ti, tw = cu(small["img_l"], True), cu(small["txt_l"], True)
+    tg, tt = cu(small["img_g"], True), cu(small["txt_g"], True)
+    seg = torch.tensor(small["seg_labels"], device="cuda")
+    loss, maps = model.calc_loss(ti, tg, tw, tt, _sents(cl, 11), seg)
+    assert relerr(loss, small["calc_loss"]) < LOGIT_TOL
+    loss.backward()
+    assert relerr(ti.grad, small["calc_d_img_l"]) < 1e-4
+    assert relerr(tw.grad, small["calc_d_txt_l"]) < 1e-4
+    assert relerr(tg.grad, small["calc_d_img_g"]) < 1e-4
+    assert relerr(tt.grad, small["calc_d_txt_g"]) < 1e-4
+    assert len(maps) == len(cl) and maps[0].shape == (1, cl[0], 4, 5)
+
+
+def test_attention_finetune_golden(gl, small):
+    """imagenome_attn_finetune config: contrastive weights 0, only the supervised-attention loss."""
+    from gloria_nlp_project_b200.gloria_model import patch_gloria
+    cl = small["cap_lens"].tolist()
+    model = patch_gloria(Holder(local_loss_weight=0, global_loss_weight=0, segmentation_loss_weight=1.0))
+    ti, tw = cu(small["img_l"], True), cu(small["txt_l"], True)
+    seg = torch.tensor(small["seg_labels"], device="cuda")
+    loss, _ = model.calc_loss(ti, cu(small["img_g"]), tw, cu(small["txt_g"]), _sents(cl, 11), seg)
+    assert relerr(loss, small["ft_loss"]) < LOGIT_TOL
+    loss.backward()
+    assert relerr(ti.grad, small["ft_d_img_l"]) < 1e-4
+    assert relerr(tw.grad, small["ft_d_txt_l"]) < 1e-4
+
+
+def test_model_similarities_golden(gl, small):
+    """Rectangular zero-shot shape (5 images x 3 prompts): CPU fp32 outputs like the reference's."""
+    from gloria_nlp_project_b200.gloria_model import patch_gloria
+    model = patch_gloria(Holder())
+    loc = model.get_local_similarities(cu(small["img_l"]), cu(small["txt_l"][:3]), small["zs_cap_lens"].tolist())
+    glo = model.get_global_similarities(cu(small["img_g"]), cu(small["txt_g"][:3]))
+    assert loc.device.type == "cpu" and loc.dtype == torch.float32 and tuple(loc.shape) == (5, 3)
+    assert glo.device.type == "cpu" and tuple(glo.shape) == (5, 3)
+    assert relerr(loc, small["zs_local"]) < LOGIT_TOL
+    assert relerr(glo, small["zs_global"]) < LOGIT_TOL
+    # cap_lens as a CUDA tensor (callbacks.py:393 passes batch['cap_lens'])
+    loc2 = model.get_local_similarities(cu(small["img_l"]), cu(small["txt_l"][:3]),
+                                        torch.tensor(small["zs_cap_lens"], device="cuda"))
+    assert torch.equal(loc, loc2)
+    maps = model.get_attn_maps(cu(small["img_l"]), cu(small["txt_l"]), _sents(small["cap_lens"].tolist(), 11))
+    for i, m in enumerate(maps):
+        assert relerr(m, small[f"model_att_{i}"]) < 1e-5
+
+
+@pytest.mark.parametrize("tag,scale", [("unit", 1.0), ("small", 0.05)])
+def test_full_dims_golden(gl, golden_dir, tag, scale):
+    """D=768, 19x19 regions, up to 97 words (B=3): logits, loss, maps and gradients vs the reference."""
+    g = dict(np.load(os.path.join(golden_dir, f"full_{tag}.npz")))
+    img_l, txt_l, _, _, cl = gen_inputs(7, 3, 768, 19, 19, 97, cap_lens=[97, 41, 5], scale=scale)
+    img, txt = cu(img_l, True), cu(txt_l, True)
+    sim, _, _, _ = gl.local_similarities(img.detach(), txt.detach(), cl)
+    assert relerr(sim * 10.0, g["f64_logits"]) < LOGIT_TOL
+    l0, l1, _, _, _, maps = gl.local_loss(img, txt, cl)
+    assert relerr(l0, g["f64_loss0"]) < LOGIT_TOL and relerr(l1, g["f64_loss1"]) < LOGIT_TOL
+    assert relerr(maps[1], g["f64_att_1"]) < 1e-5
+    (l0 + l1).backward()
+    assert relerr(img.grad[:, ::16, ::3, ::3], g["f64_d_img_sub"]) < 1e-3
+    assert relerr(txt.grad[:, ::16, ::4], g["f64_d_txt_sub"]) < 1e-3
+    zs, _, _, _ = gl.local_similarities(img.detach(), txt.detach(), [c - 1 for c in cl if c > 1] + [3], 4.0, 5.0, "max",
+                                        word_offset=1)
+    assert relerr(zs, g["zs_local_f32"]) < LOGIT_TOL
+
+
+@pytest.mark.parametrize("B,seed,scale,chunk_bytes", [(16, 3, 1.0, None), (16, 4, 0.05, 600 << 20), (48, 5, 1.0, None)])
+def test_vs_oracle_config_shapes(gl, B, seed, scale, chunk_bytes, monkeypatch):
+    """BASELINE configs[0] (B=16) and configs[1] (B=48, chexpert_pretrain) in fp32 vs the numpy oracle; one case
+    forces the caption-chunked path through a small workspace budget."""
+    from gloria_nlp_project_b200 import ops
+    if chunk_bytes is not None:
+        monkeypatch.setattr(ops, "_WS_BUDGET", chunk_bytes)
+    img_l, txt_l, img_g, txt_g, cl = gen_inputs(seed, B, 768, 19, 19, 97, scale=scale, dtype=np.float32)
+    img, txt, xg, yg = cu(img_l, True), cu(txt_l, True), cu(img_g, True), cu(txt_g, True)
+    l0, l1, _, _, _, maps = gl.local_loss(img, txt, cl)
+    g0, g1 = gl.global_loss(xg, yg)
+    (l0 + l1 + g0 + g1).backward()
+    o0, o1, _, _, _, omaps, ologits = O.local_loss(img_l.astype(np.float64), txt_l.astype(np.float64), cl)
+    og0, og1, _ = O.global_loss(img_g.astype(np.float64), txt_g.astype(np.float64))
+    assert relerr(l0, o0) < LOGIT_TOL and relerr(l1, o1) < LOGIT_TOL
+    assert relerr(g0, og0) < LOGIT_TOL and relerr(g1, og1) < LOGIT_TOL
+    sim, _, _, _ = gl.local_similarities(img.detach(), txt.detach(), cl)
+    assert relerr(sim * 10.0, ologits) < LOGIT_TOL
+    for i in (0, B // 2, B - 1):
+        assert relerr(maps[i], omaps[i]) < 1e-5
+    d_img, d_txt = O.local_loss_bwd(img_l.astype(np.float64), txt_l.astype(np.float64), cl)
+    assert relerr(img.grad, d_img) < 1e-3
+    assert relerr(txt.grad, d_txt) < 1e-3
+    dx, dy = O.global_loss_bwd(img_g.astype(np.float64), txt_g.astype(np.float64))
+    assert relerr(xg.grad, dx) < 1e-4 and relerr(yg.grad, dy) < 1e-4
+
+
+def test_properties(gl):
+    """Size-independent properties: permutation equivariance over images and captions,
+    attention rows sum to one, B_img = 1 (retrieval call shape) and L = 1."""
+    img_l, txt_l, _, _, cl = gen_inputs(9, 6, 768, 19, 19, 97, dtype=np.float32)
+    img, txt = cu(img_l), cu(txt_l)
+    sim, diag, mean, _ = gl.local_similarities(img, txt, cl, want_attn_maps=True, want_mean_attn=True)
+    pi = torch.tensor([3, 0, 5, 1, 4, 2], device="cuda")
+    pc = torch.tensor([2, 4, 0, 5, 1, 3], device="cuda")
+    sim_p, _, _, _ = gl.local_similarities(img[pi], txt[pc], [cl[i] for i in pc.tolist()])
+    assert torch.allclose(sim_p, sim[pi][:, pc], rtol=1e-6, atol=1e-6)
+    for i, L in enumerate(cl):
+        assert torch.allclose(diag[i, :L].sum(-1), torch.ones(L, device="cuda"), atol=1e-5)
+        assert torch.all(diag[i, L:] == 0)
+    assert torch.allclose(mean.sum(-1), torch.ones_like(mean[..., 0]), atol=1e-5)
+    one, _, _, _ = gl.local_similarities(img[:1], txt, cl)            # 1 image x N texts
+    assert torch.allclose(one, sim[:1], rtol=1e-6, atol=1e-6)
+    l1, _, _, _ = gl.local_similarities(img, txt, [1] * 6)            # single-word captions
+    ref = O.local_similarities(img_l.astype(np.float64), txt_l.astype(np.float64), [1] * 6)
+    assert relerr(l1, ref) < LOGIT_TOL
+
+
+def test_errors_are_runtime_errors(gl):
+    img = torch.randn(2, 8, 2, 2, device="cuda")
+    txt = torch.randn(2, 8, 5, device="cuda")
+    with pytest.raises(RuntimeError):
+        gl.local_similarities(img, txt, [9, 2])                       # cap_len beyond the word axis
+    with pytest.raises(RuntimeError):
+        gl.local_similarities(img.cpu(), txt.cpu(), [2, 2])           # no CPU fallback
+    with pytest.raises(RuntimeError):
+        gl.global_loss(torch.randn(3, 8, device="cuda"), torch.randn(4, 8, device="cuda"))   # CE needs square
