@@ -119,11 +119,11 @@ def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim, d_diag
     return torch.empty_like(ctx), torch.empty_like(words)
 
 
-def _local_setup(c, inputs, output):
-    ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, want_mean, mode = inputs
-    c.save_for_backward(ctx, words, cap_lens)
-    c.args = (lcap, word_off, temp1, temp2, agg, eps, mode)
-    c.set_materialize_grads(False)
+def _local_setup(ctx, inputs, output):
+    feats, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, want_mean, mode = inputs
+    ctx.save_for_backward(feats, words, cap_lens)
+    ctx.args = (lcap, word_off, temp1, temp2, agg, eps, mode)
+    ctx.set_materialize_grads(False)
 
 
 def _local_backward(c, dsim, d_diag, d_mean):
@@ -190,12 +190,12 @@ def _(x, y, xn, yn, dcos, eps):
     return torch.empty_like(x), torch.empty_like(y)
 
 
-def _global_setup(c, inputs, output):
+def _global_setup(ctx, inputs, output):
     x, y, eps = inputs
     _, xn, yn = output
-    c.save_for_backward(x, y, xn, yn)
-    c.eps = eps
-    c.set_materialize_grads(False)
+    ctx.save_for_backward(x, y, xn, yn)
+    ctx.eps = eps
+    ctx.set_materialize_grads(False)
 
 
 def _global_backward(c, dcos, dxn, dyn):
@@ -252,12 +252,12 @@ def _(m, scale, row, col, g):
     return torch.empty_like(m)
 
 
-def _ce_setup(c, inputs, output):
+def _ce_setup(ctx, inputs, output):
     m, scale = inputs
     _, row, col = output
-    c.save_for_backward(m, row, col)
-    c.scale = scale
-    c.set_materialize_grads(False)
+    ctx.save_for_backward(m, row, col)
+    ctx.scale = scale
+    ctx.set_materialize_grads(False)
 
 
 def _ce_backward(c, g, drow, dcol):

@@ -17,6 +17,10 @@ pytestmark = pytest.mark.gpu
 
 LOGIT_TOL = 1e-5
 GRAD_TOL = 1e-2      # the stated gate; fp32 mode is expected to sit near 1e-5
+# Attention maps have no stated gate.  With unit-variance 768-d features the scores are O(100), so fp32 accumulation
+# leaves ~1e-5 absolute error in a score and therefore ~1e-5 RELATIVE error in a softmax entry: 1e-4 is the fp32
+# floor here (the fp32 reference sits at the same distance from fp64); small-score inputs are held to 1e-5.
+MAP_TOL_UNIT = 1e-4
 
 
 @pytest.fixture(scope="module")
@@ -161,7 +165,7 @@ def test_full_dims_golden(gl, golden_dir, tag, scale):
     assert relerr(sim * 10.0, g["f64_logits"]) < LOGIT_TOL
     l0, l1, _, _, _, maps = gl.local_loss(img, txt, cl)
     assert relerr(l0, g["f64_loss0"]) < LOGIT_TOL and relerr(l1, g["f64_loss1"]) < LOGIT_TOL
-    assert relerr(maps[1], g["f64_att_1"]) < 1e-5
+    assert relerr(maps[1], g["f64_att_1"]) < (MAP_TOL_UNIT if tag == "unit" else 1e-5)
     (l0 + l1).backward()
     assert relerr(img.grad[:, ::16, ::3, ::3], g["f64_d_img_sub"]) < 1e-3
     assert relerr(txt.grad[:, ::16, ::4], g["f64_d_txt_sub"]) < 1e-3
@@ -189,7 +193,7 @@ def test_vs_oracle_config_shapes(gl, B, seed, scale, chunk_bytes, monkeypatch):
     sim, _, _, _ = gl.local_similarities(img.detach(), txt.detach(), cl)
     assert relerr(sim * 10.0, ologits) < LOGIT_TOL
     for i in (0, B // 2, B - 1):
-        assert relerr(maps[i], omaps[i]) < 1e-5
+        assert relerr(maps[i], omaps[i]) < (MAP_TOL_UNIT if scale == 1.0 else 1e-5)
     d_img, d_txt = O.local_loss_bwd(img_l.astype(np.float64), txt_l.astype(np.float64), cl)
     assert relerr(img.grad, d_img) < 1e-3
     assert relerr(txt.grad, d_txt) < 1e-3
