@@ -1,26 +1,495 @@
-// bf16 tensor-core mode (tcgen05 / TMEM / TMA) -- placeholder entry points until the kernels land.
+// bf16 tensor-core mode of the GLoRIA local similarity (sm_100a: TMA + tcgen05 + TMEM).
+//
+// One "unit" = (caption i, image j).  Per unit, inside one persistent CTA:
+//   GEMM1  D1[s, l] = sum_d Rt[j][s][d] * Wt[i][l][d]            M = 128 regions (x NT tiles), N = LPAD, K = D
+//          -> TMEM (lanes = regions, double buffered), so softmax #1 over the caption's words is thread-local
+//   softmax warps:  P = softmax_l(D1);  E = exp(temp1 * P)  (un-normalised softmax #2 numerator, in [1, e^temp1])
+//          -> bf16, written to shared memory as the MN-major A operand of GEMM2
+//   GEMM2  D2[l, d] = sum_s E[s, l] * Rn[j][d][s]                M = 128 words, N = 128 channels (x D/128), K = Spad
+//          -> TMEM (lanes = words, double buffered): C' = Z_l * weightedContext
+//   epilogue warps: dot_l = <W_l, C'_l>, |C'_l|^2 thread-local over d; cos_l is invariant to the softmax-#2
+//          normaliser Z_l, so it is never needed; then the temp2 log-sum-exp over words.
+// Only sim[Bi, Bc] reaches HBM.  gloria_loss.py:19-63 + :144-158 per pair.
 #include "common.cuh"
+#include "tc_common.cuh"
+
+namespace gloria {
+namespace tc {
+
+constexpr int KBLK = 64;                 // bf16 per 128-byte swizzle row
+constexpr int TILE = 128;                // regions per GEMM1 tile == words per GEMM2 tile == channels per D2 chunk
+constexpr int MAX_NT = 3;                // Spad <= 384
+constexpr int NSTAGE = 3;
+constexpr int STAGE_BYTES = 32768;       // A part [0,16K) + B part [16K,32K)
+constexpr int E_BYTES = 2 * MAX_NT * TILE * 128;   // [2 word blocks of 64][Spad regions][128 B]
+constexpr int OFF_E = NSTAGE * STAGE_BYTES;
+constexpr int OFF_BAR = OFF_E + E_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + barriers/scratch + alignment slack
+constexpr int NTHREADS = 384;            // warps 0-3 control, 4-7 softmax, 8-11 epilogue
+
+// barrier indices (8 B each) inside the barrier block
+enum { B_FULL = 0, B_EMPTY = 3, B_D1F = 6, B_D1E = 8, B_EF = 10, B_EE = 11, B_D2F = 12, B_D2E = 14, B_COUNT = 16 };
+
+struct FwdParams {
+  const __nv_bfloat16* wt;   // [Bc, LPAD, D]
+  const float* wnorm;        // [Bc, LPAD]
+  const int* cap_lens;
+  float* sim;                // [Bi, Bc]
+  int Bi, Bc, D, S, NT;
+  float t1_log2e;            // temp1 * log2(e)
+  float temp2;
+  int agg;
+  float eps_s;               // eps * S  (clamp on the un-normalised context, see header comment)
+};
+
+// Static unit schedule shared by all warp roles.  Captions are dealt to CTAs in blocks of gridDim.x; in a block
+// with fewer captions than CTAs, several CTAs split one caption's images.  All CTAs sweep the images in step, so
+// the region tiles of an image are read from L2 by every SM at about the same time.
+struct Units {
+  int Bi, Bc, ncta, cta;
+  int blk, i, j, j_end;
+  __device__ Units(int Bi_, int Bc_) : Bi(Bi_), Bc(Bc_), ncta(gridDim.x), cta(blockIdx.x), blk(-1), i(0), j(0), j_end(0) {}
+  __device__ bool next_caption() {
+    while (true) {
+      ++blk;
+      const int base = blk * ncta;
+      if (base >= Bc) return false;
+      const int nb = min(ncta, Bc - base);
+      const int g = ncta / nb;
+      if (cta < nb * g) {
+        i = base + cta % nb;
+        const int sl = cta / nb;
+        j = (int)((long long)sl * Bi / g);
+        j_end = (int)((long long)(sl + 1) * Bi / g);
+        if (j < j_end) return true;
+      }
+    }
+  }
+};
+
+template <int LPAD>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__ CUtensorMap tm_wt,
+              const __grid_constant__ CUtensorMap tm_rn, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + OFF_BAR;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
+  float* red = reinterpret_cast<float*>(smem + OFF_BAR + B_COUNT * 8 + 16);   // 8 floats of LSE scratch
+  auto bar = [&](int idx) { return bars + 8u * (uint32_t)idx; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Spad = p.NT * TILE;
+  const int nkb1 = p.D / KBLK;        // k-blocks of GEMM1
+  const int nkb2 = Spad / KBLK;       // k-blocks of GEMM2
+  const int nchunk = p.D / TILE;      // D2 chunks
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(B_D1F + b), 1); mbar_init(bar(B_D1E + b), 128);
+      mbar_init(bar(B_D2F + b), 1); mbar_init(bar(B_D2E + b), 128);
+    }
+    mbar_init(bar(B_EF), 128 * p.NT);
+    mbar_init(bar(B_EE), 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_rt); tma_prefetch_desc(&tm_wt); tma_prefetch_desc(&tm_rn);
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      Units u(p.Bi, p.Bc);
+      while (u.next_caption()) {
+        for (int j = u.j; j < u.j_end; ++j) {
+          for (int t = 0; t < p.NT; ++t)
+            for (int kb = 0; kb < nkb1; ++kb) {
+              mbar_wait(bar(B_EMPTY + st), ph ^ 1);
+              mbar_expect_tx(bar(B_FULL + st), TILE * 128 + LPAD * 128);
+              tma_load_2d(base + st * STAGE_BYTES, &tm_rt, kb * KBLK, j * Spad + t * TILE, bar(B_FULL + st));
+              tma_load_2d(base + st * STAGE_BYTES + 16384, &tm_wt, kb * KBLK, u.i * LPAD, bar(B_FULL + st));
+              if (++st == NSTAGE) { st = 0; ph ^= 1; }
+            }
+          for (int c = 0; c < nchunk; ++c)
+            for (int kb = 0; kb < nkb2; ++kb) {
+              mbar_wait(bar(B_EMPTY + st), ph ^ 1);
+              mbar_expect_tx(bar(B_FULL + st), TILE * 128);
+              tma_load_2d(base + st * STAGE_BYTES, &tm_rn, kb * KBLK, j * p.D + c * TILE, bar(B_FULL + st));
+              if (++st == NSTAGE) { st = 0; ph ^= 1; }
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc(TILE, LPAD, 0, 0);   // A = Rt tile (K-major), B = Wt tile (K-major)
+      constexpr uint32_t idesc2 = make_idesc(TILE, TILE, 1, 0);   // A = E (MN-major), B = Rn tile (K-major)
+      const uint32_t e_lbo = (uint32_t)Spad * 128u;               // between the two 64-word blocks of E
+      int st = 0; uint32_t ph = 0;
+      uint32_t g1 = 0, g2 = 0, nu = 0;
+      Units u(p.Bi, p.Bc);
+      while (u.next_caption()) {
+        for (int j = u.j; j < u.j_end; ++j) {
+          for (int t = 0; t < p.NT; ++t) {
+            const uint32_t b = g1 & 1;
+            mbar_wait(bar(B_D1E + b), ((g1 >> 1) & 1) ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < nkb1; ++kb) {
+              mbar_wait(bar(B_FULL + st), ph);
+              tc_fence_after();
+              const uint32_t a0 = base + st * STAGE_BYTES, b0 = a0 + 16384;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem + b * TILE, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024),
+                          idesc1, (uint32_t)((kb | k) != 0));
+              umma_commit(bar(B_EMPTY + st));
+              if (++st == NSTAGE) { st = 0; ph ^= 1; }
+            }
+            umma_commit(bar(B_D1F + b));
+            ++g1;
+          }
+          mbar_wait(bar(B_EF), nu & 1);          // every E tile of this unit is in shared memory
+          tc_fence_after();
+          for (int c = 0; c < nchunk; ++c) {
+            const uint32_t b2 = g2 & 1;
+            mbar_wait(bar(B_D2E + b2), ((g2 >> 1) & 1) ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < nkb2; ++kb) {
+              mbar_wait(bar(B_FULL + st), ph);
+              tc_fence_after();
+              const uint32_t b0 = base + st * STAGE_BYTES;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t region0 = (uint32_t)(kb * KBLK + k * 16);
+                umma_bf16(tmem + 2 * TILE + b2 * TILE,
+                          make_smem_desc(base + OFF_E + (region0 >> 3) * 1024, e_lbo, 1024),
+                          make_smem_desc(b0 + k * 32, 16, 1024), idesc2, (uint32_t)((kb | k) != 0));
+              }
+              umma_commit(bar(B_EMPTY + st));
+              if (++st == NSTAGE) { st = 0; ph ^= 1; }
+            }
+            umma_commit(bar(B_D2F + b2));
+            ++g2;
+          }
+          umma_commit(bar(B_EE));                // GEMM2 has finished reading E
+          ++nu;
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ softmax warps (TMEM lanes = regions)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;               // region row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    constexpr float LOG2E = 1.4426950408889634f;
+    uint32_t g1 = 0, nu = 0;
+    Units u(p.Bi, p.Bc);
+    while (u.next_caption()) {
+      const int L = min(max(p.cap_lens[u.i], 0), LPAD);
+      for (int j = u.j; j < u.j_end; ++j) {
+        for (int t = 0; t < p.NT; ++t) {
+          const uint32_t b = g1 & 1;
+          mbar_wait(bar(B_D1F + b), (g1 >> 1) & 1);
+          tc_fence_after();
+          float x[LPAD];
+#pragma unroll
+          for (int c = 0; c < LPAD / 16; ++c) tmem_ld16(tmem + lane_addr + b * TILE + c * 16, x + c * 16);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(bar(B_D1E + b));           // D1 buffer may be overwritten by the next tile's GEMM1
+          ++g1;
+          // softmax #1 over the caption's words (gloria_loss.py:42-43), true running max
+          float m = -INFINITY;
+#pragma unroll
+          for (int l = 0; l < LPAD; ++l) m = (l < L) ? fmaxf(m, x[l]) : m;
+          const float mb = m * LOG2E;
+          float sum = 0.f;
+#pragma unroll
+          for (int l = 0; l < LPAD; ++l) {
+            const float e = (l < L) ? ex2(fmaf(x[l], LOG2E, -mb)) : 0.f;
+            x[l] = e;
+            sum += e;
+          }
+          // numerator of softmax #2 (:51-52): exp(temp1 * P); padded regions / words contribute nothing
+          const int s_glob = t * TILE + row;
+          const bool live_row = s_glob < p.S;
+          const float sc = p.t1_log2e / sum;
+#pragma unroll
+          for (int l = 0; l < LPAD; ++l) x[l] = (live_row && l < L) ? ex2(x[l] * sc) : 0.f;
+          if (t == 0) mbar_wait(bar(B_EE), (nu & 1) ^ 1);   // previous unit's GEMM2 no longer reads E
+          // MN-major SWIZZLE_128B A operand: [word block of 64][region][64 words], 16-B chunk ^= region % 8
+          const uint32_t rowaddr = base + OFF_E + (uint32_t)(s_glob >> 3) * 1024u + (uint32_t)(s_glob & 7) * 128u;
+#pragma unroll
+          for (int wb = 0; wb < (LPAD + 63) / 64; ++wb) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const int l0 = wb * 64 + c * 8;
+              if (l0 < LPAD) {
+                const uint32_t addr = rowaddr + (uint32_t)wb * ((uint32_t)Spad * 128u) + (uint32_t)((c ^ (s_glob & 7)) << 4);
+                sts128(addr, pack_bf16(x[l0], x[l0 + 1]), pack_bf16(x[l0 + 2], x[l0 + 3]),
+                       pack_bf16(x[l0 + 4], x[l0 + 5]), pack_bf16(x[l0 + 6], x[l0 + 7]));
+              }
+            }
+          }
+          fence_proxy_async_smem();              // generic-proxy stores -> visible to the tensor core (async proxy)
+          mbar_arrive(bar(B_EF));
+        }
+        ++nu;
+      }
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------------ epilogue warps (TMEM lanes = words)
+    const int q = warp & 3;
+    const int l = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int et = threadIdx.x - 256;            // 0..127
+    uint32_t g2 = 0;
+    Units u(p.Bi, p.Bc);
+    while (u.next_caption()) {
+      const int L = min(max(p.cap_lens[u.i], 0), LPAD);
+      const bool live = l < L;
+      const float nw = (l < LPAD) ? p.wnorm[(size_t)u.i * LPAD + l] : 0.f;
+      const uint4* wrow = reinterpret_cast<const uint4*>(p.wt + ((size_t)u.i * LPAD + (l < LPAD ? l : 0)) * p.D);
+      for (int j = u.j; j < u.j_end; ++j) {
+        float dot = 0.f, c2 = 0.f;
+        for (int c = 0; c < nchunk; ++c) {
+          const uint32_t b2 = g2 & 1;
+          mbar_wait(bar(B_D2F + b2), (g2 >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int h = 0; h < TILE / 16; ++h) {
+            uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
+            if (live) {
+              w0 = __ldg(wrow + (c * TILE + h * 16) / 8);
+              w1 = __ldg(wrow + (c * TILE + h * 16) / 8 + 1);
+            }
+            float v[16];
+            tmem_ld16(tmem + lane_addr + 2 * TILE + b2 * TILE + h * 16, v);
+            tmem_ld_wait();
+            const uint32_t wr[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float wa = __uint_as_float(wr[k] << 16), wb = __uint_as_float(wr[k] & 0xFFFF0000u);
+              dot = fmaf(v[2 * k], wa, dot);
+              dot = fmaf(v[2 * k + 1], wb, dot);
+              c2 = fmaf(v[2 * k], v[2 * k], c2);
+              c2 = fmaf(v[2 * k + 1], v[2 * k + 1], c2);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(bar(B_D2E + b2));
+          ++g2;
+        }
+        // cosine (gloria_loss.py:11-16) and the temp2 aggregation over words (:153-158 / gloria_model.py:198-201)
+        const float den = fmaxf(nw * sqrtf(c2), p.eps_s);
+        const float v = live ? p.temp2 * (dot / den) : -INFINITY;
+        float mx = warp_max(v);
+        if (lane == 0) red[q] = mx;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+        float ex = live ? __expf(v - mx) : 0.f;
+        ex = warp_sum(ex);
+        if (lane == 0) red[4 + q] = ex;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+          const float tot = red[4] + red[5] + red[6] + red[7];
+          float r;
+          if (p.agg == GLORIA_AGG_MAX) r = mx;
+          else {
+            r = mx + logf(tot);
+            if (p.agg == GLORIA_AGG_MEAN) r -= logf((float)L);
+          }
+          p.sim[(size_t)j * p.Bc + u.i] = r;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // red[] reusable
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prepack: fp32 native layouts -> padded bf16 TMA-legal layouts
+// ---------------------------------------------------------------------------------------------------------------
+// ctx [Bi, D, S] -> Rn [Bi, D, Spad] and Rt [Bi, Spad, D];  grid (Spad/32, D/32, Bi), block (32, 8)
+__global__ void pack_ctx(const float* __restrict__ ctx, __nv_bfloat16* __restrict__ Rn, __nv_bfloat16* __restrict__ Rt,
+                         int D, int S, int Spad) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, s0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int d = d0 + r, s = s0 + threadIdx.x;
+    const float v = (s < S) ? ctx[((size_t)b * D + d) * S + s] : 0.f;
+    Rn[((size_t)b * D + d) * Spad + s] = __float2bfloat16_rn(v);
+    t[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int s = s0 + r, d = d0 + threadIdx.x;
+    Rt[((size_t)b * Spad + s) * D + d] = __float2bfloat16_rn(t[threadIdx.x][r]);
+  }
+}
+
+// words [Bc, D, Lw] -> Wt [Bc, LPAD, D] (rows >= cap_len zero) and wnorm [Bc, LPAD];  grid (LPAD/32.., 1, Bc), block (32, 8)
+__global__ void pack_words(const float* __restrict__ words, const int* __restrict__ cap_lens,
+                           __nv_bfloat16* __restrict__ Wt, float* __restrict__ wnorm, int D, int Lw, int lpad, int lcap,
+                           int off) {
+  __shared__ float t[32][33];
+  __shared__ float part[8][32];
+  const int i = blockIdx.z, l0 = blockIdx.x * 32;
+  const int L = min(max(cap_lens[i], 0), lcap);
+  const int lr = l0 + threadIdx.x;                 // word handled by this thread in the read phase
+  float ss = 0.f;
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    for (int r = threadIdx.y; r < 32; r += 8) {
+      const int d = d0 + r;
+      const float v = (lr < L && d < D) ? words[((size_t)i * D + d) * Lw + off + lr] : 0.f;
+      ss = fmaf(v, v, ss);
+      t[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+      const int l = l0 + r, d = d0 + threadIdx.x;
+      if (l < lpad && d < D) Wt[((size_t)i * lpad + l) * D + d] = __float2bfloat16_rn(t[threadIdx.x][r]);
+    }
+    __syncthreads();
+  }
+  part[threadIdx.y][threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.y == 0 && lr < lpad) {
+    float tot = 0.f;
+    for (int k = 0; k < 8; ++k) tot += part[k][threadIdx.x];
+    wnorm[(size_t)i * lpad + lr] = sqrtf(tot);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return (EncodeTiledFn) nullptr;
+    return (EncodeTiledFn)ptr;
+  }();
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, inner] (inner contiguous), box [box_rows, 64], SWIZZLE_128B
+int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(GLORIA_ERR_DRIVER, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {KBLK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GLORIA_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return GLORIA_OK;
+}
+
+template <int LPAD>
+int launch_fwd(const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap& rn, const FwdParams& p, int grid,
+               cudaStream_t st) {
+  GLORIA_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<LPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  tc_fwd_kernel<LPAD><<<grid, NTHREADS, SMEM_BYTES, st>>>(rt, wt, rn, p);
+  GLORIA_LAUNCHED("tc_fwd_kernel");
+  return GLORIA_OK;
+}
+
+}  // namespace tc
+}  // namespace gloria
 
 using namespace gloria;
+using namespace gloria::tc;
 
-extern "C" int gloria_b200_tc_spad(int S) { return (S + 127) / 128 * 128; }
+extern "C" int gloria_b200_tc_spad(int S) { return (S + TILE - 1) / TILE * TILE; }
 extern "C" int gloria_b200_tc_lpad(int Lcap) { return (Lcap + 15) / 16 * 16; }
+
 extern "C" int gloria_b200_tc_supported(int D, int S, int Lcap) {
-  (void)D; (void)S; (void)Lcap;
-  return GLORIA_ERR_UNSUPPORTED;
+  if (D < TILE || D % TILE != 0 || S < 1 || S > MAX_NT * TILE || Lcap < 1 || Lcap > TILE) return GLORIA_ERR_UNSUPPORTED;
+  return GLORIA_OK;
 }
-extern "C" int gloria_b200_tc_prepack(const float*, const float*, const int32_t*, int, int, int, int, int, int, int,
-                                      void*, void*, void*, float*, void*) {
-  return fail(GLORIA_ERR_UNSUPPORTED, "tensor-core path not built yet");
+
+extern "C" int gloria_b200_tc_prepack(const float* ctx, const float* words, const int32_t* cap_lens, int Bi, int Bc,
+                                      int D, int S, int Lw, int Lcap, int word_off, void* ctx_t, void* ctx_n,
+                                      void* words_t, float* wnorm, void* stream) {
+  GLORIA_CHECK_ARG(ctx && words && cap_lens && ctx_t && ctx_n && words_t && wnorm, "null pointer");
+  GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
+  if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
+  pack_ctx<<<dim3(Spad / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(ctx, (__nv_bfloat16*)ctx_n, (__nv_bfloat16*)ctx_t, D, S,
+                                                               Spad);
+  GLORIA_LAUNCHED("pack_ctx");
+  pack_words<<<dim3((lpad + 31) / 32, 1, Bc), dim3(32, 8), 0, st>>>(words, cap_lens, (__nv_bfloat16*)words_t, wnorm, D,
+                                                                    Lw, lpad, Lcap, word_off);
+  GLORIA_LAUNCHED("pack_words");
+  return GLORIA_OK;
 }
-extern "C" size_t gloria_b200_tc_workspace(int, int, int, int, int) { return 0; }
-extern "C" int gloria_b200_tc_local_sim_fwd(const void*, const void*, const void*, const float*, const int32_t*, int,
-                                            int, int, int, int, float, float, int, float, float*, float*, float*,
-                                            void*, size_t, void*) {
-  return fail(GLORIA_ERR_UNSUPPORTED, "tensor-core path not built yet");
+
+extern "C" size_t gloria_b200_tc_workspace(int, int, int, int, int) { return 256; }
+
+extern "C" int gloria_b200_tc_local_sim_fwd(const void* ctx_t, const void* ctx_n, const void* words_t,
+                                            const float* wnorm, const int32_t* cap_lens, int Bi, int Bc, int D, int S,
+                                            int Lcap, float temp1, float temp2, int agg, float eps, float* sim,
+                                            float* attn_diag, float* attn_mean, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  GLORIA_CHECK_ARG(ctx_t && ctx_n && words_t && wnorm && cap_lens && sim, "null pointer");
+  GLORIA_CHECK_ARG(Bi > 0 && Bc > 0, "bad batch sizes %d x %d", Bi, Bc);
+  if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
+  if (attn_diag || attn_mean)
+    return fail(GLORIA_ERR_UNSUPPORTED, "attention-map outputs come from the fp32 kernels in this revision");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
+  CUtensorMap rt, wt, rn;
+  int rc;
+  if ((rc = make_map(&rt, ctx_t, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;
+  if ((rc = make_map(&wt, words_t, (uint64_t)D, (uint64_t)Bc * lpad, (uint32_t)lpad))) return rc;
+  if ((rc = make_map(&rn, ctx_n, (uint64_t)Spad, (uint64_t)Bi * D, TILE))) return rc;
+  FwdParams p;
+  p.wt = (const __nv_bfloat16*)words_t; p.wnorm = wnorm; p.cap_lens = cap_lens; p.sim = sim;
+  p.Bi = Bi; p.Bc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE;
+  p.t1_log2e = temp1 * 1.4426950408889634f; p.temp2 = temp2; p.agg = agg; p.eps_s = eps * (float)S;
+  int dev = 0, sms = 0;
+  GLORIA_CUDA(cudaGetDevice(&dev));
+  GLORIA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = sms;
+  switch (lpad) {
+    case 16: return launch_fwd<16>(rt, wt, rn, p, grid, st);
+    case 32: return launch_fwd<32>(rt, wt, rn, p, grid, st);
+    case 48: return launch_fwd<48>(rt, wt, rn, p, grid, st);
+    case 64: return launch_fwd<64>(rt, wt, rn, p, grid, st);
+    case 80: return launch_fwd<80>(rt, wt, rn, p, grid, st);
+    case 96: return launch_fwd<96>(rt, wt, rn, p, grid, st);
+    case 112: return launch_fwd<112>(rt, wt, rn, p, grid, st);
+    case 128: return launch_fwd<128>(rt, wt, rn, p, grid, st);
+  }
+  return fail(GLORIA_ERR_UNSUPPORTED, "lpad %d", lpad);
 }
+
 extern "C" int gloria_b200_tc_local_sim_bwd(const void*, const void*, const void*, const float*, const int32_t*, int,
                                             int, int, int, int, int, int, float, float, int, float, const float*,
                                             const float*, const float*, float*, float*, void*, size_t, void*) {
-  return fail(GLORIA_ERR_UNSUPPORTED, "tensor-core path not built yet");
+  return fail(GLORIA_ERR_UNSUPPORTED, "tensor-core backward not built yet");
 }

@@ -19,6 +19,25 @@ AGG = {"sum": 0, "mean": 1, "max": 2}
 MODE_FP32, MODE_BF16 = 0, 1
 
 _WS_BUDGET = int(os.environ.get("GLORIA_B200_WS_BYTES", str(4 << 30)))
+_TC_BWD = False      # flipped once the tcgen05 backward kernel is in the library
+
+
+def tc_prepack(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int):
+    """fp32 native layouts -> (ctx_t [Bi,Spad,D], ctx_n [Bi,D,Spad], words_t [Bc,Lpad,D]) bf16 + wnorm [Bc,Lpad] fp32."""
+    L = _lib.lib()
+    Bi, D, S = ctx.shape
+    Bc, _, Lw = words.shape
+    spad, lpad = L.gloria_b200_tc_spad(S), L.gloria_b200_tc_lpad(lcap)
+    dev = ctx.device
+    ctx_t = torch.empty((Bi, spad, D), dtype=torch.bfloat16, device=dev)
+    ctx_n = torch.empty((Bi, D, spad), dtype=torch.bfloat16, device=dev)
+    words_t = torch.empty((Bc, lpad, D), dtype=torch.bfloat16, device=dev)
+    wnorm = torch.empty((Bc, lpad), dtype=torch.float32, device=dev)
+    rc = L.gloria_b200_tc_prepack(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S, Lw, lcap,
+                                  word_off, ctx_t.data_ptr(), ctx_n.data_ptr(), words_t.data_ptr(), wnorm.data_ptr(),
+                                  _stream(ctx))
+    _lib.check(rc, "tc_prepack")
+    return ctx_t, ctx_n, words_t, wnorm
 
 
 def _need_cuda(*ts: Tensor) -> None:
@@ -73,7 +92,27 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                                                  _ptr(diag), _ptr(mean), ws.data_ptr(), nbytes, _stream(ctx))
             _lib.check(rc, "local_sim_fwd_f32")
         else:
-            raise RuntimeError("bf16 tensor-core mode is not built in this revision")
+            if want_mean:
+                raise RuntimeError("word-mean attention output (entropy / KL / no-attn regularisers) is served by the "
+                                   "fp32 kernels: use set_precision('fp32') for those configs")
+            if L.gloria_b200_tc_supported(D, S, lcap) != 0:
+                raise RuntimeError(f"bf16 tensor-core kernels need D % 128 == 0, S <= 384, cap_len <= 128; got "
+                                   f"D={D} S={S} Lcap={lcap} (use set_precision('fp32'))")
+            packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
+            rc = L.gloria_b200_tc_local_sim_fwd(packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(),
+                                                packed[3].data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1,
+                                                temp2, agg, eps, sim.data_ptr(), None, None, None, 0, _stream(ctx))
+            _lib.check(rc, "tc_local_sim_fwd")
+            if want_diag:
+                # diagonal attention maps (B pairs, not B^2): exact fp32 kernels
+                nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
+                ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+                tmp = torch.empty((Bi, Bc), dtype=torch.float32, device=dev)
+                rc = L.gloria_b200_local_sim_fwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc,
+                                                     D, S, Lw, lcap, word_off, temp1, temp2, agg, eps,
+                                                     tmp.data_ptr(), _ptr(diag), None, ws.data_ptr(), nbytes,
+                                                     _stream(ctx))
+                _lib.check(rc, "local_sim_fwd_f32(diag)")
     return sim, diag, mean
 
 
@@ -101,7 +140,7 @@ def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
     d_ctx = torch.empty_like(ctx)
     d_words = torch.empty_like(words)
     with torch.cuda.device(dev):
-        if mode == MODE_FP32:
+        if mode == MODE_FP32 or not _TC_BWD:
             nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
             rc = L.gloria_b200_local_sim_bwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S,
@@ -110,7 +149,7 @@ def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                                                  ws.data_ptr(), nbytes, _stream(ctx))
             _lib.check(rc, "local_sim_bwd_f32")
         else:
-            raise RuntimeError("bf16 tensor-core mode is not built in this revision")
+            raise RuntimeError("tensor-core backward not built in this revision")
     return d_ctx, d_words
 
 
