@@ -168,3 +168,36 @@ def test_full_size_dims(golden_dir, tag, scale):
     close(logits_f, g["f32_logits"], 2e-5)
     zs = O.get_local_similarities(img_l, txt_l, [c - 1 for c in cap_lens if c > 1] + [3])
     close(zs, g["zs_local_f32"], 2e-5)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the torch-CPU restatement used as bench.py's multi-threaded CPU baseline is pinned to the same vectors
+# ------------------------------------------------------------------------------------------------------------
+def test_torch_port_matches_reference(small):
+    import torch
+    from oracle import gloria_oracle_torch as T
+    cl = small["cap_lens"].tolist()
+    ti = torch.tensor(small["img_l"], requires_grad=True)
+    tw = torch.tensor(small["txt_l"], requires_grad=True)
+    l0, l1, maps, logits = T.local_loss(ti, tw, cl)
+    (l0 + 0.7 * l1).backward()
+    close(l0.item(), small["local_sum_loss0"])
+    close(l1.item(), small["local_sum_loss1"])
+    close(logits.detach().numpy(), small["local_sum_logits"])
+    close(ti.grad.numpy(), small["local_sum_d_img"], 1e-9)
+    close(tw.grad.numpy(), small["local_sum_d_txt"], 1e-9)
+    for i, m in enumerate(maps):
+        close(m.detach().numpy(), small[f"local_sum_att_{i}"])
+    tg = torch.tensor(small["img_g"], requires_grad=True)
+    tt = torch.tensor(small["txt_g"], requires_grad=True)
+    g0, g1 = T.global_loss(tg, tt)
+    (g0 + 0.7 * g1).backward()
+    close(g0.item(), small["global_loss0"])
+    close(g1.item(), small["global_loss1"])
+    close(tg.grad.numpy(), small["d_img_g"], 1e-9)
+    close(T.cosine_similarity(torch.tensor(small["img_g"]), torch.tensor(small["txt_g"])).numpy(), small["cos"])
+    B = small["img_l"].shape[0]
+    q = torch.tensor(small["txt_l"][1:2, :, :9]).repeat(B, 1, 1)
+    wc, at = T.attention_fn(q, torch.tensor(small["img_l"]), 4.0)
+    close(wc.numpy(), small["attn_wctx"])
+    close(at.numpy(), small["attn_map"])
