@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- GLoRIA local+global loss forward+backward throughput on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload b512|b48] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic features: local loss (all B x B pairs, both cross
+entropies) + global loss, forward and backward, through the package's public API (gloria_loss.local_loss /
+global_loss, or distributed.sharded_loss for N > 1).  `value` = B / t_step (image-text pairs per second, whole job)
+with inputs resident in HBM; `e2e` = the same with pinned HOST inputs copied in and the loss read back every step.
+Workloads: b512 = BASELINE.json configs[2] at N GPUs (global batch 512 caption-sharded; N=1 is the north-star
+single-GPU target), b48 = configs[1] (chexpert_pretrain_config batch).  All captions have 97 words.
+
+`--impl reference` times the CPU restatement of the reference's loss (oracle/gloria_oracle_torch.py: same ATen op
+sequence and autograd as gloria/loss/gloria_loss.py) on the host cores; /root/reference does not exist on the box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D, H, W, LW = 768, 19, 19, 97
+S = H * W
+WORKLOADS = {"b512": 512, "b48": 48}
+CPU_SAMPLE = 16          # the CPU arm times a CPU_SAMPLE x CPU_SAMPLE block of the B x B pair grid
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="b512", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(tflops=float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), burst=float(j["bf16_tflops"]),
+                    hbm=float(j["hbm_gbs"]), src="measured (MEASURED_PEAKS.json; sustained bf16 figure: kernels are "
+                    "timed inside a long step)")
+    return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference loss; the checker, timed as the reported baseline)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_sample_inputs(B_sample):
+    import torch
+    g = torch.Generator().manual_seed(0)
+    img_l = torch.randn(B_sample, D, H, W, generator=g)
+    txt_l = torch.randn(B_sample, D, LW, generator=g)
+    img_g = torch.randn(B_sample, D, generator=g)
+    txt_g = torch.randn(B_sample, D, generator=g)
+    return img_l, txt_l, img_g, txt_g, [LW] * B_sample
+
+
+def cpu_arm(B, steps, warmup):
+    """Time `steps` passes of the reference's CPU loss on a CPU_SAMPLE^2 block of the B^2 pair grid; scale to B."""
+    import torch
+    from oracle import gloria_oracle_torch as T
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = cpu_sample_inputs(CPU_SAMPLE)
+    for _ in range(warmup):
+        T.loss_step(*cpu_sample_inputs(4))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        T.loss_step(*inp)
+    dt = (time.perf_counter() - t0) / steps
+    pair_s = dt / (CPU_SAMPLE * CPU_SAMPLE)              # seconds per (image, caption) grid cell
+    t_step = pair_s * B * B                              # extrapolated full step at batch B
+    return dict(value=B / t_step, ms_per_step=t_step * 1e3, cores=torch.get_num_threads(), sample_s=dt,
+                sample=f"{CPU_SAMPLE}x{CPU_SAMPLE} block of the {B}x{B} pair grid (97 words, 361 regions, D=768), "
+                       f"fwd+bwd, torch {torch.__version__} CPU, {steps} timed passes; extrapolated x{(B * B) // (CPU_SAMPLE ** 2)}")
+
+
+def run_reference(args):
+    B = WORKLOADS[args.workload]
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    r = cpu_arm(B, steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "image-text pairs/s, GLoRIA local+global loss fwd+bwd", "value": r["value"],
+            "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: global batch {B}, 97 words, 361 regions, D=768 (CPU sample)"},
+            "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    import gloria_nlp_project_b200 as G
+    from gloria_nlp_project_b200 import _lib, distributed, gloria_loss
+    lib = _lib.lib()                                       # raises if the CUDA library is missing: no fallback
+    G.set_precision(args.precision)
+
+    B = WORKLOADS[args.workload]
+    if B % world:
+        raise SystemExit(f"global batch {B} is not divisible by {world} ranks")
+    n = B // world
+    gen = torch.Generator().manual_seed(0)                 # same global tensors on every rank, sliced per rank
+    host = {}
+    for name, shape in (("img_l", (B, D, H, W)), ("txt_l", (B, D, LW)), ("img_g", (B, D)), ("txt_g", (B, D))):
+        full = torch.randn(shape, generator=gen)
+        host[name] = full[rank * n:(rank + 1) * n].contiguous().pin_memory()
+        del full
+    cap_lens = [LW] * n
+    names = ("img_l", "txt_l", "img_g", "txt_g")
+    h2d = sum(host[k].numel() * host[k].element_size() for k in names)
+
+    def loss_of(t):
+        if world == 1:
+            l0, l1, _, _, _, _ = gloria_loss.local_loss(t["img_l"], t["txt_l"], cap_lens)
+            g0, g1 = gloria_loss.global_loss(t["img_g"], t["txt_g"])
+        else:
+            l0, l1, g0, g1 = distributed.sharded_loss(t["img_l"], t["txt_l"], t["img_g"], t["txt_g"], cap_lens)
+        return l0 + l1 + g0 + g1
+
+    resident = {k: host[k].to(dev).requires_grad_(True) for k in names}
+
+    def step_resident():
+        for v in resident.values():
+            v.grad = None
+        loss = loss_of(resident)
+        loss.backward()
+        return loss
+
+    def step_e2e():
+        t = {k: host[k].to(dev, non_blocking=True).requires_grad_(True) for k in names}
+        loss = loss_of(t)
+        loss.backward()
+        return float(loss)                                  # device->host read of the step's result
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- kernel timers: caller-owned events recorded by the library around its dominant kernels
+    slots = {"tc_fwd_kernel": 0, "tc_bwd_pair_kernel": 1, "bwd_accum_gemms": 2}
+    evs = {k: [] for k in slots}
+
+    def arm_timers(i):
+        for k, s in slots.items():
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); b.record()                          # materialise the handles; re-recorded by the library
+            evs[k].append((a, b))
+            lib.gloria_b200_set_timer_events(s, a.cuda_event, b.cuda_event)
+
+    for _ in range(args.warmup):
+        step_resident()
+    sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    lib.gloria_b200_launch_count(1)
+    sync()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        arm_timers(i)
+        last = step_resident()
+    e1.record()
+    sync()
+    t_wall1 = time.time()
+    launches = int(lib.gloria_b200_launch_count(1))
+    for s in slots.values():
+        lib.gloria_b200_set_timer_events(s, None, None)
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    loss_val = float(last)
+
+    kt = {}
+    for k, lst in evs.items():
+        v = [a.elapsed_time(b) for a, b in lst]
+        v = [x for x in v if x > 1e-3]                      # slots that never fired keep their back-to-back records
+        kt[k] = sum(v) / len(v) if v else 0.0
+
+    # ---- end to end: pinned host inputs in, loss out, every step
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    sync()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    pairs_grid = B * n                                      # (image, caption) cells per rank
+    f_fwd = 4.0 * S * D * pairs_grid * LW                   # algorithmic FLOPs, SURVEY 8d (per rank)
+    f_step = 3.0 * f_fwd
+    kern_flops = {"tc_fwd_kernel": f_fwd, "tc_bwd_pair_kernel": 2.0 * f_fwd, "bwd_accum_gemms": 2.0 * f_fwd}
+    dom = max(kt, key=lambda k: kt[k]) if any(kt.values()) else None
+    roofline = None
+    if dom:
+        # the backward's algorithmic FLOPs (2 x forward) are spread over the pair kernel and the accumulation GEMMs;
+        # credit them to the backward as a whole and report the dominant piece with its share of that time
+        if dom == "tc_fwd_kernel":
+            ach, t_dom = f_fwd / (kt[dom] * 1e-3) / 1e12, kt[dom]
+        else:
+            t_dom = kt["tc_bwd_pair_kernel"] + kt["bwd_accum_gemms"]
+            ach = 2.0 * f_fwd / (t_dom * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tflops"], "traffic": None, "peak_source": pk["src"],
+                    "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
+                    "step_achieved": f_step / (ms * 1e-3) / 1e12, "step_frac": f_step / (ms * 1e-3) / 1e12 / pk["tflops"],
+                    "algorithmic_flops_per_launch": kern_flops[dom] if dom == "tc_fwd_kernel" else 2.0 * f_fwd}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_arm(B, 2, 1)
+        cpu = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {"metric": "image-text pairs/s, GLoRIA local+global loss fwd+bwd", "value": B / (ms * 1e-3), "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"{args.workload}: global batch {B} ({n} captions x {B} images per rank), 97 words, "
+                                   "361 regions (19x19), D=768, temps 4/5/10, local+global loss",
+                       "parallelism": f"caption-sharded x{world}" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2 (region features %.0f MB per rank)" % (B * D * S * 4 / 1e6)
+                             if B * D * S * 4 > 126e6 else "inputs smaller than L2; steps run back to back",
+                       "loss": loss_val},
+            "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

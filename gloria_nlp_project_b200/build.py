@@ -7,10 +7,10 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libgloria_b200.so")
-SOURCES = ["api.cu", "simt_f32.cu", "ce_global.cu", "tc_local.cu"]
+SOURCES = ["api.cu", "simt_f32.cu", "ce_global.cu", "tc_local.cu", "tc_bwd.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-shared", "-lcublas",
 ]
 
 
@@ -27,7 +27,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-lcublas"], "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES], "-lcublas"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

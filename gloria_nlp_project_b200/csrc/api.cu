@@ -1,5 +1,6 @@
 // Library-level entry points: version, thread-local error text, launch counter.
 #include <stdarg.h>
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -11,9 +12,18 @@ char* err_buf() {
   return buf;
 }
 
-long long& launch_counter() {
-  static thread_local long long n = 0;
+// Statistics only (bench.py's gpu_launches): process-wide because autograd runs the backward on its own thread.
+std::atomic<long long>& launch_counter() {
+  static std::atomic<long long> n{0};
   return n;
+}
+
+// Caller-owned cudaEvent_t pairs recorded around the named kernels (bench.py's live roofline timing).
+std::atomic<void*> g_timer[GLORIA_TIMER_SLOTS][2];
+
+void timer_record(int slot, int which, cudaStream_t st) {
+  void* ev = g_timer[slot][which].load(std::memory_order_relaxed);
+  if (ev) cudaEventRecord((cudaEvent_t)ev, st);
 }
 
 int fail(int code, const char* fmt, ...) {
@@ -36,7 +46,12 @@ extern "C" int gloria_b200_version(void) { return 100; }
 extern "C" const char* gloria_b200_last_error(void) { return gloria::err_buf(); }
 
 extern "C" long long gloria_b200_launch_count(int reset) {
-  long long v = gloria::launch_counter();
-  if (reset) gloria::launch_counter() = 0;
-  return v;
+  return reset ? gloria::launch_counter().exchange(0) : gloria::launch_counter().load();
+}
+
+extern "C" int gloria_b200_set_timer_events(int slot, void* start_event, void* stop_event) {
+  if (slot < 0 || slot >= GLORIA_TIMER_SLOTS) return gloria::fail(GLORIA_ERR_BAD_ARG, "timer slot %d", slot);
+  gloria::g_timer[slot][0].store(start_event);
+  gloria::g_timer[slot][1].store(stop_event);
+  return GLORIA_OK;
 }

@@ -1,6 +1,7 @@
 // Shared host/device helpers for libgloria_b200.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -10,7 +11,8 @@ namespace gloria {
 
 // thread-local error text + launch counter (no mutable process-global state: entry points stay re-entrant)
 char* err_buf();
-long long& launch_counter();
+std::atomic<long long>& launch_counter();
+void timer_record(int slot, int which, cudaStream_t st);   // which: 0 = before, 1 = after the kernel
 
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);

@@ -152,7 +152,7 @@ __global__ void row_norms(const float* __restrict__ x, float* __restrict__ n, lo
 
 // d_words [Bc, D, Lw] = transpose of dWt [Bc, Lw, D], zero outside [off, off + cap_len)
 __global__ void unpack_dwords(const float* __restrict__ dWt, float* __restrict__ dwords,
-                              const int* __restrict__ cap_lens, int D, int Lw, int Lcap, int off) {
+                              const int* __restrict__ cap_lens, int D, int Lw, int Lcap, int off, int accumulate) {
   __shared__ float t[32][33];
   const int b = blockIdx.z;
   const int l0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
@@ -167,7 +167,10 @@ __global__ void unpack_dwords(const float* __restrict__ dWt, float* __restrict__
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int d = d0 + r, l = l0 + threadIdx.x;
-    if (d < D && l < Lw) ob[(long long)d * Lw + l] = t[threadIdx.x][r];
+    if (d < D && l < Lw) {
+      float* o = ob + (long long)d * Lw + l;
+      *o = accumulate ? *o + t[threadIdx.x][r] : t[threadIdx.x][r];
+    }
   }
 }
 
@@ -179,9 +182,10 @@ __global__ void __launch_bounds__(256) double_softmax_fwd(float* __restrict__ sc
                                                           const int* __restrict__ cap_lens, int i0, int nc, int Bc,
                                                           int Lcap, int S, float temp1,
                                                           float* __restrict__ attn_diag,
-                                                          float* __restrict__ attn_mean) {
+                                                          float* __restrict__ attn_mean, int diag_only) {
   const int p = blockIdx.x;
-  const int j = p / nc, i = i0 + p % nc;
+  const int i = diag_only ? i0 + p : i0 + p % nc;
+  const int j = diag_only ? i : p / nc;
   const int L = min(max(cap_lens[i], 0), Lcap);
   float* s = sc + (long long)p * Lcap * S;
   float* a = at + (long long)p * Lcap * S;
@@ -337,9 +341,10 @@ __global__ void __launch_bounds__(256) double_softmax_bwd(float* __restrict__ da
                                                           const int* __restrict__ cap_lens, int i0, int nc, int Bc,
                                                           int Lcap, int S, float temp1,
                                                           const float* __restrict__ d_attn_diag,
-                                                          const float* __restrict__ d_attn_mean) {
+                                                          const float* __restrict__ d_attn_mean, int diag_only) {
   const int p = blockIdx.x;
-  const int j = p / nc, i = i0 + p % nc;
+  const int i = diag_only ? i0 + p : i0 + p % nc;
+  const int j = diag_only ? i : p / nc;
   const int L = min(max(cap_lens[i], 0), Lcap);
   float* g = da + (long long)p * Lcap * S;
   const float* a = at + (long long)p * Lcap * S;
@@ -454,7 +459,7 @@ int chunk_forward(const float* ctx, const float* Wt, const int32_t* cap_lens, in
     if ((rc = launch_gemm(g, st))) return rc;
   }
   double_softmax_fwd<<<(unsigned)(Bi * nc), 256, 0, st>>>(sc, at, cap_lens, i0, nc, Bc, Lcap, S, temp1, attn_diag,
-                                                         attn_mean);
+                                                         attn_mean, 0);
   GLORIA_LAUNCHED("double_softmax_fwd");
   {  // C[p][l][d] = sum_s A[p][l][s] * ctx[j][d][s]                  (bmm #2, gloria_loss.py:59)
     GemmArgs g{};
@@ -575,7 +580,7 @@ extern "C" int gloria_b200_local_sim_bwd_f32(const float* ctx, const float* word
       if ((rc = launch_gemm(g, st))) return rc;
     }
     double_softmax_bwd<<<(unsigned)(Bi * nc), 256, 0, st>>>(da, at, sc, cap_lens, i0, nc, Bc, Lcap, S, temp1,
-                                                           d_attn_diag, d_attn_mean);
+                                                           d_attn_diag, d_attn_mean, 0);
     GLORIA_LAUNCHED("double_softmax_bwd");
     {  // dWt[i][off+l][d] += sum_j sum_s dS[p][l][s] * ctx[j][d][s]
       GemmArgs g{};
@@ -599,7 +604,118 @@ extern "C" int gloria_b200_local_sim_bwd_f32(const float* ctx, const float* word
     }
   }
   dim3 grid((Lw + 31) / 32, (D + 31) / 32, Bc), block(32, 8);
-  unpack_dwords<<<grid, block, 0, st>>>(dWt, d_words, cap_lens, D, Lw, Lcap, word_off);
+  unpack_dwords<<<grid, block, 0, st>>>(dWt, d_words, cap_lens, D, Lw, Lcap, word_off, 0);
   GLORIA_LAUNCHED("unpack_dwords");
+  return GLORIA_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Diagonal pairs only: attention maps A_ii (att_maps, gloria_loss.py:141-143) and the gradient that flows back
+// through them (supervised-attention loss, gloria_model.py:143-147).  B pairs instead of B^2.
+// workspace: Wt [B,Lw,D], dWt [B,Lw,D], wn [B,Lw], sc / at / da [B,Lcap,S]
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct DiagPlan { size_t off_wt, off_dwt, off_wn, off_sc, off_at, off_da, total; };
+DiagPlan diag_plan(int B, int D, int S, int Lw, int Lcap) {
+  DiagPlan pl{};
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += gloria::align_up(n, 256); return r; };
+  pl.off_wt = take((size_t)B * Lw * D * sizeof(float));
+  pl.off_dwt = take((size_t)B * Lw * D * sizeof(float));
+  pl.off_wn = take((size_t)B * Lw * sizeof(float));
+  pl.off_sc = take((size_t)B * Lcap * S * sizeof(float));
+  pl.off_at = take((size_t)B * Lcap * S * sizeof(float));
+  pl.off_da = take((size_t)B * Lcap * S * sizeof(float));
+  pl.total = o;
+  return pl;
+}
+
+// scores + double softmax of the pairs (i, i); leaves P in sc and A in at (and attn_diag if given)
+int diag_forward(const float* ctx, const float* Wt, const int32_t* cap_lens, int B, int D, int S, int Lw, int Lcap,
+                 int off, float temp1, float* sc, float* at, float* attn_diag, cudaStream_t st) {
+  GemmArgs g{};
+  g.A = Wt + (long long)off * D; g.B = ctx; g.C = sc;
+  g.M = Lcap; g.N = S; g.K = D; g.R = 1;
+  g.sAm = D; g.sAk = 1; g.sAb0 = 0; g.sAb1 = (long long)Lw * D; g.sAr = 0;
+  g.sBk = S; g.sBn = 1; g.sBb0 = 0; g.sBb1 = (long long)D * S; g.sBr = 0;
+  g.sCm = S; g.sCn = 1; g.sCb0 = 0; g.sCb1 = (long long)Lcap * S;
+  g.nb0 = 1; g.nb1 = B; g.beta = 0.f; g.mlim = cap_lens; g.mlim_off = 0;
+  int rc;
+  if ((rc = launch_gemm(g, st))) return rc;
+  double_softmax_fwd<<<(unsigned)B, 256, 0, st>>>(sc, at, cap_lens, 0, B, B, Lcap, S, temp1, attn_diag, nullptr, 1);
+  GLORIA_LAUNCHED("double_softmax_fwd(diag)");
+  return GLORIA_OK;
+}
+}  // namespace
+
+extern "C" size_t gloria_b200_diag_attn_workspace(int B, int D, int S, int Lw, int Lcap) {
+  if (B <= 0 || D <= 0 || S <= 0 || Lw <= 0 || Lcap <= 0) return 0;
+  return diag_plan(B, D, S, Lw, Lcap).total;
+}
+
+extern "C" int gloria_b200_diag_attn_fwd_f32(const float* ctx, const float* words, const int32_t* cap_lens, int B,
+                                             int D, int S, int Lw, int Lcap, int word_off, float temp1,
+                                             float* attn_diag, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(ctx, words, cap_lens, B, B, D, S, Lw, Lcap, word_off, GLORIA_AGG_SUM);
+  if (rc) return rc;
+  GLORIA_CHECK_ARG(attn_diag && workspace, "null output / workspace");
+  const DiagPlan pl = diag_plan(B, D, S, Lw, Lcap);
+  if (workspace_bytes < pl.total) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, pl.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  float* Wt = (float*)(ws + pl.off_wt);
+  if ((rc = prepack_words(words, Wt, (float*)(ws + pl.off_wn), B, D, Lw, st))) return rc;
+  return diag_forward(ctx, Wt, cap_lens, B, D, S, Lw, Lcap, word_off, temp1, (float*)(ws + pl.off_sc),
+                      (float*)(ws + pl.off_at), attn_diag, st);
+}
+
+extern "C" int gloria_b200_diag_attn_bwd_f32(const float* ctx, const float* words, const int32_t* cap_lens, int B,
+                                             int D, int S, int Lw, int Lcap, int word_off, float temp1,
+                                             const float* d_attn_diag, float* d_ctx, float* d_words, int accumulate,
+                                             void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(ctx, words, cap_lens, B, B, D, S, Lw, Lcap, word_off, GLORIA_AGG_SUM);
+  if (rc) return rc;
+  GLORIA_CHECK_ARG(d_attn_diag && d_ctx && d_words && workspace, "null gradient / workspace pointer");
+  const DiagPlan pl = diag_plan(B, D, S, Lw, Lcap);
+  if (workspace_bytes < pl.total) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, pl.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  float* Wt = (float*)(ws + pl.off_wt);
+  float* dWt = (float*)(ws + pl.off_dwt);
+  float* sc = (float*)(ws + pl.off_sc);
+  float* at = (float*)(ws + pl.off_at);
+  float* da = (float*)(ws + pl.off_da);
+  if ((rc = prepack_words(words, Wt, (float*)(ws + pl.off_wn), B, D, Lw, st))) return rc;
+  if ((rc = diag_forward(ctx, Wt, cap_lens, B, D, S, Lw, Lcap, word_off, temp1, sc, at, nullptr, st))) return rc;
+  GLORIA_CUDA(cudaMemsetAsync(da, 0, (size_t)B * Lcap * S * sizeof(float), st));
+  GLORIA_CUDA(cudaMemsetAsync(dWt, 0, (size_t)B * Lw * D * sizeof(float), st));
+  double_softmax_bwd<<<(unsigned)B, 256, 0, st>>>(da, at, sc, cap_lens, 0, B, B, Lcap, S, temp1, d_attn_diag, nullptr, 1);
+  GLORIA_LAUNCHED("double_softmax_bwd(diag)");
+  {  // dWt[i][off+l][d] = sum_s dS[i][l][s] * ctx[i][d][s]
+    GemmArgs g{};
+    g.A = da; g.B = ctx; g.C = dWt + (long long)word_off * D;
+    g.M = Lcap; g.N = D; g.K = S; g.R = 1;
+    g.sAm = S; g.sAk = 1; g.sAb0 = 0; g.sAb1 = (long long)Lcap * S; g.sAr = 0;
+    g.sBk = 1; g.sBn = S; g.sBb0 = 0; g.sBb1 = (long long)D * S; g.sBr = 0;
+    g.sCm = D; g.sCn = 1; g.sCb0 = 0; g.sCb1 = (long long)Lw * D;
+    g.nb0 = 1; g.nb1 = B; g.beta = 0.f; g.mlim = cap_lens; g.mlim_off = 0;
+    if ((rc = launch_gemm(g, st))) return rc;
+  }
+  {  // d_ctx[i][d][s] (+)= sum_l Wt[i][off+l][d] * dS[i][l][s]
+    GemmArgs g{};
+    g.A = Wt + (long long)word_off * D; g.B = da; g.C = d_ctx;
+    g.M = D; g.N = S; g.K = Lcap; g.R = 1;
+    g.sAm = 1; g.sAk = D; g.sAb0 = (long long)Lw * D; g.sAb1 = 0; g.sAr = 0;
+    g.sBk = S; g.sBn = 1; g.sBb0 = (long long)Lcap * S; g.sBb1 = 0; g.sBr = 0;
+    g.sCm = S; g.sCn = 1; g.sCb0 = (long long)D * S; g.sCb1 = 0;
+    g.nb0 = B; g.nb1 = 1; g.beta = accumulate ? 1.f : 0.f;
+    // K limit per image: caption i's length (klim is indexed by r; R == 1, so offset by the image index instead)
+    g.klim = nullptr;   // rows l >= cap_len of dS are zero (double_softmax_bwd never writes them; da was cleared)
+    if ((rc = launch_gemm(g, st))) return rc;
+  }
+  dim3 grid((Lw + 31) / 32, (D + 31) / 32, B), block(32, 8);
+  unpack_dwords<<<grid, block, 0, st>>>(dWt, d_words, cap_lens, D, Lw, Lcap, word_off, accumulate);
+  GLORIA_LAUNCHED("unpack_dwords(diag)");
   return GLORIA_OK;
 }

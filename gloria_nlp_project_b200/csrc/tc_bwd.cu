@@ -1,0 +1,682 @@
+// bf16 tensor-core backward of the GLoRIA local similarity (sm_100a: TMA + tcgen05 + TMEM, plus plain GEMMs).
+//
+// Closed-form backward of gloria_loss.py:19-63 + :144-158, restated so that nothing of size
+// D x S per pair is ever accumulated with atomics.  Per pair (image j, caption i), with E = exp(temp1 * P) the
+// un-normalised softmax-#2 numerator, Z_l = sum_s E[s,l], A = E / Z, and G_j = R_j^T R_j the image's Gram matrix:
+//     T'[s,l]  = sum_s' G_j[s,s'] E[s',l]              (= Z_l * <C_l, R_s>;  replaces the D-deep GEMM  dC^T R)
+//     dP[s,l]  = E * (a_l S_[s,l] + b_l T'[s,l] - c_l)  a = t1 ddot/Z, b = t1 beta/Z^2, c = t1 (ddot dot + beta nc^2)/Z
+//     u_s      = sum_l P dP ;   dS = P (dP - u_s)
+//     X[s,l]   = (ddot_l / Z_l) E + dS                  -> dW_i += R_j X ,  dR_j += W_i X^T
+//     Eo = E,  Bo[s,l] = (beta_l / Z_l^2) E             -> dR_j += R_j (sum_i Eo Bo^T)      (the |C| term)
+// ddot / beta / gamma come from the forward's saved per-word <W, C'> and |C'|^2 (C' = Z C) and from Z, which the
+// score-shaped GEMM  G E  delivers for free through a row of ones kept in G's first padded row.
+//
+// One fused kernel per chunk of captions ("pair kernel", caption-stationary persistent CTAs like the forward):
+//   GEMM1  S_[s,l] (3 region tiles, TMEM lanes = regions, stays resident)  ->  softmax warps: P, E -> smem (bf16)
+//   GEMM-T T'[s,l] = G tile (TMA) x E (smem, N-major)                      ->  same lanes/columns as S_
+//   the 4 SIMT warps then do everything else thread-locally (one region row per thread) and write the rows of
+//   X^T, Eo^T, Bo^T as [(j,s), (i,l)] bf16 matrices.
+// The sums over images / captions are then three large plain GEMMs over those matrices (cuBLAS, the one place a
+// library GEMM is used) and a per-image [S x S] x [S x D] product; see DESIGN.md for the byte / FLOP accounting.
+#include <cublas_v2.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace gloria {
+namespace tc {
+namespace bw {
+
+constexpr int SLOT = 16384;
+constexpr int NSLOT = 6;
+constexpr int OFF_E = NSLOT * SLOT;                      // [2 word blocks of 64][Spad regions][128 B]
+constexpr int E_BYTES = 2 * MAX_NT * TILE * 128;
+constexpr int OFF_COEFA = OFF_E + E_BYTES;               // float4 (a, b, c, -) per word
+constexpr int OFF_COEFE = OFF_COEFA + 128 * 16;          // float2 (e, f) per word
+constexpr int OFF_ZBUF = OFF_COEFE + 128 * 8;            // Z per word
+constexpr int OFF_RED = OFF_ZBUF + 128 * 4;              // 16 floats of reduction scratch
+constexpr int OFF_BAR = OFF_RED + 64;
+enum { B_FULL = 0, B_EMPTY = NSLOT, B_D1F = 2 * NSLOT, B_D1E = B_D1F + MAX_NT, B_EF = B_D1E + MAX_NT, B_EE, B_TTF, B_TTE, B_COUNT };
+constexpr int SMEM_BYTES = OFF_BAR + B_COUNT * 8 + 16 + 1024;
+constexpr int NTHREADS = 256;                            // warp 0 TMA, warp 1 MMA, warps 4-7 SIMT (lanes = regions)
+
+struct PairParams {
+  const float* wnorm;       // [Bc, LPAD]
+  const int* cap_lens;      // [Bc]
+  const float* stats;       // [Bi, Bc, 2, LPAD]
+  const float* dsim;        // [Bi, Bc]
+  __nv_bfloat16* xt;        // [Bi*Spad, nc*LPAD]   X^T
+  __nv_bfloat16* et;        //                      E^T (un-normalised attention numerators)
+  __nv_bfloat16* bt;        //                      (beta / Z^2) E^T
+  float* gamma;             // [Bc, LPAD]  sum_j (dL/d|W_l|) / |W_l|   (atomicAdd)
+  int Bi, Bc, i0, nc, D, S, NT;
+  float t1, t1_log2e, t2, eps;
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// region tile processed at position idx of a pair: the tile holding the ones row of G (the last one) goes first
+__device__ __forceinline__ int tile_at(int idx, int NT) { return idx == 0 ? NT - 1 : idx - 1; }
+
+template <int LPAD>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__ CUtensorMap tm_wt,
+                   const __grid_constant__ CUtensorMap tm_g, const PairParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + OFF_BAR;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
+  float* red = reinterpret_cast<float*>(smem + OFF_RED);
+  float* zbuf = reinterpret_cast<float*>(smem + OFF_ZBUF);
+  float4* coefA = reinterpret_cast<float4*>(smem + OFF_COEFA);
+  float2* coefE = reinterpret_cast<float2*>(smem + OFF_COEFE);
+  auto bar = [&](int idx) { return bars + 8u * (uint32_t)idx; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NT = p.NT;
+  const int Spad = NT * TILE;
+  const int nkb1 = p.D / KBLK;        // k-blocks of GEMM1 (over channels)
+  const int nkb2 = Spad / KBLK;       // k-blocks of GEMM-T (over regions)
+  const uint32_t TT_COL = (uint32_t)(MAX_NT * LPAD);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
+    for (int t = 0; t < MAX_NT; ++t) { mbar_init(bar(B_D1F + t), 1); mbar_init(bar(B_D1E + t), 128); }
+    mbar_init(bar(B_EF), 128 * NT);
+    mbar_init(bar(B_EE), 1);
+    mbar_init(bar(B_TTF), 1);
+    mbar_init(bar(B_TTE), 128);
+    fence_barrier_init();
+    tma_prefetch_desc(&tm_rt); tma_prefetch_desc(&tm_wt); tma_prefetch_desc(&tm_g);
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int slot = 0; uint32_t ph = 0;
+      auto load = [&](const CUtensorMap* tm, int x, int y, uint32_t bytes) {
+        mbar_wait(bar(B_EMPTY + slot), ph ^ 1);
+        mbar_expect_tx(bar(B_FULL + slot), bytes);
+        tma_load_2d(base + slot * SLOT, tm, x, y, bar(B_FULL + slot));
+        if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+      };
+      Units u(p.Bi, p.nc);
+      while (u.next_caption()) {
+        const int i = p.i0 + u.i;
+        for (int j = u.j; j < u.j_end; ++j) {
+          for (int idx = 0; idx < NT; ++idx) {
+            const int t = tile_at(idx, NT);
+            for (int kb = 0; kb < nkb1; ++kb) {
+              load(&tm_rt, kb * KBLK, j * Spad + t * TILE, TILE * 128);
+              load(&tm_wt, kb * KBLK, i * LPAD, LPAD * 128);
+            }
+          }
+          for (int idx = 0; idx < NT; ++idx) {
+            const int t = tile_at(idx, NT);
+            for (int kb = 0; kb < nkb2; ++kb) load(&tm_g, kb * KBLK, j * Spad + t * TILE, TILE * 128);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc(TILE, LPAD, 0, 0);   // A = Rt tile (K-major), B = Wt tile (K-major)
+      constexpr uint32_t idesct = make_idesc(TILE, LPAD, 0, 1);   // A = G tile (K-major),  B = E (N-major)
+      const uint32_t e_lbo = (uint32_t)Spad * 128u;               // between the two 64-word blocks of E
+      int slot = 0; uint32_t ph = 0;
+      uint32_t n = 0, ttc = 0;
+      auto take = [&]() {
+        mbar_wait(bar(B_FULL + slot), ph);
+        const int s = slot;
+        if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+        return s;
+      };
+      Units u(p.Bi, p.nc);
+      while (u.next_caption()) {
+        for (int j = u.j; j < u.j_end; ++j) {
+          for (int idx = 0; idx < NT; ++idx) {
+            const int t = tile_at(idx, NT);
+            mbar_wait(bar(B_D1E + t), (n & 1) ^ 1);          // previous pair's SIMT pass no longer needs S_ tile t
+            tc_fence_after();
+            for (int kb = 0; kb < nkb1; ++kb) {
+              const int sa = take();
+              const int sb = take();
+              tc_fence_after();
+              const uint32_t a0 = base + sa * SLOT, b0 = base + sb * SLOT;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem + (uint32_t)(t * LPAD), make_smem_desc(a0 + k * 32, 16, 1024),
+                          make_smem_desc(b0 + k * 32, 16, 1024), idesc1, (uint32_t)((kb | k) != 0));
+              umma_commit(bar(B_EMPTY + sa));
+              umma_commit(bar(B_EMPTY + sb));
+            }
+            umma_commit(bar(B_D1F + t));
+          }
+          mbar_wait(bar(B_EF), n & 1);                       // E of this pair is complete in shared memory
+          tc_fence_after();
+          for (int idx = 0; idx < NT; ++idx) {
+            mbar_wait(bar(B_TTE), (ttc & 1) ^ 1);            // T' buffer has been read by the SIMT warps
+            tc_fence_after();
+            for (int kb = 0; kb < nkb2; ++kb) {
+              const int sa = take();
+              tc_fence_after();
+              const uint32_t a0 = base + sa * SLOT;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t region0 = (uint32_t)(kb * KBLK + k * 16);
+                umma_bf16(tmem + TT_COL, make_smem_desc(a0 + k * 32, 16, 1024),
+                          make_smem_desc(base + OFF_E + (region0 >> 3) * 1024, e_lbo, 1024), idesct,
+                          (uint32_t)((kb | k) != 0));
+              }
+              umma_commit(bar(B_EMPTY + sa));
+            }
+            umma_commit(bar(B_TTF));
+            ++ttc;
+          }
+          umma_commit(bar(B_EE));                            // GEMM-T has finished reading E
+          ++n;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ SIMT warps (TMEM lanes = regions)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                 // region row inside a tile == TMEM lane == word index for coefs
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const int zrow = p.S - (NT - 1) * TILE;        // row of the ones row of G inside the last tile
+    uint32_t n = 0, ttc = 0;
+    Units u(p.Bi, p.nc);
+    while (u.next_caption()) {
+      const int i = p.i0 + u.i;
+      const int L = min(max(p.cap_lens[i], 0), LPAD);
+      const float nw = (row < LPAD) ? p.wnorm[(size_t)i * LPAD + row] : 0.f;
+      float gacc = 0.f;
+      const size_t pitch = (size_t)p.nc * LPAD;
+      for (int j = u.j; j < u.j_end; ++j) {
+        // per-word inputs of the coefficient step (thread `row` owns word l = row); latency hidden by the softmax
+        float dotp = 0.f, c2p = 0.f;
+        if (row < LPAD) {
+          const float* sp = p.stats + ((size_t)j * p.Bc + i) * 2 * LPAD;
+          dotp = __ldg(sp + row);
+          c2p = __ldg(sp + LPAD + row);
+        }
+        const float g = __ldg(p.dsim + (size_t)j * p.Bc + i);
+        float mb[MAX_NT], inv[MAX_NT];
+        // ---------------- phase 1: word softmax, E -> shared memory (S_ stays in TMEM)
+#pragma unroll
+        for (int idx = 0; idx < MAX_NT; ++idx) {
+          if (idx < NT) {
+            const int t = tile_at(idx, NT);
+            mbar_wait(bar(B_D1F + t), n & 1);
+            tc_fence_after();
+            float x[LPAD];
+#pragma unroll
+            for (int c = 0; c < LPAD / 16; ++c) tmem_ld16(tmem + lane_addr + (uint32_t)(t * LPAD + c * 16), x + c * 16);
+            tmem_ld_wait();
+            float m = -INFINITY;
+#pragma unroll
+            for (int l = 0; l < LPAD; ++l) m = (l < L) ? fmaxf(m, x[l]) : m;
+            const float mbv = m * LOG2E;
+            float sum = 0.f;
+#pragma unroll
+            for (int l = 0; l < LPAD; ++l) {
+              const float e = (l < L) ? ex2(fmaf(x[l], LOG2E, -mbv)) : 0.f;
+              x[l] = e;
+              sum += e;
+            }
+            const float rinv = 1.f / sum;
+            mb[idx] = mbv;
+            inv[idx] = rinv;
+            const int s_glob = t * TILE + row;
+            const bool live_row = s_glob < p.S;
+            const float sc = p.t1_log2e * rinv;
+#pragma unroll
+            for (int l = 0; l < LPAD; ++l) x[l] = (live_row && l < L) ? ex2(x[l] * sc) : 0.f;
+            if (idx == 0) mbar_wait(bar(B_EE), (n & 1) ^ 1);   // previous pair's GEMM-T no longer reads E
+            const uint32_t rowaddr = base + OFF_E + (uint32_t)(s_glob >> 3) * 1024u + (uint32_t)(s_glob & 7) * 128u;
+#pragma unroll
+            for (int wb = 0; wb < (LPAD + 63) / 64; ++wb) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const int l0 = wb * 64 + c * 8;
+                if (l0 < LPAD) {
+                  const uint32_t addr = rowaddr + (uint32_t)wb * ((uint32_t)Spad * 128u) + (uint32_t)((c ^ (s_glob & 7)) << 4);
+                  sts128(addr, pack_bf16(x[l0], x[l0 + 1]), pack_bf16(x[l0 + 2], x[l0 + 3]),
+                         pack_bf16(x[l0 + 4], x[l0 + 5]), pack_bf16(x[l0 + 6], x[l0 + 7]));
+                }
+              }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(bar(B_EF));
+          }
+        }
+        // ---------------- phase 2: per region tile, T' arrives; coefficients; dP, u, X / Eo / Bo rows
+#pragma unroll
+        for (int idx = 0; idx < MAX_NT; ++idx) {
+          if (idx < NT) {
+            const int t = tile_at(idx, NT);
+            mbar_wait(bar(B_TTF), ttc & 1);
+            ++ttc;
+            tc_fence_after();
+            if (idx == 0) {
+              // Z_l = sum_s E[s,l] sits in the ones row of this tile
+              if (q == (zrow >> 5)) {
+#pragma unroll
+                for (int c = 0; c < LPAD / 16; ++c) {
+                  float z[16];
+                  tmem_ld16(tmem + lane_addr + TT_COL + (uint32_t)(c * 16), z);
+                  tmem_ld_wait();
+                  if (lane == (zrow & 31)) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) zbuf[c * 16 + k] = z[k];
+                  }
+                }
+              }
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              // closed-form coefficients of word l = row (SURVEY.md section 0 / oracle local_sim_pair_bwd)
+              const bool live = row < L;
+              const float Zl = live ? zbuf[row] : 1.f;
+              const float iz = 1.f / Zl;
+              const float nc = sqrtf(c2p) * iz;
+              const float dot = dotp * iz;
+              const float prod = nw * nc;
+              const float den = fmaxf(prod, p.eps);
+              const float cosv = dot / den;
+              const float v = live ? p.t2 * cosv : -INFINITY;
+              float mx = warp_max(v);
+              if (lane == 0) red[q] = mx;
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+              float ex = live ? __expf(v - mx) : 0.f;
+              float tot = warp_sum(ex);
+              if (lane == 0) red[4 + q] = tot;
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              tot = red[4] + red[5] + red[6] + red[7];
+              const float dr = g * p.t2 * ex / tot;
+              const float ddot = dr / den;
+              const float dden = (prod >= p.eps) ? -dr * dot / (den * den) : 0.f;
+              const float beta = nc > 0.f ? dden * nw / nc : 0.f;
+              const float gamma = nw > 0.f ? dden * nc / nw : 0.f;
+              const float rs = ddot * dot + beta * nc * nc;
+              if (row < LPAD) {
+                coefA[row] = live ? make_float4(p.t1 * ddot * iz, p.t1 * beta * iz * iz, p.t1 * rs * iz, 0.f)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                coefE[row] = live ? make_float2(ddot * iz, beta * iz * iz) : make_float2(0.f, 0.f);
+              }
+              if (live) gacc += gamma;
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            const int s_glob = t * TILE + row;
+            const uint32_t rowaddr = base + OFF_E + (uint32_t)(s_glob >> 3) * 1024u + (uint32_t)(s_glob & 7) * 128u;
+            const float mbv = mb[idx], rinv = inv[idx];
+            float dp[LPAD];
+            uint32_t pp[LPAD / 2];
+            float uacc = 0.f;
+            // pass 1: dP = E (a S_ + b T' - c), u = sum_l P dP
+#pragma unroll
+            for (int c = 0; c < LPAD / 8; ++c) {
+              float sv[8], tv[8];
+              tmem_ld8(tmem + lane_addr + (uint32_t)(t * LPAD + c * 8), sv);
+              tmem_ld8(tmem + lane_addr + TT_COL + (uint32_t)(c * 8), tv);
+              const int wb = (c * 8) / 64, cc = ((c * 8) % 64) / 8;
+              const uint4 ev = lds128(rowaddr + (uint32_t)wb * ((uint32_t)Spad * 128u) + (uint32_t)((cc ^ (s_glob & 7)) << 4));
+              tmem_ld_wait();
+              const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int l = c * 8 + k;
+                const float e = (k & 1) ? bf_hi(ew[k >> 1]) : bf_lo(ew[k >> 1]);
+                const float4 cf = lds_f4(base + OFF_COEFA + (uint32_t)l * 16u);
+                const float P = (l < L) ? ex2(fmaf(sv[k], LOG2E, -mbv)) * rinv : 0.f;
+                const float d = e * (fmaf(cf.x, sv[k], fmaf(cf.y, tv[k], -cf.z)));
+                dp[l] = d;
+                uacc = fmaf(P, d, uacc);
+                if (k & 1) {
+                  const float Pprev = __uint_as_float(pp[l >> 1]);
+                  pp[l >> 1] = pack_bf16(Pprev, P);
+                } else {
+                  pp[l >> 1] = __float_as_uint(P);
+                }
+              }
+            }
+            tc_fence_before();
+            mbar_arrive(bar(B_TTE));                 // T' buffer may be overwritten by the next tile's GEMM-T
+            mbar_arrive(bar(B_D1E + t));             // S_ tile may be overwritten by the next pair's GEMM1
+            // pass 2: rows of X^T, Eo^T, Bo^T  ([(j, s), (i, l)] bf16, 16-byte stores along l)
+            const size_t goff = ((size_t)j * Spad + s_glob) * pitch + (size_t)u.i * LPAD;
+            uint4* xo = reinterpret_cast<uint4*>(p.xt + goff);
+            uint4* eo = reinterpret_cast<uint4*>(p.et + goff);
+            uint4* bo = reinterpret_cast<uint4*>(p.bt + goff);
+#pragma unroll
+            for (int c = 0; c < LPAD / 8; ++c) {
+              const int wb = (c * 8) / 64, cc = ((c * 8) % 64) / 8;
+              const uint4 ev = lds128(rowaddr + (uint32_t)wb * ((uint32_t)Spad * 128u) + (uint32_t)((cc ^ (s_glob & 7)) << 4));
+              const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+              float xv[8], bv[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int l = c * 8 + k;
+                const float e = (k & 1) ? bf_hi(ew[k >> 1]) : bf_lo(ew[k >> 1]);
+                const float P = (k & 1) ? bf_hi(pp[l >> 1]) : bf_lo(pp[l >> 1]);
+                const float2 ce = lds_f2(base + OFF_COEFE + (uint32_t)l * 8u);
+                xv[k] = fmaf(ce.x, e, P * (dp[l] - uacc));
+                bv[k] = ce.y * e;
+              }
+              xo[c] = make_uint4(pack_bf16(xv[0], xv[1]), pack_bf16(xv[2], xv[3]), pack_bf16(xv[4], xv[5]), pack_bf16(xv[6], xv[7]));
+              bo[c] = make_uint4(pack_bf16(bv[0], bv[1]), pack_bf16(bv[2], bv[3]), pack_bf16(bv[4], bv[5]), pack_bf16(bv[6], bv[7]));
+              eo[c] = ev;
+            }
+          }
+        }
+        ++n;
+      }
+      if (row < LPAD && gacc != 0.f) atomicAdd(p.gamma + (size_t)i * LPAD + row, gacc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small SIMT helpers of the backward
+// ---------------------------------------------------------------------------------------------------------------
+// Gram matrices come out of the GEMM as bf16 [Bi, Spad, Spad]; row S (the first padded region) becomes the ones row
+__global__ void gram_ones_row(__nv_bfloat16* __restrict__ G, int S, int Spad) {
+  __nv_bfloat16* r = G + ((size_t)blockIdx.x * Spad + S) * Spad;
+  for (int x = threadIdx.x; x < Spad; x += blockDim.x) r[x] = __float2bfloat16_rn(x < S ? 1.f : 0.f);
+}
+
+__global__ void f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    uint2 o;
+    o.x = pack_bf16(v.x, v.y);
+    o.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = o;
+  } else {
+    for (size_t k = i; k < n; ++k) out[k] = __float2bfloat16_rn(in[k]);
+  }
+}
+
+// dRt [Bi, Spad, D] -> d_ctx [Bi, D, S];  grid (ceil(S/32), D/32, Bi), block (32, 8)
+__global__ void unpack_dctx(const float* __restrict__ dRt, float* __restrict__ dctx, int D, int S, int Spad) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, s0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int s = s0 + r, d = d0 + threadIdx.x;
+    t[r][threadIdx.x] = (s < S) ? dRt[((size_t)b * Spad + s) * D + d] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int d = d0 + r, s = s0 + threadIdx.x;
+    if (s < S) dctx[((size_t)b * D + d) * S + s] = t[threadIdx.x][r];
+  }
+}
+
+// dWt [Bc, LPAD, D] (+ gamma * W) -> d_words [Bc, D, Lw], zero outside [off, off + cap_len)
+// grid (ceil(Lw/32), D/32, Bc), block (32, 8)
+__global__ void unpack_dwords_tc(const float* __restrict__ dWt, const float* __restrict__ gamma,
+                                 const __nv_bfloat16* __restrict__ Wt, const int* __restrict__ cap_lens,
+                                 float* __restrict__ dwords, int D, int Lw, int lpad, int lcap, int off) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int L = min(max(cap_lens[b], 0), lcap);
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int lw = l0 + r, d = d0 + threadIdx.x;      // lw: position on the caller's word axis
+    const int l = lw - off;
+    float v = 0.f;
+    if (lw < Lw && l >= 0 && l < L) {
+      const size_t o = ((size_t)b * lpad + l) * D + d;
+      v = dWt[o] + gamma[(size_t)b * lpad + l] * __bfloat162float(Wt[o]);
+    }
+    t[r][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int d = d0 + r, lw = l0 + threadIdx.x;
+    if (lw < Lw) dwords[((size_t)b * D + d) * Lw + lw] = t[threadIdx.x][r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------------------------
+struct Plan {
+  int nc;   // captions per chunk
+  size_t off_gram, off_dwt, off_drt, off_m, off_mb, off_gamma, off_stats, off_sim, off_cublas, off_x, off_e, off_b, total;
+};
+constexpr size_t CUBLAS_WS = 64u << 20;
+
+size_t fixed_bytes(int Bi, int Bc, int D, int Spad, int lpad, bool own_stats, Plan* pl) {
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += align_up(n, 1024); return r; };
+  Plan t{};
+  t.off_gram = take((size_t)Bi * Spad * Spad * 2);
+  t.off_dwt = take((size_t)Bc * lpad * D * 4);
+  t.off_drt = take((size_t)Bi * Spad * D * 4);
+  t.off_m = take((size_t)Bi * Spad * Spad * 4);
+  t.off_mb = take((size_t)Bi * Spad * Spad * 2);
+  t.off_gamma = take((size_t)Bc * lpad * 4);
+  t.off_stats = take(own_stats ? (size_t)Bi * Bc * 2 * lpad * 4 : 0);
+  t.off_sim = take(own_stats ? (size_t)Bi * Bc * 4 : 0);
+  t.off_cublas = take(CUBLAS_WS);
+  if (pl) *pl = t;
+  return o;
+}
+size_t per_caption_bytes(int Bi, int Spad, int lpad) { return 3 * align_up((size_t)Bi * Spad * lpad * 2, 1024) / 1 + 3072; }
+
+Plan make_plan(int Bi, int Bc, int D, int Spad, int lpad, bool own_stats, size_t bytes) {
+  Plan pl{};
+  const size_t fixed = fixed_bytes(Bi, Bc, D, Spad, lpad, own_stats, &pl);
+  const size_t per = per_caption_bytes(Bi, Spad, lpad);
+  if (bytes < fixed + per) { pl.nc = 0; return pl; }
+  size_t nc = (bytes - fixed) / per;
+  if (nc > (size_t)Bc) nc = Bc;
+  pl.nc = (int)nc;
+  size_t o = fixed;
+  auto take = [&](size_t n) { size_t r = o; o += align_up(n, 1024); return r; };
+  const size_t arr = (size_t)Bi * Spad * nc * lpad * 2;
+  pl.off_x = take(arr);
+  pl.off_e = take(arr);
+  pl.off_b = take(arr);
+  pl.total = o;
+  if (pl.total > bytes) pl.nc = 0;
+  return pl;
+}
+
+cublasHandle_t cublas_handle() {
+  static thread_local cublasHandle_t h[16] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!h[dev] && cublasCreate(&h[dev]) != CUBLAS_STATUS_SUCCESS) h[dev] = nullptr;
+  return h[dev];
+}
+
+#define GLORIA_CUBLAS(expr)                                                                       \
+  do {                                                                                            \
+    cublasStatus_t _s = (expr);                                                                   \
+    if (_s != CUBLAS_STATUS_SUCCESS) return fail(GLORIA_ERR_DRIVER, "%s -> cublas status %d", #expr, (int)_s); \
+    ++launch_counter();                                                                           \
+  } while (0)
+
+template <int LPAD>
+int launch_pair(const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap& g, const PairParams& p, int grid,
+                cudaStream_t st) {
+  GLORIA_CUDA(cudaFuncSetAttribute(tc_bwd_pair_kernel<LPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  timer_record(GLORIA_TIMER_TC_BWD_PAIR, 0, st);
+  tc_bwd_pair_kernel<LPAD><<<grid, NTHREADS, SMEM_BYTES, st>>>(rt, wt, g, p);
+  timer_record(GLORIA_TIMER_TC_BWD_PAIR, 1, st);
+  GLORIA_LAUNCHED("tc_bwd_pair_kernel");
+  return GLORIA_OK;
+}
+
+}  // namespace bw
+}  // namespace tc
+}  // namespace gloria
+
+using namespace gloria;
+using namespace gloria::tc;
+
+extern "C" size_t gloria_b200_tc_bwd_workspace(int Bi, int Bc, int D, int S, int Lcap, int have_stats, size_t budget) {
+  if (Bi <= 0 || Bc <= 0 || gloria_b200_tc_supported(D, S, Lcap)) return 0;
+  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
+  const size_t fixed = bw::fixed_bytes(Bi, Bc, D, Spad, lpad, !have_stats, nullptr);
+  const size_t per = bw::per_caption_bytes(Bi, Spad, lpad);
+  size_t want = fixed + per * (size_t)Bc;
+  if (budget != 0 && want > budget) {
+    size_t nc = budget > fixed + per ? (budget - fixed) / per : 1;
+    if (nc < 1) nc = 1;
+    want = fixed + per * nc;
+  }
+  return want;
+}
+
+extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_t, const void* ctx_n, const void* words_t,
+                                            const float* wnorm, const int32_t* cap_lens, const float* stats, int Bi,
+                                            int Bc, int D, int S, int Lw, int Lcap, int word_off, float temp1,
+                                            float temp2, int agg, float eps, const float* dsim, float* d_ctx,
+                                            float* d_words, void* workspace, size_t workspace_bytes, void* stream) {
+  GLORIA_CHECK_ARG(ctx_t && ctx_n && words_t && wnorm && cap_lens && dsim && d_ctx && d_words && workspace,
+                   "null pointer");
+  GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
+  if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
+  if (agg == GLORIA_AGG_MAX) return fail(GLORIA_ERR_UNSUPPORTED, "backward of agg=max is not part of the path");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
+  const bw::Plan pl = bw::make_plan(Bi, Bc, D, Spad, lpad, stats == nullptr, workspace_bytes);
+  if (pl.nc < 1) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B too small", workspace_bytes);
+  char* ws = (char*)workspace;
+  __nv_bfloat16* gram = (__nv_bfloat16*)(ws + pl.off_gram);
+  float* dWt = (float*)(ws + pl.off_dwt);
+  float* dRt = (float*)(ws + pl.off_drt);
+  float* Mf = (float*)(ws + pl.off_m);
+  __nv_bfloat16* Mb = (__nv_bfloat16*)(ws + pl.off_mb);
+  float* gamma = (float*)(ws + pl.off_gamma);
+  __nv_bfloat16* X = (__nv_bfloat16*)(ws + pl.off_x);
+  __nv_bfloat16* E = (__nv_bfloat16*)(ws + pl.off_e);
+  __nv_bfloat16* Bm = (__nv_bfloat16*)(ws + pl.off_b);
+  int rc;
+  if (stats == nullptr) {   // stand-alone use: one forward pass regenerates the per-word statistics
+    float* own = (float*)(ws + pl.off_stats);
+    if ((rc = gloria_b200_tc_local_sim_fwd(ctx_t, ctx_n, words_t, wnorm, cap_lens, Bi, Bc, D, S, Lcap, temp1, temp2,
+                                           agg, eps, (float*)(ws + pl.off_sim), own, stream)))
+      return rc;
+    stats = own;
+  }
+  cublasHandle_t h = bw::cublas_handle();
+  if (!h) return fail(GLORIA_ERR_DRIVER, "cublasCreate failed");
+  GLORIA_CUBLAS(cublasSetStream(h, st));
+  GLORIA_CUBLAS(cublasSetWorkspace(h, ws + pl.off_cublas, bw::CUBLAS_WS));
+  const float one = 1.f, zero = 0.f;
+  const __nv_bfloat16* Rt = (const __nv_bfloat16*)ctx_t;
+  const __nv_bfloat16* Wt = (const __nv_bfloat16*)words_t;
+
+  // Gram matrices G_j = Rt_j Rt_j^T (row-major [Spad, D] == column-major [D, Spad])
+  GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_T, CUBLAS_OP_N, Spad, Spad, D, &one, Rt, CUDA_R_16BF, D,
+                                           (long long)Spad * D, Rt, CUDA_R_16BF, D, (long long)Spad * D, &zero, gram,
+                                           CUDA_R_16BF, Spad, (long long)Spad * Spad, Bi, CUBLAS_COMPUTE_32F,
+                                           CUBLAS_GEMM_DEFAULT));
+  bw::gram_ones_row<<<Bi, 128, 0, st>>>(gram, S, Spad);
+  GLORIA_LAUNCHED("gram_ones_row");
+  GLORIA_CUDA(cudaMemsetAsync(gamma, 0, (size_t)Bc * lpad * sizeof(float), st));
+
+  CUtensorMap rt, wt, gm;
+  if ((rc = make_map(&rt, ctx_t, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;
+  if ((rc = make_map(&wt, words_t, (uint64_t)D, (uint64_t)Bc * lpad, (uint32_t)lpad))) return rc;
+  if ((rc = make_map(&gm, gram, (uint64_t)Spad, (uint64_t)Bi * Spad, TILE))) return rc;
+  int dev = 0, sms = 0;
+  GLORIA_CUDA(cudaGetDevice(&dev));
+  GLORIA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+
+  const int K1 = Bi * Spad;
+  for (int i0 = 0; i0 < Bc; i0 += pl.nc) {
+    const int nc = min(pl.nc, Bc - i0);
+    const int R1 = nc * lpad;
+    bw::PairParams p;
+    p.wnorm = wnorm; p.cap_lens = cap_lens; p.stats = stats; p.dsim = dsim;
+    p.xt = X; p.et = E; p.bt = Bm; p.gamma = gamma;
+    p.Bi = Bi; p.Bc = Bc; p.i0 = i0; p.nc = nc; p.D = D; p.S = S; p.NT = Spad / TILE;
+    p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps;
+    switch (lpad) {
+      case 16: rc = bw::launch_pair<16>(rt, wt, gm, p, sms, st); break;
+      case 32: rc = bw::launch_pair<32>(rt, wt, gm, p, sms, st); break;
+      case 48: rc = bw::launch_pair<48>(rt, wt, gm, p, sms, st); break;
+      case 64: rc = bw::launch_pair<64>(rt, wt, gm, p, sms, st); break;
+      case 80: rc = bw::launch_pair<80>(rt, wt, gm, p, sms, st); break;
+      case 96: rc = bw::launch_pair<96>(rt, wt, gm, p, sms, st); break;
+      case 112: rc = bw::launch_pair<112>(rt, wt, gm, p, sms, st); break;
+      case 128: rc = bw::launch_pair<128>(rt, wt, gm, p, sms, st); break;
+      default: rc = fail(GLORIA_ERR_UNSUPPORTED, "lpad %d", lpad);
+    }
+    if (rc) return rc;
+    timer_record(GLORIA_TIMER_TC_BWD_GEMM, 0, st);
+    const float beta = i0 == 0 ? 0.f : 1.f;
+    // dWt[(i,l), d] = sum_(j,s) X^T[(j,s),(i,l)] Rt[(j,s), d]            (column-major: [D, R1] = Rt^T . (X^T)^T)
+    GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, R1, K1, &one, Rt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1,
+                               &zero, dWt + (size_t)i0 * lpad * D, CUDA_R_32F, D, CUBLAS_COMPUTE_32F,
+                               CUBLAS_GEMM_DEFAULT));
+    // dRt[(j,s), d] (+)= sum_(i,l) X^T[(j,s),(i,l)] Wt[(i,l), d]         (column-major: [D, K1] = Wt^T . X^T)
+    GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, K1, R1, &one, Wt + (size_t)i0 * lpad * D, CUDA_R_16BF,
+                               D, X, CUDA_R_16BF, R1, &beta, dRt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F,
+                               CUBLAS_GEMM_DEFAULT));
+    // M_j[a, b] (+)= sum_(i,l) E^T[(j,a),(i,l)] Bo^T[(j,b),(i,l)]
+    GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_T, CUBLAS_OP_N, Spad, Spad, R1, &one, E, CUDA_R_16BF, R1,
+                                             (long long)Spad * R1, Bm, CUDA_R_16BF, R1, (long long)Spad * R1, &beta,
+                                             Mf, CUDA_R_32F, Spad, (long long)Spad * Spad, Bi, CUBLAS_COMPUTE_32F,
+                                             CUBLAS_GEMM_DEFAULT));
+    if (i0 + nc < Bc) timer_record(GLORIA_TIMER_TC_BWD_GEMM, 1, st);
+  }
+  // dRt_j += M_j Rt_j   (M_j symmetric up to rounding; column-major: [D, Spad] = Rt_j^T . M_j)
+  const size_t nm = (size_t)Bi * Spad * Spad;
+  bw::f32_to_bf16<<<(unsigned)((nm / 4 + 255) / 256), 256, 0, st>>>(Mf, Mb, nm);
+  GLORIA_LAUNCHED("f32_to_bf16");
+  GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, Spad, Spad, &one, Rt, CUDA_R_16BF, D,
+                                           (long long)Spad * D, Mb, CUDA_R_16BF, Spad, (long long)Spad * Spad, &one,
+                                           dRt, CUDA_R_32F, D, (long long)Spad * D, Bi, CUBLAS_COMPUTE_32F,
+                                           CUBLAS_GEMM_DEFAULT));
+  timer_record(GLORIA_TIMER_TC_BWD_GEMM, 1, st);
+  bw::unpack_dctx<<<dim3((S + 31) / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(dRt, d_ctx, D, S, Spad);
+  GLORIA_LAUNCHED("unpack_dctx");
+  bw::unpack_dwords_tc<<<dim3((Lw + 31) / 32, D / 32, Bc), dim3(32, 8), 0, st>>>(dWt, gamma, Wt, cap_lens, d_words, D,
+                                                                               Lw, lpad, Lcap, word_off);
+  GLORIA_LAUNCHED("unpack_dwords_tc");
+  return GLORIA_OK;
+}

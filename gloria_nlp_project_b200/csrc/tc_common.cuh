@@ -132,5 +132,38 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// ---------------------------------------------------------------- shared by the forward and backward kernels
+constexpr int KBLK = 64;                 // bf16 per 128-byte swizzle row
+constexpr int TILE = 128;                // regions per score tile == words per context tile == channels per chunk
+constexpr int MAX_NT = 3;                // Spad <= 384
+
+// Static unit schedule shared by all warp roles.  Captions are dealt to CTAs in blocks of gridDim.x; in a block
+// with fewer captions than CTAs, several CTAs split one caption's images.  All CTAs sweep the images in step, so
+// the region tiles of an image are read from L2 by every SM at about the same time.
+struct Units {
+  int Bi, Bc, ncta, cta;
+  int blk, i, j, j_end;
+  __device__ Units(int Bi_, int Bc_) : Bi(Bi_), Bc(Bc_), ncta(gridDim.x), cta(blockIdx.x), blk(-1), i(0), j(0), j_end(0) {}
+  __device__ bool next_caption() {
+    while (true) {
+      ++blk;
+      const int base = blk * ncta;
+      if (base >= Bc) return false;
+      const int nb = min(ncta, Bc - base);
+      const int g = ncta / nb;
+      if (cta < nb * g) {
+        i = base + cta % nb;
+        const int sl = cta / nb;
+        j = (int)((long long)sl * Bi / g);
+        j_end = (int)((long long)(sl + 1) * Bi / g);
+        if (j < j_end) return true;
+      }
+    }
+  }
+};
+
+// host side (tc_local.cu): 2-D bf16 tensor map [rows, inner] (inner contiguous), box [box_rows, 64], SWIZZLE_128B
+int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint32_t box_rows);
+
 }  // namespace tc
 }  // namespace gloria

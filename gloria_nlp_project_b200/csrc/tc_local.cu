@@ -16,9 +16,6 @@
 namespace gloria {
 namespace tc {
 
-constexpr int KBLK = 64;                 // bf16 per 128-byte swizzle row
-constexpr int TILE = 128;                // regions per GEMM1 tile == words per GEMM2 tile == channels per D2 chunk
-constexpr int MAX_NT = 3;                // Spad <= 384
 constexpr int NSTAGE = 3;
 constexpr int STAGE_BYTES = 32768;       // A part [0,16K) + B part [16K,32K)
 constexpr int E_BYTES = 2 * MAX_NT * TILE * 128;   // [2 word blocks of 64][Spad regions][128 B]
@@ -35,36 +32,12 @@ struct FwdParams {
   const float* wnorm;        // [Bc, LPAD]
   const int* cap_lens;
   float* sim;                // [Bi, Bc]
+  float* stats;              // [Bi, Bc, 2, LPAD] (dot', |C'|^2 of the un-normalised context) or nullptr
   int Bi, Bc, D, S, NT;
   float t1_log2e;            // temp1 * log2(e)
   float temp2;
   int agg;
   float eps_s;               // eps * S  (clamp on the un-normalised context, see header comment)
-};
-
-// Static unit schedule shared by all warp roles.  Captions are dealt to CTAs in blocks of gridDim.x; in a block
-// with fewer captions than CTAs, several CTAs split one caption's images.  All CTAs sweep the images in step, so
-// the region tiles of an image are read from L2 by every SM at about the same time.
-struct Units {
-  int Bi, Bc, ncta, cta;
-  int blk, i, j, j_end;
-  __device__ Units(int Bi_, int Bc_) : Bi(Bi_), Bc(Bc_), ncta(gridDim.x), cta(blockIdx.x), blk(-1), i(0), j(0), j_end(0) {}
-  __device__ bool next_caption() {
-    while (true) {
-      ++blk;
-      const int base = blk * ncta;
-      if (base >= Bc) return false;
-      const int nb = min(ncta, Bc - base);
-      const int g = ncta / nb;
-      if (cta < nb * g) {
-        i = base + cta % nb;
-        const int sl = cta / nb;
-        j = (int)((long long)sl * Bi / g);
-        j_end = (int)((long long)(sl + 1) * Bi / g);
-        if (j < j_end) return true;
-      }
-    }
-  }
 };
 
 template <int LPAD>
@@ -288,6 +261,11 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
           mbar_arrive(bar(B_D2E + b2));
           ++g2;
         }
+        if (p.stats != nullptr && l < LPAD) {       // saved for the backward (per word: <W, C'> and |C'|^2)
+          float* sp = p.stats + ((size_t)j * p.Bc + u.i) * 2 * LPAD;
+          sp[l] = live ? dot : 0.f;
+          sp[LPAD + l] = live ? c2 : 0.f;
+        }
         // cosine (gloria_loss.py:11-16) and the temp2 aggregation over words (:153-158 / gloria_model.py:198-201)
         const float den = fmaxf(nw * sqrtf(c2), p.eps_s);
         const float v = live ? p.temp2 * (dot / den) : -INFINITY;
@@ -411,7 +389,9 @@ template <int LPAD>
 int launch_fwd(const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap& rn, const FwdParams& p, int grid,
                cudaStream_t st) {
   GLORIA_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<LPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  timer_record(GLORIA_TIMER_TC_FWD, 0, st);
   tc_fwd_kernel<LPAD><<<grid, NTHREADS, SMEM_BYTES, st>>>(rt, wt, rn, p);
+  timer_record(GLORIA_TIMER_TC_FWD, 1, st);
   GLORIA_LAUNCHED("tc_fwd_kernel");
   return GLORIA_OK;
 }
@@ -422,11 +402,11 @@ int launch_fwd(const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap& 
 using namespace gloria;
 using namespace gloria::tc;
 
-extern "C" int gloria_b200_tc_spad(int S) { return (S + TILE - 1) / TILE * TILE; }
+extern "C" int gloria_b200_tc_spad(int S) { return (S / TILE + 1) * TILE; }
 extern "C" int gloria_b200_tc_lpad(int Lcap) { return (Lcap + 15) / 16 * 16; }
 
 extern "C" int gloria_b200_tc_supported(int D, int S, int Lcap) {
-  if (D < TILE || D % TILE != 0 || S < 1 || S > MAX_NT * TILE || Lcap < 1 || Lcap > TILE) return GLORIA_ERR_UNSUPPORTED;
+  if (D < TILE || D % TILE != 0 || S < 1 || S >= MAX_NT * TILE || Lcap < 1 || Lcap > TILE) return GLORIA_ERR_UNSUPPORTED;
   return GLORIA_OK;
 }
 
@@ -447,19 +427,13 @@ extern "C" int gloria_b200_tc_prepack(const float* ctx, const float* words, cons
   return GLORIA_OK;
 }
 
-extern "C" size_t gloria_b200_tc_workspace(int, int, int, int, int) { return 256; }
-
 extern "C" int gloria_b200_tc_local_sim_fwd(const void* ctx_t, const void* ctx_n, const void* words_t,
                                             const float* wnorm, const int32_t* cap_lens, int Bi, int Bc, int D, int S,
                                             int Lcap, float temp1, float temp2, int agg, float eps, float* sim,
-                                            float* attn_diag, float* attn_mean, void* workspace,
-                                            size_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
+                                            float* stats, void* stream) {
   GLORIA_CHECK_ARG(ctx_t && ctx_n && words_t && wnorm && cap_lens && sim, "null pointer");
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0, "bad batch sizes %d x %d", Bi, Bc);
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
-  if (attn_diag || attn_mean)
-    return fail(GLORIA_ERR_UNSUPPORTED, "attention-map outputs come from the fp32 kernels in this revision");
   cudaStream_t st = (cudaStream_t)stream;
   const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
   CUtensorMap rt, wt, rn;
@@ -468,7 +442,7 @@ extern "C" int gloria_b200_tc_local_sim_fwd(const void* ctx_t, const void* ctx_n
   if ((rc = make_map(&wt, words_t, (uint64_t)D, (uint64_t)Bc * lpad, (uint32_t)lpad))) return rc;
   if ((rc = make_map(&rn, ctx_n, (uint64_t)Spad, (uint64_t)Bi * D, TILE))) return rc;
   FwdParams p;
-  p.wt = (const __nv_bfloat16*)words_t; p.wnorm = wnorm; p.cap_lens = cap_lens; p.sim = sim;
+  p.wt = (const __nv_bfloat16*)words_t; p.wnorm = wnorm; p.cap_lens = cap_lens; p.sim = sim; p.stats = stats;
   p.Bi = Bi; p.Bc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE;
   p.t1_log2e = temp1 * 1.4426950408889634f; p.temp2 = temp2; p.agg = agg; p.eps_s = eps * (float)S;
   int dev = 0, sms = 0;
@@ -486,10 +460,4 @@ extern "C" int gloria_b200_tc_local_sim_fwd(const void* ctx_t, const void* ctx_n
     case 128: return launch_fwd<128>(rt, wt, rn, p, grid, st);
   }
   return fail(GLORIA_ERR_UNSUPPORTED, "lpad %d", lpad);
-}
-
-extern "C" int gloria_b200_tc_local_sim_bwd(const void*, const void*, const void*, const float*, const int32_t*, int,
-                                            int, int, int, int, int, int, float, float, int, float, const float*,
-                                            const float*, const float*, float*, float*, void*, size_t, void*) {
-  return fail(GLORIA_ERR_UNSUPPORTED, "tensor-core backward not built yet");
 }

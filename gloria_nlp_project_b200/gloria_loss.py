@@ -67,8 +67,9 @@ def local_similarities(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, 
     ctx = _context(img_features, no_attn_vec)
     words = words_emb.float()
     mode = _mode(img_features, words_emb)
-    sim, diag, mean = ops.local_sim_fwd(ctx, words, dev_lens, max(lens), word_offset, float(temp1), float(temp2),
-                                        ops.AGG[agg], float(eps), bool(want_attn_maps), bool(want_mean_attn), mode)
+    sim, diag, mean, _ = ops.local_sim_fwd(ctx, words, dev_lens, max(lens), word_offset, float(temp1), float(temp2),
+                                           ops.AGG[agg], float(eps), bool(want_attn_maps), bool(want_mean_attn),
+                                           mode)
     return sim, (diag if want_attn_maps else None), (mean if want_mean_attn else None), lens
 
 

@@ -18,8 +18,8 @@ from . import _lib
 AGG = {"sum": 0, "mean": 1, "max": 2}
 MODE_FP32, MODE_BF16 = 0, 1
 
-_WS_BUDGET = int(os.environ.get("GLORIA_B200_WS_BYTES", str(4 << 30)))
-_TC_BWD = False      # flipped once the tcgen05 backward kernel is in the library
+_WS_BUDGET = int(os.environ.get("GLORIA_B200_WS_BYTES", str(4 << 30)))            # fp32 kernels
+_TC_WS_BUDGET = int(os.environ.get("GLORIA_B200_TC_WS_BYTES", str(96 << 30)))     # bf16 backward operand matrices
 
 
 def tc_prepack(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int):
@@ -64,8 +64,9 @@ def _f32c(t: Tensor) -> Tensor:
 @torch.library.custom_op("gloria_b200::local_sim_fwd", mutates_args=())
 def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int, temp1: float,
                   temp2: float, agg: int, eps: float, want_diag: bool, want_mean: bool,
-                  mode: int) -> Tuple[Tensor, Tensor, Tensor]:
-    """sim [Bi, Bc], attn_diag [Bc, lcap, S] (or empty), attn_mean [Bi, Bc, S] (or empty).
+                  mode: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """sim [Bi, Bc], attn_diag [Bc, lcap, S] (or empty), attn_mean [Bi, Bc, S] (or empty), stats (bf16 mode:
+    per-word scalars saved for the backward, else empty).
 
     ctx [Bi, D, S] fp32, words [Bc, D, Lw] fp32, cap_lens int32 [Bc] on the same device.
     Replaces the caption loop of gloria_loss.py:116-162 (attention_fn + cosine_similarity + aggregation).
@@ -83,6 +84,7 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
     sim = torch.empty((Bi, Bc), dtype=torch.float32, device=dev)
     diag = torch.empty((Bc, lcap, S) if want_diag else (0,), dtype=torch.float32, device=dev)
     mean = torch.empty((Bi, Bc, S) if want_mean else (0,), dtype=torch.float32, device=dev)
+    stats = torch.empty((0,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         if mode == MODE_FP32:
             nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
@@ -99,21 +101,23 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                 raise RuntimeError(f"bf16 tensor-core kernels need D % 128 == 0, S <= 384, cap_len <= 128; got "
                                    f"D={D} S={S} Lcap={lcap} (use set_precision('fp32'))")
             packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
+            if agg != AGG["max"] and (ctx.requires_grad or words.requires_grad or torch.is_grad_enabled()):
+                stats = torch.empty((Bi, Bc, 2, L.gloria_b200_tc_lpad(lcap)), dtype=torch.float32, device=dev)
             rc = L.gloria_b200_tc_local_sim_fwd(packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(),
                                                 packed[3].data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1,
-                                                temp2, agg, eps, sim.data_ptr(), None, None, None, 0, _stream(ctx))
+                                                temp2, agg, eps, sim.data_ptr(), _ptr(stats), _stream(ctx))
             _lib.check(rc, "tc_local_sim_fwd")
             if want_diag:
-                # diagonal attention maps (B pairs, not B^2): exact fp32 kernels
-                nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
+                if Bi != Bc:
+                    raise RuntimeError(f"diagonal attention maps need as many images as captions, got {Bi} x {Bc}")
+                # diagonal attention maps: B pairs (not B^2) through the exact fp32 kernels
+                nbytes = L.gloria_b200_diag_attn_workspace(Bc, D, S, Lw, lcap)
                 ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-                tmp = torch.empty((Bi, Bc), dtype=torch.float32, device=dev)
-                rc = L.gloria_b200_local_sim_fwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc,
-                                                     D, S, Lw, lcap, word_off, temp1, temp2, agg, eps,
-                                                     tmp.data_ptr(), _ptr(diag), None, ws.data_ptr(), nbytes,
-                                                     _stream(ctx))
-                _lib.check(rc, "local_sim_fwd_f32(diag)")
-    return sim, diag, mean
+                rc = L.gloria_b200_diag_attn_fwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bc, D, S,
+                                                     Lw, lcap, word_off, temp1, diag.data_ptr(), ws.data_ptr(),
+                                                     nbytes, _stream(ctx))
+                _lib.check(rc, "diag_attn_fwd_f32")
+    return sim, diag, mean, stats
 
 
 @local_sim_fwd.register_fake
@@ -121,61 +125,99 @@ def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, w
     Bi, D, S = ctx.shape
     Bc = words.shape[0]
     return (ctx.new_empty((Bi, Bc)), ctx.new_empty((Bc, lcap, S) if want_diag else (0,)),
-            ctx.new_empty((Bi, Bc, S) if want_mean else (0,)))
+            ctx.new_empty((Bi, Bc, S) if want_mean else (0,)),
+            ctx.new_empty((Bi, Bc, 2, (lcap + 15) // 16 * 16) if mode == MODE_BF16 else (0,)))
 
 
 @torch.library.custom_op("gloria_b200::local_sim_bwd", mutates_args=())
 def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int, temp1: float,
-                  temp2: float, agg: int, eps: float, dsim: Tensor, d_diag: Optional[Tensor],
-                  d_mean: Optional[Tensor], mode: int) -> Tuple[Tensor, Tensor]:
-    """Closed-form backward by recomputation: returns d_ctx [Bi, D, S], d_words [Bc, D, Lw]."""
-    _need_cuda(ctx, words, cap_lens, dsim)
+                  temp2: float, agg: int, eps: float, dsim: Optional[Tensor], d_diag: Optional[Tensor],
+                  d_mean: Optional[Tensor], stats: Optional[Tensor], mode: int) -> Tuple[Tensor, Tensor]:
+    """Closed-form backward by recomputation: returns d_ctx [Bi, D, S], d_words [Bc, D, Lw].
+
+    dsim None = no gradient reaches the similarity matrix (attention fine-tune with both contrastive weights 0,
+    gloria_model.py:138-147): only the B diagonal pairs are differentiated."""
+    _need_cuda(ctx, words, cap_lens)
     L = _lib.lib()
     Bi, D, S = ctx.shape
     Bc, _, Lw = words.shape
-    ctx, words, cap_lens, dsim = ctx.contiguous(), words.contiguous(), cap_lens.contiguous(), _f32c(dsim)
+    ctx, words, cap_lens = ctx.contiguous(), words.contiguous(), cap_lens.contiguous()
+    dsim = None if dsim is None else _f32c(dsim)
     d_diag = None if d_diag is None else _f32c(d_diag)
     d_mean = None if d_mean is None else _f32c(d_mean)
     dev = ctx.device
     d_ctx = torch.empty_like(ctx)
     d_words = torch.empty_like(words)
+    st = _stream(ctx)
     with torch.cuda.device(dev):
-        if mode == MODE_FP32 or not _TC_BWD:
-            nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
+        all_pairs = dsim is not None or d_mean is not None
+        diag_separately = d_diag is not None and (not all_pairs or (mode == MODE_BF16 and d_mean is None))
+        if all_pairs:
+            if dsim is None:
+                dsim = torch.zeros((Bi, Bc), dtype=torch.float32, device=dev)
+            if mode == MODE_BF16 and d_mean is None:
+                tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp2, agg, eps, dsim, d_ctx,
+                                 d_words)
+            else:
+                nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
+                ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+                rc = L.gloria_b200_local_sim_bwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D,
+                                                     S, Lw, lcap, word_off, temp1, temp2, agg, eps, dsim.data_ptr(),
+                                                     None if diag_separately else _ptr(d_diag), _ptr(d_mean),
+                                                     d_ctx.data_ptr(), d_words.data_ptr(), ws.data_ptr(), nbytes, st)
+                _lib.check(rc, "local_sim_bwd_f32")
+        if diag_separately:
+            nbytes = L.gloria_b200_diag_attn_workspace(Bc, D, S, Lw, lcap)
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-            rc = L.gloria_b200_local_sim_bwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S,
-                                                 Lw, lcap, word_off, temp1, temp2, agg, eps, dsim.data_ptr(),
-                                                 _ptr(d_diag), _ptr(d_mean), d_ctx.data_ptr(), d_words.data_ptr(),
-                                                 ws.data_ptr(), nbytes, _stream(ctx))
-            _lib.check(rc, "local_sim_bwd_f32")
-        else:
-            raise RuntimeError("tensor-core backward not built in this revision")
+            rc = L.gloria_b200_diag_attn_bwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bc, D, S, Lw,
+                                                 lcap, word_off, temp1, d_diag.data_ptr(), d_ctx.data_ptr(),
+                                                 d_words.data_ptr(), 1 if all_pairs else 0, ws.data_ptr(), nbytes, st)
+            _lib.check(rc, "diag_attn_bwd_f32")
+        elif not all_pairs:
+            d_ctx.zero_()
+            d_words.zero_()
     return d_ctx, d_words
 
 
+def tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp2, agg, eps, dsim, d_ctx, d_words):
+    """bf16 tensor-core backward: prepack, then the fused recompute kernel + accumulation GEMMs behind the C ABI."""
+    Bi, D, S = ctx.shape
+    Bc, _, Lw = words.shape
+    packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
+    have = stats is not None and stats.numel() > 0
+    free, _ = torch.cuda.mem_get_info(ctx.device)
+    budget = min(_TC_WS_BUDGET, int(free * 0.9) + torch.cuda.memory_reserved(ctx.device)
+                 - torch.cuda.memory_allocated(ctx.device))
+    nbytes = L.gloria_b200_tc_bwd_workspace(Bi, Bc, D, S, lcap, 1 if have else 0, max(budget, 1 << 30))
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=ctx.device)
+    rc = L.gloria_b200_tc_local_sim_bwd(packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(),
+                                        packed[3].data_ptr(), cap_lens.data_ptr(), stats.data_ptr() if have else None,
+                                        Bi, Bc, D, S, Lw, lcap, word_off, temp1, temp2, agg, eps, dsim.data_ptr(),
+                                        d_ctx.data_ptr(), d_words.data_ptr(), ws.data_ptr(), nbytes, _stream(ctx))
+    _lib.check(rc, "tc_local_sim_bwd")
+
+
 @local_sim_bwd.register_fake
-def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim, d_diag, d_mean, mode):
+def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim, d_diag, d_mean, stats, mode):
     return torch.empty_like(ctx), torch.empty_like(words)
 
 
 def _local_setup(ctx, inputs, output):
     feats, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, want_mean, mode = inputs
-    ctx.save_for_backward(feats, words, cap_lens)
+    ctx.save_for_backward(feats, words, cap_lens, output[3])
     ctx.args = (lcap, word_off, temp1, temp2, agg, eps, mode)
     ctx.set_materialize_grads(False)
 
 
-def _local_backward(c, dsim, d_diag, d_mean):
-    ctx, words, cap_lens = c.saved_tensors
+def _local_backward(c, dsim, d_diag, d_mean, d_stats):
+    ctx, words, cap_lens, stats = c.saved_tensors
     lcap, word_off, temp1, temp2, agg, eps, mode = c.args
-    if dsim is None:
-        dsim = torch.zeros((ctx.shape[0], words.shape[0]), dtype=torch.float32, device=ctx.device)
     if d_diag is not None and d_diag.numel() == 0:
         d_diag = None
     if d_mean is not None and d_mean.numel() == 0:
         d_mean = None
     d_ctx, d_words = local_sim_bwd(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim, d_diag,
-                                   d_mean, mode)
+                                   d_mean, stats if stats.numel() > 0 else None, mode)
     return d_ctx, d_words, None, None, None, None, None, None, None, None, None, None
 
 

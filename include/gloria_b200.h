@@ -49,6 +49,15 @@ const char* gloria_b200_last_error(void);
 /* number of kernels launched by this thread's calls since the last reset (bench.py's gpu_launches) */
 long long gloria_b200_launch_count(int reset);
 
+/* Measurement hook (bench.py's live roofline timing): record the caller's cudaEvent_t `start_event` immediately
+ * before and `stop_event` immediately after every launch of the named kernel, on the launch stream.  Pass NULLs to
+ * clear.  Events stay owned by the caller. */
+#define GLORIA_TIMER_TC_FWD 0        /* fused tcgen05 forward kernel                 */
+#define GLORIA_TIMER_TC_BWD_PAIR 1   /* fused tcgen05 backward (per-pair recompute) */
+#define GLORIA_TIMER_TC_BWD_GEMM 2   /* backward accumulation GEMMs                  */
+#define GLORIA_TIMER_SLOTS 4
+int gloria_b200_set_timer_events(int slot, void* start_event, void* stop_event);
+
 /* ------------------------------------------------------------------------------------------------------------
  * fp32 mode (CUDA-core FFMA, fp32 accumulate): replaces attention_fn + cosine_similarity + the caption loop of
  * local_loss (gloria_loss.py:11-63, 116-162) for the un-autocast reference, logits within 1e-5 relative.
@@ -79,12 +88,27 @@ int gloria_b200_local_sim_bwd_f32(const float* ctx, const float* words, const in
                                   float* d_ctx, float* d_words,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Diagonal pairs only (B pairs instead of B^2): the attention maps A_ii that local_loss returns (att_maps,
+ * gloria_loss.py:141-143; consumed by get_attn_maps, gloria_model.py:209-211) and the gradient flowing back through
+ * them (supervised-attention term of GLoRIA.calc_loss, gloria_model.py:143-147).  attn_diag / d_attn_diag are
+ * [B, Lcap, S]; rows l >= cap_len are zero.  With accumulate != 0 the backward adds into d_ctx / d_words (which then
+ * already hold the similarity gradients), otherwise it overwrites them. */
+size_t gloria_b200_diag_attn_workspace(int B, int D, int S, int Lw, int Lcap);
+int gloria_b200_diag_attn_fwd_f32(const float* ctx, const float* words, const int32_t* cap_lens,
+                                  int B, int D, int S, int Lw, int Lcap, int word_off, float temp1,
+                                  float* attn_diag, void* workspace, size_t workspace_bytes, void* stream);
+int gloria_b200_diag_attn_bwd_f32(const float* ctx, const float* words, const int32_t* cap_lens,
+                                  int B, int D, int S, int Lw, int Lcap, int word_off, float temp1,
+                                  const float* d_attn_diag, float* d_ctx, float* d_words, int accumulate,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * bf16 tensor-core mode (tcgen05 / TMEM / TMA): the fused hot path.  Same math as above with bf16 operands and
  * fp32 accumulation and softmax (the analogue of the reference under Lightning AMP).
  * ---------------------------------------------------------------------------------------------------------- */
 
-/* Padded sizes used by the packed bf16 layouts (S -> multiple of 128, L -> multiple of 16). */
+/* Padded sizes used by the packed bf16 layouts (S -> next multiple of 128 strictly above S: at least one padded
+ * region row exists, the backward's Gram matrix keeps its row of ones there; L -> multiple of 16). */
 int gloria_b200_tc_spad(int S);
 int gloria_b200_tc_lpad(int Lcap);
 /* 0 if this (D, S, Lcap) is supported by the tensor-core kernels, else GLORIA_ERR_UNSUPPORTED. */
@@ -99,24 +123,29 @@ int gloria_b200_tc_prepack(const float* ctx, const float* words, const int32_t* 
                            int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
                            void* ctx_t, void* ctx_n, void* words_t, float* wnorm, void* stream);
 
-size_t gloria_b200_tc_workspace(int Bi, int Bc, int D, int S, int Lcap);
-
 /* Fused forward over all Bi x Bc pairs: scores on tcgen05 (K = D), both softmaxes, attention-weighted context
- * on tcgen05 (K = S), per-word cosine and the temp2 log-sum-exp; only sim[Bi, Bc] (and the optional maps)
- * reach HBM.  Inputs are the prepacked buffers. */
+ * on tcgen05 (K = S), per-word cosine and the temp2 log-sum-exp; only sim[Bi, Bc] reaches HBM -- plus, when
+ * `stats` is given, the two per-word scalars the backward needs (stats [Bi, Bc, 2, Lpad]: <W_l, C'_l> and
+ * |C'_l|^2 of the un-normalised context C' = Z_l C_l).  Inputs are the prepacked buffers. */
 int gloria_b200_tc_local_sim_fwd(const void* ctx_t, const void* ctx_n, const void* words_t, const float* wnorm,
                                  const int32_t* cap_lens, int Bi, int Bc, int D, int S, int Lcap,
                                  float temp1, float temp2, int agg, float eps,
-                                 float* sim, float* attn_diag, float* attn_mean,
-                                 void* workspace, size_t workspace_bytes, void* stream);
+                                 float* sim, float* stats, void* stream);
 
-/* Fused backward by recomputation; d_ctx [Bi, D, S] fp32 and d_words [Bc, D, Lw] fp32 in the callers' native
- * layouts are fully overwritten. */
+/* Workspace of the backward.  `budget` (0 = unlimited) caps it: captions are then processed in chunks.  The three
+ * bf16 operand matrices take 3 * Bi * Spad * Lpad * 2 bytes per caption (about 260 KB per pair at the full sizes:
+ * 67.6 GB for B = 512 -- this is what the 180 GB of HBM3e are used for). */
+size_t gloria_b200_tc_bwd_workspace(int Bi, int Bc, int D, int S, int Lcap, int have_stats, size_t budget);
+
+/* Backward (agg = sum / mean).  A fused tcgen05 kernel recomputes scores and both softmaxes per pair, obtains
+ * <C_l, R_s> from the image's Gram matrix (one more score-shaped GEMM, K = S) and writes the per-pair operand rows
+ * X^T, E^T, (beta/Z^2) E^T; the sums over images / captions are plain GEMMs.  `stats` is the forward's output
+ * (NULL: recomputed with one extra forward pass).  d_ctx [Bi, D, S] and d_words [Bc, D, Lw] fp32 in the callers'
+ * native layouts are fully overwritten (padded word columns get exactly 0). */
 int gloria_b200_tc_local_sim_bwd(const void* ctx_t, const void* ctx_n, const void* words_t, const float* wnorm,
-                                 const int32_t* cap_lens, int Bi, int Bc, int D, int S, int Lw, int Lcap,
-                                 int word_off, float temp1, float temp2, int agg, float eps,
-                                 const float* dsim, const float* d_attn_diag, const float* d_attn_mean,
-                                 float* d_ctx, float* d_words,
+                                 const int32_t* cap_lens, const float* stats, int Bi, int Bc, int D, int S, int Lw,
+                                 int Lcap, int word_off, float temp1, float temp2, int agg, float eps,
+                                 const float* dsim, float* d_ctx, float* d_words,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import torch
 
-__all__ = ["cosine_similarity", "attention_fn", "local_loss", "global_loss", "loss_step"]
+__all__ = ["cosine_similarity", "attention_fn", "local_similarities", "local_loss", "global_loss", "loss_step"]
 
 
 def cosine_similarity(x1, x2, dim=1, eps=1e-8):
@@ -44,22 +44,29 @@ def _ce_arange(logits):
     return torch.nn.functional.cross_entropy(logits, torch.arange(n))
 
 
-def local_loss(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, temp3=10.0, agg="sum"):
-    """gloria_loss.py:99-170 without the optional regularisers -> (loss0, loss1, att_maps, logits)."""
+def local_similarities(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, agg="sum"):
+    """The [B_img, B_cap] matrix of gloria_loss.py:116-162 (before the temp3 scale) and the diagonal maps."""
     B = img_features.shape[0]
     sims, maps = [], []
     for i in range(words_emb.shape[0]):                              # :116
         L = int(cap_lens[i])
         word = words_emb[i, :, :L].unsqueeze(0).contiguous().repeat(B, 1, 1)    # :119-123
         wctx, attn = attention_fn(word, img_features, temp1)         # :126
-        maps.append(attn[i].unsqueeze(0).contiguous())               # :141-143
+        if i < B:
+            maps.append(attn[i].unsqueeze(0).contiguous())           # :141-143
         w2 = word.transpose(1, 2).contiguous().reshape(B * L, -1)    # :144-148
         c2 = wctx.transpose(1, 2).contiguous().reshape(B * L, -1)
         r = cosine_similarity(w2, c2).reshape(B, L)                  # :150-151
         e = (r * temp2).exp()                                        # :153
         r = e.sum(1, keepdim=True) if agg == "sum" else e.mean(1, keepdim=True)   # :154-157
         sims.append(r.log())                                         # :158
-    logits = torch.cat(sims, 1) * temp3                              # :162-164
+    return torch.cat(sims, 1), maps                                  # :162
+
+
+def local_loss(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, temp3=10.0, agg="sum"):
+    """gloria_loss.py:99-170 without the optional regularisers -> (loss0, loss1, att_maps, logits)."""
+    sim, maps = local_similarities(img_features, words_emb, cap_lens, temp1, temp2, agg)
+    logits = sim * temp3                                             # :164
     return _ce_arange(logits), _ce_arange(logits.t()), maps, logits  # :169-170
 
 

@@ -1,0 +1,98 @@
+"""world_size-2 gloo test of the caption-sharded loss (host-side collective logic).
+
+The block-similarity functions are the torch-CPU oracle here (the CUDA ops cannot run without a GPU); what is under
+test is the sharding: all_gather of image features, per-rank logit column blocks, the logit all_gather, and the
+reduce_scatter of the image-feature gradients.  Sharded result == unsharded oracle on the concatenated batch.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import gloria_oracle_torch as T
+from oracle.make_golden import gen_inputs
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _oracle_fns():
+    def local_sim(img_all, words_local, cap_lens_local, temp1, temp2, agg):
+        return T.local_similarities(img_all, words_local, cap_lens_local, temp1, temp2, agg)[0]
+
+    def global_cos(x, y, eps):
+        return (x @ y.t()) / (x.norm(dim=1, keepdim=True) @ y.norm(dim=1, keepdim=True).t()).clamp(min=eps)
+
+    def ce(m, scale):
+        n = m.shape[0]
+        lab = torch.arange(n)
+        return (torch.nn.functional.cross_entropy(m * scale, lab), torch.nn.functional.cross_entropy(m.t() * scale, lab))
+
+    return dict(local_sim_fn=local_sim, global_cos_fn=global_cos, ce_fn=ce)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gloria_nlp_project_b200 import distributed as D
+        torch.set_num_threads(2)
+        B, Dm, H, W, Lw = 4, 32, 3, 4, 9
+        img_l, txt_l, img_g, txt_g, cl = gen_inputs(31, B, Dm, H, W, Lw, cap_lens=[9, 7, 4, 2])
+        n = B // world
+        sl = slice(rank * n, (rank + 1) * n)
+        leaves = [torch.tensor(a[sl]).requires_grad_(True) for a in (img_l, txt_l, img_g, txt_g)]
+        l0, l1, g0, g1 = D.sharded_loss(leaves[0], leaves[1], leaves[2], leaves[3], cl[sl], **_oracle_fns())
+        (l0 + 0.7 * l1 + 0.5 * g0 + 0.3 * g1).backward()
+        q.put((rank, [float(v) for v in (l0, l1, g0, g1)], [t.grad.numpy() for t in leaves]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_equals_unsharded():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # unsharded oracle on the concatenated batch
+    B, Dm, H, W, Lw = 4, 32, 3, 4, 9
+    img_l, txt_l, img_g, txt_g, cl = gen_inputs(31, B, Dm, H, W, Lw, cap_lens=[9, 7, 4, 2])
+    leaves = [torch.tensor(a).requires_grad_(True) for a in (img_l, txt_l, img_g, txt_g)]
+    l0, l1, _, _ = T.local_loss(leaves[0], leaves[1], cl)
+    g0, g1 = T.global_loss(leaves[2], leaves[3])
+    (l0 + 0.7 * l1 + 0.5 * g0 + 0.3 * g1).backward()
+    want = [float(v) for v in (l0, l1, g0, g1)]
+    n = B // world
+    for rank, losses, grads in res:
+        np.testing.assert_allclose(losses, want, rtol=1e-12)
+        for gsh, leaf in zip(grads, leaves):
+            np.testing.assert_allclose(gsh, leaf.grad.numpy()[rank * n:(rank + 1) * n], rtol=1e-9, atol=1e-14)
+
+
+def test_single_process_path_matches():
+    """Without an initialised process group the function is the plain full-batch loss."""
+    from gloria_nlp_project_b200 import distributed as D
+    img_l, txt_l, img_g, txt_g, cl = gen_inputs(32, 3, 16, 2, 3, 6, cap_lens=[6, 3, 1])
+    t = [torch.tensor(a) for a in (img_l, txt_l, img_g, txt_g)]
+    l0, l1, g0, g1 = D.sharded_loss(*t, cl, **_oracle_fns())
+    r0, r1, _, _ = T.local_loss(t[0], t[1], cl)
+    q0, q1 = T.global_loss(t[2], t[3])
+    np.testing.assert_allclose([float(l0), float(l1), float(g0), float(g1)], [float(r0), float(r1), float(q0), float(q1)],
+                               rtol=1e-12)
