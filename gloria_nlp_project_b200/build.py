@@ -27,7 +27,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-lcublas"], "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES], "-lcublas"]
+    extra = os.environ.get("GLORIA_B200_NVCC_EXTRA", "").split()      # e.g. -DGLORIA_PHASE_CLOCKS (development)
+    cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-lcublas"], *extra, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES], "-lcublas"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -14,7 +14,8 @@
 // One fused kernel per chunk of captions ("pair kernel", caption-stationary persistent CTAs like the forward):
 //   GEMM1  S_[s,l] (3 region tiles, TMEM lanes = regions, stays resident)  ->  softmax warps: P, E -> smem (bf16)
 //   GEMM-T T'[s,l] = G tile (TMA) x E (smem, N-major)                      ->  same lanes/columns as S_
-//   the 4 SIMT warps then do everything else thread-locally (one region row per thread) and write the rows of
+//   12 SIMT warps (3 word-column groups x 4 lane quarters) then do everything else with one region row per thread
+//   (row reductions exchanged between the column groups through shared memory) and write the rows of
 //   X^T, Eo^T, Bo^T as [(j,s), (i,l)] bf16 matrices.
 // The sums over images / captions are then three large plain GEMMs over those matrices (cuBLAS, the one place a
 // library GEMM is used) and a per-image [S x S] x [S x D] product; see DESIGN.md for the byte / FLOP accounting.
@@ -28,17 +29,20 @@ namespace tc {
 namespace bw {
 
 constexpr int SLOT = 16384;
-constexpr int NSLOT = 6;
+constexpr int NSLOT = 7;
+constexpr int NGROUP = 3;                                // column groups of SIMT warps
 constexpr int OFF_E = NSLOT * SLOT;                      // [2 word blocks of 64][Spad regions][128 B]
 constexpr int E_BYTES = 2 * MAX_NT * TILE * 128;
 constexpr int OFF_COEFA = OFF_E + E_BYTES;               // float4 (a, b, c, -) per word
 constexpr int OFF_COEFE = OFF_COEFA + 128 * 16;          // float2 (e, f) per word
 constexpr int OFF_ZBUF = OFF_COEFE + 128 * 8;            // Z per word
-constexpr int OFF_RED = OFF_ZBUF + 128 * 4;              // 16 floats of reduction scratch
-constexpr int OFF_BAR = OFF_RED + 64;
+constexpr int OFF_RED = OFF_ZBUF + 128 * 4;              // 32 floats of reduction scratch
+constexpr int OFF_XCH = OFF_RED + 128;                   // float2 [2][NGROUP][128] row-reduction exchange
+constexpr int OFF_BAR = OFF_XCH + 2 * NGROUP * 128 * 8;
 enum { B_FULL = 0, B_EMPTY = NSLOT, B_D1F = 2 * NSLOT, B_D1E = B_D1F + MAX_NT, B_EF = B_D1E + MAX_NT, B_EE, B_TTF, B_TTE, B_COUNT };
 constexpr int SMEM_BYTES = OFF_BAR + B_COUNT * 8 + 16 + 1024;
-constexpr int NTHREADS = 256;                            // warp 0 TMA, warp 1 MMA, warps 4-7 SIMT (lanes = regions)
+constexpr int NTHREADS = 512;                            // warp 0 TMA, warp 1 MMA, warps 4-15 SIMT (lanes = regions)
+constexpr int NSIMT = NTHREADS - 128;
 
 struct PairParams {
   const float* wnorm;       // [Bc, LPAD]
@@ -51,6 +55,7 @@ struct PairParams {
   float* gamma;             // [Bc, LPAD]  sum_j (dL/d|W_l|) / |W_l|   (atomicAdd)
   int Bi, Bc, i0, nc, D, S, NT;
   float t1, t1_log2e, t2, eps;
+  long long* dbg;           // phase clocks (only read when built with -DGLORIA_PHASE_CLOCKS)
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
@@ -88,6 +93,9 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__ CUtensorMap tm_wt,
                    const __grid_constant__ CUtensorMap tm_g, const PairParams p) {
   extern __shared__ uint8_t smem_raw[];
+#ifdef GLORIA_PHASE_CLOCKS
+  long long* g_dbg = p.dbg;
+#endif
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bars = base + OFF_BAR;
@@ -107,11 +115,11 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
-    for (int t = 0; t < MAX_NT; ++t) { mbar_init(bar(B_D1F + t), 1); mbar_init(bar(B_D1E + t), 128); }
-    mbar_init(bar(B_EF), 128 * NT);
+    for (int t = 0; t < MAX_NT; ++t) { mbar_init(bar(B_D1F + t), 1); mbar_init(bar(B_D1E + t), NSIMT); }
+    mbar_init(bar(B_EF), NSIMT * NT);
     mbar_init(bar(B_EE), 1);
     mbar_init(bar(B_TTF), 1);
-    mbar_init(bar(B_TTE), 128);
+    mbar_init(bar(B_TTE), NSIMT);
     fence_barrier_init();
     tma_prefetch_desc(&tm_rt); tma_prefetch_desc(&tm_wt); tma_prefetch_desc(&tm_g);
   }
@@ -125,8 +133,14 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int slot = 0; uint32_t ph = 0;
+#ifdef GLORIA_PHASE_CLOCKS
+      long long pw_empty = 0, pt_all = clock64();
+#define PTIMED(acc, ...) do { long long _t = clock64(); __VA_ARGS__; acc += clock64() - _t; } while (0)
+#else
+#define PTIMED(acc, ...) do { __VA_ARGS__; } while (0)
+#endif
       auto load = [&](const CUtensorMap* tm, int x, int y, uint32_t bytes) {
-        mbar_wait(bar(B_EMPTY + slot), ph ^ 1);
+        PTIMED(pw_empty, mbar_wait(bar(B_EMPTY + slot), ph ^ 1));
         mbar_expect_tx(bar(B_FULL + slot), bytes);
         tma_load_2d(base + slot * SLOT, tm, x, y, bar(B_FULL + slot));
         if (++slot == NSLOT) { slot = 0; ph ^= 1; }
@@ -148,6 +162,9 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
           }
         }
       }
+#ifdef GLORIA_PHASE_CLOCKS
+      if (g_dbg) { long long* d = g_dbg + (size_t)blockIdx.x * 32 + 8; d[0] = clock64() - pt_all; d[1] = pw_empty; }
+#endif
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -157,8 +174,14 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
       const uint32_t e_lbo = (uint32_t)Spad * 128u;               // between the two 64-word blocks of E
       int slot = 0; uint32_t ph = 0;
       uint32_t n = 0, ttc = 0;
+#ifdef GLORIA_PHASE_CLOCKS
+      long long wt_full = 0, wt_d1e = 0, wt_ef = 0, wt_tte = 0, t_all = clock64();
+#define TIMED_WAIT(acc, ...) do { long long _t = clock64(); __VA_ARGS__; acc += clock64() - _t; } while (0)
+#else
+#define TIMED_WAIT(acc, ...) do { __VA_ARGS__; } while (0)
+#endif
       auto take = [&]() {
-        mbar_wait(bar(B_FULL + slot), ph);
+        TIMED_WAIT(wt_full, mbar_wait(bar(B_FULL + slot), ph));
         const int s = slot;
         if (++slot == NSLOT) { slot = 0; ph ^= 1; }
         return s;
@@ -168,7 +191,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
         for (int j = u.j; j < u.j_end; ++j) {
           for (int idx = 0; idx < NT; ++idx) {
             const int t = tile_at(idx, NT);
-            mbar_wait(bar(B_D1E + t), (n & 1) ^ 1);          // previous pair's SIMT pass no longer needs S_ tile t
+            TIMED_WAIT(wt_d1e, mbar_wait(bar(B_D1E + t), (n & 1) ^ 1));   // previous pair no longer needs S_ tile t
             tc_fence_after();
             for (int kb = 0; kb < nkb1; ++kb) {
               const int sa = take();
@@ -184,10 +207,10 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             }
             umma_commit(bar(B_D1F + t));
           }
-          mbar_wait(bar(B_EF), n & 1);                       // E of this pair is complete in shared memory
+          TIMED_WAIT(wt_ef, mbar_wait(bar(B_EF), n & 1));    // E of this pair is complete in shared memory
           tc_fence_after();
           for (int idx = 0; idx < NT; ++idx) {
-            mbar_wait(bar(B_TTE), (ttc & 1) ^ 1);            // T' buffer has been read by the SIMT warps
+            TIMED_WAIT(wt_tte, mbar_wait(bar(B_TTE), (ttc & 1) ^ 1));   // T' buffer has been read by the SIMT warps
             tc_fence_after();
             for (int kb = 0; kb < nkb2; ++kb) {
               const int sa = take();
@@ -209,74 +232,102 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
           ++n;
         }
       }
+#ifdef GLORIA_PHASE_CLOCKS
+      if (g_dbg) {
+        long long* d = g_dbg + (size_t)blockIdx.x * 32;
+        d[0] = clock64() - t_all; d[1] = wt_full; d[2] = wt_d1e; d[3] = wt_ef; d[4] = wt_tte; d[5] = n;
+      }
+#endif
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ SIMT warps (TMEM lanes = regions)
+    // 12 warps = 3 column groups x 4 lane quarters: thread (g, row) owns region row `row` of every tile and the word
+    // columns of group g.  Row-wise reductions (softmax max / sum, u) are exchanged between the 3 groups through
+    // shared memory; three resident warps per scheduler hide the MUFU / TMEM / LDS latencies.
+    constexpr int NCH = LPAD / 8;                  // 16-byte chunks (8 words) per row
+    constexpr int CW = (NCH + NGROUP - 1) / NGROUP;   // chunks per column group
+    constexpr int WG = CW * 8;                     // words per column group
+    const int g = (warp - 4) >> 2;
     const int q = warp & 3;
-    const int row = q * 32 + lane;                 // region row inside a tile == TMEM lane == word index for coefs
+    const int row = q * 32 + lane;                 // region row inside a tile == TMEM lane
+    const int wl = (warp - 4) * 32 + lane;         // 0..383: word index for the coefficient step (threads wl < LPAD)
+    const int c_lo = g * CW;                       // first chunk of this group
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     constexpr float LOG2E = 1.4426950408889634f;
     const int zrow = p.S - (NT - 1) * TILE;        // row of the ones row of G inside the last tile
-    uint32_t n = 0, ttc = 0;
+    float2* xch = reinterpret_cast<float2*>(smem + OFF_XCH);     // [2][NGROUP][128] exchange buffer
+    uint32_t n = 0, ttc = 0, xc = 0;
+#ifdef GLORIA_PHASE_CLOCKS
+    long long sw_d1f = 0, sw_ttf = 0, sw_ee = 0, sw_bar = 0, st_all = clock64();
+#define STIMED(acc, ...) do { long long _t = clock64(); __VA_ARGS__; acc += clock64() - _t; } while (0)
+#else
+#define STIMED(acc, ...) do { __VA_ARGS__; } while (0)
+#endif
     Units u(p.Bi, p.nc);
     while (u.next_caption()) {
       const int i = p.i0 + u.i;
       const int L = min(max(p.cap_lens[i], 0), LPAD);
-      const float nw = (row < LPAD) ? p.wnorm[(size_t)i * LPAD + row] : 0.f;
+      const float nw = (wl < LPAD) ? p.wnorm[(size_t)i * LPAD + wl] : 0.f;
       float gacc = 0.f;
       const size_t pitch = (size_t)p.nc * LPAD;
       for (int j = u.j; j < u.j_end; ++j) {
-        // per-word inputs of the coefficient step (thread `row` owns word l = row); latency hidden by the softmax
+        // per-word inputs of the coefficient step (thread wl owns word l = wl); latency hidden by the softmax
         float dotp = 0.f, c2p = 0.f;
-        if (row < LPAD) {
+        if (wl < LPAD) {
           const float* sp = p.stats + ((size_t)j * p.Bc + i) * 2 * LPAD;
-          dotp = __ldg(sp + row);
-          c2p = __ldg(sp + LPAD + row);
+          dotp = __ldg(sp + wl);
+          c2p = __ldg(sp + LPAD + wl);
         }
-        const float g = __ldg(p.dsim + (size_t)j * p.Bc + i);
+        const float gsim = __ldg(p.dsim + (size_t)j * p.Bc + i);
         float mb[MAX_NT], inv[MAX_NT];
         // ---------------- phase 1: word softmax, E -> shared memory (S_ stays in TMEM)
 #pragma unroll
         for (int idx = 0; idx < MAX_NT; ++idx) {
           if (idx < NT) {
             const int t = tile_at(idx, NT);
-            mbar_wait(bar(B_D1F + t), n & 1);
+            STIMED(sw_d1f, mbar_wait(bar(B_D1F + t), n & 1));
             tc_fence_after();
-            float x[LPAD];
+            float x[WG];
 #pragma unroll
-            for (int c = 0; c < LPAD / 16; ++c) tmem_ld16(tmem + lane_addr + (uint32_t)(t * LPAD + c * 16), x + c * 16);
+            for (int c = 0; c < CW; ++c)
+              if (c_lo + c < NCH) tmem_ld8(tmem + lane_addr + (uint32_t)(t * LPAD + (c_lo + c) * 8), x + c * 8);
             tmem_ld_wait();
             float m = -INFINITY;
 #pragma unroll
-            for (int l = 0; l < LPAD; ++l) m = (l < L) ? fmaxf(m, x[l]) : m;
-            const float mbv = m * LOG2E;
-            float sum = 0.f;
+            for (int k = 0; k < WG; ++k) m = (c_lo * 8 + k < L) ? fmaxf(m, x[k]) : m;
+            const float mg = (m == -INFINITY) ? 0.f : m * LOG2E;      // group without live words: contributes 0
+            float sg = 0.f;
 #pragma unroll
-            for (int l = 0; l < LPAD; ++l) {
-              const float e = (l < L) ? ex2(fmaf(x[l], LOG2E, -mbv)) : 0.f;
-              x[l] = e;
-              sum += e;
+            for (int k = 0; k < WG; ++k) {
+              const float e = (c_lo * 8 + k < L) ? ex2(fmaf(x[k], LOG2E, -mg)) : 0.f;
+              x[k] = e;
+              sg += e;
             }
-            const float rinv = 1.f / sum;
+            float2* xb = xch + (xc & 1) * (NGROUP * 128);
+            ++xc;
+            xb[g * 128 + row] = make_float2(m == -INFINITY ? -INFINITY : mg, sg);
+            STIMED(sw_bar, asm volatile("bar.sync 1, 384;" ::: "memory"));
+            const float2 v0 = xb[row], v1 = xb[128 + row], v2 = xb[256 + row];
+            const float mbv = fmaxf(v0.x, fmaxf(v1.x, v2.x));
+            const float tot = v0.y * ex2(v0.x - mbv) + v1.y * ex2(v1.x - mbv) + v2.y * ex2(v2.x - mbv);
+            const float rinv = 1.f / tot;
             mb[idx] = mbv;
             inv[idx] = rinv;
             const int s_glob = t * TILE + row;
             const bool live_row = s_glob < p.S;
-            const float sc = p.t1_log2e * rinv;
+            const float sc = p.t1_log2e * rinv * ex2(mg - mbv);       // P = e * ex2(mg - mb) / tot
 #pragma unroll
-            for (int l = 0; l < LPAD; ++l) x[l] = (live_row && l < L) ? ex2(x[l] * sc) : 0.f;
-            if (idx == 0) mbar_wait(bar(B_EE), (n & 1) ^ 1);   // previous pair's GEMM-T no longer reads E
+            for (int k = 0; k < WG; ++k) x[k] = (live_row && c_lo * 8 + k < L) ? ex2(x[k] * sc) : 0.f;
+            if (idx == 0) STIMED(sw_ee, mbar_wait(bar(B_EE), (n & 1) ^ 1));   // previous pair's GEMM-T no longer reads E
             const uint32_t rowaddr = base + OFF_E + (uint32_t)(s_glob >> 3) * 1024u + (uint32_t)(s_glob & 7) * 128u;
 #pragma unroll
-            for (int wb = 0; wb < (LPAD + 63) / 64; ++wb) {
-#pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const int l0 = wb * 64 + c * 8;
-                if (l0 < LPAD) {
-                  const uint32_t addr = rowaddr + (uint32_t)wb * ((uint32_t)Spad * 128u) + (uint32_t)((c ^ (s_glob & 7)) << 4);
-                  sts128(addr, pack_bf16(x[l0], x[l0 + 1]), pack_bf16(x[l0 + 2], x[l0 + 3]),
-                         pack_bf16(x[l0 + 4], x[l0 + 5]), pack_bf16(x[l0 + 6], x[l0 + 7]));
-                }
+            for (int c = 0; c < CW; ++c) {
+              const int ch = c_lo + c;
+              if (ch < NCH) {
+                const uint32_t addr = rowaddr + (uint32_t)(ch >> 3) * ((uint32_t)Spad * 128u) +
+                                      (uint32_t)(((ch & 7) ^ (s_glob & 7)) << 4);
+                sts128(addr, pack_bf16(x[c * 8], x[c * 8 + 1]), pack_bf16(x[c * 8 + 2], x[c * 8 + 3]),
+                       pack_bf16(x[c * 8 + 4], x[c * 8 + 5]), pack_bf16(x[c * 8 + 6], x[c * 8 + 7]));
               }
             }
             fence_proxy_async_smem();
@@ -288,27 +339,29 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
         for (int idx = 0; idx < MAX_NT; ++idx) {
           if (idx < NT) {
             const int t = tile_at(idx, NT);
-            mbar_wait(bar(B_TTF), ttc & 1);
+            STIMED(sw_ttf, mbar_wait(bar(B_TTF), ttc & 1));
             ++ttc;
             tc_fence_after();
             if (idx == 0) {
-              // Z_l = sum_s E[s,l] sits in the ones row of this tile
+              // Z_l = sum_s E[s,l] sits in the ones row of this tile; every group reads its own columns of that row
               if (q == (zrow >> 5)) {
 #pragma unroll
-                for (int c = 0; c < LPAD / 16; ++c) {
-                  float z[16];
-                  tmem_ld16(tmem + lane_addr + TT_COL + (uint32_t)(c * 16), z);
-                  tmem_ld_wait();
-                  if (lane == (zrow & 31)) {
+                for (int c = 0; c < CW; ++c) {
+                  if (c_lo + c < NCH) {
+                    float z[8];
+                    tmem_ld8(tmem + lane_addr + TT_COL + (uint32_t)((c_lo + c) * 8), z);
+                    tmem_ld_wait();
+                    if (lane == (zrow & 31)) {
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) zbuf[c * 16 + k] = z[k];
+                      for (int k = 0; k < 8; ++k) zbuf[(c_lo + c) * 8 + k] = z[k];
+                    }
                   }
                 }
               }
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              // closed-form coefficients of word l = row (SURVEY.md section 0 / oracle local_sim_pair_bwd)
-              const bool live = row < L;
-              const float Zl = live ? zbuf[row] : 1.f;
+              asm volatile("bar.sync 1, 384;" ::: "memory");
+              // closed-form coefficients of word l = wl (SURVEY.md section 0 / oracle local_sim_pair_bwd)
+              const bool live = wl < L;
+              const float Zl = live ? zbuf[wl] : 1.f;
               const float iz = 1.f / Zl;
               const float nc = sqrtf(c2p) * iz;
               const float dot = dotp * iz;
@@ -317,94 +370,129 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
               const float cosv = dot / den;
               const float v = live ? p.t2 * cosv : -INFINITY;
               float mx = warp_max(v);
-              if (lane == 0) red[q] = mx;
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+              if (lane == 0) red[warp - 4] = mx;
+              asm volatile("bar.sync 1, 384;" ::: "memory");
+              mx = red[0];
+#pragma unroll
+              for (int k = 1; k < 12; ++k) mx = fmaxf(mx, red[k]);
               float ex = live ? __expf(v - mx) : 0.f;
               float tot = warp_sum(ex);
-              if (lane == 0) red[4 + q] = tot;
-              asm volatile("bar.sync 1, 128;" ::: "memory");
-              tot = red[4] + red[5] + red[6] + red[7];
-              const float dr = g * p.t2 * ex / tot;
+              if (lane == 0) red[12 + (warp - 4)] = tot;
+              asm volatile("bar.sync 1, 384;" ::: "memory");
+              tot = 0.f;
+#pragma unroll
+              for (int k = 0; k < 12; ++k) tot += red[12 + k];
+              const float dr = gsim * p.t2 * ex / tot;
               const float ddot = dr / den;
               const float dden = (prod >= p.eps) ? -dr * dot / (den * den) : 0.f;
               const float beta = nc > 0.f ? dden * nw / nc : 0.f;
               const float gamma = nw > 0.f ? dden * nc / nw : 0.f;
               const float rs = ddot * dot + beta * nc * nc;
-              if (row < LPAD) {
-                coefA[row] = live ? make_float4(p.t1 * ddot * iz, p.t1 * beta * iz * iz, p.t1 * rs * iz, 0.f)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-                coefE[row] = live ? make_float2(ddot * iz, beta * iz * iz) : make_float2(0.f, 0.f);
+              if (wl < LPAD) {
+                coefA[wl] = live ? make_float4(p.t1 * ddot * iz, p.t1 * beta * iz * iz, p.t1 * rs * iz, 0.f)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                coefE[wl] = live ? make_float2(ddot * iz, beta * iz * iz) : make_float2(0.f, 0.f);
               }
               if (live) gacc += gamma;
-              asm volatile("bar.sync 1, 128;" ::: "memory");
+              asm volatile("bar.sync 1, 384;" ::: "memory");
             }
             const int s_glob = t * TILE + row;
-            const uint32_t rowaddr = base + OFF_E + (uint32_t)(s_glob >> 3) * 1024u + (uint32_t)(s_glob & 7) * 128u;
             const float mbv = mb[idx], rinv = inv[idx];
-            float dp[LPAD];
-            uint32_t pp[LPAD / 2];
-            float uacc = 0.f;
-            // pass 1: dP = E (a S_ + b T' - c), u = sum_l P dP
+            float dp[WG];
+            uint32_t pp[WG / 2];
+            float ug = 0.f;
+            // pass 1 (own columns, 16 at a time): dP = E (a S_ + b T' - c), partial u = sum_l P dP
+            const uint8_t* erow = smem + OFF_E + (size_t)(s_glob >> 3) * 1024u + (size_t)(s_glob & 7) * 128u;
 #pragma unroll
-            for (int c = 0; c < LPAD / 8; ++c) {
-              float sv[8], tv[8];
-              tmem_ld8(tmem + lane_addr + (uint32_t)(t * LPAD + c * 8), sv);
-              tmem_ld8(tmem + lane_addr + TT_COL + (uint32_t)(c * 8), tv);
-              const int wb = (c * 8) / 64, cc = ((c * 8) % 64) / 8;
-              const uint4 ev = lds128(rowaddr + (uint32_t)wb * ((uint32_t)Spad * 128u) + (uint32_t)((cc ^ (s_glob & 7)) << 4));
+            for (int cb = 0; cb < CW; cb += 2) {
+              float sv[16], tv[16];
+              uint4 ev[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int ch = c_lo + cb + h;
+                if (cb + h < CW && ch < NCH) {
+                  tmem_ld8(tmem + lane_addr + (uint32_t)(t * LPAD + ch * 8), sv + h * 8);
+                  tmem_ld8(tmem + lane_addr + TT_COL + (uint32_t)(ch * 8), tv + h * 8);
+                  ev[h] = *reinterpret_cast<const uint4*>(erow + (size_t)(ch >> 3) * ((size_t)Spad * 128u) +
+                                                          (size_t)(((ch & 7) ^ (s_glob & 7)) << 4));
+                }
+              }
               tmem_ld_wait();
-              const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int l = c * 8 + k;
-                const float e = (k & 1) ? bf_hi(ew[k >> 1]) : bf_lo(ew[k >> 1]);
-                const float4 cf = lds_f4(base + OFF_COEFA + (uint32_t)l * 16u);
-                const float P = (l < L) ? ex2(fmaf(sv[k], LOG2E, -mbv)) * rinv : 0.f;
-                const float d = e * (fmaf(cf.x, sv[k], fmaf(cf.y, tv[k], -cf.z)));
-                dp[l] = d;
-                uacc = fmaf(P, d, uacc);
-                if (k & 1) {
-                  const float Pprev = __uint_as_float(pp[l >> 1]);
-                  pp[l >> 1] = pack_bf16(Pprev, P);
-                } else {
-                  pp[l >> 1] = __float_as_uint(P);
+              for (int h = 0; h < 2; ++h) {
+                const int ch = c_lo + cb + h;
+                if (cb + h < CW) {
+                  if (ch < NCH) {
+                    const uint32_t ew[4] = {ev[h].x, ev[h].y, ev[h].z, ev[h].w};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                      const int l = ch * 8 + k;
+                      const int o = (cb + h) * 8 + k;
+                      const float e = (k & 1) ? bf_hi(ew[k >> 1]) : bf_lo(ew[k >> 1]);
+                      const float4 cf = coefA[l];
+                      const float P = (l < L) ? ex2(fmaf(sv[h * 8 + k], LOG2E, -mbv)) * rinv : 0.f;
+                      const float d = e * (fmaf(cf.x, sv[h * 8 + k], fmaf(cf.y, tv[h * 8 + k], -cf.z)));
+                      dp[o] = d;
+                      ug = fmaf(P, d, ug);
+                      if (k & 1) pp[o >> 1] = pack_bf16(__uint_as_float(pp[o >> 1]), P);
+                      else pp[o >> 1] = __float_as_uint(P);
+                    }
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) dp[(cb + h) * 8 + k] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pp[(cb + h) * 4 + k] = 0u;
+                  }
                 }
               }
             }
             tc_fence_before();
             mbar_arrive(bar(B_TTE));                 // T' buffer may be overwritten by the next tile's GEMM-T
             mbar_arrive(bar(B_D1E + t));             // S_ tile may be overwritten by the next pair's GEMM1
-            // pass 2: rows of X^T, Eo^T, Bo^T  ([(j, s), (i, l)] bf16, 16-byte stores along l)
+            float2* xb = xch + (xc & 1) * (NGROUP * 128);
+            ++xc;
+            xb[g * 128 + row].x = ug;
+            STIMED(sw_bar, asm volatile("bar.sync 1, 384;" ::: "memory"));
+            const float uacc = xb[row].x + xb[128 + row].x + xb[256 + row].x;
+            // pass 2 (own columns): rows of X^T, Eo^T, Bo^T  ([(j, s), (i, l)] bf16, 16-byte stores along l)
             const size_t goff = ((size_t)j * Spad + s_glob) * pitch + (size_t)u.i * LPAD;
             uint4* xo = reinterpret_cast<uint4*>(p.xt + goff);
             uint4* eo = reinterpret_cast<uint4*>(p.et + goff);
             uint4* bo = reinterpret_cast<uint4*>(p.bt + goff);
 #pragma unroll
-            for (int c = 0; c < LPAD / 8; ++c) {
-              const int wb = (c * 8) / 64, cc = ((c * 8) % 64) / 8;
-              const uint4 ev = lds128(rowaddr + (uint32_t)wb * ((uint32_t)Spad * 128u) + (uint32_t)((cc ^ (s_glob & 7)) << 4));
-              const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
-              float xv[8], bv[8];
+            for (int c = 0; c < CW; ++c) {
+              const int ch = c_lo + c;
+              if (ch < NCH) {
+                const uint4 ev = *reinterpret_cast<const uint4*>(erow + (size_t)(ch >> 3) * ((size_t)Spad * 128u) +
+                                                                 (size_t)(((ch & 7) ^ (s_glob & 7)) << 4));
+                const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+                float xv[8], bv[8];
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int l = c * 8 + k;
-                const float e = (k & 1) ? bf_hi(ew[k >> 1]) : bf_lo(ew[k >> 1]);
-                const float P = (k & 1) ? bf_hi(pp[l >> 1]) : bf_lo(pp[l >> 1]);
-                const float2 ce = lds_f2(base + OFF_COEFE + (uint32_t)l * 8u);
-                xv[k] = fmaf(ce.x, e, P * (dp[l] - uacc));
-                bv[k] = ce.y * e;
+                for (int k = 0; k < 8; ++k) {
+                  const int l = ch * 8 + k;
+                  const float e = (k & 1) ? bf_hi(ew[k >> 1]) : bf_lo(ew[k >> 1]);
+                  const float P = (k & 1) ? bf_hi(pp[(c * 8 + k) >> 1]) : bf_lo(pp[(c * 8 + k) >> 1]);
+                  const float2 ce = coefE[l];
+                  xv[k] = fmaf(ce.x, e, P * (dp[c * 8 + k] - uacc));
+                  bv[k] = ce.y * e;
+                }
+                xo[ch] = make_uint4(pack_bf16(xv[0], xv[1]), pack_bf16(xv[2], xv[3]), pack_bf16(xv[4], xv[5]), pack_bf16(xv[6], xv[7]));
+                bo[ch] = make_uint4(pack_bf16(bv[0], bv[1]), pack_bf16(bv[2], bv[3]), pack_bf16(bv[4], bv[5]), pack_bf16(bv[6], bv[7]));
+                eo[ch] = ev;
               }
-              xo[c] = make_uint4(pack_bf16(xv[0], xv[1]), pack_bf16(xv[2], xv[3]), pack_bf16(xv[4], xv[5]), pack_bf16(xv[6], xv[7]));
-              bo[c] = make_uint4(pack_bf16(bv[0], bv[1]), pack_bf16(bv[2], bv[3]), pack_bf16(bv[4], bv[5]), pack_bf16(bv[6], bv[7]));
-              eo[c] = ev;
             }
           }
         }
         ++n;
       }
-      if (row < LPAD && gacc != 0.f) atomicAdd(p.gamma + (size_t)i * LPAD + row, gacc);
+      if (wl < LPAD && gacc != 0.f) atomicAdd(p.gamma + (size_t)i * LPAD + wl, gacc);
     }
+#ifdef GLORIA_PHASE_CLOCKS
+    if (g_dbg && (lane == 0) && (q == 0)) {
+      long long* d = g_dbg + (size_t)blockIdx.x * 32 + 16 + 5 * g;
+      d[0] = clock64() - st_all; d[1] = sw_d1f; d[2] = sw_ttf; d[3] = sw_ee; d[4] = sw_bar;
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -635,6 +723,7 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_t, const void* ctx_n
     p.xt = X; p.et = E; p.bt = Bm; p.gamma = gamma;
     p.Bi = Bi; p.Bc = Bc; p.i0 = i0; p.nc = nc; p.D = D; p.S = S; p.NT = Spad / TILE;
     p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps;
+    p.dbg = (long long*)g_phase_clock_buffer;
     switch (lpad) {
       case 16: rc = bw::launch_pair<16>(rt, wt, gm, p, sms, st); break;
       case 32: rc = bw::launch_pair<32>(rt, wt, gm, p, sms, st); break;

@@ -38,6 +38,7 @@ struct FwdParams {
   float temp2;
   int agg;
   float eps_s;               // eps * S  (clamp on the un-normalised context, see header comment)
+  long long* dbg;            // phase clocks (only read when built with -DGLORIA_PHASE_CLOCKS)
 };
 
 template <int LPAD>
@@ -103,6 +104,12 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
+#ifdef GLORIA_PHASE_CLOCKS
+      long long wt_full = 0, wt_d1e = 0, wt_ef = 0, wt_d2e = 0, t_all = clock64();
+#define TIMED_WAIT(acc, ...) do { long long _t = clock64(); __VA_ARGS__; acc += clock64() - _t; } while (0)
+#else
+#define TIMED_WAIT(acc, ...) do { __VA_ARGS__; } while (0)
+#endif
       constexpr uint32_t idesc1 = make_idesc(TILE, LPAD, 0, 0);   // A = Rt tile (K-major), B = Wt tile (K-major)
       constexpr uint32_t idesc2 = make_idesc(TILE, TILE, 1, 0);   // A = E (MN-major), B = Rn tile (K-major)
       const uint32_t e_lbo = (uint32_t)Spad * 128u;               // between the two 64-word blocks of E
@@ -113,10 +120,10 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
         for (int j = u.j; j < u.j_end; ++j) {
           for (int t = 0; t < p.NT; ++t) {
             const uint32_t b = g1 & 1;
-            mbar_wait(bar(B_D1E + b), ((g1 >> 1) & 1) ^ 1);
+            TIMED_WAIT(wt_d1e, mbar_wait(bar(B_D1E + b), ((g1 >> 1) & 1) ^ 1));
             tc_fence_after();
             for (int kb = 0; kb < nkb1; ++kb) {
-              mbar_wait(bar(B_FULL + st), ph);
+              TIMED_WAIT(wt_full, mbar_wait(bar(B_FULL + st), ph));
               tc_fence_after();
               const uint32_t a0 = base + st * STAGE_BYTES, b0 = a0 + 16384;
 #pragma unroll
@@ -129,14 +136,14 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
             umma_commit(bar(B_D1F + b));
             ++g1;
           }
-          mbar_wait(bar(B_EF), nu & 1);          // every E tile of this unit is in shared memory
+          TIMED_WAIT(wt_ef, mbar_wait(bar(B_EF), nu & 1));          // every E tile of this unit is in shared memory
           tc_fence_after();
           for (int c = 0; c < nchunk; ++c) {
             const uint32_t b2 = g2 & 1;
-            mbar_wait(bar(B_D2E + b2), ((g2 >> 1) & 1) ^ 1);
+            TIMED_WAIT(wt_d2e, mbar_wait(bar(B_D2E + b2), ((g2 >> 1) & 1) ^ 1));
             tc_fence_after();
             for (int kb = 0; kb < nkb2; ++kb) {
-              mbar_wait(bar(B_FULL + st), ph);
+              TIMED_WAIT(wt_full, mbar_wait(bar(B_FULL + st), ph));
               tc_fence_after();
               const uint32_t b0 = base + st * STAGE_BYTES;
 #pragma unroll
@@ -156,6 +163,12 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
           ++nu;
         }
       }
+#ifdef GLORIA_PHASE_CLOCKS
+      if (p.dbg) {
+        long long* d = p.dbg + (size_t)blockIdx.x * 32;
+        d[0] = clock64() - t_all; d[1] = wt_full; d[2] = wt_d1e; d[3] = wt_ef; d[4] = wt_d2e; d[5] = nu;
+      }
+#endif
     }
   } else if (warp >= 4 && warp < 8) {
     // ------------------------------------------------------------------ softmax warps (TMEM lanes = regions)
@@ -402,6 +415,10 @@ int launch_fwd(const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap& 
 using namespace gloria;
 using namespace gloria::tc;
 
+// Development aid: device buffer of per-CTA phase clocks (8 x int64 per CTA), used only by -DGLORIA_PHASE_CLOCKS builds.
+void* gloria::tc::g_phase_clock_buffer = nullptr;
+extern "C" void gloria_b200_debug_phase_clocks(void* device_buffer) { gloria::tc::g_phase_clock_buffer = device_buffer; }
+
 extern "C" int gloria_b200_tc_spad(int S) { return (S / TILE + 1) * TILE; }
 extern "C" int gloria_b200_tc_lpad(int Lcap) { return (Lcap + 15) / 16 * 16; }
 
@@ -445,6 +462,7 @@ extern "C" int gloria_b200_tc_local_sim_fwd(const void* ctx_t, const void* ctx_n
   p.wt = (const __nv_bfloat16*)words_t; p.wnorm = wnorm; p.cap_lens = cap_lens; p.sim = sim; p.stats = stats;
   p.Bi = Bi; p.Bc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE;
   p.t1_log2e = temp1 * 1.4426950408889634f; p.temp2 = temp2; p.agg = agg; p.eps_s = eps * (float)S;
+  p.dbg = (long long*)g_phase_clock_buffer;
   int dev = 0, sms = 0;
   GLORIA_CUDA(cudaGetDevice(&dev));
   GLORIA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

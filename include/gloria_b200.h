@@ -57,6 +57,8 @@ long long gloria_b200_launch_count(int reset);
 #define GLORIA_TIMER_TC_BWD_GEMM 2   /* backward accumulation GEMMs                  */
 #define GLORIA_TIMER_SLOTS 4
 int gloria_b200_set_timer_events(int slot, void* start_event, void* stop_event);
+/* Development aid (builds with -DGLORIA_PHASE_CLOCKS only): device buffer receiving 8 int64 phase clocks per CTA. */
+void gloria_b200_debug_phase_clocks(void* device_buffer);
 
 /* ------------------------------------------------------------------------------------------------------------
  * fp32 mode (CUDA-core FFMA, fp32 accumulate): replaces attention_fn + cosine_similarity + the caption loop of
