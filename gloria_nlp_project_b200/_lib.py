@@ -31,6 +31,11 @@ PROTOTYPES = {
     "gloria_b200_diag_attn_workspace": (_z, [_i, _i, _i, _i, _i]),
     "gloria_b200_diag_attn_fwd_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p, _z, _p]),
     "gloria_b200_diag_attn_bwd_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p, _z, _p]),
+    "gloria_b200_attention_workspace": (_z, [_i, _i, _i, _i]),
+    "gloria_b200_attention_fwd_f32": (_i, [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _z, _p]),
+    "gloria_b200_attention_bwd_f32": (_i, [_p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _p, _z, _p]),
+    "gloria_b200_row_cosine_fwd": (_i, [_p, _p, C.c_longlong, _i, _f, _p, _p, _p]),
+    "gloria_b200_row_cosine_bwd": (_i, [_p, _p, _p, _p, C.c_longlong, _i, _f, _p, _p, _p]),
     "gloria_b200_tc_spad": (_i, [_i]),
     "gloria_b200_tc_lpad": (_i, [_i]),
     "gloria_b200_tc_supported": (_i, [_i, _i, _i]),

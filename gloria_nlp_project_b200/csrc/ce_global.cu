@@ -187,3 +187,67 @@ extern "C" int gloria_b200_ce_bidir_bwd(const float* m, int B, float scale, cons
   GLORIA_LAUNCHED("ce_bwd");
   return GLORIA_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-wise cosine of two [N, D] matrices (cosine_similarity, gloria_loss.py:11-16), forward and backward.
+// One warp per row.  stats [N, 3] = (dot, |x1|, |x2|) saved for the backward.
+// ---------------------------------------------------------------------------------------------------------------
+namespace gloria {
+namespace {
+__global__ void row_cosine_fwd(const float* __restrict__ a, const float* __restrict__ b, long long N, int D, float eps,
+                               float* __restrict__ out, float* __restrict__ stats) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int lane = threadIdx.x & 31;
+  const float* ar = a + row * D;
+  const float* br = b + row * D;
+  float dot = 0.f, na = 0.f, nb = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float x = ar[d], y = br[d];
+    dot = fmaf(x, y, dot); na = fmaf(x, x, na); nb = fmaf(y, y, nb);
+  }
+  dot = warp_sum(dot); na = sqrtf(warp_sum(na)); nb = sqrtf(warp_sum(nb));
+  if (lane == 0) {
+    out[row] = dot / fmaxf(na * nb, eps);
+    if (stats) { stats[row * 3] = dot; stats[row * 3 + 1] = na; stats[row * 3 + 2] = nb; }
+  }
+}
+__global__ void row_cosine_bwd(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ stats,
+                               const float* __restrict__ g, long long N, int D, float eps, float* __restrict__ da,
+                               float* __restrict__ db) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int lane = threadIdx.x & 31;
+  const float dot = stats[row * 3], na = stats[row * 3 + 1], nb = stats[row * 3 + 2];
+  const float prod = na * nb, den = fmaxf(prod, eps), gr = g[row];
+  const float ddot = gr / den;
+  const float dden = (prod >= eps) ? -gr * dot / (den * den) : 0.f;
+  const float ca = na > 0.f ? dden * nb / na : 0.f;    // (dL/d|a|) / |a|
+  const float cb = nb > 0.f ? dden * na / nb : 0.f;
+  const float* ar = a + row * D;
+  const float* br = b + row * D;
+  for (int d = lane; d < D; d += 32) {
+    const float x = ar[d], y = br[d];
+    da[row * D + d] = fmaf(ddot, y, ca * x);
+    db[row * D + d] = fmaf(ddot, x, cb * y);
+  }
+}
+}  // namespace
+}  // namespace gloria
+
+extern "C" int gloria_b200_row_cosine_fwd(const float* x1, const float* x2, long long N, int D, float eps, float* out,
+                                          float* stats, void* stream) {
+  GLORIA_CHECK_ARG(x1 && x2 && out && N > 0 && D > 0, "bad arguments");
+  gloria::row_cosine_fwd<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x1, x2, N, D, eps, out, stats);
+  GLORIA_LAUNCHED("row_cosine_fwd");
+  return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_row_cosine_bwd(const float* x1, const float* x2, const float* stats, const float* dout,
+                                          long long N, int D, float eps, float* dx1, float* dx2, void* stream) {
+  GLORIA_CHECK_ARG(x1 && x2 && stats && dout && dx1 && dx2 && N > 0 && D > 0, "bad arguments");
+  gloria::row_cosine_bwd<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x1, x2, stats, dout, N, D, eps, dx1, dx2);
+  GLORIA_LAUNCHED("row_cosine_bwd");
+  return GLORIA_OK;
+}

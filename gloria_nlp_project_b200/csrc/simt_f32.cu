@@ -615,6 +615,7 @@ extern "C" int gloria_b200_local_sim_bwd_f32(const float* ctx, const float* word
 // through them (supervised-attention loss, gloria_model.py:143-147).  B pairs instead of B^2.
 // workspace: Wt [B,Lw,D], dWt [B,Lw,D], wn [B,Lw], sc / at / da [B,Lcap,S]
 // ---------------------------------------------------------------------------------------------------------------
+namespace gloria {
 namespace {
 struct DiagPlan { size_t off_wt, off_dwt, off_wn, off_sc, off_at, off_da, total; };
 DiagPlan diag_plan(int B, int D, int S, int Lw, int Lcap) {
@@ -648,6 +649,7 @@ int diag_forward(const float* ctx, const float* Wt, const int32_t* cap_lens, int
   return GLORIA_OK;
 }
 }  // namespace
+}  // namespace gloria
 
 extern "C" size_t gloria_b200_diag_attn_workspace(int B, int D, int S, int Lw, int Lcap) {
   if (B <= 0 || D <= 0 || S <= 0 || Lw <= 0 || Lcap <= 0) return 0;
@@ -717,5 +719,172 @@ extern "C" int gloria_b200_diag_attn_bwd_f32(const float* ctx, const float* word
   dim3 grid((Lw + 31) / 32, (D + 31) / 32, B), block(32, 8);
   unpack_dwords<<<grid, block, 0, st>>>(dWt, d_words, cap_lens, D, Lw, Lcap, word_off, accumulate);
   GLORIA_LAUNCHED("unpack_dwords(diag)");
+  return GLORIA_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// attention_fn (gloria_loss.py:19-63) as a stand-alone paired operator: query[b] attends to context[b].
+//   query [B, D, L] (word axis contiguous), context [B, D, S]  ->  wctx [B, D, L], attn [B, L, S]
+// Backward takes d_wctx [B, D, L] and d_attn [B, L, S] (either may be NULL) and overwrites d_query, d_ctx.
+// workspace: Wt, dWt [B,L,D]; wn [B,L]; sc, at, da [B,L,S]; cx [B,L,D]
+// ---------------------------------------------------------------------------------------------------------------
+namespace gloria {
+namespace {
+struct AttnPlan { size_t off_wt, off_dwt, off_wn, off_sc, off_at, off_da, off_cx, off_lens, total; };
+AttnPlan attn_plan(int B, int D, int S, int L) {
+  AttnPlan pl{};
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += gloria::align_up(n, 256); return r; };
+  pl.off_wt = take((size_t)B * L * D * 4);
+  pl.off_dwt = take((size_t)B * L * D * 4);
+  pl.off_wn = take((size_t)B * L * 4);
+  pl.off_sc = take((size_t)B * L * S * 4);
+  pl.off_at = take((size_t)B * L * S * 4);
+  pl.off_da = take((size_t)B * L * S * 4);
+  pl.off_cx = take((size_t)B * L * D * 4);
+  pl.off_lens = take((size_t)B * 4);
+  pl.total = o;
+  return pl;
+}
+__global__ void fill_int(int* p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+// [B, L, D] -> [B, D, L]
+__global__ void transpose_ld_to_dl(const float* __restrict__ in, float* __restrict__ out, int D, int L) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const float* ib = in + (long long)b * D * L;
+  float* ob = out + (long long)b * D * L;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int l = l0 + r, d = d0 + threadIdx.x;
+    t[r][threadIdx.x] = (l < L && d < D) ? ib[(long long)l * D + d] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int d = d0 + r, l = l0 + threadIdx.x;
+    if (d < D && l < L) ob[(long long)d * L + l] = t[threadIdx.x][r];
+  }
+}
+// cx[b][l][d] = sum_s at[b][l][s] * ctx[b][d][s]   (paired)
+int paired_context(const float* at, const float* ctx, float* cx, int B, int D, int S, int L, cudaStream_t st) {
+  GemmArgs g{};
+  g.A = at; g.B = ctx; g.C = cx;
+  g.M = L; g.N = D; g.K = S; g.R = 1;
+  g.sAm = S; g.sAk = 1; g.sAb0 = 0; g.sAb1 = (long long)L * S;
+  g.sBk = 1; g.sBn = S; g.sBb0 = 0; g.sBb1 = (long long)D * S;
+  g.sCm = D; g.sCn = 1; g.sCb0 = 0; g.sCb1 = (long long)L * D;
+  g.nb0 = 1; g.nb1 = B; g.beta = 0.f;
+  return launch_gemm(g, st);
+}
+}  // namespace
+}  // namespace gloria
+
+extern "C" size_t gloria_b200_attention_workspace(int B, int D, int S, int L) {
+  if (B <= 0 || D <= 0 || S <= 0 || L <= 0) return 0;
+  return attn_plan(B, D, S, L).total;
+}
+
+extern "C" int gloria_b200_attention_fwd_f32(const float* query, const float* ctx, int B, int D, int S, int L,
+                                             float temp1, float* wctx, float* attn, void* workspace,
+                                             size_t workspace_bytes, void* stream) {
+  GLORIA_CHECK_ARG(query && ctx && wctx && attn && workspace, "null pointer");
+  GLORIA_CHECK_ARG(B > 0 && D > 0 && S > 0 && L > 0, "non-positive size");
+  const AttnPlan pl = attn_plan(B, D, S, L);
+  if (workspace_bytes < pl.total) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, pl.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  float* Wt = (float*)(ws + pl.off_wt);
+  float* cx = (float*)(ws + pl.off_cx);
+  int* lens = (int*)(ws + pl.off_lens);
+  int rc;
+  fill_int<<<(B + 255) / 256, 256, 0, st>>>(lens, B, L);
+  GLORIA_LAUNCHED("fill_int");
+  if ((rc = prepack_words(query, Wt, (float*)(ws + pl.off_wn), B, D, L, st))) return rc;
+  if ((rc = diag_forward(ctx, Wt, lens, B, D, S, L, L, 0, temp1, (float*)(ws + pl.off_sc), (float*)(ws + pl.off_at),
+                         attn, st)))
+    return rc;
+  if ((rc = paired_context((float*)(ws + pl.off_at), ctx, cx, B, D, S, L, st))) return rc;
+  dim3 grid((L + 31) / 32, (D + 31) / 32, B), block(32, 8);
+  transpose_ld_to_dl<<<grid, block, 0, st>>>(cx, wctx, D, L);
+  GLORIA_LAUNCHED("transpose_ld_to_dl");
+  return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_attention_bwd_f32(const float* query, const float* ctx, int B, int D, int S, int L,
+                                             float temp1, const float* d_wctx, const float* d_attn, float* d_query,
+                                             float* d_ctx, void* workspace, size_t workspace_bytes, void* stream) {
+  GLORIA_CHECK_ARG(query && ctx && d_query && d_ctx && workspace, "null pointer");
+  GLORIA_CHECK_ARG(B > 0 && D > 0 && S > 0 && L > 0, "non-positive size");
+  const AttnPlan pl = attn_plan(B, D, S, L);
+  if (workspace_bytes < pl.total) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, pl.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  float* Wt = (float*)(ws + pl.off_wt);
+  float* dWt = (float*)(ws + pl.off_dwt);
+  float* sc = (float*)(ws + pl.off_sc);
+  float* at = (float*)(ws + pl.off_at);
+  float* da = (float*)(ws + pl.off_da);
+  float* dCt = (float*)(ws + pl.off_cx);       // d_wctx transposed to [B, L, D]
+  int* lens = (int*)(ws + pl.off_lens);
+  int rc;
+  fill_int<<<(B + 255) / 256, 256, 0, st>>>(lens, B, L);
+  GLORIA_LAUNCHED("fill_int");
+  if ((rc = prepack_words(query, Wt, (float*)(ws + pl.off_wn), B, D, L, st))) return rc;
+  if ((rc = diag_forward(ctx, Wt, lens, B, D, S, L, L, 0, temp1, sc, at, nullptr, st))) return rc;
+  GLORIA_CUDA(cudaMemsetAsync(da, 0, (size_t)B * L * S * sizeof(float), st));
+  GLORIA_CUDA(cudaMemsetAsync(d_ctx, 0, (size_t)B * D * S * sizeof(float), st));
+  if (d_wctx) {
+    dim3 grid((L + 31) / 32, (D + 31) / 32, B), block(32, 8);
+    transpose_dl_to_ld<<<grid, block, 0, st>>>(d_wctx, dCt, D, L);
+    GLORIA_LAUNCHED("transpose_dl_to_ld");
+    {  // dA[b][l][s] = sum_d dC[b][l][d] * ctx[b][d][s]
+      GemmArgs g{};
+      g.A = dCt; g.B = ctx; g.C = da;
+      g.M = L; g.N = S; g.K = D; g.R = 1;
+      g.sAm = D; g.sAk = 1; g.sAb0 = 0; g.sAb1 = (long long)L * D;
+      g.sBk = S; g.sBn = 1; g.sBb0 = 0; g.sBb1 = (long long)D * S;
+      g.sCm = S; g.sCn = 1; g.sCb0 = 0; g.sCb1 = (long long)L * S;
+      g.nb0 = 1; g.nb1 = B; g.beta = 0.f;
+      if ((rc = launch_gemm(g, st))) return rc;
+    }
+    {  // d_ctx[b][d][s] = sum_l dC[b][l][d] * A[b][l][s]
+      GemmArgs g{};
+      g.A = dCt; g.B = at; g.C = d_ctx;
+      g.M = D; g.N = S; g.K = L; g.R = 1;
+      g.sAm = 1; g.sAk = D; g.sAb0 = (long long)L * D; g.sAb1 = 0;
+      g.sBk = S; g.sBn = 1; g.sBb0 = (long long)L * S; g.sBb1 = 0;
+      g.sCm = S; g.sCn = 1; g.sCb0 = (long long)D * S; g.sCb1 = 0;
+      g.nb0 = B; g.nb1 = 1; g.beta = 0.f;
+      if ((rc = launch_gemm(g, st))) return rc;
+    }
+  }
+  // softmax backward; d_attn (if any) is added to dA inside the kernel
+  double_softmax_bwd<<<(unsigned)B, 256, 0, st>>>(da, at, sc, lens, 0, B, B, L, S, temp1, d_attn, nullptr, 1);
+  GLORIA_LAUNCHED("double_softmax_bwd(attention)");
+  {  // dWt[b][l][d] = sum_s dS[b][l][s] * ctx[b][d][s]
+    GemmArgs g{};
+    g.A = da; g.B = ctx; g.C = dWt;
+    g.M = L; g.N = D; g.K = S; g.R = 1;
+    g.sAm = S; g.sAk = 1; g.sAb0 = 0; g.sAb1 = (long long)L * S;
+    g.sBk = 1; g.sBn = S; g.sBb0 = 0; g.sBb1 = (long long)D * S;
+    g.sCm = D; g.sCn = 1; g.sCb0 = 0; g.sCb1 = (long long)L * D;
+    g.nb0 = 1; g.nb1 = B; g.beta = 0.f;
+    if ((rc = launch_gemm(g, st))) return rc;
+  }
+  {  // d_ctx[b][d][s] += sum_l Wt[b][l][d] * dS[b][l][s]
+    GemmArgs g{};
+    g.A = Wt; g.B = da; g.C = d_ctx;
+    g.M = D; g.N = S; g.K = L; g.R = 1;
+    g.sAm = 1; g.sAk = D; g.sAb0 = (long long)L * D; g.sAb1 = 0;
+    g.sBk = S; g.sBn = 1; g.sBb0 = (long long)L * S; g.sBb1 = 0;
+    g.sCm = S; g.sCn = 1; g.sCb0 = (long long)D * S; g.sCb1 = 0;
+    g.nb0 = B; g.nb1 = 1; g.beta = 1.f;
+    if ((rc = launch_gemm(g, st))) return rc;
+  }
+  dim3 grid((L + 31) / 32, (D + 31) / 32, B), block(32, 8);
+  transpose_ld_to_dl<<<grid, block, 0, st>>>(dWt, d_query, D, L);
+  GLORIA_LAUNCHED("transpose_ld_to_dl");
   return GLORIA_OK;
 }

@@ -75,13 +75,30 @@ def local_similarities(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, 
 
 # --------------------------------------------------------------------------------------------------------------
 def cosine_similarity(x1, x2, dim=1, eps=1e-8):
-    """gloria_loss.py:11-16 -- row-wise cosine of two [N, D] tensors."""
-    raise NotImplementedError("TODO: row-wise cosine entry point")
+    """gloria_loss.py:11-16 -- cosine along `dim` with the product of norms clamped at eps, then .squeeze()."""
+    if not x1.is_cuda:
+        raise RuntimeError("gloria_b200 runs on CUDA tensors only (sm_100a); there is no CPU fallback")
+    if x1.shape != x2.shape:
+        x1, x2 = torch.broadcast_tensors(x1, x2)
+    a = x1.movedim(dim, -1)
+    b = x2.movedim(dim, -1)
+    lead = a.shape[:-1]
+    out, _ = ops.row_cosine_fwd(a.reshape(-1, a.shape[-1]).float(), b.reshape(-1, b.shape[-1]).float(), float(eps))
+    return out.reshape(lead).squeeze()
 
 
 def attention_fn(query, context, temp1, no_attn_vec=None):
-    """gloria_loss.py:19-63."""
-    raise NotImplementedError("TODO: paired attention entry point")
+    """gloria_loss.py:19-63: query [B, D, L], context [B, D, H, W] -> (weightedContext [B, D, L], attn [B, L, H, W]).
+    With no_attn_vec [D] a learned column is prepended to the context (:31-34) and stripped from the returned
+    attention only (:60-61)."""
+    if not query.is_cuda:
+        raise RuntimeError("gloria_b200 runs on CUDA tensors only (sm_100a); there is no CPU fallback")
+    B, ih, iw = context.shape[0], context.shape[2], context.shape[3]
+    ctx = _context(context, no_attn_vec)
+    wctx, attn = ops.attention_fwd(query.float(), ctx, float(temp1))
+    if no_attn_vec is not None:
+        attn = attn[:, :, 1:]
+    return wctx, attn.reshape(B, query.shape[2], ih, iw)
 
 
 def global_loss(cnn_code, rnn_code, eps=1e-8, temp3=10.0):

@@ -349,3 +349,132 @@ def _ce_backward(c, g, drow, dcol):
 
 
 ce_bidir_fwd.register_autograd(_ce_backward, setup_context=_ce_setup)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# stand-alone attention_fn (gloria_loss.py:19-63) and row-wise cosine_similarity (gloria_loss.py:11-16)
+# ----------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("gloria_b200::attention_fwd", mutates_args=())
+def attention_fwd(query: Tensor, ctx: Tensor, temp1: float) -> Tuple[Tensor, Tensor]:
+    """query [B, D, L], ctx [B, D, S] (paired) -> weighted context [B, D, L], attention [B, L, S]."""
+    _need_cuda(query, ctx)
+    L = _lib.lib()
+    query, ctx = _f32c(query), _f32c(ctx)
+    B, D, Lq = query.shape
+    S = ctx.shape[2]
+    if ctx.shape[0] != B or ctx.shape[1] != D:
+        raise RuntimeError(f"attention_fn: query {tuple(query.shape)} and context {tuple(ctx.shape)} do not pair up")
+    wctx = torch.empty((B, D, Lq), dtype=torch.float32, device=query.device)
+    attn = torch.empty((B, Lq, S), dtype=torch.float32, device=query.device)
+    with torch.cuda.device(query.device):
+        n = L.gloria_b200_attention_workspace(B, D, S, Lq)
+        ws = torch.empty((n,), dtype=torch.uint8, device=query.device)
+        _lib.check(L.gloria_b200_attention_fwd_f32(query.data_ptr(), ctx.data_ptr(), B, D, S, Lq, temp1,
+                                                   wctx.data_ptr(), attn.data_ptr(), ws.data_ptr(), n,
+                                                   _stream(query)), "attention_fwd_f32")
+    return wctx, attn
+
+
+@attention_fwd.register_fake
+def _(query, ctx, temp1):
+    B, D, Lq = query.shape
+    return query.new_empty((B, D, Lq)), query.new_empty((B, Lq, ctx.shape[2]))
+
+
+@torch.library.custom_op("gloria_b200::attention_bwd", mutates_args=())
+def attention_bwd(query: Tensor, ctx: Tensor, temp1: float, d_wctx: Optional[Tensor],
+                  d_attn: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    _need_cuda(query, ctx)
+    L = _lib.lib()
+    query, ctx = _f32c(query), _f32c(ctx)
+    B, D, Lq = query.shape
+    S = ctx.shape[2]
+    d_wctx = None if d_wctx is None else _f32c(d_wctx)
+    d_attn = None if d_attn is None else _f32c(d_attn)
+    dq, dc = torch.empty_like(query), torch.empty_like(ctx)
+    with torch.cuda.device(query.device):
+        n = L.gloria_b200_attention_workspace(B, D, S, Lq)
+        ws = torch.empty((n,), dtype=torch.uint8, device=query.device)
+        _lib.check(L.gloria_b200_attention_bwd_f32(query.data_ptr(), ctx.data_ptr(), B, D, S, Lq, temp1,
+                                                   _ptr(d_wctx), _ptr(d_attn), dq.data_ptr(), dc.data_ptr(),
+                                                   ws.data_ptr(), n, _stream(query)), "attention_bwd_f32")
+    return dq, dc
+
+
+@attention_bwd.register_fake
+def _(query, ctx, temp1, d_wctx, d_attn):
+    return torch.empty_like(query), torch.empty_like(ctx)
+
+
+def _attn_setup(ctx, inputs, output):
+    q, c, temp1 = inputs
+    ctx.save_for_backward(q, c)
+    ctx.temp1 = temp1
+    ctx.set_materialize_grads(False)
+
+
+def _attn_backward(c, d_wctx, d_attn):
+    q, cx = c.saved_tensors
+    if d_wctx is None and d_attn is None:
+        return torch.zeros_like(q), torch.zeros_like(cx), None
+    dq, dc = attention_bwd(q, cx, c.temp1, d_wctx, d_attn)
+    return dq, dc, None
+
+
+attention_fwd.register_autograd(_attn_backward, setup_context=_attn_setup)
+
+
+@torch.library.custom_op("gloria_b200::row_cosine_fwd", mutates_args=())
+def row_cosine_fwd(x1: Tensor, x2: Tensor, eps: float) -> Tuple[Tensor, Tensor]:
+    """cos [N] of the rows of two [N, D] matrices, plus the saved (dot, |x1|, |x2|) per row."""
+    _need_cuda(x1, x2)
+    L = _lib.lib()
+    x1, x2 = _f32c(x1), _f32c(x2)
+    N, D = x1.shape
+    out = torch.empty((N,), dtype=torch.float32, device=x1.device)
+    stats = torch.empty((N, 3), dtype=torch.float32, device=x1.device)
+    with torch.cuda.device(x1.device):
+        _lib.check(L.gloria_b200_row_cosine_fwd(x1.data_ptr(), x2.data_ptr(), N, D, eps, out.data_ptr(),
+                                                stats.data_ptr(), _stream(x1)), "row_cosine_fwd")
+    return out, stats
+
+
+@row_cosine_fwd.register_fake
+def _(x1, x2, eps):
+    return x1.new_empty((x1.shape[0],)), x1.new_empty((x1.shape[0], 3))
+
+
+@torch.library.custom_op("gloria_b200::row_cosine_bwd", mutates_args=())
+def row_cosine_bwd(x1: Tensor, x2: Tensor, stats: Tensor, g: Tensor, eps: float) -> Tuple[Tensor, Tensor]:
+    _need_cuda(x1, x2, g)
+    L = _lib.lib()
+    x1, x2, g = _f32c(x1), _f32c(x2), _f32c(g)
+    N, D = x1.shape
+    d1, d2 = torch.empty_like(x1), torch.empty_like(x2)
+    with torch.cuda.device(x1.device):
+        _lib.check(L.gloria_b200_row_cosine_bwd(x1.data_ptr(), x2.data_ptr(), stats.data_ptr(), g.data_ptr(), N, D, eps,
+                                                d1.data_ptr(), d2.data_ptr(), _stream(x1)), "row_cosine_bwd")
+    return d1, d2
+
+
+@row_cosine_bwd.register_fake
+def _(x1, x2, stats, g, eps):
+    return torch.empty_like(x1), torch.empty_like(x2)
+
+
+def _rc_setup(ctx, inputs, output):
+    x1, x2, eps = inputs
+    ctx.save_for_backward(x1, x2, output[1])
+    ctx.eps = eps
+    ctx.set_materialize_grads(False)
+
+
+def _rc_backward(c, g, gstats):
+    x1, x2, stats = c.saved_tensors
+    if g is None:
+        return torch.zeros_like(x1), torch.zeros_like(x2), None
+    d1, d2 = row_cosine_bwd(x1, x2, stats, g, c.eps)
+    return d1, d2, None
+
+
+row_cosine_fwd.register_autograd(_rc_backward, setup_context=_rc_setup)

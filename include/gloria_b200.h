@@ -104,6 +104,24 @@ int gloria_b200_diag_attn_bwd_f32(const float* ctx, const float* words, const in
                                   const float* d_attn_diag, float* d_ctx, float* d_words, int accumulate,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* attention_fn (gloria_loss.py:19-63) as a stand-alone paired operator, for callers that use it directly
+ * (get_local_similarities, gloria_model.py:185; Retriver, retrival_model.py:147): query[b] [D, L] attends to
+ * context[b] [D, S]; wctx [B, D, L], attn [B, L, S].  The backward takes d_wctx and / or d_attn (NULL = none) and
+ * overwrites d_query [B, D, L] and d_ctx [B, D, S]. */
+size_t gloria_b200_attention_workspace(int B, int D, int S, int L);
+int gloria_b200_attention_fwd_f32(const float* query, const float* ctx, int B, int D, int S, int L, float temp1,
+                                  float* wctx, float* attn, void* workspace, size_t workspace_bytes, void* stream);
+int gloria_b200_attention_bwd_f32(const float* query, const float* ctx, int B, int D, int S, int L, float temp1,
+                                  const float* d_wctx, const float* d_attn, float* d_query, float* d_ctx,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* cosine_similarity (gloria_loss.py:11-16) of the rows of two [N, D] matrices; stats [N, 3] (dot, |x1|, |x2|) is
+ * saved by the forward for the backward. */
+int gloria_b200_row_cosine_fwd(const float* x1, const float* x2, long long N, int D, float eps, float* out,
+                               float* stats, void* stream);
+int gloria_b200_row_cosine_bwd(const float* x1, const float* x2, const float* stats, const float* dout,
+                               long long N, int D, float eps, float* dx1, float* dx2, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * bf16 tensor-core mode (tcgen05 / TMEM / TMA): the fused hot path.  Same math as above with bf16 operands and
  * fp32 accumulation and softmax (the analogue of the reference under Lightning AMP).

@@ -231,3 +231,31 @@ def test_errors_are_runtime_errors(gl):
         gl.local_similarities(img.cpu(), txt.cpu(), [2, 2])           # no CPU fallback
     with pytest.raises(RuntimeError):
         gl.global_loss(torch.randn(3, 8, device="cuda"), torch.randn(4, 8, device="cuda"))   # CE needs square
+
+
+def test_attention_fn_and_cosine_golden(gl, small):
+    """Stand-alone attention_fn / cosine_similarity (gloria_loss.py:11-63) vs the real reference's outputs, and their
+    gradients vs torch autograd of the same closed form (oracle port)."""
+    from oracle import gloria_oracle_torch as T
+    B = small["img_l"].shape[0]
+    q = np.repeat(small["txt_l"][1:2, :, :9], B, axis=0)
+    wc, at = gl.attention_fn(cu(q), cu(small["img_l"]), 4.0)
+    assert relerr(wc, small["attn_wctx"]) < 1e-5 and relerr(at, small["attn_map"]) < 1e-5
+    wc, at = gl.attention_fn(cu(q), cu(small["img_l"]), 4.0, no_attn_vec=cu(small["nav"]))
+    assert relerr(wc, small["attn_wctx_nav"]) < 1e-5 and relerr(at, small["attn_map_nav"]) < 1e-5
+    assert relerr(gl.cosine_similarity(cu(small["img_g"]), cu(small["txt_g"])), small["cos"]) < 1e-5
+    # gradients through both outputs
+    tq, tc = cu(q, True), cu(small["img_l"], True)
+    wc, at = gl.attention_fn(tq, tc, 4.0)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    gw, ga = torch.randn(wc.shape, device="cuda", generator=gen), torch.randn(at.shape, device="cuda", generator=gen)
+    ((wc * gw).sum() + (at * ga).sum()).backward()
+    rq, rc = torch.tensor(q, requires_grad=True), torch.tensor(small["img_l"], requires_grad=True)
+    rwc, rat = T.attention_fn(rq, rc, 4.0)
+    ((rwc * gw.cpu().double()).sum() + (rat * ga.cpu().double()).sum()).backward()
+    assert relerr(tq.grad, rq.grad.numpy()) < 1e-4 and relerr(tc.grad, rc.grad.numpy()) < 1e-4
+    x1, x2 = cu(small["img_g"], True), cu(small["txt_g"], True)
+    gl.cosine_similarity(x1, x2).sum().backward()
+    r1, r2 = torch.tensor(small["img_g"], requires_grad=True), torch.tensor(small["txt_g"], requires_grad=True)
+    T.cosine_similarity(r1, r2).sum().backward()
+    assert relerr(x1.grad, r1.grad.numpy()) < 1e-5 and relerr(x2.grad, r2.grad.numpy()) < 1e-5
