@@ -21,26 +21,27 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) expires, so a waiting
+// warp does not compete for issue slots with the working warps of its scheduler.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(200000u)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.  try_wait suspends in hardware
-// for a while per call, so the counter stays small in normal operation; no printf here (its call frame costs
-// registers in every warp role).
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU (each iteration may sleep up to
+// the hint above, so the bound is tens of seconds).  No printf here (its call frame costs registers in every role).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    if (++spins > (1u << 22)) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
