@@ -55,7 +55,7 @@ struct PairParams {
   const float* dsim;        // [Bi, Bc]
   __nv_bfloat16* xt;        // [Bi*Spad, nc*LPAD]   X^T
   __nv_bfloat16* et;        //                      E^T (un-normalised attention numerators)
-  __nv_bfloat16* bt;        //                      (beta / Z^2) E^T
+  float* fo;                // [Bi, nc*LPAD]  f = beta / Z^2 per pair and word (Bo = f * Eo is formed by scale_rows)
   float* gamma;             // [Bc, LPAD]  sum_j (dL/d|W_l|) / |W_l|   (atomicAdd)
   int Bi, Bc, i0, nc, D, S, NT;
   float t1, t1_log2e, t2, eps;
@@ -95,7 +95,8 @@ __device__ __forceinline__ int tile_at(int idx, int NT) { return idx == 0 ? NT -
 template <int LPAD>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__ CUtensorMap tm_wt,
-                   const __grid_constant__ CUtensorMap tm_g, const PairParams p) {
+                   const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_e,
+                   const PairParams p) {
   extern __shared__ uint8_t smem_raw[];
 #ifdef GLORIA_PHASE_CLOCKS
   long long* g_dbg = p.dbg;
@@ -108,7 +109,6 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
   float* zbuf = reinterpret_cast<float*>(smem + OFF_ZBUF);
   float4* coefA = reinterpret_cast<float4*>(smem + OFF_COEFA);
   float* coefX = reinterpret_cast<float*>(smem + OFF_COEFX);
-  uint32_t* coefF = reinterpret_cast<uint32_t*>(smem + OFF_COEFF);
   float* negm = reinterpret_cast<float*>(smem + OFF_NEGM);
   uint32_t* cmask = reinterpret_cast<uint32_t*>(smem + OFF_CMASK);
   auto bar = [&](int idx) { return bars + 8u * (uint32_t)idx; };
@@ -124,11 +124,11 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
     for (int s = 0; s < NSLOT; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
     for (int t = 0; t < MAX_NT; ++t) { mbar_init(bar(B_D1F + t), 1); mbar_init(bar(B_D1E + t), NSIMT); }
     mbar_init(bar(B_EF), NSIMT * NT);
-    mbar_init(bar(B_EE), 1);
+    mbar_init(bar(B_EE), 2);            // GEMM-T done reading E (tcgen05.commit) + Eo bulk stores done reading E
     mbar_init(bar(B_TTF), 1);
     mbar_init(bar(B_TTE), NSIMT);
     fence_barrier_init();
-    tma_prefetch_desc(&tm_rt); tma_prefetch_desc(&tm_wt); tma_prefetch_desc(&tm_g);
+    tma_prefetch_desc(&tm_rt); tma_prefetch_desc(&tm_wt); tma_prefetch_desc(&tm_g); tma_prefetch_desc(&tm_e);
   }
   if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
   tc_fence_before();
@@ -216,6 +216,13 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
           }
           TIMED_WAIT(wt_ef, mbar_wait(bar(B_EF), n & 1));    // E of this pair is complete in shared memory
           tc_fence_after();
+          // Eo rows: straight from the E buffer by bulk tensor stores (columns >= LPAD are clipped by the map)
+          for (int t = 0; t < NT; ++t)
+#pragma unroll
+            for (int wb = 0; wb < (LPAD + 63) / 64; ++wb)
+              tma_store_3d(&tm_e, base + OFF_E + (uint32_t)wb * e_lbo + (uint32_t)t * (TILE * 128), wb * 64, u.i,
+                           j * Spad + t * TILE);
+          tma_store_commit();
           for (int idx = 0; idx < NT; ++idx) {
             TIMED_WAIT(wt_tte, mbar_wait(bar(B_TTE), (ttc & 1) ^ 1));   // T' buffer has been read by the SIMT warps
             tc_fence_after();
@@ -236,6 +243,8 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             ++ttc;
           }
           umma_commit(bar(B_EE));                            // GEMM-T has finished reading E
+          tma_store_wait_read();                             // ... and so have the Eo stores
+          mbar_arrive(bar(B_EE));
           ++n;
         }
       }
@@ -270,7 +279,6 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
     const size_t e_blk = (size_t)Spad * 128u;      // bytes between the two 64-word blocks of E
     const float4* cA = coefA + col0;
     const float* cX = coefX + col0;
-    const uint32_t* cF = coefF + (col0 >> 1);
     const float* nM = negm + col0;
     const uint32_t* cM = cmask + (col0 >> 1);
     uint32_t n = 0, ttc = 0, xc = 0;
@@ -436,8 +444,8 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
                 coefA[wl] = live ? make_float4(p.t1 * ddot * iz, p.t1 * beta * iz * iz, -p.t1 * rs * iz, 0.f)
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                 coefX[wl] = live ? ddot * iz : 0.f;
-                reinterpret_cast<__nv_bfloat16*>(coefF)[wl] = __float2bfloat16_rn(live ? beta * iz * iz : 0.f);
               }
+              if (wl < LPAD) p.fo[((size_t)j * p.nc + u.i) * LPAD + wl] = live ? beta * iz * iz : 0.f;
               if (live) gacc += gamma;
               asm volatile("bar.sync 1, 384;" ::: "memory");
             }
@@ -492,41 +500,28 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             xb[g * 128 + row].x = ug;
             STIMED(sw_bar, asm volatile("bar.sync 1, 384;" ::: "memory"));
             const float uacc = xb[row].x + xb[128 + row].x + xb[256 + row].x;
-            // pass 2: rows of X^T, Eo^T, Bo^T  ([(j, s), (i, l)] bf16, 16-byte stores along l)
+            // pass 2: rows of X^T  ([(j, s), (i, l)] bf16, 16-byte stores along l)
             const size_t goff = ((size_t)j * Spad + s_glob) * pitch + (size_t)u.i * LPAD;
             uint4* xo = reinterpret_cast<uint4*>(p.xt + goff);
-            uint4* eo = reinterpret_cast<uint4*>(p.et + goff);
-            uint4* bo = reinterpret_cast<uint4*>(p.bt + goff);
 #pragma unroll
             for (int c = 0; c < CW; ++c) {
               const int ch = c_lo + c;
               if (ch < NCH) {
                 const uint4 ev = *reinterpret_cast<const uint4*>(erow + (size_t)(ch >> 3) * e_blk +
                                                                  (size_t)((((uint32_t)ch & 7u) ^ sw) << 4));
-                const uint4 fv = *reinterpret_cast<const uint4*>(cF + c * 4);
                 const float4 x0 = *reinterpret_cast<const float4*>(cX + c * 8);
                 const float4 x1 = *reinterpret_cast<const float4*>(cX + c * 8 + 4);
                 const float ce[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                 const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
-                const uint32_t fw[4] = {fv.x, fv.y, fv.z, fv.w};
-                uint32_t xw[4], bw_[4];
+                uint32_t xw[4];
 #pragma unroll
                 for (int k = 0; k < 8; k += 2) {
                   const int o = c * 8 + k;
                   const float e0 = bf_lo(ew[k >> 1]), e1 = bf_hi(ew[k >> 1]);
                   const float P0 = bf_lo(pp[o >> 1]), P1 = bf_hi(pp[o >> 1]);
                   xw[k >> 1] = pack_bf16(fmaf(ce[k], e0, P0 * (dp[o] - uacc)), fmaf(ce[k + 1], e1, P1 * (dp[o + 1] - uacc)));
-                  const __nv_bfloat162 bb = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&fw[k >> 1]),
-                                                    *reinterpret_cast<const __nv_bfloat162*>(&ew[k >> 1]));
-                  bw_[k >> 1] = *reinterpret_cast<const uint32_t*>(&bb);
                 }
-#ifdef GLORIA_EXP_NOSTORE
-                if (xw[0] == 0x12345678u && bw_[1] == 0x9abcdef0u) xo[ch] = make_uint4(xw[0], xw[1], xw[2], xw[3]);
-#else
                 xo[ch] = make_uint4(xw[0], xw[1], xw[2], xw[3]);
-                bo[ch] = make_uint4(bw_[0], bw_[1], bw_[2], bw_[3]);
-                eo[ch] = ev;
-#endif
               }
             }
           }
@@ -557,6 +552,23 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
 __global__ void gram_ones_row(__nv_bfloat16* __restrict__ G, int S, int Spad) {
   __nv_bfloat16* r = G + ((size_t)blockIdx.x * Spad + S) * Spad;
   for (int x = threadIdx.x; x < Spad; x += blockDim.x) r[x] = __float2bfloat16_rn(x < S ? 1.f : 0.f);
+}
+
+// Bo[(j,s), c] = f[j, c] * Eo[(j,s), c]   (c = (i,l));  grid (Bi*Spad, ceil(R1/8/256)), 8 columns per thread
+__global__ void scale_rows(const __nv_bfloat16* __restrict__ E, const float* __restrict__ f,
+                           __nv_bfloat16* __restrict__ Bo, int R1, int Spad) {
+  const size_t rowi = blockIdx.x;
+  const int c8 = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (c8 >= R1) return;
+  const uint4 ev = *reinterpret_cast<const uint4*>(E + rowi * R1 + c8);
+  const float* fr = f + (rowi / Spad) * R1 + c8;
+  const float4 f0 = *reinterpret_cast<const float4*>(fr), f1 = *reinterpret_cast<const float4*>(fr + 4);
+  const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+  const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o[k] = pack_bf16(bf_lo(ew[k]) * fv[2 * k], bf_hi(ew[k]) * fv[2 * k + 1]);
+  *reinterpret_cast<uint4*>(Bo + rowi * R1 + c8) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 __global__ void f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
@@ -617,7 +629,7 @@ __global__ void unpack_dwords_tc(const float* __restrict__ dWt, const float* __r
 // ---------------------------------------------------------------------------------------------------------------
 struct Plan {
   int nc;   // captions per chunk
-  size_t off_gram, off_dwt, off_drt, off_m, off_mb, off_gamma, off_stats, off_sim, off_cublas, off_x, off_e, off_b, total;
+  size_t off_gram, off_dwt, off_drt, off_m, off_mb, off_gamma, off_stats, off_sim, off_cublas, off_x, off_e, off_b, off_f, total;
 };
 constexpr size_t CUBLAS_WS = 64u << 20;
 
@@ -637,7 +649,9 @@ size_t fixed_bytes(int Bi, int Bc, int D, int Spad, int lpad, bool own_stats, Pl
   if (pl) *pl = t;
   return o;
 }
-size_t per_caption_bytes(int Bi, int Spad, int lpad) { return 3 * align_up((size_t)Bi * Spad * lpad * 2, 1024) / 1 + 3072; }
+size_t per_caption_bytes(int Bi, int Spad, int lpad) {
+  return 3 * align_up((size_t)Bi * Spad * lpad * 2, 1024) + align_up((size_t)Bi * lpad * 4, 1024) + 4096;
+}
 
 Plan make_plan(int Bi, int Bc, int D, int Spad, int lpad, bool own_stats, size_t bytes) {
   Plan pl{};
@@ -653,6 +667,7 @@ Plan make_plan(int Bi, int Bc, int D, int Spad, int lpad, bool own_stats, size_t
   pl.off_x = take(arr);
   pl.off_e = take(arr);
   pl.off_b = take(arr);
+  pl.off_f = take((size_t)Bi * nc * lpad * 4);
   pl.total = o;
   if (pl.total > bytes) pl.nc = 0;
   return pl;
@@ -674,11 +689,11 @@ cublasHandle_t cublas_handle() {
   } while (0)
 
 template <int LPAD>
-int launch_pair(const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap& g, const PairParams& p, int grid,
-                cudaStream_t st) {
+int launch_pair(const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap& g, const CUtensorMap& e,
+                const PairParams& p, int grid, cudaStream_t st) {
   GLORIA_CUDA(cudaFuncSetAttribute(tc_bwd_pair_kernel<LPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   timer_record(GLORIA_TIMER_TC_BWD_PAIR, 0, st);
-  tc_bwd_pair_kernel<LPAD><<<grid, NTHREADS, SMEM_BYTES, st>>>(rt, wt, g, p);
+  tc_bwd_pair_kernel<LPAD><<<grid, NTHREADS, SMEM_BYTES, st>>>(rt, wt, g, e, p);
   timer_record(GLORIA_TIMER_TC_BWD_PAIR, 1, st);
   GLORIA_LAUNCHED("tc_bwd_pair_kernel");
   return GLORIA_OK;
@@ -729,6 +744,7 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_t, const void* ctx_n
   __nv_bfloat16* X = (__nv_bfloat16*)(ws + pl.off_x);
   __nv_bfloat16* E = (__nv_bfloat16*)(ws + pl.off_e);
   __nv_bfloat16* Bm = (__nv_bfloat16*)(ws + pl.off_b);
+  float* Fo = (float*)(ws + pl.off_f);
   int rc;
   if (stats == nullptr) {   // stand-alone use: one forward pass regenerates the per-word statistics
     float* own = (float*)(ws + pl.off_stats);
@@ -768,23 +784,27 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_t, const void* ctx_n
     const int R1 = nc * lpad;
     bw::PairParams p;
     p.wnorm = wnorm; p.cap_lens = cap_lens; p.stats = stats; p.dsim = dsim;
-    p.xt = X; p.et = E; p.bt = Bm; p.gamma = gamma;
+    p.xt = X; p.et = E; p.fo = Fo; p.gamma = gamma;
+    CUtensorMap em;
+    if ((rc = make_map3(&em, E, (uint64_t)lpad, (uint64_t)nc, (uint64_t)K1, (uint64_t)lpad, (uint64_t)R1, TILE))) return rc;
     p.Bi = Bi; p.Bc = Bc; p.i0 = i0; p.nc = nc; p.D = D; p.S = S; p.NT = Spad / TILE;
     p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps;
     p.dbg = (long long*)g_phase_clock_buffer;
     switch (lpad) {
-      case 16: rc = bw::launch_pair<16>(rt, wt, gm, p, sms, st); break;
-      case 32: rc = bw::launch_pair<32>(rt, wt, gm, p, sms, st); break;
-      case 48: rc = bw::launch_pair<48>(rt, wt, gm, p, sms, st); break;
-      case 64: rc = bw::launch_pair<64>(rt, wt, gm, p, sms, st); break;
-      case 80: rc = bw::launch_pair<80>(rt, wt, gm, p, sms, st); break;
-      case 96: rc = bw::launch_pair<96>(rt, wt, gm, p, sms, st); break;
-      case 112: rc = bw::launch_pair<112>(rt, wt, gm, p, sms, st); break;
-      case 128: rc = bw::launch_pair<128>(rt, wt, gm, p, sms, st); break;
+      case 16: rc = bw::launch_pair<16>(rt, wt, gm, em, p, sms, st); break;
+      case 32: rc = bw::launch_pair<32>(rt, wt, gm, em, p, sms, st); break;
+      case 48: rc = bw::launch_pair<48>(rt, wt, gm, em, p, sms, st); break;
+      case 64: rc = bw::launch_pair<64>(rt, wt, gm, em, p, sms, st); break;
+      case 80: rc = bw::launch_pair<80>(rt, wt, gm, em, p, sms, st); break;
+      case 96: rc = bw::launch_pair<96>(rt, wt, gm, em, p, sms, st); break;
+      case 112: rc = bw::launch_pair<112>(rt, wt, gm, em, p, sms, st); break;
+      case 128: rc = bw::launch_pair<128>(rt, wt, gm, em, p, sms, st); break;
       default: rc = fail(GLORIA_ERR_UNSUPPORTED, "lpad %d", lpad);
     }
     if (rc) return rc;
     timer_record(GLORIA_TIMER_TC_BWD_GEMM, 0, st);
+    bw::scale_rows<<<dim3((unsigned)K1, (unsigned)((R1 / 8 + 255) / 256)), 256, 0, st>>>(E, Fo, Bm, R1, Spad);
+    GLORIA_LAUNCHED("scale_rows");
     const float beta = i0 == 0 ? 0.f : 1.f;
     // dWt[(i,l), d] = sum_(j,s) X^T[(j,s),(i,l)] Rt[(j,s), d]            (column-major: [D, R1] = Rt^T . (X^T)^T)
     GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, R1, K1, &one, Rt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1,

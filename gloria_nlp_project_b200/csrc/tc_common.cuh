@@ -58,6 +58,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
+// shared memory (SWIZZLE_128B box) -> global, 3-D tensor map; elements outside the tensor's extents are not written
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -164,6 +174,9 @@ struct Units {
 extern void* g_phase_clock_buffer;
 // host side (tc_local.cu): 2-D bf16 tensor map [rows, inner] (inner contiguous), box [box_rows, 64], SWIZZLE_128B
 int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint32_t box_rows);
+// 3-D bf16 tensor [rows, mid, inner] with pitches in elements, box [box_rows, 1, 64], SWIZZLE_128B (TMA stores)
+int make_map3(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t mid, uint64_t rows, uint64_t mid_pitch,
+              uint64_t row_pitch, uint32_t box_rows);
 
 }  // namespace tc
 }  // namespace gloria

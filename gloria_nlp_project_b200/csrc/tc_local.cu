@@ -398,6 +398,21 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uin
   return GLORIA_OK;
 }
 
+int make_map3(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t mid, uint64_t rows, uint64_t mid_pitch,
+              uint64_t row_pitch, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(GLORIA_ERR_DRIVER, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {inner, mid, rows};
+  cuuint64_t strides[2] = {mid_pitch * 2, row_pitch * 2};
+  cuuint32_t box[3] = {KBLK, 1, box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GLORIA_ERR_DRIVER, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
+  return GLORIA_OK;
+}
+
 template <int LPAD>
 int launch_fwd(const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap& rn, const FwdParams& p, int grid,
                cudaStream_t st) {
