@@ -152,22 +152,32 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
         tma_load_2d(base + slot * SLOT, tm, x, y, bar(B_FULL + slot));
         if (++slot == NSLOT) { slot = 0; ph ^= 1; }
       };
-      Units u(p.Bi, p.nc);
-      while (u.next_caption()) {
-        const int i = p.i0 + u.i;
-        for (int j = u.j; j < u.j_end; ++j) {
-          for (int idx = 0; idx < NT; ++idx) {
-            const int t = tile_at(idx, NT);
-            for (int kb = 0; kb < nkb1; ++kb) {
-              load(&tm_rt, kb * KBLK, j * Spad + t * TILE, TILE * 128);
-              load(&tm_wt, kb * KBLK, i * LPAD, LPAD * 128);
-            }
-          }
-          for (int idx = 0; idx < NT; ++idx) {
-            const int t = tile_at(idx, NT);
-            for (int kb = 0; kb < nkb2; ++kb) load(&tm_g, kb * KBLK, j * Spad + t * TILE, TILE * 128);
-          }
+      // load order mirrors the MMA issuer: GEMM1 of the first pair, then per pair: G tiles of GEMM-T tile k followed
+      // by the GEMM1 operands of the NEXT pair's tile k-1 (see the issuer for why)
+      auto load_g1 = [&](int i_loc, int j, int t) {
+        for (int kb = 0; kb < nkb1; ++kb) {
+          load(&tm_rt, kb * KBLK, j * Spad + t * TILE, TILE * 128);
+          load(&tm_wt, kb * KBLK, (p.i0 + i_loc) * LPAD, LPAD * 128);
         }
+      };
+      auto load_tt = [&](int j, int t) {
+        for (int kb = 0; kb < nkb2; ++kb) load(&tm_g, kb * KBLK, j * Spad + t * TILE, TILE * 128);
+      };
+      UnitIter it(p.Bi, p.nc);
+      bool has = it.next();
+      int ci = it.cap(), cj = it.j;
+      if (has)
+        for (int idx = 0; idx < NT; ++idx) load_g1(ci, cj, tile_at(idx, NT));
+      while (has) {
+        const bool hasn = it.next();
+        const int ni = it.cap(), nj = it.j;
+        load_tt(cj, tile_at(0, NT));
+        for (int k = 1; k < NT; ++k) {
+          load_tt(cj, tile_at(k, NT));
+          if (hasn) load_g1(ni, nj, tile_at(k - 1, NT));
+        }
+        if (hasn) load_g1(ni, nj, tile_at(NT - 1, NT));
+        has = hasn; ci = ni; cj = nj;
       }
 #ifdef GLORIA_PHASE_CLOCKS
       if (g_dbg) { long long* d = g_dbg + (size_t)blockIdx.x * 32 + 8; d[0] = clock64() - pt_all; d[1] = pw_empty; }
@@ -193,60 +203,76 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
         if (++slot == NSLOT) { slot = 0; ph ^= 1; }
         return s;
       };
-      Units u(p.Bi, p.nc);
-      while (u.next_caption()) {
-        for (int j = u.j; j < u.j_end; ++j) {
-          for (int idx = 0; idx < NT; ++idx) {
-            const int t = tile_at(idx, NT);
-            TIMED_WAIT(wt_d1e, mbar_wait(bar(B_D1E + t), (n & 1) ^ 1));   // previous pair no longer needs S_ tile t
-            tc_fence_after();
-            for (int kb = 0; kb < nkb1; ++kb) {
-              const int sa = take();
-              const int sb = take();
-              tc_fence_after();
-              const uint32_t a0 = base + sa * SLOT, b0 = base + sb * SLOT;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem + (uint32_t)(t * LPAD), make_smem_desc(a0 + k * 32, 16, 1024),
-                          make_smem_desc(b0 + k * 32, 16, 1024), idesc1, (uint32_t)((kb | k) != 0));
-              umma_commit(bar(B_EMPTY + sa));
-              umma_commit(bar(B_EMPTY + sb));
-            }
-            umma_commit(bar(B_D1F + t));
-          }
-          TIMED_WAIT(wt_ef, mbar_wait(bar(B_EF), n & 1));    // E of this pair is complete in shared memory
+      // GEMM1 of one S_ tile of pair number `pn` (waits until the SIMT warps are done with that tile of pair pn-1)
+      auto gemm1 = [&](uint32_t pn, int t) {
+        TIMED_WAIT(wt_d1e, mbar_wait(bar(B_D1E + t), (pn & 1) ^ 1));
+        tc_fence_after();
+        for (int kb = 0; kb < nkb1; ++kb) {
+          const int sa = take();
+          const int sb = take();
           tc_fence_after();
-          // Eo rows: straight from the E buffer by bulk tensor stores (columns >= LPAD are clipped by the map)
-          for (int t = 0; t < NT; ++t)
+          const uint32_t a0 = base + sa * SLOT, b0 = base + sb * SLOT;
 #pragma unroll
-            for (int wb = 0; wb < (LPAD + 63) / 64; ++wb)
-              tma_store_3d(&tm_e, base + OFF_E + (uint32_t)wb * e_lbo + (uint32_t)t * (TILE * 128), wb * 64, u.i,
-                           j * Spad + t * TILE);
-          tma_store_commit();
-          for (int idx = 0; idx < NT; ++idx) {
-            TIMED_WAIT(wt_tte, mbar_wait(bar(B_TTE), (ttc & 1) ^ 1));   // T' buffer has been read by the SIMT warps
-            tc_fence_after();
-            for (int kb = 0; kb < nkb2; ++kb) {
-              const int sa = take();
-              tc_fence_after();
-              const uint32_t a0 = base + sa * SLOT;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t region0 = (uint32_t)(kb * KBLK + k * 16);
-                umma_bf16(tmem + TT_COL, make_smem_desc(a0 + k * 32, 16, 1024),
-                          make_smem_desc(base + OFF_E + (region0 >> 3) * 1024, e_lbo, 1024), idesct,
-                          (uint32_t)((kb | k) != 0));
-              }
-              umma_commit(bar(B_EMPTY + sa));
-            }
-            umma_commit(bar(B_TTF));
-            ++ttc;
-          }
-          umma_commit(bar(B_EE));                            // GEMM-T has finished reading E
-          tma_store_wait_read();                             // ... and so have the Eo stores
-          mbar_arrive(bar(B_EE));
-          ++n;
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + (uint32_t)(t * LPAD), make_smem_desc(a0 + k * 32, 16, 1024),
+                      make_smem_desc(b0 + k * 32, 16, 1024), idesc1, (uint32_t)((kb | k) != 0));
+          umma_commit(bar(B_EMPTY + sa));
+          umma_commit(bar(B_EMPTY + sb));
         }
+        umma_commit(bar(B_D1F + t));
+      };
+      // GEMM-T of one tile (T' buffer must have been read by the SIMT warps)
+      auto gemmt = [&]() {
+        TIMED_WAIT(wt_tte, mbar_wait(bar(B_TTE), (ttc & 1) ^ 1));
+        tc_fence_after();
+        for (int kb = 0; kb < nkb2; ++kb) {
+          const int sa = take();
+          tc_fence_after();
+          const uint32_t a0 = base + sa * SLOT;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t region0 = (uint32_t)(kb * KBLK + k * 16);
+            umma_bf16(tmem + TT_COL, make_smem_desc(a0 + k * 32, 16, 1024),
+                      make_smem_desc(base + OFF_E + (region0 >> 3) * 1024, e_lbo, 1024), idesct,
+                      (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(bar(B_EMPTY + sa));
+        }
+        umma_commit(bar(B_TTF));
+        ++ttc;
+      };
+      // Issue order.  The tensor pipe runs MMAs in issue order, so the next pair's GEMM1 is interleaved with this
+      // pair's GEMM-T tiles: the SIMT event that frees the T' buffer for tile k (pass 1 of tile k-1 done) also frees
+      // S_ tile k-1, whose GEMM1 for the next pair is issued right behind GEMM-T tile k.  By the time the SIMT warps
+      // finish this pair, the next pair's scores are already in TMEM.
+      UnitIter it(p.Bi, p.nc);
+      bool has = it.next();
+      int ci = it.cap(), cj = it.j;
+      if (has)
+        for (int idx = 0; idx < NT; ++idx) gemm1(0, tile_at(idx, NT));
+      while (has) {
+        const bool hasn = it.next();
+        const int ni = it.cap(), nj = it.j;
+        TIMED_WAIT(wt_ef, mbar_wait(bar(B_EF), n & 1));      // E of this pair is complete in shared memory
+        tc_fence_after();
+        // Eo rows: straight from the E buffer by bulk tensor stores (columns >= LPAD are clipped by the map)
+        for (int t = 0; t < NT; ++t)
+#pragma unroll
+          for (int wb = 0; wb < (LPAD + 63) / 64; ++wb)
+            tma_store_3d(&tm_e, base + OFF_E + (uint32_t)wb * e_lbo + (uint32_t)t * (TILE * 128), wb * 64, ci,
+                         cj * Spad + t * TILE);
+        tma_store_commit();
+        gemmt();
+        for (int k = 1; k < NT; ++k) {
+          gemmt();
+          if (hasn) gemm1(n + 1, tile_at(k - 1, NT));
+        }
+        umma_commit(bar(B_EE));                              // GEMM-T has finished reading E
+        tma_store_wait_read();                               // ... and so have the Eo stores (issued long ago)
+        mbar_arrive(bar(B_EE));
+        if (hasn) gemm1(n + 1, tile_at(NT - 1, NT));
+        ++n;
+        has = hasn; ci = ni; cj = nj;
       }
 #ifdef GLORIA_PHASE_CLOCKS
       if (g_dbg) {

@@ -172,6 +172,22 @@ struct Units {
 };
 
 extern void* g_phase_clock_buffer;
+// Flat (caption, image) iterator over the same schedule, for roles that look one unit ahead.
+struct UnitIter {
+  Units u;
+  int j;
+  bool started;
+  __device__ UnitIter(int Bi, int Bc) : u(Bi, Bc), j(0), started(false) {}
+  __device__ bool next() {
+    if (started && ++j < u.j_end) return true;
+    started = true;
+    if (!u.next_caption()) return false;
+    j = u.j;
+    return true;
+  }
+  __device__ int cap() const { return u.i; }
+};
+
 // host side (tc_local.cu): 2-D bf16 tensor map [rows, inner] (inner contiguous), box [box_rows, 64], SWIZZLE_128B
 int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint32_t box_rows);
 // 3-D bf16 tensor [rows, mid, inner] with pitches in elements, box [box_rows, 1, 64], SWIZZLE_128B (TMA stores)
