@@ -203,6 +203,8 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
         if (++slot == NSLOT) { slot = 0; ph ^= 1; }
         return s;
       };
+      const uint64_t d_slot0 = make_smem_desc(base, 16, 1024);            // K-major tile in slot 0
+      const uint64_t d_e0 = make_smem_desc(base + OFF_E, e_lbo, 1024);    // E, N-major
       // GEMM1 of one S_ tile of pair number `pn` (waits until the SIMT warps are done with that tile of pair pn-1)
       auto gemm1 = [&](uint32_t pn, int t) {
         TIMED_WAIT(wt_d1e, mbar_wait(bar(B_D1E + t), (pn & 1) ^ 1));
@@ -211,11 +213,10 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
           const int sa = take();
           const int sb = take();
           tc_fence_after();
-          const uint32_t a0 = base + sa * SLOT, b0 = base + sb * SLOT;
+          const uint64_t ad = d_slot0 + (uint64_t)(sa * (SLOT >> 4)), bd = d_slot0 + (uint64_t)(sb * (SLOT >> 4));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + (uint32_t)(t * LPAD), make_smem_desc(a0 + k * 32, 16, 1024),
-                      make_smem_desc(b0 + k * 32, 16, 1024), idesc1, (uint32_t)((kb | k) != 0));
+            umma_bf16(tmem + (uint32_t)(t * LPAD), ad + 2 * k, bd + 2 * k, idesc1, (uint32_t)((kb | k) != 0));
           umma_commit(bar(B_EMPTY + sa));
           umma_commit(bar(B_EMPTY + sb));
         }
@@ -228,14 +229,11 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
         for (int kb = 0; kb < nkb2; ++kb) {
           const int sa = take();
           tc_fence_after();
-          const uint32_t a0 = base + sa * SLOT;
+          const uint64_t ad = d_slot0 + (uint64_t)(sa * (SLOT >> 4));
+          const uint64_t ed = d_e0 + (uint64_t)(kb * (KBLK / 8) * 64);          // 8 regions per 1024-byte atom
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t region0 = (uint32_t)(kb * KBLK + k * 16);
-            umma_bf16(tmem + TT_COL, make_smem_desc(a0 + k * 32, 16, 1024),
-                      make_smem_desc(base + OFF_E + (region0 >> 3) * 1024, e_lbo, 1024), idesct,
-                      (uint32_t)((kb | k) != 0));
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + TT_COL, ad + 2 * k, ed + 128 * k, idesct, (uint32_t)((kb | k) != 0));
           umma_commit(bar(B_EMPTY + sa));
         }
         umma_commit(bar(B_TTF));

@@ -16,16 +16,17 @@
 namespace gloria {
 namespace tc {
 
-constexpr int NSTAGE = 3;
-constexpr int STAGE_BYTES = 32768;       // A part [0,16K) + B part [16K,32K)
+constexpr int SLOT = 16384;              // one operand tile of one k-block (128 rows x 128 B)
+constexpr int NSLOT = 6;                 // TMA ring: GEMM1 takes two slots per k-block (Rt, Wt), GEMM2 one (Rn)
 constexpr int E_BYTES = 2 * MAX_NT * TILE * 128;   // [2 word blocks of 64][Spad regions][128 B]
-constexpr int OFF_E = NSTAGE * STAGE_BYTES;
+constexpr int OFF_E = NSLOT * SLOT;
 constexpr int OFF_BAR = OFF_E + E_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;   // + barriers/scratch + alignment slack
 constexpr int NTHREADS = 384;            // warps 0-3 control, 4-7 softmax, 8-11 epilogue
 
 // barrier indices (8 B each) inside the barrier block
-enum { B_FULL = 0, B_EMPTY = 3, B_D1F = 6, B_D1E = 8, B_EF = 10, B_EE = 11, B_D2F = 12, B_D2E = 14, B_COUNT = 16 };
+enum { B_FULL = 0, B_EMPTY = NSLOT, B_D1F = 2 * NSLOT, B_D1E = B_D1F + 2, B_EF = B_D1E + 2, B_EE, B_D2F, B_D2E = B_D2F + 2,
+       B_COUNT = B_D2E + 2 };
 
 struct FwdParams {
   const __nv_bfloat16* wt;   // [Bc, LPAD, D]
@@ -60,7 +61,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
   const int nchunk = p.D / TILE;      // D2 chunks
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(B_D1F + b), 1); mbar_init(bar(B_D1E + b), 128);
       mbar_init(bar(B_D2F + b), 1); mbar_init(bar(B_D2E + b), 128);
@@ -79,26 +80,37 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int st = 0; uint32_t ph = 0;
-      Units u(p.Bi, p.Bc);
-      while (u.next_caption()) {
-        for (int j = u.j; j < u.j_end; ++j) {
-          for (int t = 0; t < p.NT; ++t)
-            for (int kb = 0; kb < nkb1; ++kb) {
-              mbar_wait(bar(B_EMPTY + st), ph ^ 1);
-              mbar_expect_tx(bar(B_FULL + st), TILE * 128 + LPAD * 128);
-              tma_load_2d(base + st * STAGE_BYTES, &tm_rt, kb * KBLK, j * Spad + t * TILE, bar(B_FULL + st));
-              tma_load_2d(base + st * STAGE_BYTES + 16384, &tm_wt, kb * KBLK, u.i * LPAD, bar(B_FULL + st));
-              if (++st == NSTAGE) { st = 0; ph ^= 1; }
-            }
-          for (int c = 0; c < nchunk; ++c)
-            for (int kb = 0; kb < nkb2; ++kb) {
-              mbar_wait(bar(B_EMPTY + st), ph ^ 1);
-              mbar_expect_tx(bar(B_FULL + st), TILE * 128);
-              tma_load_2d(base + st * STAGE_BYTES, &tm_rn, kb * KBLK, j * p.D + c * TILE, bar(B_FULL + st));
-              if (++st == NSTAGE) { st = 0; ph ^= 1; }
-            }
+      int slot = 0; uint32_t ph = 0;
+      auto load = [&](const CUtensorMap* tm, int x, int y, uint32_t bytes) {
+        mbar_wait(bar(B_EMPTY + slot), ph ^ 1);
+        mbar_expect_tx(bar(B_FULL + slot), bytes);
+        tma_load_2d(base + slot * SLOT, tm, x, y, bar(B_FULL + slot));
+        if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+      };
+      auto load_g1 = [&](int i, int j, int t) {
+        for (int kb = 0; kb < nkb1; ++kb) {
+          load(&tm_rt, kb * KBLK, j * Spad + t * TILE, TILE * 128);
+          load(&tm_wt, kb * KBLK, i * LPAD, LPAD * 128);
         }
+      };
+      auto load_g2 = [&](int j) {
+        for (int c = 0; c < nchunk; ++c)
+          for (int kb = 0; kb < nkb2; ++kb) load(&tm_rn, kb * KBLK, j * p.D + c * TILE, TILE * 128);
+      };
+      // same order as the MMA issuer (see there)
+      UnitIter it(p.Bi, p.Bc);
+      bool has = it.next();
+      int ci = it.cap(), cj = it.j;
+      if (has)
+        for (int t = 0; t < p.NT; ++t) load_g1(ci, cj, t);
+      while (has) {
+        const bool hasn = it.next();
+        const int ni = it.cap(), nj = it.j;
+        if (hasn) load_g1(ni, nj, 0);
+        load_g2(cj);
+        if (hasn)
+          for (int t = 1; t < p.NT; ++t) load_g1(ni, nj, t);
+        has = hasn; ci = ni; cj = nj;
       }
     }
   } else if (warp == 1) {
@@ -113,55 +125,72 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
       constexpr uint32_t idesc1 = make_idesc(TILE, LPAD, 0, 0);   // A = Rt tile (K-major), B = Wt tile (K-major)
       constexpr uint32_t idesc2 = make_idesc(TILE, TILE, 1, 0);   // A = E (MN-major), B = Rn tile (K-major)
       const uint32_t e_lbo = (uint32_t)Spad * 128u;               // between the two 64-word blocks of E
-      int st = 0; uint32_t ph = 0;
+      int slot = 0; uint32_t ph = 0;
       uint32_t g1 = 0, g2 = 0, nu = 0;
-      Units u(p.Bi, p.Bc);
-      while (u.next_caption()) {
-        for (int j = u.j; j < u.j_end; ++j) {
-          for (int t = 0; t < p.NT; ++t) {
-            const uint32_t b = g1 & 1;
-            TIMED_WAIT(wt_d1e, mbar_wait(bar(B_D1E + b), ((g1 >> 1) & 1) ^ 1));
-            tc_fence_after();
-            for (int kb = 0; kb < nkb1; ++kb) {
-              TIMED_WAIT(wt_full, mbar_wait(bar(B_FULL + st), ph));
-              tc_fence_after();
-              const uint32_t a0 = base + st * STAGE_BYTES, b0 = a0 + 16384;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem + b * TILE, make_smem_desc(a0 + k * 32, 16, 1024), make_smem_desc(b0 + k * 32, 16, 1024),
-                          idesc1, (uint32_t)((kb | k) != 0));
-              umma_commit(bar(B_EMPTY + st));
-              if (++st == NSTAGE) { st = 0; ph ^= 1; }
-            }
-            umma_commit(bar(B_D1F + b));
-            ++g1;
-          }
-          TIMED_WAIT(wt_ef, mbar_wait(bar(B_EF), nu & 1));          // every E tile of this unit is in shared memory
+      // descriptors are built once; per MMA only the 16-byte-unit address field is advanced (the issuing thread's
+      // instruction count, not the tensor pipe, bounded this loop before)
+      const uint64_t d_slot0 = make_smem_desc(base, 16, 1024);            // K-major tile in slot 0
+      const uint64_t d_e0 = make_smem_desc(base + OFF_E, e_lbo, 1024);    // E, MN-major
+      auto take = [&]() {
+        TIMED_WAIT(wt_full, mbar_wait(bar(B_FULL + slot), ph));
+        const int s = slot;
+        if (++slot == NSLOT) { slot = 0; ph ^= 1; }
+        return s;
+      };
+      auto gemm1 = [&]() {                       // one score tile into the next D1 buffer
+        const uint32_t b = g1 & 1;
+        TIMED_WAIT(wt_d1e, mbar_wait(bar(B_D1E + b), ((g1 >> 1) & 1) ^ 1));
+        tc_fence_after();
+        for (int kb = 0; kb < nkb1; ++kb) {
+          const int sa = take();
+          const int sb = take();
           tc_fence_after();
-          for (int c = 0; c < nchunk; ++c) {
-            const uint32_t b2 = g2 & 1;
-            TIMED_WAIT(wt_d2e, mbar_wait(bar(B_D2E + b2), ((g2 >> 1) & 1) ^ 1));
-            tc_fence_after();
-            for (int kb = 0; kb < nkb2; ++kb) {
-              TIMED_WAIT(wt_full, mbar_wait(bar(B_FULL + st), ph));
-              tc_fence_after();
-              const uint32_t b0 = base + st * STAGE_BYTES;
+          const uint64_t ad = d_slot0 + (uint64_t)(sa * (SLOT >> 4)), bd = d_slot0 + (uint64_t)(sb * (SLOT >> 4));
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t region0 = (uint32_t)(kb * KBLK + k * 16);
-                umma_bf16(tmem + 2 * TILE + b2 * TILE,
-                          make_smem_desc(base + OFF_E + (region0 >> 3) * 1024, e_lbo, 1024),
-                          make_smem_desc(b0 + k * 32, 16, 1024), idesc2, (uint32_t)((kb | k) != 0));
-              }
-              umma_commit(bar(B_EMPTY + st));
-              if (++st == NSTAGE) { st = 0; ph ^= 1; }
-            }
-            umma_commit(bar(B_D2F + b2));
-            ++g2;
-          }
-          umma_commit(bar(B_EE));                // GEMM2 has finished reading E
-          ++nu;
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem + b * TILE, ad + 2 * k, bd + 2 * k, idesc1, (uint32_t)((kb | k) != 0));
+          umma_commit(bar(B_EMPTY + sa));
+          umma_commit(bar(B_EMPTY + sb));
         }
+        umma_commit(bar(B_D1F + b));
+        ++g1;
+      };
+      auto gemm2 = [&]() {                       // the whole context GEMM of the current pair
+        TIMED_WAIT(wt_ef, mbar_wait(bar(B_EF), nu & 1));          // every E tile of this unit is in shared memory
+        tc_fence_after();
+        for (int c = 0; c < nchunk; ++c) {
+          const uint32_t b2 = g2 & 1;
+          TIMED_WAIT(wt_d2e, mbar_wait(bar(B_D2E + b2), ((g2 >> 1) & 1) ^ 1));
+          tc_fence_after();
+          for (int kb = 0; kb < nkb2; ++kb) {
+            const int sa = take();
+            tc_fence_after();
+            const uint64_t bd = d_slot0 + (uint64_t)(sa * (SLOT >> 4));
+            const uint64_t ed = d_e0 + (uint64_t)(kb * (KBLK / 8) * 64);        // 8 regions per 1024-byte atom
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem + 2 * TILE + b2 * TILE, ed + 128 * k, bd + 2 * k, idesc2, (uint32_t)((kb | k) != 0));
+            umma_commit(bar(B_EMPTY + sa));
+          }
+          umma_commit(bar(B_D2F + b2));
+          ++g2;
+        }
+        umma_commit(bar(B_EE));                  // GEMM2 has finished reading E
+        ++nu;
+      };
+      // Issue order: the tensor pipe runs MMAs in issue order, so the NEXT pair's first score tile is issued before
+      // this pair's context GEMM (it fills the wait for the last softmax tile), its other tiles after it.
+      UnitIter it(p.Bi, p.Bc);
+      bool has = it.next();
+      if (has)
+        for (int t = 0; t < p.NT; ++t) gemm1();
+      while (has) {
+        const bool hasn = it.next();
+        if (hasn) gemm1();
+        gemm2();
+        if (hasn)
+          for (int t = 1; t < p.NT; ++t) gemm1();
+        has = hasn;
       }
 #ifdef GLORIA_PHASE_CLOCKS
       if (p.dbg) {
