@@ -186,7 +186,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc1 = make_idesc(TILE, LPAD, 0, 0);   // A = Rt tile (K-major), B = Wt tile (K-major)
+      constexpr uint32_t idesc1 = make_idesc(TILE, LPAD, 0, 0, 0);   // fp16: A = Rh tile (K-major), B = Wh tile (K-major)
       constexpr uint32_t idesct = make_idesc(TILE, LPAD, 0, 1);   // A = G tile (K-major),  B = E (N-major)
       const uint32_t e_lbo = (uint32_t)Spad * 128u;               // between the two 64-word blocks of E
       int slot = 0; uint32_t ph = 0;
@@ -744,12 +744,13 @@ extern "C" size_t gloria_b200_tc_bwd_workspace(int Bi, int Bc, int D, int S, int
   return want;
 }
 
-extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_t, const void* ctx_n, const void* words_t,
-                                            const float* wnorm, const int32_t* cap_lens, const float* stats, int Bi,
+extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t, const void* ctx_n,
+                                            const void* words_h, const void* words_t, const float* wnorm, const int32_t* cap_lens, const float* stats, int Bi,
                                             int Bc, int D, int S, int Lw, int Lcap, int word_off, float temp1,
                                             float temp2, int agg, float eps, const float* dsim, float* d_ctx,
                                             float* d_words, void* workspace, size_t workspace_bytes, void* stream) {
-  GLORIA_CHECK_ARG(ctx_t && ctx_n && words_t && wnorm && cap_lens && dsim && d_ctx && d_words && workspace,
+  GLORIA_CHECK_ARG(ctx_h && ctx_t && ctx_n && words_h && words_t && wnorm && cap_lens && dsim && d_ctx && d_words &&
+                       workspace,
                    "null pointer");
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
@@ -772,7 +773,7 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_t, const void* ctx_n
   int rc;
   if (stats == nullptr) {   // stand-alone use: one forward pass regenerates the per-word statistics
     float* own = (float*)(ws + pl.off_stats);
-    if ((rc = gloria_b200_tc_local_sim_fwd(ctx_t, ctx_n, words_t, wnorm, cap_lens, Bi, Bc, D, S, Lcap, temp1, temp2,
+    if ((rc = gloria_b200_tc_local_sim_fwd(ctx_h, ctx_n, words_h, wnorm, cap_lens, Bi, Bc, D, S, Lcap, temp1, temp2,
                                            agg, eps, (float*)(ws + pl.off_sim), own, stream)))
       return rc;
     stats = own;
@@ -795,8 +796,8 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_t, const void* ctx_n
   GLORIA_CUDA(cudaMemsetAsync(gamma, 0, (size_t)Bc * lpad * sizeof(float), st));
 
   CUtensorMap rt, wt, gm;
-  if ((rc = make_map(&rt, ctx_t, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;
-  if ((rc = make_map(&wt, words_t, (uint64_t)D, (uint64_t)Bc * lpad, (uint32_t)lpad))) return rc;
+  if ((rc = make_map(&rt, ctx_h, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;
+  if ((rc = make_map(&wt, words_h, (uint64_t)D, (uint64_t)Bc * lpad, (uint32_t)lpad))) return rc;
   if ((rc = make_map(&gm, gram, (uint64_t)Spad, (uint64_t)Bi * Spad, TILE))) return rc;
   int dev = 0, sms = 0;
   GLORIA_CUDA(cudaGetDevice(&dev));

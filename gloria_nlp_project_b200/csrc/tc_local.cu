@@ -29,7 +29,7 @@ enum { B_FULL = 0, B_EMPTY = NSLOT, B_D1F = 2 * NSLOT, B_D1E = B_D1F + 2, B_EF =
        B_COUNT = B_D2E + 2 };
 
 struct FwdParams {
-  const __nv_bfloat16* wt;   // [Bc, LPAD, D]
+  const __half* wt;          // [Bc, LPAD, D] fp16 (the score GEMM's operands are fp16, see pack_ctx)
   const float* wnorm;        // [Bc, LPAD]
   const int* cap_lens;
   float* sim;                // [Bi, Bc]
@@ -122,7 +122,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
 #else
 #define TIMED_WAIT(acc, ...) do { __VA_ARGS__; } while (0)
 #endif
-      constexpr uint32_t idesc1 = make_idesc(TILE, LPAD, 0, 0);   // A = Rt tile (K-major), B = Wt tile (K-major)
+      constexpr uint32_t idesc1 = make_idesc(TILE, LPAD, 0, 0, 0);   // fp16: A = Rh tile (K-major), B = Wh tile (K-major)
       constexpr uint32_t idesc2 = make_idesc(TILE, TILE, 1, 0);   // A = E (MN-major), B = Rn tile (K-major)
       const uint32_t e_lbo = (uint32_t)Spad * 128u;               // between the two 64-word blocks of E
       int slot = 0; uint32_t ph = 0;
@@ -292,7 +292,8 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
             const uint32_t wr[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const float wa = __uint_as_float(wr[k] << 16), wb = __uint_as_float(wr[k] & 0xFFFF0000u);
+              const float2 w2 = __half22float2(*reinterpret_cast<const __half2*>(&wr[k]));
+              const float wa = w2.x, wb = w2.y;
               dot = fmaf(v[2 * k], wa, dot);
               dot = fmaf(v[2 * k + 1], wb, dot);
               c2 = fmaf(v[2 * k], v[2 * k], c2);
@@ -344,9 +345,12 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
 // ---------------------------------------------------------------------------------------------------------------
 // prepack: fp32 native layouts -> padded bf16 TMA-legal layouts
 // ---------------------------------------------------------------------------------------------------------------
-// ctx [Bi, D, S] -> Rn [Bi, D, Spad] and Rt [Bi, Spad, D];  grid (Spad/32, D/32, Bi), block (32, 8)
+// ctx [Bi, D, S] -> Rn [Bi, D, Spad] (bf16), Rt [Bi, Spad, D] (bf16) and Rh [Bi, Spad, D] (fp16)
+// grid (Spad/32, D/32, Bi), block (32, 8).  The score GEMM runs on the fp16 copies: the word softmax amplifies operand
+// rounding (scores of unit-variance 768-d features have std 27.7) and fp16 carries 3 more mantissa bits than bf16 at
+// the same tensor rate -- it is also the dtype the reference's AMP runs this bmm in.
 __global__ void pack_ctx(const float* __restrict__ ctx, __nv_bfloat16* __restrict__ Rn, __nv_bfloat16* __restrict__ Rt,
-                         int D, int S, int Spad) {
+                         __half* __restrict__ Rh, int D, int S, int Spad) {
   __shared__ float t[32][33];
   const int b = blockIdx.z, s0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += 8) {
@@ -359,13 +363,14 @@ __global__ void pack_ctx(const float* __restrict__ ctx, __nv_bfloat16* __restric
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int s = s0 + r, d = d0 + threadIdx.x;
     Rt[((size_t)b * Spad + s) * D + d] = __float2bfloat16_rn(t[threadIdx.x][r]);
+    Rh[((size_t)b * Spad + s) * D + d] = __float2half_rn(t[threadIdx.x][r]);
   }
 }
 
 // words [Bc, D, Lw] -> Wt [Bc, LPAD, D] (rows >= cap_len zero) and wnorm [Bc, LPAD];  grid (LPAD/32.., 1, Bc), block (32, 8)
 __global__ void pack_words(const float* __restrict__ words, const int* __restrict__ cap_lens,
-                           __nv_bfloat16* __restrict__ Wt, float* __restrict__ wnorm, int D, int Lw, int lpad, int lcap,
-                           int off) {
+                           __nv_bfloat16* __restrict__ Wt, __half* __restrict__ Wh, float* __restrict__ wnorm, int D,
+                           int Lw, int lpad, int lcap, int off) {
   __shared__ float t[32][33];
   __shared__ float part[8][32];
   const int i = blockIdx.z, l0 = blockIdx.x * 32;
@@ -382,7 +387,10 @@ __global__ void pack_words(const float* __restrict__ words, const int* __restric
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8) {
       const int l = l0 + r, d = d0 + threadIdx.x;
-      if (l < lpad && d < D) Wt[((size_t)i * lpad + l) * D + d] = __float2bfloat16_rn(t[threadIdx.x][r]);
+      if (l < lpad && d < D) {
+        Wt[((size_t)i * lpad + l) * D + d] = __float2bfloat16_rn(t[threadIdx.x][r]);
+        Wh[((size_t)i * lpad + l) * D + d] = __float2half_rn(t[threadIdx.x][r]);
+      }
     }
     __syncthreads();
   }
@@ -472,38 +480,38 @@ extern "C" int gloria_b200_tc_supported(int D, int S, int Lcap) {
 }
 
 extern "C" int gloria_b200_tc_prepack(const float* ctx, const float* words, const int32_t* cap_lens, int Bi, int Bc,
-                                      int D, int S, int Lw, int Lcap, int word_off, void* ctx_t, void* ctx_n,
-                                      void* words_t, float* wnorm, void* stream) {
-  GLORIA_CHECK_ARG(ctx && words && cap_lens && ctx_t && ctx_n && words_t && wnorm, "null pointer");
+                                      int D, int S, int Lw, int Lcap, int word_off, void* ctx_h, void* ctx_t,
+                                      void* ctx_n, void* words_h, void* words_t, float* wnorm, void* stream) {
+  GLORIA_CHECK_ARG(ctx && words && cap_lens && ctx_h && ctx_t && ctx_n && words_h && words_t && wnorm, "null pointer");
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
   cudaStream_t st = (cudaStream_t)stream;
   const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
-  pack_ctx<<<dim3(Spad / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(ctx, (__nv_bfloat16*)ctx_n, (__nv_bfloat16*)ctx_t, D, S,
-                                                               Spad);
+  pack_ctx<<<dim3(Spad / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(ctx, (__nv_bfloat16*)ctx_n, (__nv_bfloat16*)ctx_t,
+                                                               (__half*)ctx_h, D, S, Spad);
   GLORIA_LAUNCHED("pack_ctx");
-  pack_words<<<dim3((lpad + 31) / 32, 1, Bc), dim3(32, 8), 0, st>>>(words, cap_lens, (__nv_bfloat16*)words_t, wnorm, D,
-                                                                    Lw, lpad, Lcap, word_off);
+  pack_words<<<dim3((lpad + 31) / 32, 1, Bc), dim3(32, 8), 0, st>>>(words, cap_lens, (__nv_bfloat16*)words_t,
+                                                                    (__half*)words_h, wnorm, D, Lw, lpad, Lcap, word_off);
   GLORIA_LAUNCHED("pack_words");
   return GLORIA_OK;
 }
 
-extern "C" int gloria_b200_tc_local_sim_fwd(const void* ctx_t, const void* ctx_n, const void* words_t,
+extern "C" int gloria_b200_tc_local_sim_fwd(const void* ctx_h, const void* ctx_n, const void* words_h,
                                             const float* wnorm, const int32_t* cap_lens, int Bi, int Bc, int D, int S,
                                             int Lcap, float temp1, float temp2, int agg, float eps, float* sim,
                                             float* stats, void* stream) {
-  GLORIA_CHECK_ARG(ctx_t && ctx_n && words_t && wnorm && cap_lens && sim, "null pointer");
+  GLORIA_CHECK_ARG(ctx_h && ctx_n && words_h && wnorm && cap_lens && sim, "null pointer");
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0, "bad batch sizes %d x %d", Bi, Bc);
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
   cudaStream_t st = (cudaStream_t)stream;
   const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
   CUtensorMap rt, wt, rn;
   int rc;
-  if ((rc = make_map(&rt, ctx_t, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;
-  if ((rc = make_map(&wt, words_t, (uint64_t)D, (uint64_t)Bc * lpad, (uint32_t)lpad))) return rc;
+  if ((rc = make_map(&rt, ctx_h, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;      // 2-byte elements: the map
+  if ((rc = make_map(&wt, words_h, (uint64_t)D, (uint64_t)Bc * lpad, (uint32_t)lpad))) return rc;   // is dtype-agnostic
   if ((rc = make_map(&rn, ctx_n, (uint64_t)Spad, (uint64_t)Bi * D, TILE))) return rc;
   FwdParams p;
-  p.wt = (const __nv_bfloat16*)words_t; p.wnorm = wnorm; p.cap_lens = cap_lens; p.sim = sim; p.stats = stats;
+  p.wt = (const __half*)words_h; p.wnorm = wnorm; p.cap_lens = cap_lens; p.sim = sim; p.stats = stats;
   p.Bi = Bi; p.Bc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE;
   p.t1_log2e = temp1 * 1.4426950408889634f; p.temp2 = temp2; p.agg = agg; p.eps_s = eps * (float)S;
   p.dbg = (long long*)g_phase_clock_buffer;

@@ -22,22 +22,33 @@ _WS_BUDGET = int(os.environ.get("GLORIA_B200_WS_BYTES", str(4 << 30)))          
 _TC_WS_BUDGET = int(os.environ.get("GLORIA_B200_TC_WS_BYTES", str(96 << 30)))     # bf16 backward operand matrices
 
 
-def tc_prepack(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int):
-    """fp32 native layouts -> (ctx_t [Bi,Spad,D], ctx_n [Bi,D,Spad], words_t [Bc,Lpad,D]) bf16 + wnorm [Bc,Lpad] fp32."""
+class Packed:
+    """TMA-legal 16-bit copies of one (context, words) pair (see gloria_b200_tc_prepack in include/gloria_b200.h)."""
+    __slots__ = ("ctx_h", "ctx_t", "ctx_n", "words_h", "words_t", "wnorm")
+
+    def __init__(self, *t):
+        self.ctx_h, self.ctx_t, self.ctx_n, self.words_h, self.words_t, self.wnorm = t
+
+
+def tc_prepack(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int) -> Packed:
+    """fp32 native layouts -> ctx_h/ctx_t [Bi,Spad,D] (fp16/bf16), ctx_n [Bi,D,Spad] bf16, words_h/words_t [Bc,Lpad,D]
+    (fp16/bf16), wnorm [Bc,Lpad] fp32."""
     L = _lib.lib()
     Bi, D, S = ctx.shape
     Bc, _, Lw = words.shape
     spad, lpad = L.gloria_b200_tc_spad(S), L.gloria_b200_tc_lpad(lcap)
     dev = ctx.device
+    ctx_h = torch.empty((Bi, spad, D), dtype=torch.float16, device=dev)
     ctx_t = torch.empty((Bi, spad, D), dtype=torch.bfloat16, device=dev)
     ctx_n = torch.empty((Bi, D, spad), dtype=torch.bfloat16, device=dev)
+    words_h = torch.empty((Bc, lpad, D), dtype=torch.float16, device=dev)
     words_t = torch.empty((Bc, lpad, D), dtype=torch.bfloat16, device=dev)
     wnorm = torch.empty((Bc, lpad), dtype=torch.float32, device=dev)
     rc = L.gloria_b200_tc_prepack(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S, Lw, lcap,
-                                  word_off, ctx_t.data_ptr(), ctx_n.data_ptr(), words_t.data_ptr(), wnorm.data_ptr(),
-                                  _stream(ctx))
+                                  word_off, ctx_h.data_ptr(), ctx_t.data_ptr(), ctx_n.data_ptr(), words_h.data_ptr(),
+                                  words_t.data_ptr(), wnorm.data_ptr(), _stream(ctx))
     _lib.check(rc, "tc_prepack")
-    return ctx_t, ctx_n, words_t, wnorm
+    return Packed(ctx_h, ctx_t, ctx_n, words_h, words_t, wnorm)
 
 
 def _need_cuda(*ts: Tensor) -> None:
@@ -103,9 +114,10 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
             packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
             if agg != AGG["max"] and (ctx.requires_grad or words.requires_grad or torch.is_grad_enabled()):
                 stats = torch.empty((Bi, Bc, 2, L.gloria_b200_tc_lpad(lcap)), dtype=torch.float32, device=dev)
-            rc = L.gloria_b200_tc_local_sim_fwd(packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(),
-                                                packed[3].data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1,
-                                                temp2, agg, eps, sim.data_ptr(), _ptr(stats), _stream(ctx))
+            rc = L.gloria_b200_tc_local_sim_fwd(packed.ctx_h.data_ptr(), packed.ctx_n.data_ptr(),
+                                                packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
+                                                cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg, eps,
+                                                sim.data_ptr(), _ptr(stats), _stream(ctx))
             _lib.check(rc, "tc_local_sim_fwd")
             if want_diag:
                 if Bi != Bc:
@@ -190,8 +202,9 @@ def tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp
                  - torch.cuda.memory_allocated(ctx.device))
     nbytes = L.gloria_b200_tc_bwd_workspace(Bi, Bc, D, S, lcap, 1 if have else 0, max(budget, 1 << 30))
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=ctx.device)
-    rc = L.gloria_b200_tc_local_sim_bwd(packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(),
-                                        packed[3].data_ptr(), cap_lens.data_ptr(), stats.data_ptr() if have else None,
+    rc = L.gloria_b200_tc_local_sim_bwd(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(), packed.ctx_n.data_ptr(),
+                                        packed.words_h.data_ptr(), packed.words_t.data_ptr(), packed.wnorm.data_ptr(),
+                                        cap_lens.data_ptr(), stats.data_ptr() if have else None,
                                         Bi, Bc, D, S, Lw, lcap, word_off, temp1, temp2, agg, eps, dsim.data_ptr(),
                                         d_ctx.data_ptr(), d_words.data_ptr(), ws.data_ptr(), nbytes, _stream(ctx))
     _lib.check(rc, "tc_local_sim_bwd")

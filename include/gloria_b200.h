@@ -134,20 +134,25 @@ int gloria_b200_tc_lpad(int Lcap);
 /* 0 if this (D, S, Lcap) is supported by the tensor-core kernels, else GLORIA_ERR_UNSUPPORTED. */
 int gloria_b200_tc_supported(int D, int S, int Lcap);
 
-/* Cast + transpose into TMA-legal bf16 layouts (native row pitches 722 B / 194 B are not 16 B multiples):
- *   ctx_t  [Bi, Spad, D]  region-major copy (d contiguous), rows s >= S zero
- *   ctx_n  [Bi, D, Spad]  channel-major copy (s contiguous), cols s >= S zero
- *   words_t[Bc, Lpad, D]  word-major copy of columns [word_off, word_off+cap_len), other rows zero
- *   wnorm  [Bc, Lpad]     fp32 |W_l| computed from the fp32 input (gloria_loss.py:14)                         */
+/* Cast + transpose into TMA-legal 16-bit layouts (native row pitches 1444 B / 388 B are not 16 B multiples):
+ *   ctx_h   [Bi, Spad, D] fp16  region-major copy (d contiguous), rows s >= S zero   -> score GEMM (A operand)
+ *   ctx_t   [Bi, Spad, D] bf16  same layout                                           -> backward GEMMs, Gram matrix
+ *   ctx_n   [Bi, D, Spad] bf16  channel-major copy (s contiguous), cols s >= S zero   -> context GEMM (B operand)
+ *   words_h [Bc, Lpad, D] fp16  word-major copy of columns [word_off, word_off+cap_len), other rows zero
+ *   words_t [Bc, Lpad, D] bf16  same layout                                           -> backward GEMMs
+ *   wnorm   [Bc, Lpad]    fp32  |W_l| computed from the fp32 input (gloria_loss.py:14)
+ * The score GEMM (K = D, feeds the word softmax, which amplifies operand rounding) runs on fp16 operands -- the dtype
+ * the reference's AMP runs this bmm in; everything after the softmax is bf16 x bf16.  All accumulate in fp32. */
 int gloria_b200_tc_prepack(const float* ctx, const float* words, const int32_t* cap_lens,
                            int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
-                           void* ctx_t, void* ctx_n, void* words_t, float* wnorm, void* stream);
+                           void* ctx_h, void* ctx_t, void* ctx_n, void* words_h, void* words_t, float* wnorm,
+                           void* stream);
 
 /* Fused forward over all Bi x Bc pairs: scores on tcgen05 (K = D), both softmaxes, attention-weighted context
  * on tcgen05 (K = S), per-word cosine and the temp2 log-sum-exp; only sim[Bi, Bc] reaches HBM -- plus, when
  * `stats` is given, the two per-word scalars the backward needs (stats [Bi, Bc, 2, Lpad]: <W_l, C'_l> and
  * |C'_l|^2 of the un-normalised context C' = Z_l C_l).  Inputs are the prepacked buffers. */
-int gloria_b200_tc_local_sim_fwd(const void* ctx_t, const void* ctx_n, const void* words_t, const float* wnorm,
+int gloria_b200_tc_local_sim_fwd(const void* ctx_h, const void* ctx_n, const void* words_h, const float* wnorm,
                                  const int32_t* cap_lens, int Bi, int Bc, int D, int S, int Lcap,
                                  float temp1, float temp2, int agg, float eps,
                                  float* sim, float* stats, void* stream);
@@ -162,8 +167,8 @@ size_t gloria_b200_tc_bwd_workspace(int Bi, int Bc, int D, int S, int Lcap, int 
  * X^T, E^T, (beta/Z^2) E^T; the sums over images / captions are plain GEMMs.  `stats` is the forward's output
  * (NULL: recomputed with one extra forward pass).  d_ctx [Bi, D, S] and d_words [Bc, D, Lw] fp32 in the callers'
  * native layouts are fully overwritten (padded word columns get exactly 0). */
-int gloria_b200_tc_local_sim_bwd(const void* ctx_t, const void* ctx_n, const void* words_t, const float* wnorm,
-                                 const int32_t* cap_lens, const float* stats, int Bi, int Bc, int D, int S, int Lw,
+int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t, const void* ctx_n, const void* words_h,
+                                 const void* words_t, const float* wnorm, const int32_t* cap_lens, const float* stats, int Bi, int Bc, int D, int S, int Lw,
                                  int Lcap, int word_off, float temp1, float temp2, int agg, float eps,
                                  const float* dsim, float* d_ctx, float* d_words,
                                  void* workspace, size_t workspace_bytes, void* stream);

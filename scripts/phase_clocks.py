@@ -16,7 +16,7 @@ st = torch.cuda.current_stream().cuda_stream
 dbg = torch.zeros(148, 32, dtype=torch.int64, device="cuda")
 lib.gloria_b200_debug_phase_clocks(dbg.data_ptr())
 def fwd():
-    assert lib.gloria_b200_tc_local_sim_fwd(packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(), packed[3].data_ptr(),
+    assert lib.gloria_b200_tc_local_sim_fwd(packed.ctx_h.data_ptr(), packed.ctx_n.data_ptr(), packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
         lens.data_ptr(), B, B, 768, 361, L, 4.0, 5.0, 0, 1e-8, sim.data_ptr(), stats.data_ptr(), st) == 0
 fwd(); fwd(); torch.cuda.synchronize()
 d = dbg.cpu().double(); act = d[:, 5] > 0
@@ -28,7 +28,7 @@ ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
 d_ctx, d_words = torch.empty_like(ctx), torch.empty_like(words)
 dbg.zero_()
 for _ in range(2):
-    assert lib.gloria_b200_tc_local_sim_bwd(packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(), packed[3].data_ptr(),
+    assert lib.gloria_b200_tc_local_sim_bwd(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(), packed.ctx_n.data_ptr(), packed.words_h.data_ptr(), packed.words_t.data_ptr(), packed.wnorm.data_ptr(),
         lens.data_ptr(), stats.data_ptr(), B, B, 768, 361, 97, L, 0, 4.0, 5.0, 0, 1e-8, dsim.data_ptr(), d_ctx.data_ptr(),
         d_words.data_ptr(), ws.data_ptr(), nbytes, st) == 0
 torch.cuda.synchronize()

@@ -35,9 +35,8 @@ for B, L in cases:
     st = torch.cuda.current_stream().cuda_stream
 
     def fwd():
-        rc = lib.gloria_b200_tc_local_sim_fwd(packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(),
-                                              packed[3].data_ptr(), lens.data_ptr(), B, B, 768, 361, L, 4.0, 5.0, 0,
-                                              1e-8, sim.data_ptr(), None, None, None, 0, st)
+        rc = lib.gloria_b200_tc_local_sim_fwd(packed.ctx_h.data_ptr(), packed.ctx_n.data_ptr(), packed.words_h.data_ptr(), packed.wnorm.data_ptr(), lens.data_ptr(), B, B, 768, 361, L, 4.0, 5.0, 0,
+                                              1e-8, sim.data_ptr(), None, st)
         assert rc == 0, lib.gloria_b200_last_error()
 
     t = timeit(fwd, n=n_it)

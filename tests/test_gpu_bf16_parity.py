@@ -37,18 +37,23 @@ def test_prepack_layouts(gl):
     ctx = cu(img_l).reshape(3, 768, 361)
     words = cu(txt_l)
     lens = torch.tensor(cl, dtype=torch.int32, device="cuda")
-    ctx_t, ctx_n, words_t, wnorm = ops.tc_prepack(ctx, words, lens, 97, 0)
+    pk = ops.tc_prepack(ctx, words, lens, 97, 0)
+    ctx_t, ctx_n, words_t, wnorm = pk.ctx_t, pk.ctx_n, pk.words_t, pk.wnorm
     assert ctx_t.shape == (3, 384, 768) and ctx_n.shape == (3, 768, 384) and words_t.shape == (3, 112, 768)
     ref = ctx.to(torch.bfloat16)
     assert torch.equal(ctx_n[:, :, :361], ref) and torch.all(ctx_n[:, :, 361:] == 0)
     assert torch.equal(ctx_t[:, :361], ref.transpose(1, 2)) and torch.all(ctx_t[:, 361:] == 0)
+    # fp16 copies feeding the score GEMM
+    assert pk.ctx_h.dtype == torch.float16 and pk.words_h.dtype == torch.float16
+    assert torch.equal(pk.ctx_h[:, :361], ctx.to(torch.float16).transpose(1, 2)) and torch.all(pk.ctx_h[:, 361:] == 0)
     for i, L in enumerate(cl):
         assert torch.equal(words_t[i, :L], words[i, :, :L].t().to(torch.bfloat16))
-        assert torch.all(words_t[i, L:] == 0)
+        assert torch.equal(pk.words_h[i, :L], words[i, :, :L].t().to(torch.float16))
+        assert torch.all(words_t[i, L:] == 0) and torch.all(pk.words_h[i, L:] == 0)
         assert torch.allclose(wnorm[i, :L], words[i, :, :L].norm(dim=0), rtol=1e-6)
     # word offset 1 (get_local_similarities, gloria_model.py:179)
     lens1 = torch.tensor([96, 40, 3], dtype=torch.int32, device="cuda")
-    _, _, w1, _ = ops.tc_prepack(ctx, words, lens1, 96, 1)
+    w1 = ops.tc_prepack(ctx, words, lens1, 96, 1).words_t
     assert torch.equal(w1[1, :40], words[1, :, 1:41].t().to(torch.bfloat16))
 
 
@@ -101,11 +106,13 @@ def test_loss_and_gradients(gl):
     (6, 9, 0.05, [33, 30, 21, 12, 7, 3], dict(agg="mean", temp1=3.0, temp2=6.0, temp3=7.0), False),
     (48, 5, 0.05, None, {}, False),
     (48, 6, 1.0, None, {}, True),
+    (3, 7, 1.0, [97, 41, 5], {}, False),
+    (16, 3, 1.0, None, {}, False),
 ])
 def test_gradients_tensor_core_backward(gl, B, seed, scale, lens, kw, exact):
     """tcgen05 backward (pair kernel + accumulation GEMMs) vs the oracle's closed form, both loss directions.
-    Unit-variance cases use bf16-representable features (identical inputs for kernel and oracle); the effect of
-    rounding arbitrary fp32 features to bf16 is bounded separately in test_unit_variance_operand_rounding."""
+    Unit-variance cases run both on bf16-representable features (identical inputs for kernel and oracle: the
+    kernel's own arithmetic) and on raw fp32 features (adds the fp16 rounding of the score operands)."""
     img_l, txt_l, _, _, cl = gen_inputs(seed, B, 768, 19, 19, 97, cap_lens=lens, scale=scale, dtype=np.float32)
     if exact:
         img_l, txt_l = bf16_exact(img_l, txt_l)
@@ -116,15 +123,19 @@ def test_gradients_tensor_core_backward(gl, B, seed, scale, lens, kw, exact):
     d_img, d_txt = O.local_loss_bwd(img_l.astype(np.float64), txt_l.astype(np.float64), cl, g0=1.0, g1=0.7, **kw)
     e_img, e_txt = relerr(img.grad, d_img), relerr(txt.grad, d_txt)
     print(f"bf16 backward B={B} scale={scale}: d_img rel err {e_img:.3e}, d_txt rel err {e_txt:.3e}")
-    assert e_img < GRAD_TOL and e_txt < GRAD_TOL
+    # raw (not 16-bit-representable) unit-variance features: the gate is the inherent fp16 operand rounding of the
+    # score GEMM (~1 %, quantified in test_unit_variance_operand_rounding), hence 2e-2 there and 1e-2 everywhere else
+    tol = 2 * GRAD_TOL if (scale == 1.0 and not exact) else GRAD_TOL
+    assert e_img < tol and e_txt < tol
     for i, L in enumerate(cl):                                   # padded word columns: exactly zero
         assert torch.all(txt.grad[i, :, L:] == 0)
 
 
 def test_unit_variance_operand_rounding(gl):
-    """Unit-variance 768-d features give scores with std 27.7, so the word softmax amplifies the 2^-9 rounding of the
-    bf16 operands: EXACT arithmetic on bf16-rounded features already differs from the fp32-feature gradient by ~9 %.
-    The kernel on fp32 features must stay within that inherent bound (it is not allowed to add to it)."""
+    """Unit-variance 768-d features give scores with std 27.7, so the word softmax amplifies operand rounding: EXACT
+    arithmetic on bf16-rounded features differs from the fp32-feature gradient by ~9 %, on fp16-rounded features by
+    ~1 %.  The score GEMM therefore runs on fp16 operands (the reference's AMP dtype); on arbitrary fp32 unit-variance
+    features the kernel must stay near that inherent fp16 bound."""
     B, cl = 3, [97, 41, 5]
     img_l, txt_l, _, _, _ = gen_inputs(7, B, 768, 19, 19, 97, cap_lens=cl, dtype=np.float32)
     img, txt = cu(img_l, True), cu(txt_l, True)
@@ -132,15 +143,16 @@ def test_unit_variance_operand_rounding(gl):
     (l0 + 0.7 * l1).backward()
     i64, t64 = img_l.astype(np.float64), txt_l.astype(np.float64)
     d_img, d_txt = O.local_loss_bwd(i64, t64, cl, g0=1.0, g1=0.7)
-    ri, rt = bf16_exact(img_l, txt_l)
-    q_img, q_txt = O.local_loss_bwd(ri.astype(np.float64), rt.astype(np.float64), cl, g0=1.0, g1=0.7)
-    inherent = max(relerr(q_img, d_img), relerr(q_txt, d_txt))
+    inherent = {}
+    for name, dt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        ri, rt = (torch.tensor(a).to(dt).double().numpy() for a in (img_l, txt_l))
+        q_img, q_txt = O.local_loss_bwd(ri, rt, cl, g0=1.0, g1=0.7)
+        inherent[name] = max(relerr(q_img, d_img), relerr(q_txt, d_txt))
     got = max(relerr(img.grad, d_img), relerr(txt.grad, d_txt))
-    vs_rounded = max(relerr(img.grad, q_img), relerr(txt.grad, q_txt))
-    print(f"unit variance: inherent bf16-operand error {inherent:.3e}, kernel vs fp32-feature oracle {got:.3e}, "
-          f"kernel vs oracle on the rounded features {vs_rounded:.3e}")
-    assert vs_rounded < GRAD_TOL           # the kernel's own arithmetic
-    assert got < inherent * 1.25 + GRAD_TOL
+    print(f"unit variance, fp32 features: kernel vs oracle {got:.3e}; exact arithmetic on rounded features: "
+          f"bf16 {inherent['bf16']:.3e}, fp16 {inherent['fp16']:.3e}")
+    assert got < inherent["fp16"] + GRAD_TOL / 2
+    assert got < inherent["bf16"] / 4
 
 
 def test_backward_chunked_workspace_and_no_stats(gl):
@@ -162,8 +174,7 @@ def test_backward_chunked_workspace_and_no_stats(gl):
     for budget, use_stats in ((0, True), (None, False)):
         stats = torch.empty(B, B, 2, L.gloria_b200_tc_lpad(lcap), device="cuda")
         sim = torch.empty(B, B, device="cuda")
-        _lib.check(L.gloria_b200_tc_local_sim_fwd(packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(),
-                                                  packed[3].data_ptr(), lens.data_ptr(), B, B, 768, 361, lcap, 4.0,
+        _lib.check(L.gloria_b200_tc_local_sim_fwd(packed.ctx_h.data_ptr(), packed.ctx_n.data_ptr(), packed.words_h.data_ptr(), packed.wnorm.data_ptr(), lens.data_ptr(), B, B, 768, 361, lcap, 4.0,
                                                   5.0, 0, 1e-8, sim.data_ptr(), stats.data_ptr(), st), "fwd")
         if budget is None:   # room for two captions per chunk only
             one = L.gloria_b200_tc_bwd_workspace(B, 1, 768, 361, lcap, 0, 0)
@@ -173,8 +184,7 @@ def test_backward_chunked_workspace_and_no_stats(gl):
         nbytes = L.gloria_b200_tc_bwd_workspace(B, B, 768, 361, lcap, 1 if use_stats else 0, budget)
         ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
         d_ctx, d_words = torch.empty_like(ctx), torch.empty_like(words)
-        _lib.check(L.gloria_b200_tc_local_sim_bwd(packed[0].data_ptr(), packed[1].data_ptr(), packed[2].data_ptr(),
-                                                  packed[3].data_ptr(), lens.data_ptr(),
+        _lib.check(L.gloria_b200_tc_local_sim_bwd(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(), packed.ctx_n.data_ptr(), packed.words_h.data_ptr(), packed.words_t.data_ptr(), packed.wnorm.data_ptr(), lens.data_ptr(),
                                                   stats.data_ptr() if use_stats else None, B, B, 768, 361, 97, lcap, 0,
                                                   4.0, 5.0, 0, 1e-8, dsim.data_ptr(), d_ctx.data_ptr(),
                                                   d_words.data_ptr(), ws.data_ptr(), nbytes, st), "bwd")
