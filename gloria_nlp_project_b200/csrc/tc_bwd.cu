@@ -578,21 +578,28 @@ __global__ void gram_ones_row(__nv_bfloat16* __restrict__ G, int S, int Spad) {
   for (int x = threadIdx.x; x < Spad; x += blockDim.x) r[x] = __float2bfloat16_rn(x < S ? 1.f : 0.f);
 }
 
-// Bo[(j,s), c] = f[j, c] * Eo[(j,s), c]   (c = (i,l));  grid (Bi*Spad, ceil(R1/8/256)), 8 columns per thread
-__global__ void scale_rows(const __nv_bfloat16* __restrict__ E, const float* __restrict__ f,
-                           __nv_bfloat16* __restrict__ Bo, int R1, int Spad) {
-  const size_t rowi = blockIdx.x;
-  const int c8 = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+// Bo[(j,s), c] = f[j, c] * Eo[(j,s), c]   (c = (i,l)).  grid (ceil(R1/8/256), Spad/ROWS, Bi): each thread owns 8 columns
+// of one image, keeps their 8 f values in registers and streams ROWS region rows (16-byte loads / stores).
+constexpr int SCALE_ROWS = 16;
+__global__ void __launch_bounds__(256) scale_rows(const __nv_bfloat16* __restrict__ E, const float* __restrict__ f,
+                                                  __nv_bfloat16* __restrict__ Bo, int R1, int Spad) {
+  const int c8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (c8 >= R1) return;
-  const uint4 ev = *reinterpret_cast<const uint4*>(E + rowi * R1 + c8);
-  const float* fr = f + (rowi / Spad) * R1 + c8;
+  const int j = blockIdx.z;
+  const float* fr = f + (size_t)j * R1 + c8;
   const float4 f0 = *reinterpret_cast<const float4*>(fr), f1 = *reinterpret_cast<const float4*>(fr + 4);
-  const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
   const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-  uint32_t o[4];
+  const size_t row0 = (size_t)j * Spad + (size_t)blockIdx.y * SCALE_ROWS;
+#pragma unroll 4
+  for (int r = 0; r < SCALE_ROWS; ++r) {
+    const size_t o = (row0 + r) * R1 + c8;
+    const uint4 ev = __ldcs(reinterpret_cast<const uint4*>(E + o));
+    const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+    uint32_t w[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) o[k] = pack_bf16(bf_lo(ew[k]) * fv[2 * k], bf_hi(ew[k]) * fv[2 * k + 1]);
-  *reinterpret_cast<uint4*>(Bo + rowi * R1 + c8) = make_uint4(o[0], o[1], o[2], o[3]);
+    for (int k = 0; k < 4; ++k) w[k] = pack_bf16(bf_lo(ew[k]) * fv[2 * k], bf_hi(ew[k]) * fv[2 * k + 1]);
+    *reinterpret_cast<uint4*>(Bo + o) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
 }
 
 __global__ void f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
@@ -828,7 +835,8 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
     }
     if (rc) return rc;
     timer_record(GLORIA_TIMER_TC_BWD_GEMM, 0, st);
-    bw::scale_rows<<<dim3((unsigned)K1, (unsigned)((R1 / 8 + 255) / 256)), 256, 0, st>>>(E, Fo, Bm, R1, Spad);
+    bw::scale_rows<<<dim3((unsigned)((R1 / 8 + 255) / 256), (unsigned)(Spad / bw::SCALE_ROWS), (unsigned)Bi), 256, 0, st>>>(
+        E, Fo, Bm, R1, Spad);
     GLORIA_LAUNCHED("scale_rows");
     const float beta = i0 == 0 ? 0.f : 1.f;
     // dWt[(i,l), d] = sum_(j,s) X^T[(j,s),(i,l)] Rt[(j,s), d]            (column-major: [D, R1] = Rt^T . (X^T)^T)

@@ -129,7 +129,20 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                                                      Lw, lcap, word_off, temp1, diag.data_ptr(), ws.data_ptr(),
                                                      nbytes, _stream(ctx))
                 _lib.check(rc, "diag_attn_fwd_f32")
+    if mode == MODE_BF16 and stats.numel() > 0:
+        _PACK_CACHE[stats.data_ptr()] = packed          # handed to the backward (same step), dropped there
     return sim, diag, mean, stats
+
+
+# forward -> backward hand-over of the prepacked 16-bit copies, keyed by the data pointer of the `stats` tensor the
+# autograd context saves (so the backward does not repeat the prepack).  Entries are popped by the backward; a
+# forward that is never differentiated leaves at most a few entries, evicted FIFO.
+_PACK_CACHE: "dict[int, Packed]" = {}
+
+
+def _pack_cache_trim(limit: int = 8) -> None:
+    while len(_PACK_CACHE) > limit:
+        _PACK_CACHE.pop(next(iter(_PACK_CACHE)))
 
 
 @local_sim_fwd.register_fake
@@ -195,8 +208,11 @@ def tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp
     """bf16 tensor-core backward: prepack, then the fused recompute kernel + accumulation GEMMs behind the C ABI."""
     Bi, D, S = ctx.shape
     Bc, _, Lw = words.shape
-    packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
     have = stats is not None and stats.numel() > 0
+    packed = _PACK_CACHE.pop(stats.data_ptr(), None) if have else None
+    _pack_cache_trim()
+    if packed is None or packed.ctx_h.shape[0] != Bi or packed.words_h.shape[0] != Bc:
+        packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
     free, _ = torch.cuda.mem_get_info(ctx.device)
     budget = min(_TC_WS_BUDGET, int(free * 0.9) + torch.cuda.memory_reserved(ctx.device)
                  - torch.cuda.memory_allocated(ctx.device))
