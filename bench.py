@@ -318,8 +318,13 @@ def run_b200(args):
         else:
             t_dom = kt["tc_bwd_pair_kernel"] + kt["bwd_accum_gemms"]
             ach = 2.0 * f_fwd / (t_dom * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r01_traffic_B512_ncu.csv (B=512, N=1)
+        traffic = None
+        if args.workload == "b512" and world == 1:
+            traffic = {"tc_fwd_kernel": 2511333120 + 237689344, "tc_bwd_pair_kernel": 5648215808 + 45244279296,
+                       "bwd_accum_gemms": None}[dom]
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tflops"], "traffic": None, "peak_source": pk["src"],
+                    "frac": ach / pk["tflops"], "traffic": traffic, "peak_source": pk["src"],
                     "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
                     "step_achieved": f_step / (ms * 1e-3) / 1e12, "step_frac": f_step / (ms * 1e-3) / 1e12 / pk["tflops"],
                     "algorithmic_flops_per_launch": kern_flops[dom] if dom == "tc_fwd_kernel" else 2.0 * f_fwd}
