@@ -41,7 +41,8 @@ constexpr int OFF_NEGM = OFF_COEFF + NCOL * 2 + 32;      // float 0 / -inf per w
 constexpr int OFF_CMASK = OFF_NEGM + NCOL * 4;           // uint16 0xFFFF / 0 per word
 constexpr int OFF_ZBUF = OFF_CMASK + NCOL * 2 + 32;      // Z per word
 constexpr int OFF_RED = OFF_ZBUF + 128 * 4;              // 32 floats of reduction scratch
-constexpr int OFF_XCH = OFF_RED + 128;                   // float2 [2][NGROUP][128] row-reduction exchange
+constexpr int OFF_ACCS = OFF_RED + 128;                  // FUSED: float [2][NCOL] column sums (dot', |C'|^2) of the pair
+constexpr int OFF_XCH = OFF_ACCS + 2 * NCOL * 4;         // float2 [2][NGROUP][128] row-reduction exchange
 constexpr int OFF_BAR = OFF_XCH + 2 * NGROUP * 128 * 8;
 enum { B_FULL = 0, B_EMPTY = NSLOT, B_D1F = 2 * NSLOT, B_D1E = B_D1F + MAX_NT, B_EF = B_D1E + MAX_NT, B_EE, B_TTF, B_TTE, B_COUNT };
 constexpr int SMEM_BYTES = OFF_BAR + B_COUNT * 8 + 16 + 1024;
@@ -56,6 +57,9 @@ struct PairParams {
   __nv_bfloat16* xt;        // [Bi*Spad, nc*LPAD]   X^T
   __nv_bfloat16* et;        //                      E^T (un-normalised attention numerators)
   float* fo;                // [Bi, nc*LPAD]  f = beta / Z^2 per pair and word (Bo = f * Eo is formed by scale_rows)
+  float* go;                // FUSED: [Bi, nc*LPAD]  gamma per pair and word for g = 1
+  float* sim;               // FUSED: [Bi, Bc]  the forward's similarities
+  int agg;                  // FUSED: GLORIA_AGG_SUM / _MEAN
   float* gamma;             // [Bc, LPAD]  sum_j (dL/d|W_l|) / |W_l|   (atomicAdd)
   int Bi, Bc, i0, nc, D, S, NT;
   float t1, t1_log2e, t2, eps;
@@ -89,10 +93,43 @@ __device__ __forceinline__ float2 lds_f2(uint32_t addr) {
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
+// Column sums over the 32 lanes of a warp for N per-lane values (N a multiple of 8): halving butterfly -- at each
+// step a lane keeps one half of its remaining columns and trades the other half with its partner (N + N/2 + ... ~ 2N
+// shuffles instead of 5N); the survivors are added into dst[] (shared memory, one atomic per surviving value).
+template <int N, int STEP>
+__device__ __forceinline__ void warp_colsum_step(float* v, int lane, int lo, float* dst, int total) {
+  if constexpr (STEP == 5) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (lo + i < total) atomicAdd(dst + lo + i, v[i]);
+  } else {
+    constexpr int H = (N + 1) / 2;                  // columns kept
+    constexpr int MASK = 16 >> STEP;
+    const bool up = (lane & MASK) != 0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const float hi = (i + H < N) ? v[i + H] : 0.f;
+      const float send = up ? v[i] : hi;
+      const float keep = up ? hi : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+    }
+    warp_colsum_step<H, STEP + 1>(v, lane, lo + (up ? H : 0), dst, total);
+  }
+}
+template <int N>
+__device__ __forceinline__ void warp_colsum(float* v, int lane, float* dst) {
+  warp_colsum_step<N, 0>(v, lane, 0, dst, N);
+}
+
 // region tile processed at position idx of a pair: the tile holding the ones row of G (the last one) goes first
 __device__ __forceinline__ int tile_at(int idx, int NT) { return idx == 0 ? NT - 1 : idx - 1; }
 
-template <int LPAD>
+// FUSED = false: backward by recomputation (needs the forward's stats and dsim).
+// FUSED = true : training forward.  Every backward quantity is linear in g = dsim[j,i], so this mode computes sim AND
+//   the backward operand rows for g = 1 in one pass; the backward proper is then a scale by g plus the GEMMs.  The
+//   per-word <W,C'> and |C'|^2 are reduced in-kernel (Gram form: sum_s E S_ and sum_s E T'), which takes a first
+//   GEMM-T pass (pass A) before the coefficients exist; GEMM-T is then issued again for the element pass (pass B).
+template <int LPAD, bool FUSED>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__ CUtensorMap tm_wt,
                    const __grid_constant__ CUtensorMap tm_g, const __grid_constant__ CUtensorMap tm_e,
@@ -107,6 +144,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + OFF_BAR + B_COUNT * 8);
   float* red = reinterpret_cast<float*>(smem + OFF_RED);
   float* zbuf = reinterpret_cast<float*>(smem + OFF_ZBUF);
+  float* accs = reinterpret_cast<float*>(smem + OFF_ACCS);
   float4* coefA = reinterpret_cast<float4*>(smem + OFF_COEFA);
   float* coefX = reinterpret_cast<float*>(smem + OFF_COEFX);
   float* negm = reinterpret_cast<float*>(smem + OFF_NEGM);
@@ -171,6 +209,8 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
       while (has) {
         const bool hasn = it.next();
         const int ni = it.cap(), nj = it.j;
+        if (FUSED)
+          for (int k = 0; k < NT; ++k) load_tt(cj, tile_at(k, NT));      // pass A
         load_tt(cj, tile_at(0, NT));
         for (int k = 1; k < NT; ++k) {
           load_tt(cj, tile_at(k, NT));
@@ -260,6 +300,8 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             tma_store_3d(&tm_e, base + OFF_E + (uint32_t)wb * e_lbo + (uint32_t)t * (TILE * 128), wb * 64, ci,
                          cj * Spad + t * TILE);
         tma_store_commit();
+        if (FUSED)
+          for (int k = 0; k < NT; ++k) gemmt();              // pass A: T' for the in-kernel |C'|^2 reduction
         gemmt();
         for (int k = 1; k < NT; ++k) {
           gemmt();
@@ -329,12 +371,18 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
       for (int j = u.j; j < u.j_end; ++j) {
         // per-word inputs of the coefficient step (thread wl owns word l = wl); latency hidden by the softmax
         float dotp = 0.f, c2p = 0.f;
-        if (wl < LPAD) {
-          const float* sp = p.stats + ((size_t)j * p.Bc + i) * 2 * LPAD;
-          dotp = __ldg(sp + wl);
-          c2p = __ldg(sp + LPAD + wl);
+        float gsim = 1.f;
+        if (!FUSED) {
+          if (wl < LPAD) {
+            const float* sp = p.stats + ((size_t)j * p.Bc + i) * 2 * LPAD;
+            dotp = __ldg(sp + wl);
+            c2p = __ldg(sp + LPAD + wl);
+          }
+          gsim = __ldg(p.dsim + (size_t)j * p.Bc + i);
+        } else if (wl < NCOL) {
+          accs[wl] = 0.f;                                    // column sums of this pair (ordered by the softmax barriers)
+          accs[NCOL + wl] = 0.f;
         }
-        const float gsim = __ldg(p.dsim + (size_t)j * p.Bc + i);
         float nmb[MAX_NT], inv[MAX_NT];
         // ---------------- phase 1: word softmax, E -> shared memory (S_ stays in TMEM)
 #pragma unroll
@@ -409,6 +457,56 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             mbar_arrive(bar(B_EF));
           }
         }
+        if (FUSED) {
+          // ---------------- pass A: dot'_l = sum_s E S_,  |C'_l|^2 = sum_s E T'  (own columns, all tiles), Z row
+          float a1[WG], a2[WG];
+#pragma unroll
+          for (int k = 0; k < WG; ++k) a1[k] = a2[k] = 0.f;
+#pragma unroll
+          for (int idx = 0; idx < MAX_NT; ++idx) {
+            if (idx < NT) {
+              const int t = tile_at(idx, NT);
+              STIMED(sw_ttf, mbar_wait(bar(B_TTF), ttc & 1));
+              ++ttc;
+              tc_fence_after();
+              const int s_glob = t * TILE + row;
+              const uint32_t sw = (uint32_t)(s_glob & 7);
+              const uint8_t* erow = smem + OFF_E + (size_t)(s_glob >> 3) * 1024u + (size_t)sw * 128u;
+              const uint32_t ts = tmem + lane_addr + (uint32_t)(t * LPAD + col0);
+              const uint32_t tt = tmem + lane_addr + TT_COL + (uint32_t)col0;
+#pragma unroll
+              for (int c = 0; c < CW; ++c) {
+                if (c_lo + c < NCH) {
+                  float sv[8], tv[8];
+                  tmem_ld8(ts + c * 8, sv);
+                  tmem_ld8(tt + c * 8, tv);
+                  const int ch = c_lo + c;
+                  const uint4 ev = *reinterpret_cast<const uint4*>(erow + (size_t)(ch >> 3) * e_blk +
+                                                                   (size_t)((((uint32_t)ch & 7u) ^ sw) << 4));
+                  tmem_ld_wait();
+                  const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+                  if (idx == 0 && q == (zrow >> 5) && lane == (zrow & 31)) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) zbuf[col0 + c * 8 + k] = tv[k];     // the ones row: Z_l
+                  }
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const float e = (k & 1) ? bf_hi(ew[k >> 1]) : bf_lo(ew[k >> 1]);   // 0 in padded rows / words
+                    a1[c * 8 + k] = fmaf(e, sv[k], a1[c * 8 + k]);
+                    a2[c * 8 + k] = fmaf(e, tv[k], a2[c * 8 + k]);
+                  }
+                }
+              }
+              tc_fence_before();
+              mbar_arrive(bar(B_TTE));               // T' buffer may be overwritten by the next GEMM-T tile
+            }
+          }
+          // column sums over the 32 rows of this warp (halving butterfly), then over warps through shared memory
+          warp_colsum<WG>(a1, lane, accs + col0);
+          warp_colsum<WG>(a2, lane, accs + NCOL + col0);
+          asm volatile("bar.sync 1, 384;" ::: "memory");
+          if (wl < NCOL) { dotp = accs[wl]; c2p = accs[NCOL + wl]; }
+        }
         // ---------------- phase 2: per region tile, T' arrives; coefficients; dP, u, X / Eo / Bo rows
 #pragma unroll
         for (int idx = 0; idx < MAX_NT; ++idx) {
@@ -419,7 +517,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             tc_fence_after();
             if (idx == 0) {
               // Z_l = sum_s E[s,l] sits in the ones row of this tile; the owning lane quarter reads it
-              if (q == (zrow >> 5)) {
+              if (!FUSED && q == (zrow >> 5)) {
 #pragma unroll
                 for (int c = 0; c < CW; ++c) {
                   if (c_lo + c < NCH) {
@@ -470,7 +568,16 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
                 coefX[wl] = live ? ddot * iz : 0.f;
               }
               if (wl < LPAD) p.fo[((size_t)j * p.nc + u.i) * LPAD + wl] = live ? beta * iz * iz : 0.f;
-              if (live) gacc += gamma;
+              if (FUSED) {
+                if (wl < LPAD) p.go[((size_t)j * p.nc + u.i) * LPAD + wl] = live ? gamma : 0.f;
+                if (wl == 0) {      // sim = log sum_l exp(t2 cos_l)  (mean: minus log L), gloria_loss.py:153-158
+                  float r = mx + logf(tot);
+                  if (p.agg == GLORIA_AGG_MEAN) r -= logf((float)L);
+                  p.sim[(size_t)j * p.Bc + i] = r;
+                }
+              } else if (live) {
+                gacc += gamma;
+              }
               asm volatile("bar.sync 1, 384;" ::: "memory");
             }
             const int s_glob = t * TILE + row;
@@ -552,7 +659,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
         }
         ++n;
       }
-      if (wl < LPAD && gacc != 0.f) atomicAdd(p.gamma + (size_t)i * LPAD + wl, gacc);
+      if (!FUSED && wl < LPAD && gacc != 0.f) atomicAdd(p.gamma + (size_t)i * LPAD + wl, gacc);
     }
 #ifdef GLORIA_PHASE_CLOCKS
     if (g_dbg && (lane == 0) && (q == 0)) {
@@ -581,14 +688,17 @@ __global__ void gram_ones_row(__nv_bfloat16* __restrict__ G, int S, int Spad) {
 // Bo[(j,s), c] = f[j, c] * Eo[(j,s), c]   (c = (i,l)).  grid (ceil(R1/8/256), Spad/ROWS, Bi): each thread owns 8 columns
 // of one image, keeps their 8 f values in registers and streams ROWS region rows (16-byte loads / stores).
 constexpr int SCALE_ROWS = 16;
+// g (optional): dsim [Bi, Bc] -- the fused training forward stores f for g = 1 and the backward multiplies it in here
 __global__ void __launch_bounds__(256) scale_rows(const __nv_bfloat16* __restrict__ E, const float* __restrict__ f,
-                                                  __nv_bfloat16* __restrict__ Bo, int R1, int Spad) {
+                                                  __nv_bfloat16* __restrict__ Bo, int R1, int Spad,
+                                                  const float* __restrict__ g, int Bc, int i0, int lpad) {
   const int c8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (c8 >= R1) return;
   const int j = blockIdx.z;
   const float* fr = f + (size_t)j * R1 + c8;
   const float4 f0 = *reinterpret_cast<const float4*>(fr), f1 = *reinterpret_cast<const float4*>(fr + 4);
-  const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+  const float gs = g ? g[(size_t)j * Bc + i0 + c8 / lpad] : 1.f;       // 8 columns never straddle a caption
+  const float fv[8] = {f0.x * gs, f0.y * gs, f0.z * gs, f0.w * gs, f1.x * gs, f1.y * gs, f1.z * gs, f1.w * gs};
   const size_t row0 = (size_t)j * Spad + (size_t)blockIdx.y * SCALE_ROWS;
 #pragma unroll 4
   for (int r = 0; r < SCALE_ROWS; ++r) {
@@ -600,6 +710,37 @@ __global__ void __launch_bounds__(256) scale_rows(const __nv_bfloat16* __restric
     for (int k = 0; k < 4; ++k) w[k] = pack_bf16(bf_lo(ew[k]) * fv[2 * k], bf_hi(ew[k]) * fv[2 * k + 1]);
     *reinterpret_cast<uint4*>(Bo + o) = make_uint4(w[0], w[1], w[2], w[3]);
   }
+}
+
+// X[(j,s), (i,l)] *= g[j, i]  in place (fused training path: X was produced for g = 1); same grid as scale_rows
+__global__ void __launch_bounds__(256) scale_x(__nv_bfloat16* __restrict__ X, const float* __restrict__ g, int R1,
+                                               int Spad, int Bc, int i0, int lpad) {
+  const int c8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (c8 >= R1) return;
+  const int j = blockIdx.z;
+  const float gs = g[(size_t)j * Bc + i0 + c8 / lpad];
+  const size_t row0 = (size_t)j * Spad + (size_t)blockIdx.y * SCALE_ROWS;
+#pragma unroll 4
+  for (int r = 0; r < SCALE_ROWS; ++r) {
+    uint4* ptr = reinterpret_cast<uint4*>(X + (row0 + r) * R1 + c8);
+    const uint4 ev = *ptr;
+    const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = pack_bf16(bf_lo(ew[k]) * gs, bf_hi(ew[k]) * gs);
+    *ptr = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// gamma[i, l] = sum_j g[j, i] * go[j, (i,l)]   (fused training path);  one thread per column
+__global__ void gamma_sum(const float* __restrict__ go, const float* __restrict__ g, float* __restrict__ gamma, int Bi,
+                          int R1, int Bc, int i0, int lpad) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= R1) return;
+  const int i = i0 + c / lpad;
+  float acc = 0.f;
+  for (int j = 0; j < Bi; ++j) acc = fmaf(g[(size_t)j * Bc + i], go[(size_t)j * R1 + c], acc);
+  gamma[(size_t)i0 * lpad + c] = acc;
 }
 
 __global__ void f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
@@ -719,14 +860,113 @@ cublasHandle_t cublas_handle() {
     ++launch_counter();                                                                           \
   } while (0)
 
-template <int LPAD>
+template <int LPAD, bool FUSED>
 int launch_pair(const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap& g, const CUtensorMap& e,
                 const PairParams& p, int grid, cudaStream_t st) {
-  GLORIA_CUDA(cudaFuncSetAttribute(tc_bwd_pair_kernel<LPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  timer_record(GLORIA_TIMER_TC_BWD_PAIR, 0, st);
-  tc_bwd_pair_kernel<LPAD><<<grid, NTHREADS, SMEM_BYTES, st>>>(rt, wt, g, e, p);
-  timer_record(GLORIA_TIMER_TC_BWD_PAIR, 1, st);
+  GLORIA_CUDA(cudaFuncSetAttribute(tc_bwd_pair_kernel<LPAD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   SMEM_BYTES));
+  const int slot = FUSED ? GLORIA_TIMER_TC_FWD : GLORIA_TIMER_TC_BWD_PAIR;
+  timer_record(slot, 0, st);
+  tc_bwd_pair_kernel<LPAD, FUSED><<<grid, NTHREADS, SMEM_BYTES, st>>>(rt, wt, g, e, p);
+  timer_record(slot, 1, st);
   GLORIA_LAUNCHED("tc_bwd_pair_kernel");
+  return GLORIA_OK;
+}
+
+template <bool FUSED>
+int launch_pair_lpad(int lpad, const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap& g, const CUtensorMap& e,
+                     const PairParams& p, int grid, cudaStream_t st) {
+  switch (lpad) {
+    case 16: return launch_pair<16, FUSED>(rt, wt, g, e, p, grid, st);
+    case 32: return launch_pair<32, FUSED>(rt, wt, g, e, p, grid, st);
+    case 48: return launch_pair<48, FUSED>(rt, wt, g, e, p, grid, st);
+    case 64: return launch_pair<64, FUSED>(rt, wt, g, e, p, grid, st);
+    case 80: return launch_pair<80, FUSED>(rt, wt, g, e, p, grid, st);
+    case 96: return launch_pair<96, FUSED>(rt, wt, g, e, p, grid, st);
+    case 112: return launch_pair<112, FUSED>(rt, wt, g, e, p, grid, st);
+    case 128: return launch_pair<128, FUSED>(rt, wt, g, e, p, grid, st);
+  }
+  return fail(GLORIA_ERR_UNSUPPORTED, "lpad %d", lpad);
+}
+
+// ---- fused training path: one workspace shared by the forward (gram, X, E, fo, go) and the backward (the rest)
+struct TrainPlan {
+  size_t off_gram, off_x, off_e, off_fo, off_go, off_b, off_dwt, off_drt, off_m, off_mb, off_gamma, off_cublas, total;
+};
+TrainPlan train_plan(int Bi, int Bc, int D, int Spad, int lpad) {
+  TrainPlan t{};
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += align_up(n, 1024); return r; };
+  const size_t arr = (size_t)Bi * Spad * Bc * lpad * 2;
+  t.off_gram = take((size_t)Bi * Spad * Spad * 2);
+  t.off_x = take(arr);
+  t.off_e = take(arr);
+  t.off_fo = take((size_t)Bi * Bc * lpad * 4);
+  t.off_go = take((size_t)Bi * Bc * lpad * 4);
+  t.off_b = take(arr);
+  t.off_dwt = take((size_t)Bc * lpad * D * 4);
+  t.off_drt = take((size_t)Bi * Spad * D * 4);
+  t.off_m = take((size_t)Bi * Spad * Spad * 4);
+  t.off_mb = take((size_t)Bi * Spad * Spad * 2);
+  t.off_gamma = take((size_t)Bc * lpad * 4);
+  t.off_cublas = take(CUBLAS_WS);
+  t.total = o;
+  return t;
+}
+
+int gram_matrices(cublasHandle_t h, const __nv_bfloat16* Rt, __nv_bfloat16* gram, int Bi, int D, int S, int Spad,
+                  cudaStream_t st) {
+  const float one = 1.f, zero = 0.f;
+  // G_j = Rt_j Rt_j^T (row-major [Spad, D] == column-major [D, Spad]); row S becomes the row of ones
+  GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_T, CUBLAS_OP_N, Spad, Spad, D, &one, Rt, CUDA_R_16BF, D,
+                                           (long long)Spad * D, Rt, CUDA_R_16BF, D, (long long)Spad * D, &zero, gram,
+                                           CUDA_R_16BF, Spad, (long long)Spad * Spad, Bi, CUBLAS_COMPUTE_32F,
+                                           CUBLAS_GEMM_DEFAULT));
+  gram_ones_row<<<Bi, 128, 0, st>>>(gram, S, Spad);
+  GLORIA_LAUNCHED("gram_ones_row");
+  return GLORIA_OK;
+}
+
+// the accumulation GEMMs + unpack shared by both backward flavours (X, E, Bm hold nc captions starting at i0)
+int accumulate_chunk(cublasHandle_t h, const __nv_bfloat16* Rt, const __nv_bfloat16* Wt, const __nv_bfloat16* X,
+                     const __nv_bfloat16* E, const __nv_bfloat16* Bm, float* dWt, float* dRt, float* Mf, int Bi, int D,
+                     int Spad, int lpad, int i0, int nc, bool first) {
+  const float one = 1.f, zero = 0.f;
+  const float beta = first ? 0.f : 1.f;
+  const int K1 = Bi * Spad, R1 = nc * lpad;
+  // dWt[(i,l), d] = sum_(j,s) X^T[(j,s),(i,l)] Rt[(j,s), d]            (column-major: [D, R1] = Rt^T . (X^T)^T)
+  GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, R1, K1, &one, Rt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1, &zero,
+                             dWt + (size_t)i0 * lpad * D, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+  // dRt[(j,s), d] (+)= sum_(i,l) X^T[(j,s),(i,l)] Wt[(i,l), d]         (column-major: [D, K1] = Wt^T . X^T)
+  GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, K1, R1, &one, Wt + (size_t)i0 * lpad * D, CUDA_R_16BF, D, X,
+                             CUDA_R_16BF, R1, &beta, dRt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+  // M_j[a, b] (+)= sum_(i,l) E^T[(j,a),(i,l)] Bo^T[(j,b),(i,l)]
+  GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_T, CUBLAS_OP_N, Spad, Spad, R1, &one, E, CUDA_R_16BF, R1,
+                                           (long long)Spad * R1, Bm, CUDA_R_16BF, R1, (long long)Spad * R1, &beta, Mf,
+                                           CUDA_R_32F, Spad, (long long)Spad * Spad, Bi, CUBLAS_COMPUTE_32F,
+                                           CUBLAS_GEMM_DEFAULT));
+  return GLORIA_OK;
+}
+
+int finish_backward(cublasHandle_t h, const __nv_bfloat16* Rt, const __nv_bfloat16* Wt, const int32_t* cap_lens,
+                    float* dWt, float* dRt, float* Mf, __nv_bfloat16* Mb, const float* gamma, float* d_ctx,
+                    float* d_words, int Bi, int Bc, int D, int S, int Spad, int Lw, int lpad, int Lcap, int word_off,
+                    cudaStream_t st) {
+  const float one = 1.f;
+  // dRt_j += M_j Rt_j   (M_j symmetric up to rounding; column-major: [D, Spad] = Rt_j^T . M_j)
+  const size_t nm = (size_t)Bi * Spad * Spad;
+  f32_to_bf16<<<(unsigned)((nm / 4 + 255) / 256), 256, 0, st>>>(Mf, Mb, nm);
+  GLORIA_LAUNCHED("f32_to_bf16");
+  GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, Spad, Spad, &one, Rt, CUDA_R_16BF, D,
+                                           (long long)Spad * D, Mb, CUDA_R_16BF, Spad, (long long)Spad * Spad, &one, dRt,
+                                           CUDA_R_32F, D, (long long)Spad * D, Bi, CUBLAS_COMPUTE_32F,
+                                           CUBLAS_GEMM_DEFAULT));
+  timer_record(GLORIA_TIMER_TC_BWD_GEMM, 1, st);
+  unpack_dctx<<<dim3((S + 31) / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(dRt, d_ctx, D, S, Spad);
+  GLORIA_LAUNCHED("unpack_dctx");
+  unpack_dwords_tc<<<dim3((Lw + 31) / 32, D / 32, Bc), dim3(32, 8), 0, st>>>(dWt, gamma, Wt, cap_lens, d_words, D, Lw,
+                                                                           lpad, Lcap, word_off);
+  GLORIA_LAUNCHED("unpack_dwords_tc");
   return GLORIA_OK;
 }
 
@@ -752,7 +992,8 @@ extern "C" size_t gloria_b200_tc_bwd_workspace(int Bi, int Bc, int D, int S, int
 }
 
 extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t, const void* ctx_n,
-                                            const void* words_h, const void* words_t, const float* wnorm, const int32_t* cap_lens, const float* stats, int Bi,
+                                            const void* words_h, const void* words_t, const float* wnorm,
+                                            const int32_t* cap_lens, const float* stats, int Bi,
                                             int Bc, int D, int S, int Lw, int Lcap, int word_off, float temp1,
                                             float temp2, int agg, float eps, const float* dsim, float* d_ctx,
                                             float* d_words, void* workspace, size_t workspace_bytes, void* stream) {
@@ -789,17 +1030,9 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
   if (!h) return fail(GLORIA_ERR_DRIVER, "cublasCreate failed");
   GLORIA_CUBLAS(cublasSetStream(h, st));
   GLORIA_CUBLAS(cublasSetWorkspace(h, ws + pl.off_cublas, bw::CUBLAS_WS));
-  const float one = 1.f, zero = 0.f;
   const __nv_bfloat16* Rt = (const __nv_bfloat16*)ctx_t;
   const __nv_bfloat16* Wt = (const __nv_bfloat16*)words_t;
-
-  // Gram matrices G_j = Rt_j Rt_j^T (row-major [Spad, D] == column-major [D, Spad])
-  GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_T, CUBLAS_OP_N, Spad, Spad, D, &one, Rt, CUDA_R_16BF, D,
-                                           (long long)Spad * D, Rt, CUDA_R_16BF, D, (long long)Spad * D, &zero, gram,
-                                           CUDA_R_16BF, Spad, (long long)Spad * Spad, Bi, CUBLAS_COMPUTE_32F,
-                                           CUBLAS_GEMM_DEFAULT));
-  bw::gram_ones_row<<<Bi, 128, 0, st>>>(gram, S, Spad);
-  GLORIA_LAUNCHED("gram_ones_row");
+  if ((rc = bw::gram_matrices(h, Rt, gram, Bi, D, S, Spad, st))) return rc;
   GLORIA_CUDA(cudaMemsetAsync(gamma, 0, (size_t)Bc * lpad * sizeof(float), st));
 
   CUtensorMap rt, wt, gm;
@@ -814,59 +1047,111 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
   for (int i0 = 0; i0 < Bc; i0 += pl.nc) {
     const int nc = min(pl.nc, Bc - i0);
     const int R1 = nc * lpad;
-    bw::PairParams p;
+    bw::PairParams p{};
     p.wnorm = wnorm; p.cap_lens = cap_lens; p.stats = stats; p.dsim = dsim;
     p.xt = X; p.et = E; p.fo = Fo; p.gamma = gamma;
     CUtensorMap em;
     if ((rc = make_map3(&em, E, (uint64_t)lpad, (uint64_t)nc, (uint64_t)K1, (uint64_t)lpad, (uint64_t)R1, TILE))) return rc;
     p.Bi = Bi; p.Bc = Bc; p.i0 = i0; p.nc = nc; p.D = D; p.S = S; p.NT = Spad / TILE;
-    p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps;
+    p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps; p.agg = agg;
     p.dbg = (long long*)g_phase_clock_buffer;
-    switch (lpad) {
-      case 16: rc = bw::launch_pair<16>(rt, wt, gm, em, p, sms, st); break;
-      case 32: rc = bw::launch_pair<32>(rt, wt, gm, em, p, sms, st); break;
-      case 48: rc = bw::launch_pair<48>(rt, wt, gm, em, p, sms, st); break;
-      case 64: rc = bw::launch_pair<64>(rt, wt, gm, em, p, sms, st); break;
-      case 80: rc = bw::launch_pair<80>(rt, wt, gm, em, p, sms, st); break;
-      case 96: rc = bw::launch_pair<96>(rt, wt, gm, em, p, sms, st); break;
-      case 112: rc = bw::launch_pair<112>(rt, wt, gm, em, p, sms, st); break;
-      case 128: rc = bw::launch_pair<128>(rt, wt, gm, em, p, sms, st); break;
-      default: rc = fail(GLORIA_ERR_UNSUPPORTED, "lpad %d", lpad);
-    }
-    if (rc) return rc;
+    if ((rc = bw::launch_pair_lpad<false>(lpad, rt, wt, gm, em, p, sms, st))) return rc;
     timer_record(GLORIA_TIMER_TC_BWD_GEMM, 0, st);
     bw::scale_rows<<<dim3((unsigned)((R1 / 8 + 255) / 256), (unsigned)(Spad / bw::SCALE_ROWS), (unsigned)Bi), 256, 0, st>>>(
-        E, Fo, Bm, R1, Spad);
+        E, Fo, Bm, R1, Spad, nullptr, Bc, i0, lpad);
     GLORIA_LAUNCHED("scale_rows");
-    const float beta = i0 == 0 ? 0.f : 1.f;
-    // dWt[(i,l), d] = sum_(j,s) X^T[(j,s),(i,l)] Rt[(j,s), d]            (column-major: [D, R1] = Rt^T . (X^T)^T)
-    GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, R1, K1, &one, Rt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1,
-                               &zero, dWt + (size_t)i0 * lpad * D, CUDA_R_32F, D, CUBLAS_COMPUTE_32F,
-                               CUBLAS_GEMM_DEFAULT));
-    // dRt[(j,s), d] (+)= sum_(i,l) X^T[(j,s),(i,l)] Wt[(i,l), d]         (column-major: [D, K1] = Wt^T . X^T)
-    GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, K1, R1, &one, Wt + (size_t)i0 * lpad * D, CUDA_R_16BF,
-                               D, X, CUDA_R_16BF, R1, &beta, dRt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F,
-                               CUBLAS_GEMM_DEFAULT));
-    // M_j[a, b] (+)= sum_(i,l) E^T[(j,a),(i,l)] Bo^T[(j,b),(i,l)]
-    GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_T, CUBLAS_OP_N, Spad, Spad, R1, &one, E, CUDA_R_16BF, R1,
-                                             (long long)Spad * R1, Bm, CUDA_R_16BF, R1, (long long)Spad * R1, &beta,
-                                             Mf, CUDA_R_32F, Spad, (long long)Spad * Spad, Bi, CUBLAS_COMPUTE_32F,
-                                             CUBLAS_GEMM_DEFAULT));
+    if ((rc = bw::accumulate_chunk(h, Rt, Wt, X, E, Bm, dWt, dRt, Mf, Bi, D, Spad, lpad, i0, nc, i0 == 0))) return rc;
     if (i0 + nc < Bc) timer_record(GLORIA_TIMER_TC_BWD_GEMM, 1, st);
   }
-  // dRt_j += M_j Rt_j   (M_j symmetric up to rounding; column-major: [D, Spad] = Rt_j^T . M_j)
-  const size_t nm = (size_t)Bi * Spad * Spad;
-  bw::f32_to_bf16<<<(unsigned)((nm / 4 + 255) / 256), 256, 0, st>>>(Mf, Mb, nm);
-  GLORIA_LAUNCHED("f32_to_bf16");
-  GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, Spad, Spad, &one, Rt, CUDA_R_16BF, D,
-                                           (long long)Spad * D, Mb, CUDA_R_16BF, Spad, (long long)Spad * Spad, &one,
-                                           dRt, CUDA_R_32F, D, (long long)Spad * D, Bi, CUBLAS_COMPUTE_32F,
-                                           CUBLAS_GEMM_DEFAULT));
-  timer_record(GLORIA_TIMER_TC_BWD_GEMM, 1, st);
-  bw::unpack_dctx<<<dim3((S + 31) / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(dRt, d_ctx, D, S, Spad);
-  GLORIA_LAUNCHED("unpack_dctx");
-  bw::unpack_dwords_tc<<<dim3((Lw + 31) / 32, D / 32, Bc), dim3(32, 8), 0, st>>>(dWt, gamma, Wt, cap_lens, d_words, D,
-                                                                               Lw, lpad, Lcap, word_off);
-  GLORIA_LAUNCHED("unpack_dwords_tc");
-  return GLORIA_OK;
+  return bw::finish_backward(h, Rt, Wt, cap_lens, dWt, dRt, Mf, Mb, gamma, d_ctx, d_words, Bi, Bc, D, S, Spad, Lw, lpad,
+                             Lcap, word_off, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused training path
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" size_t gloria_b200_tc_train_workspace(int Bi, int Bc, int D, int S, int Lcap) {
+  if (Bi <= 0 || Bc <= 0 || gloria_b200_tc_supported(D, S, Lcap)) return 0;
+  return bw::train_plan(Bi, Bc, D, gloria_b200_tc_spad(S), gloria_b200_tc_lpad(Lcap)).total;
+}
+
+extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void* ctx_t, const void* words_h,
+                                                  const float* wnorm, const int32_t* cap_lens, int Bi, int Bc, int D,
+                                                  int S, int Lcap, float temp1, float temp2, int agg, float eps,
+                                                  float* sim, void* workspace, size_t workspace_bytes, void* stream) {
+  GLORIA_CHECK_ARG(ctx_h && ctx_t && words_h && wnorm && cap_lens && sim && workspace, "null pointer");
+  GLORIA_CHECK_ARG(Bi > 0 && Bc > 0, "bad batch sizes %d x %d", Bi, Bc);
+  if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
+  if (agg == GLORIA_AGG_MAX) return fail(GLORIA_ERR_UNSUPPORTED, "agg=max has no backward: use the plain forward");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
+  const bw::TrainPlan pl = bw::train_plan(Bi, Bc, D, Spad, lpad);
+  if (workspace_bytes < pl.total) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, pl.total);
+  char* ws = (char*)workspace;
+  __nv_bfloat16* gram = (__nv_bfloat16*)(ws + pl.off_gram);
+  cublasHandle_t h = bw::cublas_handle();
+  if (!h) return fail(GLORIA_ERR_DRIVER, "cublasCreate failed");
+  GLORIA_CUBLAS(cublasSetStream(h, st));
+  GLORIA_CUBLAS(cublasSetWorkspace(h, ws + pl.off_cublas, bw::CUBLAS_WS));
+  int rc;
+  if ((rc = bw::gram_matrices(h, (const __nv_bfloat16*)ctx_t, gram, Bi, D, S, Spad, st))) return rc;
+  CUtensorMap rt, wt, gm, em;
+  const int K1 = Bi * Spad, R1 = Bc * lpad;
+  if ((rc = make_map(&rt, ctx_h, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;
+  if ((rc = make_map(&wt, words_h, (uint64_t)D, (uint64_t)Bc * lpad, (uint32_t)lpad))) return rc;
+  if ((rc = make_map(&gm, gram, (uint64_t)Spad, (uint64_t)Bi * Spad, TILE))) return rc;
+  if ((rc = make_map3(&em, ws + pl.off_e, (uint64_t)lpad, (uint64_t)Bc, (uint64_t)K1, (uint64_t)lpad, (uint64_t)R1, TILE)))
+    return rc;
+  int dev = 0, sms = 0;
+  GLORIA_CUDA(cudaGetDevice(&dev));
+  GLORIA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  bw::PairParams p{};
+  p.wnorm = wnorm; p.cap_lens = cap_lens; p.stats = nullptr; p.dsim = nullptr;
+  p.xt = (__nv_bfloat16*)(ws + pl.off_x); p.et = (__nv_bfloat16*)(ws + pl.off_e);
+  p.fo = (float*)(ws + pl.off_fo); p.go = (float*)(ws + pl.off_go); p.gamma = nullptr; p.sim = sim;
+  p.Bi = Bi; p.Bc = Bc; p.i0 = 0; p.nc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE;
+  p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps; p.agg = agg;
+  p.dbg = (long long*)g_phase_clock_buffer;
+  return bw::launch_pair_lpad<true>(lpad, rt, wt, gm, em, p, sms, st);
+}
+
+extern "C" int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void* words_t, const int32_t* cap_lens,
+                                                  int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                                  const float* dsim, float* d_ctx, float* d_words, void* workspace,
+                                                  size_t workspace_bytes, void* stream) {
+  GLORIA_CHECK_ARG(ctx_t && words_t && cap_lens && dsim && d_ctx && d_words && workspace, "null pointer");
+  GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
+  if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
+  const bw::TrainPlan pl = bw::train_plan(Bi, Bc, D, Spad, lpad);
+  if (workspace_bytes < pl.total) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, pl.total);
+  char* ws = (char*)workspace;
+  __nv_bfloat16* X = (__nv_bfloat16*)(ws + pl.off_x);
+  __nv_bfloat16* E = (__nv_bfloat16*)(ws + pl.off_e);
+  __nv_bfloat16* Bm = (__nv_bfloat16*)(ws + pl.off_b);
+  float* gamma = (float*)(ws + pl.off_gamma);
+  cublasHandle_t h = bw::cublas_handle();
+  if (!h) return fail(GLORIA_ERR_DRIVER, "cublasCreate failed");
+  GLORIA_CUBLAS(cublasSetStream(h, st));
+  GLORIA_CUBLAS(cublasSetWorkspace(h, ws + pl.off_cublas, bw::CUBLAS_WS));
+  const int R1 = Bc * lpad;
+  const dim3 sgrid((unsigned)((R1 / 8 + 255) / 256), (unsigned)(Spad / bw::SCALE_ROWS), (unsigned)Bi);
+  timer_record(GLORIA_TIMER_TC_BWD_GEMM, 0, st);
+  // everything the forward stored is for g = 1 and linear in g = dsim[j, i]: apply it now
+  bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, Spad, Bc, 0, lpad);
+  GLORIA_LAUNCHED("scale_x");
+  bw::scale_rows<<<sgrid, 256, 0, st>>>(E, (const float*)(ws + pl.off_fo), Bm, R1, Spad, dsim, Bc, 0, lpad);
+  GLORIA_LAUNCHED("scale_rows");
+  bw::gamma_sum<<<(R1 + 255) / 256, 256, 0, st>>>((const float*)(ws + pl.off_go), dsim, gamma, Bi, R1, Bc, 0, lpad);
+  GLORIA_LAUNCHED("gamma_sum");
+  int rc;
+  if ((rc = bw::accumulate_chunk(h, (const __nv_bfloat16*)ctx_t, (const __nv_bfloat16*)words_t, X, E, Bm,
+                                 (float*)(ws + pl.off_dwt), (float*)(ws + pl.off_drt), (float*)(ws + pl.off_m), Bi, D,
+                                 Spad, lpad, 0, Bc, true)))
+    return rc;
+  return bw::finish_backward(h, (const __nv_bfloat16*)ctx_t, (const __nv_bfloat16*)words_t, cap_lens,
+                             (float*)(ws + pl.off_dwt), (float*)(ws + pl.off_drt), (float*)(ws + pl.off_m),
+                             (__nv_bfloat16*)(ws + pl.off_mb), gamma, d_ctx, d_words, Bi, Bc, D, S, Spad, Lw, lpad, Lcap,
+                             word_off, st);
 }

@@ -20,6 +20,7 @@ MODE_FP32, MODE_BF16 = 0, 1
 
 _WS_BUDGET = int(os.environ.get("GLORIA_B200_WS_BYTES", str(4 << 30)))            # fp32 kernels
 _TC_WS_BUDGET = int(os.environ.get("GLORIA_B200_TC_WS_BYTES", str(96 << 30)))     # bf16 backward operand matrices
+_FUSED_TRAIN = os.environ.get("GLORIA_B200_FUSED_TRAIN", "1") != "0"               # fused forward+backward-operand kernel
 
 
 class Packed:
@@ -112,13 +113,32 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                 raise RuntimeError(f"bf16 tensor-core kernels need D % 128 == 0, S <= 384, cap_len <= 128; got "
                                    f"D={D} S={S} Lcap={lcap} (use set_precision('fp32'))")
             packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
-            if agg != AGG["max"] and (ctx.requires_grad or words.requires_grad or torch.is_grad_enabled()):
-                stats = torch.empty((Bi, Bc, 2, L.gloria_b200_tc_lpad(lcap)), dtype=torch.float32, device=dev)
-            rc = L.gloria_b200_tc_local_sim_fwd(packed.ctx_h.data_ptr(), packed.ctx_n.data_ptr(),
-                                                packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
-                                                cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg, eps,
-                                                sim.data_ptr(), _ptr(stats), _stream(ctx))
-            _lib.check(rc, "tc_local_sim_fwd")
+            need_grad = agg != AGG["max"] and (ctx.requires_grad or words.requires_grad or torch.is_grad_enabled())
+            fused = False
+            if need_grad and _FUSED_TRAIN:
+                # fused training forward: sim AND the backward's operand rows (for dsim = 1) in one kernel; the state
+                # tensor is the workspace the backward consumes.  Falls back to forward + recompute-backward when the
+                # workspace does not fit.
+                nbytes = L.gloria_b200_tc_train_workspace(Bi, Bc, D, S, lcap)
+                free, _ = torch.cuda.mem_get_info(dev)
+                avail = free + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+                if 0 < nbytes <= min(_TC_WS_BUDGET, int(avail * 0.92)):
+                    stats = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+                    rc = L.gloria_b200_tc_local_sim_fwd_train(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(),
+                                                              packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
+                                                              cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg,
+                                                              eps, sim.data_ptr(), stats.data_ptr(), nbytes,
+                                                              _stream(ctx))
+                    _lib.check(rc, "tc_local_sim_fwd_train")
+                    fused = True
+            if not fused:
+                if need_grad:
+                    stats = torch.empty((Bi, Bc, 2, L.gloria_b200_tc_lpad(lcap)), dtype=torch.float32, device=dev)
+                rc = L.gloria_b200_tc_local_sim_fwd(packed.ctx_h.data_ptr(), packed.ctx_n.data_ptr(),
+                                                    packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
+                                                    cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg, eps,
+                                                    sim.data_ptr(), _ptr(stats), _stream(ctx))
+                _lib.check(rc, "tc_local_sim_fwd")
             if want_diag:
                 if Bi != Bc:
                     raise RuntimeError(f"diagonal attention maps need as many images as captions, got {Bi} x {Bc}")
@@ -213,6 +233,17 @@ def tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp
     _pack_cache_trim()
     if packed is None or packed.ctx_h.shape[0] != Bi or packed.words_h.shape[0] != Bc:
         packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
+    if have and stats.dtype == torch.uint8:
+        # state of the fused training forward: scale by dsim + accumulation GEMMs, nothing is recomputed
+        if getattr(stats, "_gloria_consumed", False):
+            raise RuntimeError("gloria_b200: the fused training state was already consumed by a backward pass "
+                               "(set GLORIA_B200_FUSED_TRAIN=0 to differentiate the same forward twice)")
+        rc = L.gloria_b200_tc_local_sim_bwd_train(packed.ctx_t.data_ptr(), packed.words_t.data_ptr(), cap_lens.data_ptr(),
+                                                  Bi, Bc, D, S, Lw, lcap, word_off, dsim.data_ptr(), d_ctx.data_ptr(),
+                                                  d_words.data_ptr(), stats.data_ptr(), stats.numel(), _stream(ctx))
+        _lib.check(rc, "tc_local_sim_bwd_train")
+        stats._gloria_consumed = True
+        return
     free, _ = torch.cuda.mem_get_info(ctx.device)
     budget = min(_TC_WS_BUDGET, int(free * 0.9) + torch.cuda.memory_reserved(ctx.device)
                  - torch.cuda.memory_allocated(ctx.device))

@@ -173,6 +173,21 @@ int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t, const voi
                                  const float* dsim, float* d_ctx, float* d_words,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Fused training path (used when the workspace fits): every backward quantity of a pair is linear in
+ * g = dsim[j, i], so ONE kernel computes sim and, for g = 1, the backward operand rows (X^T, E^T, f, gamma) during the
+ * forward; the backward is a scale by g plus the accumulation GEMMs -- nothing is recomputed.  The same workspace
+ * (gloria_b200_tc_train_workspace bytes; 69 GB at B = 512) is passed to both calls and must stay untouched in between;
+ * the backward consumes it (X is scaled in place), so it can run once per forward. */
+size_t gloria_b200_tc_train_workspace(int Bi, int Bc, int D, int S, int Lcap);
+int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void* ctx_t, const void* words_h, const float* wnorm,
+                                       const int32_t* cap_lens, int Bi, int Bc, int D, int S, int Lcap,
+                                       float temp1, float temp2, int agg, float eps, float* sim,
+                                       void* workspace, size_t workspace_bytes, void* stream);
+int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void* words_t, const int32_t* cap_lens,
+                                       int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                       const float* dsim, float* d_ctx, float* d_words,
+                                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Global similarity (global_loss, gloria_loss.py:75-80; get_global_similarities, gloria_model.py:164-169):
  *   cosm[a, b] = <x_a, y_b> / max(|x_a| |y_b|, eps),  x [Bi, D], y [Bc, D];  xn [Bi], yn [Bc] are saved norms.
