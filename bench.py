@@ -32,6 +32,10 @@ D, H, W, LW = 768, 19, 19, 97
 S = H * W
 WORKLOADS = {"b512": 512, "b48": 48}
 CPU_SAMPLE = 16          # the CPU arm times a CPU_SAMPLE x CPU_SAMPLE block of the B x B pair grid
+# DRAM bytes per launch (read + write) of the dominant kernels at B=512, N=1, from the ncu captures under profiles/
+TRAFFIC_B512 = {("tc_fwd_kernel", False): 2511333120 + 237689344,            # r01_traffic_B512_ncu.csv
+                ("tc_bwd_pair_kernel", False): 5648215808 + 45244279296,
+                ("tc_fwd_kernel", True): 17035313920 + 45348764416}           # r01_final_bench_B512_ncu_launch_list.txt
 
 
 def parse():
@@ -307,27 +311,36 @@ def run_b200(args):
     pairs_grid = B * n                                      # (image, caption) cells per rank
     f_fwd = 4.0 * S * D * pairs_grid * LW                   # algorithmic FLOPs, SURVEY 8d (per rank)
     f_step = 3.0 * f_fwd
-    kern_flops = {"tc_fwd_kernel": f_fwd, "tc_bwd_pair_kernel": 2.0 * f_fwd, "bwd_accum_gemms": 2.0 * f_fwd}
-    dom = max(kt, key=lambda k: kt[k]) if any(kt.values()) else None
+    # Algorithmic FLOPs (12 S D L per pair and step, no recompute credit) attributed per timed kernel.
+    # Fused training path (timer slot 0 = tc_bwd_pair_kernel<FUSED>): forward 4SDL + the backward's dC^T R 2SDL in the
+    # fused kernel, the remaining 6SDL (dW, dR, dC A) in the accumulation phase.  Recompute path: forward kernel 4SDL,
+    # pair kernel + accumulation 8SDL.
+    fused = kt["tc_bwd_pair_kernel"] < 0.05 * max(kt["tc_fwd_kernel"], 1e-9)
+    if fused:
+        names_ = {"tc_fwd_kernel": "tc_fused_train_kernel (tc_bwd_pair_kernel<LPAD, FUSED=true>)",
+                  "bwd_accum_gemms": "backward accumulation phase (scale by dsim + cuBLAS GEMMs)"}
+        kflops = {"tc_fwd_kernel": 1.5 * f_fwd, "bwd_accum_gemms": 1.5 * f_fwd}
+        kt_rep = {names_[k]: round(kt[k], 4) for k in names_}
+    else:
+        names_ = {"tc_fwd_kernel": "tc_fwd_kernel", "tc_bwd_pair_kernel": "tc_bwd_pair_kernel",
+                  "bwd_accum_gemms": "backward accumulation phase"}
+        kflops = {"tc_fwd_kernel": f_fwd, "tc_bwd_pair_kernel": 1.0 * f_fwd, "bwd_accum_gemms": 1.0 * f_fwd}
+        kt_rep = {names_[k]: round(kt[k], 4) for k in names_}
+    cand = [k for k in kflops if kt[k] > 0 and k != "bwd_accum_gemms"] or [k for k in kflops if kt[k] > 0]
+    dom = max(cand, key=lambda k: kt[k]) if cand else None
     roofline = None
     if dom:
-        # the backward's algorithmic FLOPs (2 x forward) are spread over the pair kernel and the accumulation GEMMs;
-        # credit them to the backward as a whole and report the dominant piece with its share of that time
-        if dom == "tc_fwd_kernel":
-            ach, t_dom = f_fwd / (kt[dom] * 1e-3) / 1e12, kt[dom]
-        else:
-            t_dom = kt["tc_bwd_pair_kernel"] + kt["bwd_accum_gemms"]
-            ach = 2.0 * f_fwd / (t_dom * 1e-3) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r01_traffic_B512_ncu.csv (B=512, N=1)
+        ach = kflops[dom] / (kt[dom] * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/ (B=512, N=1 captures), else null
         traffic = None
         if args.workload == "b512" and world == 1:
-            traffic = {"tc_fwd_kernel": 2511333120 + 237689344, "tc_bwd_pair_kernel": 5648215808 + 45244279296,
-                       "bwd_accum_gemms": None}[dom]
-        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
+            traffic = TRAFFIC_B512.get((dom, fused))
+        roofline = {"bound": "tensor", "kernel": names_[dom], "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
                     "frac": ach / pk["tflops"], "traffic": traffic, "peak_source": pk["src"],
-                    "kernel_ms": {k: round(v, 4) for k, v in kt.items()},
-                    "step_achieved": f_step / (ms * 1e-3) / 1e12, "step_frac": f_step / (ms * 1e-3) / 1e12 / pk["tflops"],
-                    "algorithmic_flops_per_launch": kern_flops[dom] if dom == "tc_fwd_kernel" else 2.0 * f_fwd}
+                    "kernel_ms": kt_rep, "algorithmic_flops_per_launch": kflops[dom],
+                    "step_achieved": f_step / (ms * 1e-3) / 1e12,
+                    "step_frac": f_step / (ms * 1e-3) / 1e12 / pk["tflops"],
+                    "step_frac_of_burst": f_step / (ms * 1e-3) / 1e12 / pk["burst"]}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
