@@ -237,3 +237,73 @@ def test_attention_finetune_through_diagonal_maps(gl):
         d_maps.append(np.broadcast_to(d_mm / mp_.shape[1], mp_.shape[1:]).copy()[None])
     d_img, d_txt = O.local_loss_bwd(i64, t64, cl, g0=0.0, g1=0.0, d_att_maps=d_maps)
     assert relerr(img.grad, d_img) < 1e-3 and relerr(txt.grad, d_txt) < 1e-3
+
+
+def test_fused_training_path_c_abi(gl):
+    """C ABI of the fused training path: fwd_train gives the same sim as the plain forward (bit-for-bit inputs, same
+    arithmetic up to the Gram-form reductions), bwd_train the same gradients as the recompute backward for an arbitrary
+    dsim; rectangular Bi != Bc."""
+    from gloria_nlp_project_b200 import _lib, ops
+    L = _lib.lib()
+    Bi, Bc = 7, 5
+    img_l, txt_l, _, _, _ = gen_inputs(29, Bi, 768, 19, 19, 97, scale=0.05, dtype=np.float32)
+    cl = [97, 50, 33, 8, 2]
+    txt_l = txt_l[:Bc].copy()
+    for i, Lc in enumerate(cl):
+        txt_l[i, :, Lc:] = 0
+    ctx, words = cu(img_l).reshape(Bi, 768, 361), cu(txt_l)
+    lens = torch.tensor(cl, dtype=torch.int32, device="cuda")
+    lcap = max(cl)
+    pk = ops.tc_prepack(ctx, words, lens, lcap, 0)
+    st = torch.cuda.current_stream().cuda_stream
+    lpad = L.gloria_b200_tc_lpad(lcap)
+    sim0 = torch.empty(Bi, Bc, device="cuda")
+    stats = torch.empty(Bi, Bc, 2, lpad, device="cuda")
+    _lib.check(L.gloria_b200_tc_local_sim_fwd(pk.ctx_h.data_ptr(), pk.ctx_n.data_ptr(), pk.words_h.data_ptr(),
+                                              pk.wnorm.data_ptr(), lens.data_ptr(), Bi, Bc, 768, 361, lcap, 4.0, 5.0, 0,
+                                              1e-8, sim0.data_ptr(), stats.data_ptr(), st), "fwd")
+    n = L.gloria_b200_tc_train_workspace(Bi, Bc, 768, 361, lcap)
+    assert n > 0
+    tws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    sim1 = torch.empty(Bi, Bc, device="cuda")
+    _lib.check(L.gloria_b200_tc_local_sim_fwd_train(pk.ctx_h.data_ptr(), pk.ctx_t.data_ptr(), pk.words_h.data_ptr(),
+                                                    pk.wnorm.data_ptr(), lens.data_ptr(), Bi, Bc, 768, 361, lcap, 4.0,
+                                                    5.0, 0, 1e-8, sim1.data_ptr(), tws.data_ptr(), n, st), "fwd_train")
+    torch.cuda.synchronize()
+    ref = O.local_similarities(img_l.astype(np.float64), txt_l.astype(np.float64), cl)
+    assert relerr(sim1, ref) < LOGIT_TOL and relerr(sim0, ref) < LOGIT_TOL
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    dsim = torch.randn(Bi, Bc, device="cuda", generator=gen) * 0.1
+    d_ctx1, d_words1 = torch.empty_like(ctx), torch.empty_like(words)
+    _lib.check(L.gloria_b200_tc_local_sim_bwd_train(pk.ctx_t.data_ptr(), pk.words_t.data_ptr(), lens.data_ptr(), Bi, Bc,
+                                                    768, 361, 97, lcap, 0, dsim.data_ptr(), d_ctx1.data_ptr(),
+                                                    d_words1.data_ptr(), tws.data_ptr(), n, st), "bwd_train")
+    nb = L.gloria_b200_tc_bwd_workspace(Bi, Bc, 768, 361, lcap, 1, 0)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    d_ctx0, d_words0 = torch.empty_like(ctx), torch.empty_like(words)
+    _lib.check(L.gloria_b200_tc_local_sim_bwd(pk.ctx_h.data_ptr(), pk.ctx_t.data_ptr(), pk.ctx_n.data_ptr(),
+                                              pk.words_h.data_ptr(), pk.words_t.data_ptr(), pk.wnorm.data_ptr(),
+                                              lens.data_ptr(), stats.data_ptr(), Bi, Bc, 768, 361, 97, lcap, 0, 4.0, 5.0, 0,
+                                              1e-8, dsim.data_ptr(), d_ctx0.data_ptr(), d_words0.data_ptr(), ws.data_ptr(),
+                                              nb, st), "bwd")
+    torch.cuda.synchronize()
+    # the two paths round X differently (fused: bf16(g * bf16(X for g=1))), each must sit inside the gradient gate
+    assert relerr(d_ctx1, d_ctx0) < GRAD_TOL and relerr(d_words1, d_words0) < GRAD_TOL
+    ctx64, w64, g = img_l.astype(np.float64).reshape(Bi, 768, 361), txt_l.astype(np.float64), dsim.cpu().numpy().astype(np.float64)
+    d_ctx_o, d_w_o = np.zeros_like(ctx64), np.zeros_like(w64)
+    for i, Lc in enumerate(cl):
+        dc, dw = O.local_sim_pair_bwd(ctx64, w64[i, :, :Lc], 4.0, 5.0, g[:, i])
+        d_ctx_o += dc
+        d_w_o[i, :, :Lc] = dw
+    assert relerr(d_ctx1, d_ctx_o) < GRAD_TOL and relerr(d_words1, d_w_o) < GRAD_TOL
+
+
+def test_fused_state_is_consumed_once(gl):
+    """The fused backward scales its state in place: a second backward through the same forward must raise, not
+    silently return gradients scaled twice."""
+    img_l, txt_l, _, _, cl = gen_inputs(30, 3, 768, 19, 19, 97, cap_lens=[20, 11, 4], scale=0.05, dtype=np.float32)
+    img, txt = cu(img_l, True), cu(txt_l, True)
+    l0, l1, *_ = gl.local_loss(img, txt, cl)
+    (l0 + l1).backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="consumed"):
+        (l0 + l1).backward()
