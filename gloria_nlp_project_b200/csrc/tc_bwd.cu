@@ -62,6 +62,7 @@ struct PairParams {
   int agg;                  // FUSED: GLORIA_AGG_SUM / _MEAN
   float* gamma;             // [Bc, LPAD]  sum_j (dL/d|W_l|) / |W_l|   (atomicAdd)
   int Bi, Bc, i0, nc, D, S, NT;
+  int lp;                   // column pitch per caption of X^T / E^T / fo / go: round_up(Lcap, 8) <= LPAD
   float t1, t1_log2e, t2, eps;
   long long* dbg;           // phase clocks (only read when built with -DGLORIA_PHASE_CLOCKS)
 };
@@ -367,7 +368,8 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
       }
       asm volatile("bar.sync 1, 384;" ::: "memory");
       float gacc = 0.f;
-      const size_t pitch = (size_t)p.nc * LPAD;
+      const size_t pitch = (size_t)p.nc * p.lp;
+      const int nchs = p.lp >> 3;                      // chunks that exist in the output matrices
       for (int j = u.j; j < u.j_end; ++j) {
         // per-word inputs of the coefficient step (thread wl owns word l = wl); latency hidden by the softmax
         float dotp = 0.f, c2p = 0.f;
@@ -567,9 +569,9 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                 coefX[wl] = live ? ddot * iz : 0.f;
               }
-              if (wl < LPAD) p.fo[((size_t)j * p.nc + u.i) * LPAD + wl] = live ? beta * iz * iz : 0.f;
+              if (wl < p.lp) p.fo[((size_t)j * p.nc + u.i) * p.lp + wl] = live ? beta * iz * iz : 0.f;
               if (FUSED) {
-                if (wl < LPAD) p.go[((size_t)j * p.nc + u.i) * LPAD + wl] = live ? gamma : 0.f;
+                if (wl < p.lp) p.go[((size_t)j * p.nc + u.i) * p.lp + wl] = live ? gamma : 0.f;
                 if (wl == 0) {      // sim = log sum_l exp(t2 cos_l)  (mean: minus log L), gloria_loss.py:153-158
                   float r = mx + logf(tot);
                   if (p.agg == GLORIA_AGG_MEAN) r -= logf((float)L);
@@ -632,12 +634,12 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             STIMED(sw_bar, asm volatile("bar.sync 1, 384;" ::: "memory"));
             const float uacc = xb[row].x + xb[128 + row].x + xb[256 + row].x;
             // pass 2: rows of X^T  ([(j, s), (i, l)] bf16, 16-byte stores along l)
-            const size_t goff = ((size_t)j * Spad + s_glob) * pitch + (size_t)u.i * LPAD;
+            const size_t goff = ((size_t)j * Spad + s_glob) * pitch + (size_t)u.i * p.lp;
             uint4* xo = reinterpret_cast<uint4*>(p.xt + goff);
 #pragma unroll
             for (int c = 0; c < CW; ++c) {
               const int ch = c_lo + c;
-              if (ch < NCH) {
+              if (ch < nchs) {
                 const uint4 ev = *reinterpret_cast<const uint4*>(erow + (size_t)(ch >> 3) * e_blk +
                                                                  (size_t)((((uint32_t)ch & 7u) ^ sw) << 4));
                 const float4 x0 = *reinterpret_cast<const float4*>(cX + c * 8);
@@ -652,14 +654,18 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
                   const float P0 = bf_lo(pp[o >> 1]), P1 = bf_hi(pp[o >> 1]);
                   xw[k >> 1] = pack_bf16(fmaf(ce[k], e0, P0 * (dp[o] - uacc)), fmaf(ce[k + 1], e1, P1 * (dp[o + 1] - uacc)));
                 }
+#ifdef GLORIA_EXP_NOSTORE
+                if (xw[0] == 0x12345678u && xw[3] == 0x9abcdef0u) xo[ch] = make_uint4(xw[0], xw[1], xw[2], xw[3]);
+#else
                 xo[ch] = make_uint4(xw[0], xw[1], xw[2], xw[3]);
+#endif
               }
             }
           }
         }
         ++n;
       }
-      if (!FUSED && wl < LPAD && gacc != 0.f) atomicAdd(p.gamma + (size_t)i * LPAD + wl, gacc);
+      if (!FUSED && wl < p.lp && gacc != 0.f) atomicAdd(p.gamma + (size_t)i * p.lp + wl, gacc);
     }
 #ifdef GLORIA_PHASE_CLOCKS
     if (g_dbg && (lane == 0) && (q == 0)) {
@@ -805,41 +811,42 @@ struct Plan {
 };
 constexpr size_t CUBLAS_WS = 64u << 20;
 
-size_t fixed_bytes(int Bi, int Bc, int D, int Spad, int lpad, bool own_stats, Plan* pl) {
+// lp = column pitch of the operand matrices (round_up(Lcap, 8)), lpad = the kernels' word padding (stats pitch)
+size_t fixed_bytes(int Bi, int Bc, int D, int Spad, int lp, int lpad, bool own_stats, Plan* pl) {
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += align_up(n, 1024); return r; };
   Plan t{};
   t.off_gram = take((size_t)Bi * Spad * Spad * 2);
-  t.off_dwt = take((size_t)Bc * lpad * D * 4);
+  t.off_dwt = take((size_t)Bc * lp * D * 4);
   t.off_drt = take((size_t)Bi * Spad * D * 4);
   t.off_m = take((size_t)Bi * Spad * Spad * 4);
   t.off_mb = take((size_t)Bi * Spad * Spad * 2);
-  t.off_gamma = take((size_t)Bc * lpad * 4);
+  t.off_gamma = take((size_t)Bc * lp * 4);
   t.off_stats = take(own_stats ? (size_t)Bi * Bc * 2 * lpad * 4 : 0);
   t.off_sim = take(own_stats ? (size_t)Bi * Bc * 4 : 0);
   t.off_cublas = take(CUBLAS_WS);
   if (pl) *pl = t;
   return o;
 }
-size_t per_caption_bytes(int Bi, int Spad, int lpad) {
-  return 3 * align_up((size_t)Bi * Spad * lpad * 2, 1024) + align_up((size_t)Bi * lpad * 4, 1024) + 4096;
+size_t per_caption_bytes(int Bi, int Spad, int lp) {
+  return 3 * align_up((size_t)Bi * Spad * lp * 2, 1024) + align_up((size_t)Bi * lp * 4, 1024) + 4096;
 }
 
-Plan make_plan(int Bi, int Bc, int D, int Spad, int lpad, bool own_stats, size_t bytes) {
+Plan make_plan(int Bi, int Bc, int D, int Spad, int lp, int lpad, bool own_stats, size_t bytes) {
   Plan pl{};
-  const size_t fixed = fixed_bytes(Bi, Bc, D, Spad, lpad, own_stats, &pl);
-  const size_t per = per_caption_bytes(Bi, Spad, lpad);
+  const size_t fixed = fixed_bytes(Bi, Bc, D, Spad, lp, lpad, own_stats, &pl);
+  const size_t per = per_caption_bytes(Bi, Spad, lp);
   if (bytes < fixed + per) { pl.nc = 0; return pl; }
   size_t nc = (bytes - fixed) / per;
   if (nc > (size_t)Bc) nc = Bc;
   pl.nc = (int)nc;
   size_t o = fixed;
   auto take = [&](size_t n) { size_t r = o; o += align_up(n, 1024); return r; };
-  const size_t arr = (size_t)Bi * Spad * nc * lpad * 2;
+  const size_t arr = (size_t)Bi * Spad * nc * lp * 2;
   pl.off_x = take(arr);
   pl.off_e = take(arr);
   pl.off_b = take(arr);
-  pl.off_f = take((size_t)Bi * nc * lpad * 4);
+  pl.off_f = take((size_t)Bi * nc * lp * 4);
   pl.total = o;
   if (pl.total > bytes) pl.nc = 0;
   return pl;
@@ -979,9 +986,9 @@ using namespace gloria::tc;
 
 extern "C" size_t gloria_b200_tc_bwd_workspace(int Bi, int Bc, int D, int S, int Lcap, int have_stats, size_t budget) {
   if (Bi <= 0 || Bc <= 0 || gloria_b200_tc_supported(D, S, Lcap)) return 0;
-  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
-  const size_t fixed = bw::fixed_bytes(Bi, Bc, D, Spad, lpad, !have_stats, nullptr);
-  const size_t per = bw::per_caption_bytes(Bi, Spad, lpad);
+  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap), lp = gloria_b200_tc_lp(Lcap);
+  const size_t fixed = bw::fixed_bytes(Bi, Bc, D, Spad, lp, lpad, !have_stats, nullptr);
+  const size_t per = bw::per_caption_bytes(Bi, Spad, lp);
   size_t want = fixed + per * (size_t)Bc;
   if (budget != 0 && want > budget) {
     size_t nc = budget > fixed + per ? (budget - fixed) / per : 1;
@@ -1004,8 +1011,8 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
   if (agg == GLORIA_AGG_MAX) return fail(GLORIA_ERR_UNSUPPORTED, "backward of agg=max is not part of the path");
   cudaStream_t st = (cudaStream_t)stream;
-  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
-  const bw::Plan pl = bw::make_plan(Bi, Bc, D, Spad, lpad, stats == nullptr, workspace_bytes);
+  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap), lp = gloria_b200_tc_lp(Lcap);
+  const bw::Plan pl = bw::make_plan(Bi, Bc, D, Spad, lp, lpad, stats == nullptr, workspace_bytes);
   if (pl.nc < 1) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B too small", workspace_bytes);
   char* ws = (char*)workspace;
   __nv_bfloat16* gram = (__nv_bfloat16*)(ws + pl.off_gram);
@@ -1033,7 +1040,7 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
   const __nv_bfloat16* Rt = (const __nv_bfloat16*)ctx_t;
   const __nv_bfloat16* Wt = (const __nv_bfloat16*)words_t;
   if ((rc = bw::gram_matrices(h, Rt, gram, Bi, D, S, Spad, st))) return rc;
-  GLORIA_CUDA(cudaMemsetAsync(gamma, 0, (size_t)Bc * lpad * sizeof(float), st));
+  GLORIA_CUDA(cudaMemsetAsync(gamma, 0, (size_t)Bc * lp * sizeof(float), st));
 
   CUtensorMap rt, wt, gm;
   if ((rc = make_map(&rt, ctx_h, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;
@@ -1046,24 +1053,24 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
   const int K1 = Bi * Spad;
   for (int i0 = 0; i0 < Bc; i0 += pl.nc) {
     const int nc = min(pl.nc, Bc - i0);
-    const int R1 = nc * lpad;
+    const int R1 = nc * lp;
     bw::PairParams p{};
     p.wnorm = wnorm; p.cap_lens = cap_lens; p.stats = stats; p.dsim = dsim;
     p.xt = X; p.et = E; p.fo = Fo; p.gamma = gamma;
     CUtensorMap em;
-    if ((rc = make_map3(&em, E, (uint64_t)lpad, (uint64_t)nc, (uint64_t)K1, (uint64_t)lpad, (uint64_t)R1, TILE))) return rc;
-    p.Bi = Bi; p.Bc = Bc; p.i0 = i0; p.nc = nc; p.D = D; p.S = S; p.NT = Spad / TILE;
+    if ((rc = make_map3(&em, E, (uint64_t)lp, (uint64_t)nc, (uint64_t)K1, (uint64_t)lp, (uint64_t)R1, TILE))) return rc;
+    p.Bi = Bi; p.Bc = Bc; p.i0 = i0; p.nc = nc; p.D = D; p.S = S; p.NT = Spad / TILE; p.lp = lp;
     p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps; p.agg = agg;
     p.dbg = (long long*)g_phase_clock_buffer;
     if ((rc = bw::launch_pair_lpad<false>(lpad, rt, wt, gm, em, p, sms, st))) return rc;
     timer_record(GLORIA_TIMER_TC_BWD_GEMM, 0, st);
     bw::scale_rows<<<dim3((unsigned)((R1 / 8 + 255) / 256), (unsigned)(Spad / bw::SCALE_ROWS), (unsigned)Bi), 256, 0, st>>>(
-        E, Fo, Bm, R1, Spad, nullptr, Bc, i0, lpad);
+        E, Fo, Bm, R1, Spad, nullptr, Bc, i0, lp);
     GLORIA_LAUNCHED("scale_rows");
-    if ((rc = bw::accumulate_chunk(h, Rt, Wt, X, E, Bm, dWt, dRt, Mf, Bi, D, Spad, lpad, i0, nc, i0 == 0))) return rc;
+    if ((rc = bw::accumulate_chunk(h, Rt, Wt, X, E, Bm, dWt, dRt, Mf, Bi, D, Spad, lp, i0, nc, i0 == 0))) return rc;
     if (i0 + nc < Bc) timer_record(GLORIA_TIMER_TC_BWD_GEMM, 1, st);
   }
-  return bw::finish_backward(h, Rt, Wt, cap_lens, dWt, dRt, Mf, Mb, gamma, d_ctx, d_words, Bi, Bc, D, S, Spad, Lw, lpad,
+  return bw::finish_backward(h, Rt, Wt, cap_lens, dWt, dRt, Mf, Mb, gamma, d_ctx, d_words, Bi, Bc, D, S, Spad, Lw, lp,
                              Lcap, word_off, st);
 }
 
@@ -1072,7 +1079,7 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" size_t gloria_b200_tc_train_workspace(int Bi, int Bc, int D, int S, int Lcap) {
   if (Bi <= 0 || Bc <= 0 || gloria_b200_tc_supported(D, S, Lcap)) return 0;
-  return bw::train_plan(Bi, Bc, D, gloria_b200_tc_spad(S), gloria_b200_tc_lpad(Lcap)).total;
+  return bw::train_plan(Bi, Bc, D, gloria_b200_tc_spad(S), gloria_b200_tc_lp(Lcap)).total;
 }
 
 extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void* ctx_t, const void* words_h,
@@ -1084,8 +1091,8 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void*
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
   if (agg == GLORIA_AGG_MAX) return fail(GLORIA_ERR_UNSUPPORTED, "agg=max has no backward: use the plain forward");
   cudaStream_t st = (cudaStream_t)stream;
-  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
-  const bw::TrainPlan pl = bw::train_plan(Bi, Bc, D, Spad, lpad);
+  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap), lp = gloria_b200_tc_lp(Lcap);
+  const bw::TrainPlan pl = bw::train_plan(Bi, Bc, D, Spad, lp);
   if (workspace_bytes < pl.total) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, pl.total);
   char* ws = (char*)workspace;
   __nv_bfloat16* gram = (__nv_bfloat16*)(ws + pl.off_gram);
@@ -1096,11 +1103,11 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void*
   int rc;
   if ((rc = bw::gram_matrices(h, (const __nv_bfloat16*)ctx_t, gram, Bi, D, S, Spad, st))) return rc;
   CUtensorMap rt, wt, gm, em;
-  const int K1 = Bi * Spad, R1 = Bc * lpad;
+  const int K1 = Bi * Spad, R1 = Bc * lp;
   if ((rc = make_map(&rt, ctx_h, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;
   if ((rc = make_map(&wt, words_h, (uint64_t)D, (uint64_t)Bc * lpad, (uint32_t)lpad))) return rc;
   if ((rc = make_map(&gm, gram, (uint64_t)Spad, (uint64_t)Bi * Spad, TILE))) return rc;
-  if ((rc = make_map3(&em, ws + pl.off_e, (uint64_t)lpad, (uint64_t)Bc, (uint64_t)K1, (uint64_t)lpad, (uint64_t)R1, TILE)))
+  if ((rc = make_map3(&em, ws + pl.off_e, (uint64_t)lp, (uint64_t)Bc, (uint64_t)K1, (uint64_t)lp, (uint64_t)R1, TILE)))
     return rc;
   int dev = 0, sms = 0;
   GLORIA_CUDA(cudaGetDevice(&dev));
@@ -1109,7 +1116,7 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void*
   p.wnorm = wnorm; p.cap_lens = cap_lens; p.stats = nullptr; p.dsim = nullptr;
   p.xt = (__nv_bfloat16*)(ws + pl.off_x); p.et = (__nv_bfloat16*)(ws + pl.off_e);
   p.fo = (float*)(ws + pl.off_fo); p.go = (float*)(ws + pl.off_go); p.gamma = nullptr; p.sim = sim;
-  p.Bi = Bi; p.Bc = Bc; p.i0 = 0; p.nc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE;
+  p.Bi = Bi; p.Bc = Bc; p.i0 = 0; p.nc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE; p.lp = lp;
   p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps; p.agg = agg;
   p.dbg = (long long*)g_phase_clock_buffer;
   return bw::launch_pair_lpad<true>(lpad, rt, wt, gm, em, p, sms, st);
@@ -1123,8 +1130,8 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void*
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
   cudaStream_t st = (cudaStream_t)stream;
-  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
-  const bw::TrainPlan pl = bw::train_plan(Bi, Bc, D, Spad, lpad);
+  const int Spad = gloria_b200_tc_spad(S), lp = gloria_b200_tc_lp(Lcap);
+  const bw::TrainPlan pl = bw::train_plan(Bi, Bc, D, Spad, lp);
   if (workspace_bytes < pl.total) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, pl.total);
   char* ws = (char*)workspace;
   __nv_bfloat16* X = (__nv_bfloat16*)(ws + pl.off_x);
@@ -1135,23 +1142,23 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void*
   if (!h) return fail(GLORIA_ERR_DRIVER, "cublasCreate failed");
   GLORIA_CUBLAS(cublasSetStream(h, st));
   GLORIA_CUBLAS(cublasSetWorkspace(h, ws + pl.off_cublas, bw::CUBLAS_WS));
-  const int R1 = Bc * lpad;
+  const int R1 = Bc * lp;
   const dim3 sgrid((unsigned)((R1 / 8 + 255) / 256), (unsigned)(Spad / bw::SCALE_ROWS), (unsigned)Bi);
   timer_record(GLORIA_TIMER_TC_BWD_GEMM, 0, st);
   // everything the forward stored is for g = 1 and linear in g = dsim[j, i]: apply it now
-  bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, Spad, Bc, 0, lpad);
+  bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, Spad, Bc, 0, lp);
   GLORIA_LAUNCHED("scale_x");
-  bw::scale_rows<<<sgrid, 256, 0, st>>>(E, (const float*)(ws + pl.off_fo), Bm, R1, Spad, dsim, Bc, 0, lpad);
+  bw::scale_rows<<<sgrid, 256, 0, st>>>(E, (const float*)(ws + pl.off_fo), Bm, R1, Spad, dsim, Bc, 0, lp);
   GLORIA_LAUNCHED("scale_rows");
-  bw::gamma_sum<<<(R1 + 255) / 256, 256, 0, st>>>((const float*)(ws + pl.off_go), dsim, gamma, Bi, R1, Bc, 0, lpad);
+  bw::gamma_sum<<<(R1 + 255) / 256, 256, 0, st>>>((const float*)(ws + pl.off_go), dsim, gamma, Bi, R1, Bc, 0, lp);
   GLORIA_LAUNCHED("gamma_sum");
   int rc;
   if ((rc = bw::accumulate_chunk(h, (const __nv_bfloat16*)ctx_t, (const __nv_bfloat16*)words_t, X, E, Bm,
                                  (float*)(ws + pl.off_dwt), (float*)(ws + pl.off_drt), (float*)(ws + pl.off_m), Bi, D,
-                                 Spad, lpad, 0, Bc, true)))
+                                 Spad, lp, 0, Bc, true)))
     return rc;
   return bw::finish_backward(h, (const __nv_bfloat16*)ctx_t, (const __nv_bfloat16*)words_t, cap_lens,
                              (float*)(ws + pl.off_dwt), (float*)(ws + pl.off_drt), (float*)(ws + pl.off_m),
-                             (__nv_bfloat16*)(ws + pl.off_mb), gamma, d_ctx, d_words, Bi, Bc, D, S, Spad, Lw, lpad, Lcap,
+                             (__nv_bfloat16*)(ws + pl.off_mb), gamma, d_ctx, d_words, Bi, Bc, D, S, Spad, Lw, lp, Lcap,
                              word_off, st);
 }

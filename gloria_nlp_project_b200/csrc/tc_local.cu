@@ -370,7 +370,7 @@ __global__ void pack_ctx(const float* __restrict__ ctx, __nv_bfloat16* __restric
 // words [Bc, D, Lw] -> Wt [Bc, LPAD, D] (rows >= cap_len zero) and wnorm [Bc, LPAD];  grid (LPAD/32.., 1, Bc), block (32, 8)
 __global__ void pack_words(const float* __restrict__ words, const int* __restrict__ cap_lens,
                            __nv_bfloat16* __restrict__ Wt, __half* __restrict__ Wh, float* __restrict__ wnorm, int D,
-                           int Lw, int lpad, int lcap, int off) {
+                           int Lw, int lpad, int lpb, int lcap, int off) {
   __shared__ float t[32][33];
   __shared__ float part[8][32];
   const int i = blockIdx.z, l0 = blockIdx.x * 32;
@@ -388,8 +388,8 @@ __global__ void pack_words(const float* __restrict__ words, const int* __restric
     for (int r = threadIdx.y; r < 32; r += 8) {
       const int l = l0 + r, d = d0 + threadIdx.x;
       if (l < lpad && d < D) {
-        Wt[((size_t)i * lpad + l) * D + d] = __float2bfloat16_rn(t[threadIdx.x][r]);
-        Wh[((size_t)i * lpad + l) * D + d] = __float2half_rn(t[threadIdx.x][r]);
+        if (l < lpb) Wt[((size_t)i * lpb + l) * D + d] = __float2bfloat16_rn(t[threadIdx.x][r]);   // GEMM pitch
+        Wh[((size_t)i * lpad + l) * D + d] = __float2half_rn(t[threadIdx.x][r]);                  // tile pitch
       }
     }
     __syncthreads();
@@ -473,6 +473,7 @@ extern "C" void gloria_b200_debug_phase_clocks(void* device_buffer) { gloria::tc
 
 extern "C" int gloria_b200_tc_spad(int S) { return (S / TILE + 1) * TILE; }
 extern "C" int gloria_b200_tc_lpad(int Lcap) { return (Lcap + 15) / 16 * 16; }
+extern "C" int gloria_b200_tc_lp(int Lcap) { return (Lcap + 7) / 8 * 8; }
 
 extern "C" int gloria_b200_tc_supported(int D, int S, int Lcap) {
   if (D < TILE || D % TILE != 0 || S < 1 || S >= MAX_NT * TILE || Lcap < 1 || Lcap > TILE) return GLORIA_ERR_UNSUPPORTED;
@@ -491,7 +492,8 @@ extern "C" int gloria_b200_tc_prepack(const float* ctx, const float* words, cons
                                                                (__half*)ctx_h, D, S, Spad);
   GLORIA_LAUNCHED("pack_ctx");
   pack_words<<<dim3((lpad + 31) / 32, 1, Bc), dim3(32, 8), 0, st>>>(words, cap_lens, (__nv_bfloat16*)words_t,
-                                                                    (__half*)words_h, wnorm, D, Lw, lpad, Lcap, word_off);
+                                                                    (__half*)words_h, wnorm, D, Lw, lpad,
+                                                                    gloria_b200_tc_lp(Lcap), Lcap, word_off);
   GLORIA_LAUNCHED("pack_words");
   return GLORIA_OK;
 }

@@ -43,7 +43,7 @@ def tc_prepack(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off
     ctx_t = torch.empty((Bi, spad, D), dtype=torch.bfloat16, device=dev)
     ctx_n = torch.empty((Bi, D, spad), dtype=torch.bfloat16, device=dev)
     words_h = torch.empty((Bc, lpad, D), dtype=torch.float16, device=dev)
-    words_t = torch.empty((Bc, lpad, D), dtype=torch.bfloat16, device=dev)
+    words_t = torch.empty((Bc, L.gloria_b200_tc_lp(lcap), D), dtype=torch.bfloat16, device=dev)
     wnorm = torch.empty((Bc, lpad), dtype=torch.float32, device=dev)
     rc = L.gloria_b200_tc_prepack(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S, Lw, lcap,
                                   word_off, ctx_h.data_ptr(), ctx_t.data_ptr(), ctx_n.data_ptr(), words_h.data_ptr(),

@@ -131,6 +131,8 @@ int gloria_b200_row_cosine_bwd(const float* x1, const float* x2, const float* st
  * region row exists, the backward's Gram matrix keeps its row of ones there; L -> multiple of 16). */
 int gloria_b200_tc_spad(int S);
 int gloria_b200_tc_lpad(int Lcap);
+/* Row pitch per caption of words_t and column pitch of the backward's operand matrices: round_up(Lcap, 8) <= Lpad. */
+int gloria_b200_tc_lp(int Lcap);
 /* 0 if this (D, S, Lcap) is supported by the tensor-core kernels, else GLORIA_ERR_UNSUPPORTED. */
 int gloria_b200_tc_supported(int D, int S, int Lcap);
 
@@ -139,7 +141,7 @@ int gloria_b200_tc_supported(int D, int S, int Lcap);
  *   ctx_t   [Bi, Spad, D] bf16  same layout                                           -> backward GEMMs, Gram matrix
  *   ctx_n   [Bi, D, Spad] bf16  channel-major copy (s contiguous), cols s >= S zero   -> context GEMM (B operand)
  *   words_h [Bc, Lpad, D] fp16  word-major copy of columns [word_off, word_off+cap_len), other rows zero
- *   words_t [Bc, Lpad, D] bf16  same layout                                           -> backward GEMMs
+ *   words_t [Bc, Lp, D]   bf16  same rows, pitch Lp = round_up(Lcap, 8)               -> backward GEMMs
  *   wnorm   [Bc, Lpad]    fp32  |W_l| computed from the fp32 input (gloria_loss.py:14)
  * The score GEMM (K = D, feeds the word softmax, which amplifies operand rounding) runs on fp16 operands -- the dtype
  * the reference's AMP runs this bmm in; everything after the softmax is bf16 x bf16.  All accumulate in fp32. */

@@ -40,3 +40,19 @@ print(f"      producer total {m[8]/n:.0f}: wait empty slot {m[9]/n:.0f}")
 for g in range(3):
     o = 16 + 5 * g
     print(f"      SIMT group {g} warp: total {m[o]/n:.0f}: wait S_ ready {m[o+1]/n:.0f}, T' ready {m[o+2]/n:.0f}, E free {m[o+3]/n:.0f}, bar.sync exchange {m[o+4]/n:.0f}")
+
+# fused training kernel
+n = lib.gloria_b200_tc_train_workspace(B, B, 768, 361, L)
+tws = torch.empty(n, dtype=torch.uint8, device="cuda")
+dbg.zero_()
+for _ in range(2):
+    assert lib.gloria_b200_tc_local_sim_fwd_train(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(), packed.words_h.data_ptr(),
+        packed.wnorm.data_ptr(), lens.data_ptr(), B, B, 768, 361, L, 4.0, 5.0, 0, 1e-8, sim.data_ptr(), tws.data_ptr(), n, st) == 0
+torch.cuda.synchronize()
+d = dbg.cpu().double(); act = d[:, 5] > 0
+m = d[act].mean(0); n_ = m[5]
+print(f"fused B={B}: per pair cycles: MMA issuer total {m[0]/n_:.0f}: wait full(TMA) {m[1]/n_:.0f}, S_ free {m[2]/n_:.0f}, E full {m[3]/n_:.0f}, T' free {m[4]/n_:.0f}  (pairs/CTA {n_:.0f})")
+print(f"      producer total {m[8]/n_:.0f}: wait empty slot {m[9]/n_:.0f}")
+for g in range(3):
+    o = 16 + 5 * g
+    print(f"      SIMT group {g} warp: total {m[o]/n_:.0f}: wait S_ ready {m[o+1]/n_:.0f}, T' ready {m[o+2]/n_:.0f}, E free {m[o+3]/n_:.0f}, bar.sync exchange {m[o+4]/n_:.0f}")
