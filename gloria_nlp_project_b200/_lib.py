@@ -39,6 +39,7 @@ PROTOTYPES = {
     "gloria_b200_tc_spad": (_i, [_i]),
     "gloria_b200_tc_lpad": (_i, [_i]),
     "gloria_b200_tc_lp": (_i, [_i]),
+    "gloria_b200_tc_sp": (_i, [_i]),
     "gloria_b200_tc_supported": (_i, [_i, _i, _i]),
     "gloria_b200_tc_prepack": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "gloria_b200_tc_local_sim_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p]),

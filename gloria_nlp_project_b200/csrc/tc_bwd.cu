@@ -63,6 +63,7 @@ struct PairParams {
   float* gamma;             // [Bc, LPAD]  sum_j (dL/d|W_l|) / |W_l|   (atomicAdd)
   int Bi, Bc, i0, nc, D, S, NT;
   int lp;                   // column pitch per caption of X^T / E^T / fo / go: round_up(Lcap, 8) <= LPAD
+  int sp;                   // region rows per image in X^T / E^T: round_up(S, 16) <= Spad
   float t1, t1_log2e, t2, eps;
   long long* dbg;           // phase clocks (only read when built with -DGLORIA_PHASE_CLOCKS)
 };
@@ -298,8 +299,8 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
         for (int t = 0; t < NT; ++t)
 #pragma unroll
           for (int wb = 0; wb < (LPAD + 63) / 64; ++wb)
-            tma_store_3d(&tm_e, base + OFF_E + (uint32_t)wb * e_lbo + (uint32_t)t * (TILE * 128), wb * 64, ci,
-                         cj * Spad + t * TILE);
+            tma_store_4d(&tm_e, base + OFF_E + (uint32_t)wb * e_lbo + (uint32_t)t * (TILE * 128), wb * 64, ci,
+                         t * TILE, cj);
         tma_store_commit();
         if (FUSED)
           for (int k = 0; k < NT; ++k) gemmt();              // pass A: T' for the in-kernel |C'|^2 reduction
@@ -634,12 +635,13 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             STIMED(sw_bar, asm volatile("bar.sync 1, 384;" ::: "memory"));
             const float uacc = xb[row].x + xb[128 + row].x + xb[256 + row].x;
             // pass 2: rows of X^T  ([(j, s), (i, l)] bf16, 16-byte stores along l)
-            const size_t goff = ((size_t)j * Spad + s_glob) * pitch + (size_t)u.i * p.lp;
+            const size_t goff = ((size_t)j * p.sp + s_glob) * pitch + (size_t)u.i * p.lp;
             uint4* xo = reinterpret_cast<uint4*>(p.xt + goff);
+            const bool row_out = s_glob < p.sp;              // padded region rows beyond sp do not exist in X^T
 #pragma unroll
             for (int c = 0; c < CW; ++c) {
               const int ch = c_lo + c;
-              if (ch < nchs) {
+              if (ch < nchs && row_out) {
                 const uint4 ev = *reinterpret_cast<const uint4*>(erow + (size_t)(ch >> 3) * e_blk +
                                                                  (size_t)((((uint32_t)ch & 7u) ^ sw) << 4));
                 const float4 x0 = *reinterpret_cast<const float4*>(cX + c * 8);
@@ -812,15 +814,16 @@ struct Plan {
 constexpr size_t CUBLAS_WS = 64u << 20;
 
 // lp = column pitch of the operand matrices (round_up(Lcap, 8)), lpad = the kernels' word padding (stats pitch)
-size_t fixed_bytes(int Bi, int Bc, int D, int Spad, int lp, int lpad, bool own_stats, Plan* pl) {
+// sp = region rows per image of the operand matrices (round_up(S, 16)), Spad = the kernels' tile padding (Gram buffer)
+size_t fixed_bytes(int Bi, int Bc, int D, int Spad, int sp, int lp, int lpad, bool own_stats, Plan* pl) {
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += align_up(n, 1024); return r; };
   Plan t{};
   t.off_gram = take((size_t)Bi * Spad * Spad * 2);
   t.off_dwt = take((size_t)Bc * lp * D * 4);
-  t.off_drt = take((size_t)Bi * Spad * D * 4);
-  t.off_m = take((size_t)Bi * Spad * Spad * 4);
-  t.off_mb = take((size_t)Bi * Spad * Spad * 2);
+  t.off_drt = take((size_t)Bi * sp * D * 4);
+  t.off_m = take((size_t)Bi * sp * sp * 4);
+  t.off_mb = take((size_t)Bi * sp * sp * 2);
   t.off_gamma = take((size_t)Bc * lp * 4);
   t.off_stats = take(own_stats ? (size_t)Bi * Bc * 2 * lpad * 4 : 0);
   t.off_sim = take(own_stats ? (size_t)Bi * Bc * 4 : 0);
@@ -828,21 +831,21 @@ size_t fixed_bytes(int Bi, int Bc, int D, int Spad, int lp, int lpad, bool own_s
   if (pl) *pl = t;
   return o;
 }
-size_t per_caption_bytes(int Bi, int Spad, int lp) {
-  return 3 * align_up((size_t)Bi * Spad * lp * 2, 1024) + align_up((size_t)Bi * lp * 4, 1024) + 4096;
+size_t per_caption_bytes(int Bi, int sp, int lp) {
+  return 3 * align_up((size_t)Bi * sp * lp * 2, 1024) + align_up((size_t)Bi * lp * 4, 1024) + 4096;
 }
 
-Plan make_plan(int Bi, int Bc, int D, int Spad, int lp, int lpad, bool own_stats, size_t bytes) {
+Plan make_plan(int Bi, int Bc, int D, int Spad, int sp, int lp, int lpad, bool own_stats, size_t bytes) {
   Plan pl{};
-  const size_t fixed = fixed_bytes(Bi, Bc, D, Spad, lp, lpad, own_stats, &pl);
-  const size_t per = per_caption_bytes(Bi, Spad, lp);
+  const size_t fixed = fixed_bytes(Bi, Bc, D, Spad, sp, lp, lpad, own_stats, &pl);
+  const size_t per = per_caption_bytes(Bi, sp, lp);
   if (bytes < fixed + per) { pl.nc = 0; return pl; }
   size_t nc = (bytes - fixed) / per;
   if (nc > (size_t)Bc) nc = Bc;
   pl.nc = (int)nc;
   size_t o = fixed;
   auto take = [&](size_t n) { size_t r = o; o += align_up(n, 1024); return r; };
-  const size_t arr = (size_t)Bi * Spad * nc * lp * 2;
+  const size_t arr = (size_t)Bi * sp * nc * lp * 2;
   pl.off_x = take(arr);
   pl.off_e = take(arr);
   pl.off_b = take(arr);
@@ -900,11 +903,11 @@ int launch_pair_lpad(int lpad, const CUtensorMap& rt, const CUtensorMap& wt, con
 struct TrainPlan {
   size_t off_gram, off_x, off_e, off_fo, off_go, off_b, off_dwt, off_drt, off_m, off_mb, off_gamma, off_cublas, total;
 };
-TrainPlan train_plan(int Bi, int Bc, int D, int Spad, int lpad) {
+TrainPlan train_plan(int Bi, int Bc, int D, int Spad, int sp, int lpad) {
   TrainPlan t{};
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += align_up(n, 1024); return r; };
-  const size_t arr = (size_t)Bi * Spad * Bc * lpad * 2;
+  const size_t arr = (size_t)Bi * sp * Bc * lpad * 2;
   t.off_gram = take((size_t)Bi * Spad * Spad * 2);
   t.off_x = take(arr);
   t.off_e = take(arr);
@@ -912,9 +915,9 @@ TrainPlan train_plan(int Bi, int Bc, int D, int Spad, int lpad) {
   t.off_go = take((size_t)Bi * Bc * lpad * 4);
   t.off_b = take(arr);
   t.off_dwt = take((size_t)Bc * lpad * D * 4);
-  t.off_drt = take((size_t)Bi * Spad * D * 4);
-  t.off_m = take((size_t)Bi * Spad * Spad * 4);
-  t.off_mb = take((size_t)Bi * Spad * Spad * 2);
+  t.off_drt = take((size_t)Bi * sp * D * 4);
+  t.off_m = take((size_t)Bi * sp * sp * 4);
+  t.off_mb = take((size_t)Bi * sp * sp * 2);
   t.off_gamma = take((size_t)Bc * lpad * 4);
   t.off_cublas = take(CUBLAS_WS);
   t.total = o;
@@ -922,11 +925,13 @@ TrainPlan train_plan(int Bi, int Bc, int D, int Spad, int lpad) {
 }
 
 int gram_matrices(cublasHandle_t h, const __nv_bfloat16* Rt, __nv_bfloat16* gram, int Bi, int D, int S, int Spad,
-                  cudaStream_t st) {
+                  int sp, cudaStream_t st) {
   const float one = 1.f, zero = 0.f;
-  // G_j = Rt_j Rt_j^T (row-major [Spad, D] == column-major [D, Spad]); row S becomes the row of ones
-  GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_T, CUBLAS_OP_N, Spad, Spad, D, &one, Rt, CUDA_R_16BF, D,
-                                           (long long)Spad * D, Rt, CUDA_R_16BF, D, (long long)Spad * D, &zero, gram,
+  // G_j = Rt_j Rt_j^T (Rt_j row-major [sp, D] == column-major [D, sp]) into the [Spad, Spad] tile buffer (rows / columns
+  // >= sp stay zero); row S becomes the row of ones
+  GLORIA_CUDA(cudaMemsetAsync(gram, 0, (size_t)Bi * Spad * Spad * 2, st));
+  GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_T, CUBLAS_OP_N, sp, sp, D, &one, Rt, CUDA_R_16BF, D,
+                                           (long long)sp * D, Rt, CUDA_R_16BF, D, (long long)sp * D, &zero, gram,
                                            CUDA_R_16BF, Spad, (long long)Spad * Spad, Bi, CUBLAS_COMPUTE_32F,
                                            CUBLAS_GEMM_DEFAULT));
   gram_ones_row<<<Bi, 128, 0, st>>>(gram, S, Spad);
@@ -937,7 +942,8 @@ int gram_matrices(cublasHandle_t h, const __nv_bfloat16* Rt, __nv_bfloat16* gram
 // the accumulation GEMMs + unpack shared by both backward flavours (X, E, Bm hold nc captions starting at i0)
 int accumulate_chunk(cublasHandle_t h, const __nv_bfloat16* Rt, const __nv_bfloat16* Wt, const __nv_bfloat16* X,
                      const __nv_bfloat16* E, const __nv_bfloat16* Bm, float* dWt, float* dRt, float* Mf, int Bi, int D,
-                     int Spad, int lpad, int i0, int nc, bool first) {
+                     int Spad /* = sp: region rows per image of the operand matrices */, int lpad, int i0, int nc,
+                     bool first) {
   const float one = 1.f, zero = 0.f;
   const float beta = first ? 0.f : 1.f;
   const int K1 = Bi * Spad, R1 = nc * lpad;
@@ -987,8 +993,9 @@ using namespace gloria::tc;
 extern "C" size_t gloria_b200_tc_bwd_workspace(int Bi, int Bc, int D, int S, int Lcap, int have_stats, size_t budget) {
   if (Bi <= 0 || Bc <= 0 || gloria_b200_tc_supported(D, S, Lcap)) return 0;
   const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap), lp = gloria_b200_tc_lp(Lcap);
-  const size_t fixed = bw::fixed_bytes(Bi, Bc, D, Spad, lp, lpad, !have_stats, nullptr);
-  const size_t per = bw::per_caption_bytes(Bi, Spad, lp);
+  const int sp = gloria_b200_tc_sp(S);
+  const size_t fixed = bw::fixed_bytes(Bi, Bc, D, Spad, sp, lp, lpad, !have_stats, nullptr);
+  const size_t per = bw::per_caption_bytes(Bi, sp, lp);
   size_t want = fixed + per * (size_t)Bc;
   if (budget != 0 && want > budget) {
     size_t nc = budget > fixed + per ? (budget - fixed) / per : 1;
@@ -1012,7 +1019,8 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
   if (agg == GLORIA_AGG_MAX) return fail(GLORIA_ERR_UNSUPPORTED, "backward of agg=max is not part of the path");
   cudaStream_t st = (cudaStream_t)stream;
   const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap), lp = gloria_b200_tc_lp(Lcap);
-  const bw::Plan pl = bw::make_plan(Bi, Bc, D, Spad, lp, lpad, stats == nullptr, workspace_bytes);
+  const int sp = gloria_b200_tc_sp(S);
+  const bw::Plan pl = bw::make_plan(Bi, Bc, D, Spad, sp, lp, lpad, stats == nullptr, workspace_bytes);
   if (pl.nc < 1) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B too small", workspace_bytes);
   char* ws = (char*)workspace;
   __nv_bfloat16* gram = (__nv_bfloat16*)(ws + pl.off_gram);
@@ -1039,7 +1047,7 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
   GLORIA_CUBLAS(cublasSetWorkspace(h, ws + pl.off_cublas, bw::CUBLAS_WS));
   const __nv_bfloat16* Rt = (const __nv_bfloat16*)ctx_t;
   const __nv_bfloat16* Wt = (const __nv_bfloat16*)words_t;
-  if ((rc = bw::gram_matrices(h, Rt, gram, Bi, D, S, Spad, st))) return rc;
+  if ((rc = bw::gram_matrices(h, Rt, gram, Bi, D, S, Spad, sp, st))) return rc;
   GLORIA_CUDA(cudaMemsetAsync(gamma, 0, (size_t)Bc * lp * sizeof(float), st));
 
   CUtensorMap rt, wt, gm;
@@ -1050,7 +1058,6 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
   GLORIA_CUDA(cudaGetDevice(&dev));
   GLORIA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
 
-  const int K1 = Bi * Spad;
   for (int i0 = 0; i0 < Bc; i0 += pl.nc) {
     const int nc = min(pl.nc, Bc - i0);
     const int R1 = nc * lp;
@@ -1058,19 +1065,21 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
     p.wnorm = wnorm; p.cap_lens = cap_lens; p.stats = stats; p.dsim = dsim;
     p.xt = X; p.et = E; p.fo = Fo; p.gamma = gamma;
     CUtensorMap em;
-    if ((rc = make_map3(&em, E, (uint64_t)lp, (uint64_t)nc, (uint64_t)K1, (uint64_t)lp, (uint64_t)R1, TILE))) return rc;
-    p.Bi = Bi; p.Bc = Bc; p.i0 = i0; p.nc = nc; p.D = D; p.S = S; p.NT = Spad / TILE; p.lp = lp;
+    if ((rc = make_map4(&em, E, (uint64_t)lp, (uint64_t)nc, (uint64_t)sp, (uint64_t)Bi, (uint64_t)lp, (uint64_t)R1,
+                        (uint64_t)sp * R1, TILE)))
+      return rc;
+    p.Bi = Bi; p.Bc = Bc; p.i0 = i0; p.nc = nc; p.D = D; p.S = S; p.NT = Spad / TILE; p.lp = lp; p.sp = sp;
     p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps; p.agg = agg;
     p.dbg = (long long*)g_phase_clock_buffer;
     if ((rc = bw::launch_pair_lpad<false>(lpad, rt, wt, gm, em, p, sms, st))) return rc;
     timer_record(GLORIA_TIMER_TC_BWD_GEMM, 0, st);
-    bw::scale_rows<<<dim3((unsigned)((R1 / 8 + 255) / 256), (unsigned)(Spad / bw::SCALE_ROWS), (unsigned)Bi), 256, 0, st>>>(
-        E, Fo, Bm, R1, Spad, nullptr, Bc, i0, lp);
+    bw::scale_rows<<<dim3((unsigned)((R1 / 8 + 255) / 256), (unsigned)(sp / bw::SCALE_ROWS), (unsigned)Bi), 256, 0, st>>>(
+        E, Fo, Bm, R1, sp, nullptr, Bc, i0, lp);
     GLORIA_LAUNCHED("scale_rows");
-    if ((rc = bw::accumulate_chunk(h, Rt, Wt, X, E, Bm, dWt, dRt, Mf, Bi, D, Spad, lp, i0, nc, i0 == 0))) return rc;
+    if ((rc = bw::accumulate_chunk(h, Rt, Wt, X, E, Bm, dWt, dRt, Mf, Bi, D, sp, lp, i0, nc, i0 == 0))) return rc;
     if (i0 + nc < Bc) timer_record(GLORIA_TIMER_TC_BWD_GEMM, 1, st);
   }
-  return bw::finish_backward(h, Rt, Wt, cap_lens, dWt, dRt, Mf, Mb, gamma, d_ctx, d_words, Bi, Bc, D, S, Spad, Lw, lp,
+  return bw::finish_backward(h, Rt, Wt, cap_lens, dWt, dRt, Mf, Mb, gamma, d_ctx, d_words, Bi, Bc, D, S, sp, Lw, lp,
                              Lcap, word_off, st);
 }
 
@@ -1079,7 +1088,7 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" size_t gloria_b200_tc_train_workspace(int Bi, int Bc, int D, int S, int Lcap) {
   if (Bi <= 0 || Bc <= 0 || gloria_b200_tc_supported(D, S, Lcap)) return 0;
-  return bw::train_plan(Bi, Bc, D, gloria_b200_tc_spad(S), gloria_b200_tc_lp(Lcap)).total;
+  return bw::train_plan(Bi, Bc, D, gloria_b200_tc_spad(S), gloria_b200_tc_sp(S), gloria_b200_tc_lp(Lcap)).total;
 }
 
 extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void* ctx_t, const void* words_h,
@@ -1092,7 +1101,8 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void*
   if (agg == GLORIA_AGG_MAX) return fail(GLORIA_ERR_UNSUPPORTED, "agg=max has no backward: use the plain forward");
   cudaStream_t st = (cudaStream_t)stream;
   const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap), lp = gloria_b200_tc_lp(Lcap);
-  const bw::TrainPlan pl = bw::train_plan(Bi, Bc, D, Spad, lp);
+  const int sp = gloria_b200_tc_sp(S);
+  const bw::TrainPlan pl = bw::train_plan(Bi, Bc, D, Spad, sp, lp);
   if (workspace_bytes < pl.total) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, pl.total);
   char* ws = (char*)workspace;
   __nv_bfloat16* gram = (__nv_bfloat16*)(ws + pl.off_gram);
@@ -1101,13 +1111,14 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void*
   GLORIA_CUBLAS(cublasSetStream(h, st));
   GLORIA_CUBLAS(cublasSetWorkspace(h, ws + pl.off_cublas, bw::CUBLAS_WS));
   int rc;
-  if ((rc = bw::gram_matrices(h, (const __nv_bfloat16*)ctx_t, gram, Bi, D, S, Spad, st))) return rc;
+  if ((rc = bw::gram_matrices(h, (const __nv_bfloat16*)ctx_t, gram, Bi, D, S, Spad, sp, st))) return rc;
   CUtensorMap rt, wt, gm, em;
-  const int K1 = Bi * Spad, R1 = Bc * lp;
+  const int R1 = Bc * lp;
   if ((rc = make_map(&rt, ctx_h, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;
   if ((rc = make_map(&wt, words_h, (uint64_t)D, (uint64_t)Bc * lpad, (uint32_t)lpad))) return rc;
   if ((rc = make_map(&gm, gram, (uint64_t)Spad, (uint64_t)Bi * Spad, TILE))) return rc;
-  if ((rc = make_map3(&em, ws + pl.off_e, (uint64_t)lp, (uint64_t)Bc, (uint64_t)K1, (uint64_t)lp, (uint64_t)R1, TILE)))
+  if ((rc = make_map4(&em, ws + pl.off_e, (uint64_t)lp, (uint64_t)Bc, (uint64_t)sp, (uint64_t)Bi, (uint64_t)lp, (uint64_t)R1,
+                      (uint64_t)sp * R1, TILE)))
     return rc;
   int dev = 0, sms = 0;
   GLORIA_CUDA(cudaGetDevice(&dev));
@@ -1116,7 +1127,7 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void*
   p.wnorm = wnorm; p.cap_lens = cap_lens; p.stats = nullptr; p.dsim = nullptr;
   p.xt = (__nv_bfloat16*)(ws + pl.off_x); p.et = (__nv_bfloat16*)(ws + pl.off_e);
   p.fo = (float*)(ws + pl.off_fo); p.go = (float*)(ws + pl.off_go); p.gamma = nullptr; p.sim = sim;
-  p.Bi = Bi; p.Bc = Bc; p.i0 = 0; p.nc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE; p.lp = lp;
+  p.Bi = Bi; p.Bc = Bc; p.i0 = 0; p.nc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE; p.lp = lp; p.sp = sp;
   p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps; p.agg = agg;
   p.dbg = (long long*)g_phase_clock_buffer;
   return bw::launch_pair_lpad<true>(lpad, rt, wt, gm, em, p, sms, st);
@@ -1130,8 +1141,8 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void*
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
   cudaStream_t st = (cudaStream_t)stream;
-  const int Spad = gloria_b200_tc_spad(S), lp = gloria_b200_tc_lp(Lcap);
-  const bw::TrainPlan pl = bw::train_plan(Bi, Bc, D, Spad, lp);
+  const int Spad = gloria_b200_tc_spad(S), lp = gloria_b200_tc_lp(Lcap), sp = gloria_b200_tc_sp(S);
+  const bw::TrainPlan pl = bw::train_plan(Bi, Bc, D, Spad, sp, lp);
   if (workspace_bytes < pl.total) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, pl.total);
   char* ws = (char*)workspace;
   __nv_bfloat16* X = (__nv_bfloat16*)(ws + pl.off_x);
@@ -1143,22 +1154,22 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void*
   GLORIA_CUBLAS(cublasSetStream(h, st));
   GLORIA_CUBLAS(cublasSetWorkspace(h, ws + pl.off_cublas, bw::CUBLAS_WS));
   const int R1 = Bc * lp;
-  const dim3 sgrid((unsigned)((R1 / 8 + 255) / 256), (unsigned)(Spad / bw::SCALE_ROWS), (unsigned)Bi);
+  const dim3 sgrid((unsigned)((R1 / 8 + 255) / 256), (unsigned)(sp / bw::SCALE_ROWS), (unsigned)Bi);
   timer_record(GLORIA_TIMER_TC_BWD_GEMM, 0, st);
   // everything the forward stored is for g = 1 and linear in g = dsim[j, i]: apply it now
-  bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, Spad, Bc, 0, lp);
+  bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, sp, Bc, 0, lp);
   GLORIA_LAUNCHED("scale_x");
-  bw::scale_rows<<<sgrid, 256, 0, st>>>(E, (const float*)(ws + pl.off_fo), Bm, R1, Spad, dsim, Bc, 0, lp);
+  bw::scale_rows<<<sgrid, 256, 0, st>>>(E, (const float*)(ws + pl.off_fo), Bm, R1, sp, dsim, Bc, 0, lp);
   GLORIA_LAUNCHED("scale_rows");
   bw::gamma_sum<<<(R1 + 255) / 256, 256, 0, st>>>((const float*)(ws + pl.off_go), dsim, gamma, Bi, R1, Bc, 0, lp);
   GLORIA_LAUNCHED("gamma_sum");
   int rc;
   if ((rc = bw::accumulate_chunk(h, (const __nv_bfloat16*)ctx_t, (const __nv_bfloat16*)words_t, X, E, Bm,
                                  (float*)(ws + pl.off_dwt), (float*)(ws + pl.off_drt), (float*)(ws + pl.off_m), Bi, D,
-                                 Spad, lp, 0, Bc, true)))
+                                 sp, lp, 0, Bc, true)))
     return rc;
   return bw::finish_backward(h, (const __nv_bfloat16*)ctx_t, (const __nv_bfloat16*)words_t, cap_lens,
                              (float*)(ws + pl.off_dwt), (float*)(ws + pl.off_drt), (float*)(ws + pl.off_m),
-                             (__nv_bfloat16*)(ws + pl.off_mb), gamma, d_ctx, d_words, Bi, Bc, D, S, Spad, Lw, lp, Lcap,
+                             (__nv_bfloat16*)(ws + pl.off_mb), gamma, d_ctx, d_words, Bi, Bc, D, S, sp, Lw, lp, Lcap,
                              word_off, st);
 }

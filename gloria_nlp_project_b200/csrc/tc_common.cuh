@@ -65,6 +65,11 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src
                ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores of this thread have finished READING shared memory
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -191,6 +196,10 @@ struct UnitIter {
 
 // host side (tc_local.cu): 2-D bf16 tensor map [rows, inner] (inner contiguous), box [box_rows, 64], SWIZZLE_128B
 int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint32_t box_rows);
+// 4-D bf16 tensor [imgs, rows, mid, inner] (pitches in elements), box [1, box_rows, 1, 64], SWIZZLE_128B (TMA stores
+// of E^T rows: clipped at `inner` columns per caption and at `rows` region rows per image)
+int make_map4(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t mid, uint64_t rows, uint64_t imgs,
+              uint64_t mid_pitch, uint64_t row_pitch, uint64_t img_pitch, uint32_t box_rows);
 // 3-D bf16 tensor [rows, mid, inner] with pitches in elements, box [box_rows, 1, 64], SWIZZLE_128B (TMA stores)
 int make_map3(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t mid, uint64_t rows, uint64_t mid_pitch,
               uint64_t row_pitch, uint32_t box_rows);

@@ -350,7 +350,7 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
 // rounding (scores of unit-variance 768-d features have std 27.7) and fp16 carries 3 more mantissa bits than bf16 at
 // the same tensor rate -- it is also the dtype the reference's AMP runs this bmm in.
 __global__ void pack_ctx(const float* __restrict__ ctx, __nv_bfloat16* __restrict__ Rn, __nv_bfloat16* __restrict__ Rt,
-                         __half* __restrict__ Rh, int D, int S, int Spad) {
+                         __half* __restrict__ Rh, int D, int S, int Spad, int sp) {
   __shared__ float t[32][33];
   const int b = blockIdx.z, s0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += 8) {
@@ -362,8 +362,8 @@ __global__ void pack_ctx(const float* __restrict__ ctx, __nv_bfloat16* __restric
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int s = s0 + r, d = d0 + threadIdx.x;
-    Rt[((size_t)b * Spad + s) * D + d] = __float2bfloat16_rn(t[threadIdx.x][r]);
-    Rh[((size_t)b * Spad + s) * D + d] = __float2half_rn(t[threadIdx.x][r]);
+    if (s < sp) Rt[((size_t)b * sp + s) * D + d] = __float2bfloat16_rn(t[threadIdx.x][r]);   // GEMM pitch
+    Rh[((size_t)b * Spad + s) * D + d] = __float2half_rn(t[threadIdx.x][r]);                // tile pitch
   }
 }
 
@@ -450,6 +450,21 @@ int make_map3(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t mid, uin
   return GLORIA_OK;
 }
 
+int make_map4(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t mid, uint64_t rows, uint64_t imgs,
+              uint64_t mid_pitch, uint64_t row_pitch, uint64_t img_pitch, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(GLORIA_ERR_DRIVER, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {inner, mid, rows, imgs};
+  cuuint64_t strides[3] = {mid_pitch * 2, row_pitch * 2, img_pitch * 2};
+  cuuint32_t box[4] = {KBLK, 1, box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GLORIA_ERR_DRIVER, "cuTensorMapEncodeTiled(4d) failed with CUresult %d", (int)r);
+  return GLORIA_OK;
+}
+
 template <int LPAD>
 int launch_fwd(const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap& rn, const FwdParams& p, int grid,
                cudaStream_t st) {
@@ -474,6 +489,7 @@ extern "C" void gloria_b200_debug_phase_clocks(void* device_buffer) { gloria::tc
 extern "C" int gloria_b200_tc_spad(int S) { return (S / TILE + 1) * TILE; }
 extern "C" int gloria_b200_tc_lpad(int Lcap) { return (Lcap + 15) / 16 * 16; }
 extern "C" int gloria_b200_tc_lp(int Lcap) { return (Lcap + 7) / 8 * 8; }
+extern "C" int gloria_b200_tc_sp(int S) { return (S + 15) / 16 * 16; }
 
 extern "C" int gloria_b200_tc_supported(int D, int S, int Lcap) {
   if (D < TILE || D % TILE != 0 || S < 1 || S >= MAX_NT * TILE || Lcap < 1 || Lcap > TILE) return GLORIA_ERR_UNSUPPORTED;
@@ -489,7 +505,7 @@ extern "C" int gloria_b200_tc_prepack(const float* ctx, const float* words, cons
   cudaStream_t st = (cudaStream_t)stream;
   const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
   pack_ctx<<<dim3(Spad / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(ctx, (__nv_bfloat16*)ctx_n, (__nv_bfloat16*)ctx_t,
-                                                               (__half*)ctx_h, D, S, Spad);
+                                                               (__half*)ctx_h, D, S, Spad, gloria_b200_tc_sp(S));
   GLORIA_LAUNCHED("pack_ctx");
   pack_words<<<dim3((lpad + 31) / 32, 1, Bc), dim3(32, 8), 0, st>>>(words, cap_lens, (__nv_bfloat16*)words_t,
                                                                     (__half*)words_h, wnorm, D, Lw, lpad,

@@ -40,7 +40,7 @@ def tc_prepack(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off
     spad, lpad = L.gloria_b200_tc_spad(S), L.gloria_b200_tc_lpad(lcap)
     dev = ctx.device
     ctx_h = torch.empty((Bi, spad, D), dtype=torch.float16, device=dev)
-    ctx_t = torch.empty((Bi, spad, D), dtype=torch.bfloat16, device=dev)
+    ctx_t = torch.empty((Bi, L.gloria_b200_tc_sp(S), D), dtype=torch.bfloat16, device=dev)
     ctx_n = torch.empty((Bi, D, spad), dtype=torch.bfloat16, device=dev)
     words_h = torch.empty((Bc, lpad, D), dtype=torch.float16, device=dev)
     words_t = torch.empty((Bc, L.gloria_b200_tc_lp(lcap), D), dtype=torch.bfloat16, device=dev)

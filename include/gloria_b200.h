@@ -133,12 +133,14 @@ int gloria_b200_tc_spad(int S);
 int gloria_b200_tc_lpad(int Lcap);
 /* Row pitch per caption of words_t and column pitch of the backward's operand matrices: round_up(Lcap, 8) <= Lpad. */
 int gloria_b200_tc_lp(int Lcap);
+/* Row pitch per image of ctx_t and of the backward's operand matrices: round_up(S, 16) <= Spad. */
+int gloria_b200_tc_sp(int S);
 /* 0 if this (D, S, Lcap) is supported by the tensor-core kernels, else GLORIA_ERR_UNSUPPORTED. */
 int gloria_b200_tc_supported(int D, int S, int Lcap);
 
 /* Cast + transpose into TMA-legal 16-bit layouts (native row pitches 1444 B / 388 B are not 16 B multiples):
  *   ctx_h   [Bi, Spad, D] fp16  region-major copy (d contiguous), rows s >= S zero   -> score GEMM (A operand)
- *   ctx_t   [Bi, Spad, D] bf16  same layout                                           -> backward GEMMs, Gram matrix
+ *   ctx_t   [Bi, Sp, D]   bf16  same rows, pitch Sp = round_up(S, 16)                 -> backward GEMMs, Gram matrix
  *   ctx_n   [Bi, D, Spad] bf16  channel-major copy (s contiguous), cols s >= S zero   -> context GEMM (B operand)
  *   words_h [Bc, Lpad, D] fp16  word-major copy of columns [word_off, word_off+cap_len), other rows zero
  *   words_t [Bc, Lp, D]   bf16  same rows, pitch Lp = round_up(Lcap, 8)               -> backward GEMMs

@@ -39,8 +39,8 @@ def test_prepack_layouts(gl):
     lens = torch.tensor(cl, dtype=torch.int32, device="cuda")
     pk = ops.tc_prepack(ctx, words, lens, 97, 0)
     ctx_t, ctx_n, words_t, wnorm = pk.ctx_t, pk.ctx_n, pk.words_t, pk.wnorm
-    assert ctx_t.shape == (3, 384, 768) and ctx_n.shape == (3, 768, 384) and words_t.shape == (3, 104, 768)
-    assert pk.words_h.shape == (3, 112, 768)
+    assert ctx_t.shape == (3, 368, 768) and ctx_n.shape == (3, 768, 384) and words_t.shape == (3, 104, 768)
+    assert pk.words_h.shape == (3, 112, 768) and pk.ctx_h.shape == (3, 384, 768)
     ref = ctx.to(torch.bfloat16)
     assert torch.equal(ctx_n[:, :, :361], ref) and torch.all(ctx_n[:, :, 361:] == 0)
     assert torch.equal(ctx_t[:, :361], ref.transpose(1, 2)) and torch.all(ctx_t[:, 361:] == 0)
