@@ -693,34 +693,9 @@ __global__ void gram_ones_row(__nv_bfloat16* __restrict__ G, int S, int Spad) {
   for (int x = threadIdx.x; x < Spad; x += blockDim.x) r[x] = __float2bfloat16_rn(x < S ? 1.f : 0.f);
 }
 
-// Bo[(j,s), c] = f[j, c] * Eo[(j,s), c]   (c = (i,l)).  grid (ceil(R1/8/256), Spad/ROWS, Bi): each thread owns 8 columns
-// of one image, keeps their 8 f values in registers and streams ROWS region rows (16-byte loads / stores).
 constexpr int SCALE_ROWS = 16;
-// g (optional): dsim [Bi, Bc] -- the fused training forward stores f for g = 1 and the backward multiplies it in here
-__global__ void __launch_bounds__(256) scale_rows(const __nv_bfloat16* __restrict__ E, const float* __restrict__ f,
-                                                  __nv_bfloat16* __restrict__ Bo, int R1, int Spad,
-                                                  const float* __restrict__ g, int Bc, int i0, int lpad) {
-  const int c8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (c8 >= R1) return;
-  const int j = blockIdx.z;
-  const float* fr = f + (size_t)j * R1 + c8;
-  const float4 f0 = *reinterpret_cast<const float4*>(fr), f1 = *reinterpret_cast<const float4*>(fr + 4);
-  const float gs = g ? g[(size_t)j * Bc + i0 + c8 / lpad] : 1.f;       // 8 columns never straddle a caption
-  const float fv[8] = {f0.x * gs, f0.y * gs, f0.z * gs, f0.w * gs, f1.x * gs, f1.y * gs, f1.z * gs, f1.w * gs};
-  const size_t row0 = (size_t)j * Spad + (size_t)blockIdx.y * SCALE_ROWS;
-#pragma unroll 4
-  for (int r = 0; r < SCALE_ROWS; ++r) {
-    const size_t o = (row0 + r) * R1 + c8;
-    const uint4 ev = __ldcs(reinterpret_cast<const uint4*>(E + o));
-    const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
-    uint32_t w[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) w[k] = pack_bf16(bf_lo(ew[k]) * fv[2 * k], bf_hi(ew[k]) * fv[2 * k + 1]);
-    *reinterpret_cast<uint4*>(Bo + o) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-}
-
-// X[(j,s), (i,l)] *= g[j, i]  in place (fused training path: X was produced for g = 1); same grid as scale_rows
+// X[(j,s), (i,l)] *= g[j, i]  in place (fused training path: X was produced for g = 1).
+// grid (ceil(R1/8/256), sp/SCALE_ROWS, Bi): each thread owns 8 columns of one image and streams SCALE_ROWS rows
 __global__ void __launch_bounds__(256) scale_x(__nv_bfloat16* __restrict__ X, const float* __restrict__ g, int R1,
                                                int Spad, int Bc, int i0, int lpad) {
   const int c8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
@@ -809,7 +784,7 @@ __global__ void unpack_dwords_tc(const float* __restrict__ dWt, const float* __r
 // ---------------------------------------------------------------------------------------------------------------
 struct Plan {
   int nc;   // captions per chunk
-  size_t off_gram, off_dwt, off_drt, off_m, off_mb, off_gamma, off_stats, off_sim, off_cublas, off_x, off_e, off_b, off_f, total;
+  size_t off_gram, off_dwt, off_drt, off_m, off_mb, off_gamma, off_stats, off_sim, off_cublas, off_x, off_e, off_f, total;
 };
 constexpr size_t CUBLAS_WS = 64u << 20;
 
@@ -832,7 +807,7 @@ size_t fixed_bytes(int Bi, int Bc, int D, int Spad, int sp, int lp, int lpad, bo
   return o;
 }
 size_t per_caption_bytes(int Bi, int sp, int lp) {
-  return 3 * align_up((size_t)Bi * sp * lp * 2, 1024) + align_up((size_t)Bi * lp * 4, 1024) + 4096;
+  return 2 * align_up((size_t)Bi * sp * lp * 2, 1024) + align_up((size_t)Bi * lp * 4, 1024) + 4096;
 }
 
 Plan make_plan(int Bi, int Bc, int D, int Spad, int sp, int lp, int lpad, bool own_stats, size_t bytes) {
@@ -848,7 +823,6 @@ Plan make_plan(int Bi, int Bc, int D, int Spad, int sp, int lp, int lpad, bool o
   const size_t arr = (size_t)Bi * sp * nc * lp * 2;
   pl.off_x = take(arr);
   pl.off_e = take(arr);
-  pl.off_b = take(arr);
   pl.off_f = take((size_t)Bi * nc * lp * 4);
   pl.total = o;
   if (pl.total > bytes) pl.nc = 0;
@@ -901,7 +875,7 @@ int launch_pair_lpad(int lpad, const CUtensorMap& rt, const CUtensorMap& wt, con
 
 // ---- fused training path: one workspace shared by the forward (gram, X, E, fo, go) and the backward (the rest)
 struct TrainPlan {
-  size_t off_gram, off_x, off_e, off_fo, off_go, off_b, off_dwt, off_drt, off_m, off_mb, off_gamma, off_cublas, total;
+  size_t off_gram, off_x, off_e, off_fo, off_go, off_dwt, off_drt, off_m, off_mb, off_gamma, off_cublas, total;
 };
 TrainPlan train_plan(int Bi, int Bc, int D, int Spad, int sp, int lpad) {
   TrainPlan t{};
@@ -913,7 +887,6 @@ TrainPlan train_plan(int Bi, int Bc, int D, int Spad, int sp, int lpad) {
   t.off_e = take(arr);
   t.off_fo = take((size_t)Bi * Bc * lpad * 4);
   t.off_go = take((size_t)Bi * Bc * lpad * 4);
-  t.off_b = take(arr);
   t.off_dwt = take((size_t)Bc * lpad * D * 4);
   t.off_drt = take((size_t)Bi * sp * D * 4);
   t.off_m = take((size_t)Bi * sp * sp * 4);
@@ -939,26 +912,21 @@ int gram_matrices(cublasHandle_t h, const __nv_bfloat16* Rt, __nv_bfloat16* gram
   return GLORIA_OK;
 }
 
-// the accumulation GEMMs + unpack shared by both backward flavours (X, E, Bm hold nc captions starting at i0)
+// the accumulation GEMMs shared by both backward flavours (X, E hold nc captions starting at i0; f, g: see launch_mterm)
 int accumulate_chunk(cublasHandle_t h, const __nv_bfloat16* Rt, const __nv_bfloat16* Wt, const __nv_bfloat16* X,
-                     const __nv_bfloat16* E, const __nv_bfloat16* Bm, float* dWt, float* dRt, float* Mf, int Bi, int D,
-                     int Spad /* = sp: region rows per image of the operand matrices */, int lpad, int i0, int nc,
-                     bool first) {
+                     const __nv_bfloat16* E, const float* f, const float* g, float* dWt, float* dRt, float* Mf, int Bi,
+                     int Bc, int D, int sp, int lp, int i0, int nc, bool first, cudaStream_t st) {
   const float one = 1.f, zero = 0.f;
   const float beta = first ? 0.f : 1.f;
-  const int K1 = Bi * Spad, R1 = nc * lpad;
+  const int K1 = Bi * sp, R1 = nc * lp;
   // dWt[(i,l), d] = sum_(j,s) X^T[(j,s),(i,l)] Rt[(j,s), d]            (column-major: [D, R1] = Rt^T . (X^T)^T)
   GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, R1, K1, &one, Rt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1, &zero,
-                             dWt + (size_t)i0 * lpad * D, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+                             dWt + (size_t)i0 * lp * D, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
   // dRt[(j,s), d] (+)= sum_(i,l) X^T[(j,s),(i,l)] Wt[(i,l), d]         (column-major: [D, K1] = Wt^T . X^T)
-  GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, K1, R1, &one, Wt + (size_t)i0 * lpad * D, CUDA_R_16BF, D, X,
+  GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, K1, R1, &one, Wt + (size_t)i0 * lp * D, CUDA_R_16BF, D, X,
                              CUDA_R_16BF, R1, &beta, dRt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
-  // M_j[a, b] (+)= sum_(i,l) E^T[(j,a),(i,l)] Bo^T[(j,b),(i,l)]
-  GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_T, CUBLAS_OP_N, Spad, Spad, R1, &one, E, CUDA_R_16BF, R1,
-                                           (long long)Spad * R1, Bm, CUDA_R_16BF, R1, (long long)Spad * R1, &beta, Mf,
-                                           CUDA_R_32F, Spad, (long long)Spad * Spad, Bi, CUBLAS_COMPUTE_32F,
-                                           CUBLAS_GEMM_DEFAULT));
-  return GLORIA_OK;
+  // M_j[a, b] (+)= sum_(i,l) E^T[(j,a),(i,l)] g[j,i] f[j,(i,l)] E^T[(j,b),(i,l)]   (own tcgen05 kernel, tc_mterm.cu)
+  return launch_mterm(E, f, g, Mf, Bi, Bc, i0, R1, lp, sp, !first, st);
 }
 
 int finish_backward(cublasHandle_t h, const __nv_bfloat16* Rt, const __nv_bfloat16* Wt, const int32_t* cap_lens,
@@ -1031,7 +999,6 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
   float* gamma = (float*)(ws + pl.off_gamma);
   __nv_bfloat16* X = (__nv_bfloat16*)(ws + pl.off_x);
   __nv_bfloat16* E = (__nv_bfloat16*)(ws + pl.off_e);
-  __nv_bfloat16* Bm = (__nv_bfloat16*)(ws + pl.off_b);
   float* Fo = (float*)(ws + pl.off_f);
   int rc;
   if (stats == nullptr) {   // stand-alone use: one forward pass regenerates the per-word statistics
@@ -1073,10 +1040,8 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
     p.dbg = (long long*)g_phase_clock_buffer;
     if ((rc = bw::launch_pair_lpad<false>(lpad, rt, wt, gm, em, p, sms, st))) return rc;
     timer_record(GLORIA_TIMER_TC_BWD_GEMM, 0, st);
-    bw::scale_rows<<<dim3((unsigned)((R1 / 8 + 255) / 256), (unsigned)(sp / bw::SCALE_ROWS), (unsigned)Bi), 256, 0, st>>>(
-        E, Fo, Bm, R1, sp, nullptr, Bc, i0, lp);
-    GLORIA_LAUNCHED("scale_rows");
-    if ((rc = bw::accumulate_chunk(h, Rt, Wt, X, E, Bm, dWt, dRt, Mf, Bi, D, sp, lp, i0, nc, i0 == 0))) return rc;
+    if ((rc = bw::accumulate_chunk(h, Rt, Wt, X, E, Fo, nullptr, dWt, dRt, Mf, Bi, Bc, D, sp, lp, i0, nc, i0 == 0, st)))
+      return rc;
     if (i0 + nc < Bc) timer_record(GLORIA_TIMER_TC_BWD_GEMM, 1, st);
   }
   return bw::finish_backward(h, Rt, Wt, cap_lens, dWt, dRt, Mf, Mb, gamma, d_ctx, d_words, Bi, Bc, D, S, sp, Lw, lp,
@@ -1147,7 +1112,6 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void*
   char* ws = (char*)workspace;
   __nv_bfloat16* X = (__nv_bfloat16*)(ws + pl.off_x);
   __nv_bfloat16* E = (__nv_bfloat16*)(ws + pl.off_e);
-  __nv_bfloat16* Bm = (__nv_bfloat16*)(ws + pl.off_b);
   float* gamma = (float*)(ws + pl.off_gamma);
   cublasHandle_t h = bw::cublas_handle();
   if (!h) return fail(GLORIA_ERR_DRIVER, "cublasCreate failed");
@@ -1159,14 +1123,12 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void*
   // everything the forward stored is for g = 1 and linear in g = dsim[j, i]: apply it now
   bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, sp, Bc, 0, lp);
   GLORIA_LAUNCHED("scale_x");
-  bw::scale_rows<<<sgrid, 256, 0, st>>>(E, (const float*)(ws + pl.off_fo), Bm, R1, sp, dsim, Bc, 0, lp);
-  GLORIA_LAUNCHED("scale_rows");
   bw::gamma_sum<<<(R1 + 255) / 256, 256, 0, st>>>((const float*)(ws + pl.off_go), dsim, gamma, Bi, R1, Bc, 0, lp);
   GLORIA_LAUNCHED("gamma_sum");
   int rc;
-  if ((rc = bw::accumulate_chunk(h, (const __nv_bfloat16*)ctx_t, (const __nv_bfloat16*)words_t, X, E, Bm,
-                                 (float*)(ws + pl.off_dwt), (float*)(ws + pl.off_drt), (float*)(ws + pl.off_m), Bi, D,
-                                 sp, lp, 0, Bc, true)))
+  if ((rc = bw::accumulate_chunk(h, (const __nv_bfloat16*)ctx_t, (const __nv_bfloat16*)words_t, X, E,
+                                 (const float*)(ws + pl.off_fo), dsim, (float*)(ws + pl.off_dwt),
+                                 (float*)(ws + pl.off_drt), (float*)(ws + pl.off_m), Bi, Bc, D, sp, lp, 0, Bc, true, st)))
     return rc;
   return bw::finish_backward(h, (const __nv_bfloat16*)ctx_t, (const __nv_bfloat16*)words_t, cap_lens,
                              (float*)(ws + pl.off_dwt), (float*)(ws + pl.off_drt), (float*)(ws + pl.off_m),

@@ -196,6 +196,9 @@ struct UnitIter {
 
 // host side (tc_local.cu): 2-D bf16 tensor map [rows, inner] (inner contiguous), box [box_rows, 64], SWIZZLE_128B
 int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint32_t box_rows);
+// tc_mterm.cu: M[j] (+)= Eo_j^T diag(g[j,i] f[j,k]) Eo_j for all images (g may be null)
+int launch_mterm(const void* Et, const float* f, const float* g, float* M, int Bi, int Bc, int i0, int R1, int lp, int sp,
+                 bool accumulate, cudaStream_t st);
 // 4-D bf16 tensor [imgs, rows, mid, inner] (pitches in elements), box [1, box_rows, 1, 64], SWIZZLE_128B (TMA stores
 // of E^T rows: clipped at `inner` columns per caption and at `rows` region rows per image)
 int make_map4(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t mid, uint64_t rows, uint64_t imgs,
