@@ -114,17 +114,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
       const int nb = NT - a;
       const float* fr = p.f + (size_t)j * p.R1;
       const float* gr = p.g ? p.g + (size_t)j * p.Bc + p.i0 : nullptr;
+      // weight of column t64 of a k-block; loaded one k-block ahead so that its L2 latency is off the critical path
+      auto load_w = [&](int kb) {
+        float w = 0.f;
+        const int k = kb * KBLK + t64;
+        if (t64 < KBLK && kb < nkb && k < p.R1) w = __ldg(fr + k) * (gr ? __ldg(gr + k / p.lp) : 1.f);
+        return w;
+      };
+      float w_next = load_w(0);
       for (int kb = 0; kb < nkb; ++kb) {
         uint8_t* sbase = smem + (size_t)st * STAGE;
         __nv_bfloat16* wsm = reinterpret_cast<__nv_bfloat16*>(sbase + OFF_W);
-        // weights of this k-block (the stage's previous use has been released: the producer waited for it)
+        const float w_cur = w_next;
+        w_next = load_w(kb + 1);
+        // the stage's previous use has been released (the producer waited for it) once its tiles have landed
         mbar_wait(bar(B_FULL + st), ph);
-        if (t64 < KBLK) {
-          const int k = kb * KBLK + t64;
-          float w = 0.f;
-          if (k < p.R1) w = __ldg(fr + k) * (gr ? __ldg(gr + k / p.lp) : 1.f);
-          wsm[t64] = __float2bfloat16_rn(w);
-        }
+        if (t64 < KBLK) wsm[t64] = __float2bfloat16_rn(w_cur);
         asm volatile("bar.sync 2, 128;" ::: "memory");
         // A' = (tile a) * w per column; tile a is the stage's first tile; 128-byte swizzle: chunk c of row r sits at c ^ (r & 7)
         const uint8_t* src = sbase + (size_t)row * 128;
