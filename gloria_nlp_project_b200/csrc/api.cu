@@ -1,4 +1,5 @@
 // Library-level entry points: version, thread-local error text, launch counter.
+#include <cublas_v2.h>
 #include <stdarg.h>
 #include <atomic>
 #include <string.h>
@@ -32,6 +33,14 @@ int fail(int code, const char* fmt, ...) {
   vsnprintf(err_buf(), 512, fmt, ap);
   va_end(ap);
   return code;
+}
+
+void* cublas_handle_opaque() {
+  static thread_local cublasHandle_t h[16] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!h[dev] && cublasCreate(&h[dev]) != CUBLAS_STATUS_SUCCESS) h[dev] = nullptr;
+  return h[dev];
 }
 
 int cuda_fail(cudaError_t e, const char* what) {

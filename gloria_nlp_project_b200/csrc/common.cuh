@@ -13,6 +13,9 @@ namespace gloria {
 char* err_buf();
 std::atomic<long long>& launch_counter();
 void timer_record(int slot, int which, cudaStream_t st);   // which: 0 = before, 1 = after the kernel
+// one cuBLAS handle per host thread and device, created on first use (plain library GEMMs only); returned as void*
+// so that only the translation units that call cuBLAS include its header
+void* cublas_handle_opaque();
 
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);

@@ -7,6 +7,7 @@
 // the backward recomputes scores / P / A / C per chunk and applies the closed-form gradients.
 //
 // Pair index inside a chunk of `nc` captions starting at i0:  p = j * nc + (i - i0)   (image-major).
+#include <cublas_v2.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -635,15 +636,20 @@ DiagPlan diag_plan(int B, int D, int S, int Lw, int Lcap) {
 // scores + double softmax of the pairs (i, i); leaves P in sc and A in at (and attn_diag if given)
 int diag_forward(const float* ctx, const float* Wt, const int32_t* cap_lens, int B, int D, int S, int Lw, int Lcap,
                  int off, float temp1, float* sc, float* at, float* attn_diag, cudaStream_t st) {
-  GemmArgs g{};
-  g.A = Wt + (long long)off * D; g.B = ctx; g.C = sc;
-  g.M = Lcap; g.N = S; g.K = D; g.R = 1;
-  g.sAm = D; g.sAk = 1; g.sAb0 = 0; g.sAb1 = (long long)Lw * D; g.sAr = 0;
-  g.sBk = S; g.sBn = 1; g.sBb0 = 0; g.sBb1 = (long long)D * S; g.sBr = 0;
-  g.sCm = S; g.sCn = 1; g.sCb0 = 0; g.sCb1 = (long long)Lcap * S;
-  g.nb0 = 1; g.nb1 = B; g.beta = 0.f; g.mlim = cap_lens; g.mlim_off = 0;
-  int rc;
-  if ((rc = launch_gemm(g, st))) return rc;
+  // S_[i][l][s] = sum_d Wt[i][off+l][d] ctx[i][d][s]: a plain strided-batched fp32 GEMM (cuBLAS SGEMM, no TF32);
+  // row-major [Lcap, S] = [Lcap, D] [D, S]  ==  column-major [S, Lcap] = ctx_i [S, D] . Wt_i^T [D, Lcap]
+  cublasHandle_t h = (cublasHandle_t)cublas_handle_opaque();
+  if (!h) return fail(GLORIA_ERR_DRIVER, "cublasCreate failed");
+  const float one = 1.f, zero = 0.f;
+  cublasStatus_t cs = cublasSetStream(h, st);
+  if (cs == CUBLAS_STATUS_SUCCESS) cs = cublasSetWorkspace(h, nullptr, 0);       // default pool (never a stale caller buffer)
+  if (cs == CUBLAS_STATUS_SUCCESS) cs = cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
+  if (cs == CUBLAS_STATUS_SUCCESS)
+    cs = cublasSgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, S, Lcap, D, &one, ctx, S, (long long)D * S,
+                                   Wt + (long long)off * D, D, (long long)Lw * D, &zero, sc, S, (long long)Lcap * S, B);
+  if (cs == CUBLAS_STATUS_SUCCESS) cs = cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
+  if (cs != CUBLAS_STATUS_SUCCESS) return fail(GLORIA_ERR_DRIVER, "cublasSgemmStridedBatched -> status %d", (int)cs);
+  ++launch_counter();
   double_softmax_fwd<<<(unsigned)B, 256, 0, st>>>(sc, at, cap_lens, 0, B, B, Lcap, S, temp1, attn_diag, nullptr, 1);
   GLORIA_LAUNCHED("double_softmax_fwd(diag)");
   return GLORIA_OK;

@@ -829,13 +829,7 @@ Plan make_plan(int Bi, int Bc, int D, int Spad, int sp, int lp, int lpad, bool o
   return pl;
 }
 
-cublasHandle_t cublas_handle() {
-  static thread_local cublasHandle_t h[16] = {nullptr};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  if (!h[dev] && cublasCreate(&h[dev]) != CUBLAS_STATUS_SUCCESS) h[dev] = nullptr;
-  return h[dev];
-}
+cublasHandle_t cublas_handle() { return (cublasHandle_t)cublas_handle_opaque(); }
 
 #define GLORIA_CUBLAS(expr)                                                                       \
   do {                                                                                            \

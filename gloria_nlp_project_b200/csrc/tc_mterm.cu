@@ -20,7 +20,8 @@ constexpr int STAGE = OFF_W + 1024;                              // keeps every 
 constexpr int OFF_BAR = NSTAGE * STAGE;
 enum { B_FULL = 0, B_SCALED = NSTAGE, B_EMPTY = 2 * NSTAGE, B_ACCF = 3 * NSTAGE, B_ACCE, B_COUNT };
 constexpr int SMEM_BYTES = OFF_BAR + B_COUNT * 8 + 16 + 1024;
-constexpr int NTHREADS = 256;                                    // warp 0 TMA, warp 1 MMA, warps 4-7 scale + epilogue
+constexpr int NTHREADS = 384;                                    // warp 0 TMA, warp 1 MMA, warps 4-7 / 8-11 scale (k-blocks
+                                                                 // alternate between the two groups), warps 4-7 epilogue
 
 struct Params {
   const float* f;        // [Bi, R1]
@@ -104,33 +105,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ scale warps (thread = tile row) + epilogue
+    // two groups of four warps take alternate k-blocks, so one group's wait -> scale -> publish chain overlaps the other's
+    const int grp = (warp - 4) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int t64 = threadIdx.x - 128;                           // 0..127
+    const int t64 = (threadIdx.x - 128) & 127;                   // 0..127 inside the group
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    int st = 0; uint32_t ph = 0, nu = 0;
+    uint32_t nk = 0, nu = 0;                                     // running k-block / unit counters of this CTA
     for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
       const int j = u / NT, a = u % NT;
       const int nb = NT - a;
       const float* fr = p.f + (size_t)j * p.R1;
       const float* gr = p.g ? p.g + (size_t)j * p.Bc + p.i0 : nullptr;
-      // weight of column t64 of a k-block; loaded one k-block ahead so that its L2 latency is off the critical path
+      // weight of column t64 of a k-block; loaded one k-block (of this group) ahead: its L2 latency is off the chain
       auto load_w = [&](int kb) {
         float w = 0.f;
         const int k = kb * KBLK + t64;
         if (t64 < KBLK && kb < nkb && k < p.R1) w = __ldg(fr + k) * (gr ? __ldg(gr + k / p.lp) : 1.f);
         return w;
       };
-      float w_next = load_w(0);
+      // Both groups observe EVERY k-block's `full` barrier (parity waits must not skip a phase of a stage), the owner
+      // (k-block parity == group) scales it.
+      int kb_mine = (int)((grp + 2u - (nk & 1u)) & 1u);          // first k-block of this unit owned by this group
+      float w_next = load_w(kb_mine);
       for (int kb = 0; kb < nkb; ++kb) {
-        uint8_t* sbase = smem + (size_t)st * STAGE;
-        __nv_bfloat16* wsm = reinterpret_cast<__nv_bfloat16*>(sbase + OFF_W);
-        const float w_cur = w_next;
-        w_next = load_w(kb + 1);
+        const uint32_t n = nk + (uint32_t)kb;
+        const int st = (int)(n % NSTAGE);
+        const uint32_t ph = (n / NSTAGE) & 1u;
+        const bool mine = (n & 1u) == (uint32_t)grp;
+        float w_cur = 0.f;
+        if (mine) {
+          w_cur = w_next;
+          w_next = load_w(kb + 2);
+        }
         // the stage's previous use has been released (the producer waited for it) once its tiles have landed
         mbar_wait(bar(B_FULL + st), ph);
+        if (!mine) continue;
+        uint8_t* sbase = smem + (size_t)st * STAGE;
+        __nv_bfloat16* wsm = reinterpret_cast<__nv_bfloat16*>(sbase + OFF_W);
         if (t64 < KBLK) wsm[t64] = __float2bfloat16_rn(w_cur);
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+        else asm volatile("bar.sync 3, 128;" ::: "memory");
         // A' = (tile a) * w per column; tile a is the stage's first tile; 128-byte swizzle: chunk c of row r sits at c ^ (r & 7)
         const uint8_t* src = sbase + (size_t)row * 128;
         uint8_t* dst = sbase + OFF_AS + (size_t)row * 128;
@@ -139,7 +154,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
           const int pc = (c ^ (row & 7)) << 4;
           const uint4 v = *reinterpret_cast<const uint4*>(src + pc);
           const uint4 wv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(wsm) + c * 16);
-          uint4 o;
           const uint32_t vi[4] = {v.x, v.y, v.z, v.w}, wi[4] = {wv.x, wv.y, wv.z, wv.w};
           uint32_t oi[4];
 #pragma unroll
@@ -148,41 +162,48 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
                                               *reinterpret_cast<const __nv_bfloat162*>(&wi[k]));
             oi[k] = *reinterpret_cast<const uint32_t*>(&r2);
           }
-          o = make_uint4(oi[0], oi[1], oi[2], oi[3]);
-          *reinterpret_cast<uint4*>(dst + pc) = o;
+          *reinterpret_cast<uint4*>(dst + pc) = make_uint4(oi[0], oi[1], oi[2], oi[3]);
         }
         fence_proxy_async_smem();
         mbar_arrive(bar(B_SCALED + st));
-        if (++st == NSTAGE) { st = 0; ph ^= 1; }
       }
-      // ---- epilogue: blocks (a, a+b) from TMEM, mirrored to (a+b, a)
-      mbar_wait(bar(B_ACCF), nu & 1);
-      tc_fence_after();
-      const int r_glob = a * TILE + row;
-      float* Mj = p.M + (size_t)j * p.sp * p.sp;
-      for (int b = 0; b < nb; ++b) {
+      nk += (uint32_t)nkb;
+      if (grp == 0) {
+        // ---- epilogue: blocks (a, a+b) from TMEM, mirrored to (a+b, a)
+        mbar_wait(bar(B_ACCF), nu & 1);
+        tc_fence_after();
+        const int r_glob = a * TILE + row;
+        float* Mj = p.M + (size_t)j * p.sp * p.sp;
+        for (int b = 0; b < nb; ++b) {
 #pragma unroll 1
-        for (int c = 0; c < TILE / 16; ++c) {
-          float v[16];
-          tmem_ld16(tmem + lane_addr + (uint32_t)(b * TILE + c * 16), v);
-          tmem_ld_wait();
-          const int col0 = (a + b) * TILE + c * 16;
+          for (int c = 0; c < TILE / 16; ++c) {
+            float v[16];
+            tmem_ld16(tmem + lane_addr + (uint32_t)(b * TILE + c * 16), v);
+            tmem_ld_wait();
+            const int col0 = (a + b) * TILE + c * 16;
+            if (r_glob < p.sp) {
+              if (col0 + 16 <= p.sp) {                           // sp is a multiple of 16: whole group in or out
+                float4* d1 = reinterpret_cast<float4*>(Mj + (size_t)r_glob * p.sp + col0);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int col = col0 + k;
-            if (r_glob < p.sp && col < p.sp) {
-              float* d1 = Mj + (size_t)r_glob * p.sp + col;
-              *d1 = p.accumulate ? *d1 + v[k] : v[k];
-              if (b > 0) {                                       // mirror (lanes write consecutive floats: coalesced)
-                float* d2 = Mj + (size_t)col * p.sp + r_glob;
-                *d2 = p.accumulate ? *d2 + v[k] : v[k];
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  float4 o = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+                  if (p.accumulate) { const float4 t = d1[k4]; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
+                  d1[k4] = o;
+                }
+                if (b > 0) {                                     // mirror (lanes write consecutive floats: coalesced)
+#pragma unroll
+                  for (int k = 0; k < 16; ++k) {
+                    float* d2 = Mj + (size_t)(col0 + k) * p.sp + r_glob;
+                    *d2 = p.accumulate ? *d2 + v[k] : v[k];
+                  }
+                }
               }
             }
           }
         }
+        tc_fence_before();
+        mbar_arrive(bar(B_ACCE));
       }
-      tc_fence_before();
-      mbar_arrive(bar(B_ACCE));
       ++nu;
     }
   }

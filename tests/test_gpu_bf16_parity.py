@@ -308,3 +308,45 @@ def test_fused_state_is_consumed_once(gl):
     (l0 + l1).backward(retain_graph=True)
     with pytest.raises(RuntimeError, match="consumed"):
         (l0 + l1).backward()
+
+
+def test_mterm_many_units_per_cta(gl):
+    """The |C|-term kernel with several (image, row-tile) units per CTA and hundreds of k-blocks (B = 64: 192 units on
+    148 CTAs) -- the multi-unit pipeline state (stage / phase counters across units) is what is under test: the
+    fused-path gradients must still match the recompute path and the oracle-checked small cases."""
+    from gloria_nlp_project_b200 import _lib, ops
+    L = _lib.lib()
+    B = 64
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    ctx = (torch.randn(B, 768, 361, device="cuda", generator=gen) * 0.05)
+    words = (torch.randn(B, 768, 97, device="cuda", generator=gen) * 0.05)
+    lens = torch.full((B,), 97, dtype=torch.int32, device="cuda")
+    pk = ops.tc_prepack(ctx, words, lens, 97, 0)
+    st = torch.cuda.current_stream().cuda_stream
+    n = L.gloria_b200_tc_train_workspace(B, B, 768, 361, 97)
+    tws = torch.empty(n, dtype=torch.uint8, device="cuda")
+    sim = torch.empty(B, B, device="cuda")
+    stats = torch.empty(B, B, 2, 112, device="cuda")
+    sim0 = torch.empty(B, B, device="cuda")
+    _lib.check(L.gloria_b200_tc_local_sim_fwd(pk.ctx_h.data_ptr(), pk.ctx_n.data_ptr(), pk.words_h.data_ptr(),
+                                              pk.wnorm.data_ptr(), lens.data_ptr(), B, B, 768, 361, 97, 4.0, 5.0, 0, 1e-8,
+                                              sim0.data_ptr(), stats.data_ptr(), st), "fwd")
+    _lib.check(L.gloria_b200_tc_local_sim_fwd_train(pk.ctx_h.data_ptr(), pk.ctx_t.data_ptr(), pk.words_h.data_ptr(),
+                                                    pk.wnorm.data_ptr(), lens.data_ptr(), B, B, 768, 361, 97, 4.0, 5.0, 0,
+                                                    1e-8, sim.data_ptr(), tws.data_ptr(), n, st), "fwd_train")
+    dsim = torch.randn(B, B, device="cuda", generator=gen) * 0.1
+    g1 = (torch.empty_like(ctx), torch.empty_like(words))
+    _lib.check(L.gloria_b200_tc_local_sim_bwd_train(pk.ctx_t.data_ptr(), pk.words_t.data_ptr(), lens.data_ptr(), B, B, 768,
+                                                    361, 97, 97, 0, dsim.data_ptr(), g1[0].data_ptr(), g1[1].data_ptr(),
+                                                    tws.data_ptr(), n, st), "bwd_train")
+    nb = L.gloria_b200_tc_bwd_workspace(B, B, 768, 361, 97, 1, 0)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    g0 = (torch.empty_like(ctx), torch.empty_like(words))
+    _lib.check(L.gloria_b200_tc_local_sim_bwd(pk.ctx_h.data_ptr(), pk.ctx_t.data_ptr(), pk.ctx_n.data_ptr(),
+                                              pk.words_h.data_ptr(), pk.words_t.data_ptr(), pk.wnorm.data_ptr(),
+                                              lens.data_ptr(), stats.data_ptr(), B, B, 768, 361, 97, 97, 0, 4.0, 5.0, 0, 1e-8,
+                                              dsim.data_ptr(), g0[0].data_ptr(), g0[1].data_ptr(), ws.data_ptr(), nb, st),
+               "bwd")
+    torch.cuda.synchronize()
+    assert relerr(sim, sim0) < 1e-3
+    assert relerr(g1[0], g0[0]) < GRAD_TOL and relerr(g1[1], g0[1]) < GRAD_TOL
