@@ -125,6 +125,15 @@ __device__ __forceinline__ void warp_colsum(float* v, int lane, float* dst) {
 
 // region tile processed at position idx of a pair: the tile holding the ones row of G (the last one) goes first
 __device__ __forceinline__ int tile_at(int idx, int NT) { return idx == 0 ? NT - 1 : idx - 1; }
+// FUSED: pass A runs in tile_at order; the softmax, pass B and the next pair's GEMM1 run in an order that STARTS with
+// pass A's last tile, whose T' is still in TMEM when the coefficients are ready (one GEMM-T per pair saved)
+template <bool FUSED>
+__device__ __forceinline__ int tile_ord(int idx, int NT) {
+  if (!FUSED) return tile_at(idx, NT);
+  int k = idx + NT - 1;
+  if (k >= NT) k -= NT;
+  return tile_at(k, NT);
+}
 
 // FUSED = false: backward by recomputation (needs the forward's stats and dsim).
 // FUSED = true : training forward.  Every backward quantity is linear in g = dsim[j,i], so this mode computes sim AND
@@ -207,18 +216,19 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
       bool has = it.next();
       int ci = it.cap(), cj = it.j;
       if (has)
-        for (int idx = 0; idx < NT; ++idx) load_g1(ci, cj, tile_at(idx, NT));
+        for (int idx = 0; idx < NT; ++idx) load_g1(ci, cj, tile_ord<FUSED>(idx, NT));
       while (has) {
         const bool hasn = it.next();
         const int ni = it.cap(), nj = it.j;
         if (FUSED)
-          for (int k = 0; k < NT; ++k) load_tt(cj, tile_at(k, NT));      // pass A
-        load_tt(cj, tile_at(0, NT));
+          for (int k = 0; k < NT; ++k) load_tt(cj, tile_at(k, NT));      // pass A (its last T' tile is pass B's first)
+        else
+          load_tt(cj, tile_at(0, NT));
         for (int k = 1; k < NT; ++k) {
-          load_tt(cj, tile_at(k, NT));
-          if (hasn) load_g1(ni, nj, tile_at(k - 1, NT));
+          load_tt(cj, tile_ord<FUSED>(k, NT));
+          if (hasn) load_g1(ni, nj, tile_ord<FUSED>(k - 1, NT));
         }
-        if (hasn) load_g1(ni, nj, tile_at(NT - 1, NT));
+        if (hasn) load_g1(ni, nj, tile_ord<FUSED>(NT - 1, NT));
         has = hasn; ci = ni; cj = nj;
       }
 #ifdef GLORIA_PHASE_CLOCKS
@@ -289,7 +299,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
       bool has = it.next();
       int ci = it.cap(), cj = it.j;
       if (has)
-        for (int idx = 0; idx < NT; ++idx) gemm1(0, tile_at(idx, NT));
+        for (int idx = 0; idx < NT; ++idx) gemm1(0, tile_ord<FUSED>(idx, NT));
       while (has) {
         const bool hasn = it.next();
         const int ni = it.cap(), nj = it.j;
@@ -303,16 +313,17 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
                          t * TILE, cj);
         tma_store_commit();
         if (FUSED)
-          for (int k = 0; k < NT; ++k) gemmt();              // pass A: T' for the in-kernel |C'|^2 reduction
-        gemmt();
+          for (int k = 0; k < NT; ++k) gemmt();              // pass A: T' for the in-kernel |C'|^2 reduction; the last
+        else                                                 // tile stays in TMEM as pass B's first
+          gemmt();
         for (int k = 1; k < NT; ++k) {
           gemmt();
-          if (hasn) gemm1(n + 1, tile_at(k - 1, NT));
+          if (hasn) gemm1(n + 1, tile_ord<FUSED>(k - 1, NT));
         }
         umma_commit(bar(B_EE));                              // GEMM-T has finished reading E
         tma_store_wait_read();                               // ... and so have the Eo stores (issued long ago)
         mbar_arrive(bar(B_EE));
-        if (hasn) gemm1(n + 1, tile_at(NT - 1, NT));
+        if (hasn) gemm1(n + 1, tile_ord<FUSED>(NT - 1, NT));
         ++n;
         has = hasn; ci = ni; cj = nj;
       }
@@ -391,7 +402,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
 #pragma unroll
         for (int idx = 0; idx < MAX_NT; ++idx) {
           if (idx < NT) {
-            const int t = tile_at(idx, NT);
+            const int t = tile_ord<FUSED>(idx, NT);
             const int s_glob = t * TILE + row;
             const uint32_t sw = (uint32_t)(s_glob & 7);
             uint8_t* erow = smem + OFF_E + (size_t)(s_glob >> 3) * 1024u + (size_t)sw * 128u;
@@ -500,8 +511,10 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
                   }
                 }
               }
-              tc_fence_before();
-              mbar_arrive(bar(B_TTE));               // T' buffer may be overwritten by the next GEMM-T tile
+              if (idx < NT - 1) {                    // (the last tile's T' is kept: pass B starts with it)
+                tc_fence_before();
+                mbar_arrive(bar(B_TTE));             // T' buffer may be overwritten by the next GEMM-T tile
+              }
             }
           }
           // column sums over the 32 rows of this warp (halving butterfly), then over warps through shared memory
@@ -514,10 +527,12 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
 #pragma unroll
         for (int idx = 0; idx < MAX_NT; ++idx) {
           if (idx < NT) {
-            const int t = tile_at(idx, NT);
-            STIMED(sw_ttf, mbar_wait(bar(B_TTF), ttc & 1));
-            ++ttc;
-            tc_fence_after();
+            const int t = tile_ord<FUSED>(idx, NT);
+            if (!FUSED || idx > 0) {
+              STIMED(sw_ttf, mbar_wait(bar(B_TTF), ttc & 1));
+              ++ttc;
+              tc_fence_after();
+            }
             if (idx == 0) {
               // Z_l = sum_s E[s,l] sits in the ones row of this tile; the owning lane quarter reads it
               if (!FUSED && q == (zrow >> 5)) {
