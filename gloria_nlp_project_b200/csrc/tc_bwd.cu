@@ -61,6 +61,10 @@ struct PairParams {
   float* sim;               // FUSED: [Bi, Bc]  the forward's similarities
   int agg;                  // FUSED: GLORIA_AGG_SUM / _MEAN
   float* gamma;             // [Bc, LPAD]  sum_j (dL/d|W_l|) / |W_l|   (atomicAdd)
+  // word-mean attention (regularisers of gloria_loss.py:108-139): mean[j,i,s] = (1/L_i) sum_l E[s,l] / Z_l
+  float* mean_out;          // FUSED with xt == nullptr ("lean" forward): [Bi, Bc, S]
+  float* stats_out;         // FUSED: [Bi, Bc, 2, LPAD]  <W,C'>, |C'|^2 per word for a later recompute backward (or null)
+  const float* dmean;       // !FUSED: [Bi, Bc, S]  dL/d mean (or null)
   int Bi, Bc, i0, nc, D, S, NT;
   int lp;                   // column pitch per caption of X^T / E^T / fo / go: round_up(Lcap, 8) <= LPAD
   int sp;                   // region rows per image in X^T / E^T: round_up(S, 16) <= Spad
@@ -168,6 +172,9 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
   const int nkb1 = p.D / KBLK;        // k-blocks of GEMM1 (over channels)
   const int nkb2 = Spad / KBLK;       // k-blocks of GEMM-T (over regions)
   const uint32_t TT_COL = (uint32_t)(MAX_NT * LPAD);
+  // "lean" forward: sim (+ word-mean attention, per-word stats) only -- no operand rows, so no element pass and no
+  // pass-B GEMM-T
+  const bool lean = FUSED && p.xt == nullptr;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(bar(B_FULL + s), 1); mbar_init(bar(B_EMPTY + s), 1); }
@@ -225,7 +232,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
         else
           load_tt(cj, tile_at(0, NT));
         for (int k = 1; k < NT; ++k) {
-          load_tt(cj, tile_ord<FUSED>(k, NT));
+          if (!lean) load_tt(cj, tile_ord<FUSED>(k, NT));
           if (hasn) load_g1(ni, nj, tile_ord<FUSED>(k - 1, NT));
         }
         if (hasn) load_g1(ni, nj, tile_ord<FUSED>(NT - 1, NT));
@@ -306,18 +313,20 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
         TIMED_WAIT(wt_ef, mbar_wait(bar(B_EF), n & 1));      // E of this pair is complete in shared memory
         tc_fence_after();
         // Eo rows: straight from the E buffer by bulk tensor stores (columns >= LPAD are clipped by the map)
-        for (int t = 0; t < NT; ++t)
+        if (p.et != nullptr) {
+          for (int t = 0; t < NT; ++t)
 #pragma unroll
-          for (int wb = 0; wb < (LPAD + 63) / 64; ++wb)
-            tma_store_4d(&tm_e, base + OFF_E + (uint32_t)wb * e_lbo + (uint32_t)t * (TILE * 128), wb * 64, ci,
-                         t * TILE, cj);
-        tma_store_commit();
+            for (int wb = 0; wb < (LPAD + 63) / 64; ++wb)
+              tma_store_4d(&tm_e, base + OFF_E + (uint32_t)wb * e_lbo + (uint32_t)t * (TILE * 128), wb * 64, ci,
+                           t * TILE, cj);
+          tma_store_commit();
+        }
         if (FUSED)
           for (int k = 0; k < NT; ++k) gemmt();              // pass A: T' for the in-kernel |C'|^2 reduction; the last
         else                                                 // tile stays in TMEM as pass B's first
           gemmt();
         for (int k = 1; k < NT; ++k) {
-          gemmt();
+          if (!lean) gemmt();
           if (hasn) gemm1(n + 1, tile_ord<FUSED>(k - 1, NT));
         }
         umma_commit(bar(B_EE));                              // GEMM-T has finished reading E
@@ -397,6 +406,19 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
           accs[wl] = 0.f;                                    // column sums of this pair (ordered by the softmax barriers)
           accs[NCOL + wl] = 0.f;
         }
+        // gradient of the word-mean attention (recompute backward only): t1 * dL/dmean[j, i, s] of this thread's rows
+        float ms[MAX_NT];
+#pragma unroll
+        for (int idx = 0; idx < MAX_NT; ++idx) ms[idx] = 0.f;
+        if (!FUSED && p.dmean != nullptr) {
+          if (wl < NCOL) accs[wl] = 0.f;
+          const float* dm = p.dmean + ((size_t)j * p.Bc + i) * p.S;
+#pragma unroll
+          for (int idx = 0; idx < MAX_NT; ++idx) {
+            const int s_glob = tile_ord<FUSED>(idx, NT) * TILE + row;
+            if (idx < NT && s_glob < p.S) ms[idx] = p.t1 * __ldg(dm + s_glob);
+          }
+        }
         float nmb[MAX_NT], inv[MAX_NT];
         // ---------------- phase 1: word softmax, E -> shared memory (S_ stays in TMEM)
 #pragma unroll
@@ -471,6 +493,33 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             mbar_arrive(bar(B_EF));
           }
         }
+        if (!FUSED && p.dmean != nullptr) {
+          // ---------------- q'_l = sum_s E[s,l] t1 m_s  (A = softmax_s(t1 P): d(t1 P) = A (dA - sum_s A dA), dA = m_s / L)
+          float a0[WG];
+#pragma unroll
+          for (int k = 0; k < WG; ++k) a0[k] = 0.f;
+#pragma unroll
+          for (int idx = 0; idx < MAX_NT; ++idx) {
+            if (idx < NT) {
+              const int s_glob = tile_ord<FUSED>(idx, NT) * TILE + row;
+              const uint32_t sw = (uint32_t)(s_glob & 7);
+              const uint8_t* erow = smem + OFF_E + (size_t)(s_glob >> 3) * 1024u + (size_t)sw * 128u;
+#pragma unroll
+              for (int c = 0; c < CW; ++c) {
+                if (c_lo + c < NCH) {
+                  const int ch = c_lo + c;
+                  const uint4 ev = *reinterpret_cast<const uint4*>(erow + (size_t)(ch >> 3) * e_blk +
+                                                                   (size_t)((((uint32_t)ch & 7u) ^ sw) << 4));
+                  const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+                  for (int k = 0; k < 8; ++k)
+                    a0[c * 8 + k] = fmaf((k & 1) ? bf_hi(ew[k >> 1]) : bf_lo(ew[k >> 1]), ms[idx], a0[c * 8 + k]);
+                }
+              }
+            }
+          }
+          warp_colsum<WG>(a0, lane, accs + col0);      // read after the barriers of the coefficient step
+        }
         if (FUSED) {
           // ---------------- pass A: dot'_l = sum_s E S_,  |C'_l|^2 = sum_s E T'  (own columns, all tiles), Z row
           float a1[WG], a2[WG];
@@ -528,7 +577,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
         for (int idx = 0; idx < MAX_NT; ++idx) {
           if (idx < NT) {
             const int t = tile_ord<FUSED>(idx, NT);
-            if (!FUSED || idx > 0) {
+            if ((!FUSED || idx > 0) && !lean) {
               STIMED(sw_ttf, mbar_wait(bar(B_TTF), ttc & 1));
               ++ttc;
               tc_fence_after();
@@ -580,14 +629,22 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
               const float gamma = nw > 0.f ? dden * nc / nw : 0.f;
               const float rs = ddot * dot + beta * nc * nc;
               if (wl < NCOL) {
-                // dP = E (a S_ + b T' + c'),  X = e E + dS,  Bo = f E;  zero beyond the caption
-                coefA[wl] = live ? make_float4(p.t1 * ddot * iz, p.t1 * beta * iz * iz, -p.t1 * rs * iz, 0.f)
+                // dP = E (a S_ + b T' + c' + w t1 m_s),  X = e E + dS,  Bo = f E;  zero beyond the caption.
+                // w = 1 / (Z_l L): weight of E[s,l] in the word-mean attention; its gradient adds w (t1 m_s - t1 q_l)
+                const float wm = iz / (float)max(L, 1);
+                const float qt = (!FUSED && p.dmean != nullptr) ? accs[wl] * iz : 0.f;      // t1 sum_s A[s,l] m_s
+                coefA[wl] = live ? make_float4(p.t1 * ddot * iz, p.t1 * beta * iz * iz, -p.t1 * rs * iz - wm * qt, wm)
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                 coefX[wl] = live ? ddot * iz : 0.f;
               }
-              if (wl < p.lp) p.fo[((size_t)j * p.nc + u.i) * p.lp + wl] = live ? beta * iz * iz : 0.f;
+              if (p.fo != nullptr && wl < p.lp) p.fo[((size_t)j * p.nc + u.i) * p.lp + wl] = live ? beta * iz * iz : 0.f;
               if (FUSED) {
-                if (wl < p.lp) p.go[((size_t)j * p.nc + u.i) * p.lp + wl] = live ? gamma : 0.f;
+                if (p.stats_out != nullptr && wl < LPAD) {
+                  float* so = p.stats_out + ((size_t)j * p.Bc + i) * 2 * LPAD;
+                  so[wl] = dotp;
+                  so[LPAD + wl] = c2p;
+                }
+                if (p.go != nullptr && wl < p.lp) p.go[((size_t)j * p.nc + u.i) * p.lp + wl] = live ? gamma : 0.f;
                 if (wl == 0) {      // sim = log sum_l exp(t2 cos_l)  (mean: minus log L), gloria_loss.py:153-158
                   float r = mx + logf(tot);
                   if (p.agg == GLORIA_AGG_MEAN) r -= logf((float)L);
@@ -601,7 +658,36 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             const int s_glob = t * TILE + row;
             const uint32_t sw = (uint32_t)(s_glob & 7);
             const uint8_t* erow = smem + OFF_E + (size_t)(s_glob >> 3) * 1024u + (size_t)sw * 128u;
+            if (lean) {
+              // word-mean attention row: sum_l E[s,l] / (Z_l L) over this group's words, then over the 3 groups
+              float macc = 0.f;
+#pragma unroll
+              for (int c = 0; c < CW; ++c) {
+                if (c_lo + c < NCH) {
+                  const int ch = c_lo + c;
+                  const uint4 ev = *reinterpret_cast<const uint4*>(erow + (size_t)(ch >> 3) * e_blk +
+                                                                   (size_t)((((uint32_t)ch & 7u) ^ sw) << 4));
+                  const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+                  for (int k = 0; k < 8; ++k)
+                    macc = fmaf((k & 1) ? bf_hi(ew[k >> 1]) : bf_lo(ew[k >> 1]), cA[c * 8 + k].w, macc);
+                }
+              }
+              if (idx == 0) {
+                tc_fence_before();
+                mbar_arrive(bar(B_TTE));               // the T' tile pass A left behind is released
+              }
+              mbar_arrive(bar(B_D1E + t));             // S_ tile may be overwritten by the next pair's GEMM1
+              float2* xb = xch + (xc & 1) * (NGROUP * 128);
+              ++xc;
+              xb[g * 128 + row].x = macc;
+              asm volatile("bar.sync 1, 384;" ::: "memory");
+              if (g == 0 && p.mean_out != nullptr && s_glob < p.S)
+                p.mean_out[((size_t)j * p.Bc + i) * p.S + s_glob] = xb[row].x + xb[128 + row].x + xb[256 + row].x;
+              continue;
+            }
             const float nmbv = nmb[idx], rinv = inv[idx];
+            const float msv = ms[idx];
             const uint32_t ts = tmem + lane_addr + (uint32_t)(t * LPAD + col0);
             const uint32_t tt = tmem + lane_addr + TT_COL + (uint32_t)col0;
             float dp[WG];
@@ -631,8 +717,9 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
                 const float e0 = bf_lo(ew[k >> 1]), e1 = bf_hi(ew[k >> 1]);
                 const float4 f0 = cA[o], f1 = cA[o + 1];
                 const float P0 = ex2(fmaf(sv[k], LOG2E, nmbv)) * rinv, P1 = ex2(fmaf(sv[k + 1], LOG2E, nmbv)) * rinv;
-                const float d0 = e0 * fmaf(f0.x, sv[k], fmaf(f0.y, tv[k], f0.z));
-                const float d1 = e1 * fmaf(f1.x, sv[k + 1], fmaf(f1.y, tv[k + 1], f1.z));
+                const float c0 = FUSED ? f0.z : fmaf(f0.w, msv, f0.z), c1 = FUSED ? f1.z : fmaf(f1.w, msv, f1.z);
+                const float d0 = e0 * fmaf(f0.x, sv[k], fmaf(f0.y, tv[k], c0));
+                const float d1 = e1 * fmaf(f1.x, sv[k + 1], fmaf(f1.y, tv[k + 1], c1));
                 const uint32_t pk = pack_bf16(P0, P1) & mk[k >> 1];   // P = 0 beyond the caption (so dS = 0 there)
                 dp[o] = d0;
                 dp[o + 1] = d1;
@@ -652,7 +739,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             // pass 2: rows of X^T  ([(j, s), (i, l)] bf16, 16-byte stores along l)
             const size_t goff = ((size_t)j * p.sp + s_glob) * pitch + (size_t)u.i * p.lp;
             uint4* xo = reinterpret_cast<uint4*>(p.xt + goff);
-            const bool row_out = s_glob < p.sp;              // padded region rows beyond sp do not exist in X^T
+            const bool row_out = s_glob < p.sp && p.xt != nullptr;   // padded region rows beyond sp do not exist in X^T
 #pragma unroll
             for (int c = 0; c < CW; ++c) {
               const int ch = c_lo + c;
@@ -986,8 +1073,9 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
                                             const void* words_h, const void* words_t, const float* wnorm,
                                             const int32_t* cap_lens, const float* stats, int Bi,
                                             int Bc, int D, int S, int Lw, int Lcap, int word_off, float temp1,
-                                            float temp2, int agg, float eps, const float* dsim, float* d_ctx,
-                                            float* d_words, void* workspace, size_t workspace_bytes, void* stream) {
+                                            float temp2, int agg, float eps, const float* dsim,
+                                            const float* d_attn_mean, float* d_ctx, float* d_words, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
   GLORIA_CHECK_ARG(ctx_h && ctx_t && ctx_n && words_h && words_t && wnorm && cap_lens && dsim && d_ctx && d_words &&
                        workspace,
                    "null pointer");
@@ -1038,7 +1126,7 @@ extern "C" int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t
     const int nc = min(pl.nc, Bc - i0);
     const int R1 = nc * lp;
     bw::PairParams p{};
-    p.wnorm = wnorm; p.cap_lens = cap_lens; p.stats = stats; p.dsim = dsim;
+    p.wnorm = wnorm; p.cap_lens = cap_lens; p.stats = stats; p.dsim = dsim; p.dmean = d_attn_mean;
     p.xt = X; p.et = E; p.fo = Fo; p.gamma = gamma;
     CUtensorMap em;
     if ((rc = make_map4(&em, E, (uint64_t)lp, (uint64_t)nc, (uint64_t)sp, (uint64_t)Bi, (uint64_t)lp, (uint64_t)R1,
@@ -1105,6 +1193,50 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void*
   p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps; p.agg = agg;
   p.dbg = (long long*)g_phase_clock_buffer;
   return bw::launch_pair_lpad<true>(lpad, rt, wt, gm, em, p, sms, st);
+}
+
+// "lean" forward: sim + word-mean attention (+ the per-word statistics a later recompute backward needs)
+extern "C" size_t gloria_b200_tc_mean_workspace(int Bi, int Bc, int D, int S, int Lcap) {
+  if (Bi <= 0 || Bc <= 0 || gloria_b200_tc_supported(D, S, Lcap)) return 0;
+  const int Spad = gloria_b200_tc_spad(S);
+  return align_up((size_t)Bi * Spad * Spad * 2, 1024) + bw::CUBLAS_WS;
+}
+
+extern "C" int gloria_b200_tc_local_sim_fwd_mean(const void* ctx_h, const void* ctx_t, const void* words_h,
+                                                 const float* wnorm, const int32_t* cap_lens, int Bi, int Bc, int D,
+                                                 int S, int Lcap, float temp1, float temp2, int agg, float eps,
+                                                 float* sim, float* attn_mean, float* stats, void* workspace,
+                                                 size_t workspace_bytes, void* stream) {
+  GLORIA_CHECK_ARG(ctx_h && ctx_t && words_h && wnorm && cap_lens && sim && attn_mean && workspace, "null pointer");
+  GLORIA_CHECK_ARG(Bi > 0 && Bc > 0, "bad batch sizes %d x %d", Bi, Bc);
+  if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
+  if (agg == GLORIA_AGG_MAX) return fail(GLORIA_ERR_UNSUPPORTED, "agg=max: use the plain forward");
+  const size_t need = gloria_b200_tc_mean_workspace(Bi, Bc, D, S, Lcap);
+  if (workspace_bytes < need) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap), lp = gloria_b200_tc_lp(Lcap);
+  const int sp = gloria_b200_tc_sp(S);
+  char* ws = (char*)workspace;
+  __nv_bfloat16* gram = (__nv_bfloat16*)ws;
+  cublasHandle_t h = bw::cublas_handle();
+  if (!h) return fail(GLORIA_ERR_DRIVER, "cublasCreate failed");
+  GLORIA_CUBLAS(cublasSetStream(h, st));
+  GLORIA_CUBLAS(cublasSetWorkspace(h, ws + align_up((size_t)Bi * Spad * Spad * 2, 1024), bw::CUBLAS_WS));
+  int rc;
+  if ((rc = bw::gram_matrices(h, (const __nv_bfloat16*)ctx_t, gram, Bi, D, S, Spad, sp, st))) return rc;
+  CUtensorMap rt, wt, gm;
+  if ((rc = make_map(&rt, ctx_h, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;
+  if ((rc = make_map(&wt, words_h, (uint64_t)D, (uint64_t)Bc * lpad, (uint32_t)lpad))) return rc;
+  if ((rc = make_map(&gm, gram, (uint64_t)Spad, (uint64_t)Bi * Spad, TILE))) return rc;
+  int dev = 0, sms = 0;
+  GLORIA_CUDA(cudaGetDevice(&dev));
+  GLORIA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  bw::PairParams p{};
+  p.wnorm = wnorm; p.cap_lens = cap_lens; p.sim = sim; p.mean_out = attn_mean; p.stats_out = stats;
+  p.Bi = Bi; p.Bc = Bc; p.i0 = 0; p.nc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE; p.lp = lp; p.sp = sp;
+  p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps; p.agg = agg;
+  p.dbg = (long long*)g_phase_clock_buffer;
+  return bw::launch_pair_lpad<true>(lpad, rt, wt, gm, gm /* E^T map unused: nothing is stored */, p, sms, st);
 }
 
 extern "C" int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void* words_t, const int32_t* cap_lens,

@@ -106,16 +106,29 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                                                  _ptr(diag), _ptr(mean), ws.data_ptr(), nbytes, _stream(ctx))
             _lib.check(rc, "local_sim_fwd_f32")
         else:
-            if want_mean:
-                raise RuntimeError("word-mean attention output (entropy / KL / no-attn regularisers) is served by the "
-                                   "fp32 kernels: use set_precision('fp32') for those configs")
+            if want_mean and agg == AGG["max"]:
+                raise RuntimeError("word-mean attention output is not available with agg='max'")
             if L.gloria_b200_tc_supported(D, S, lcap) != 0:
                 raise RuntimeError(f"bf16 tensor-core kernels need D % 128 == 0, S <= 384, cap_len <= 128; got "
                                    f"D={D} S={S} Lcap={lcap} (use set_precision('fp32'))")
             packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
             need_grad = agg != AGG["max"] and (ctx.requires_grad or words.requires_grad or torch.is_grad_enabled())
             fused = False
-            if need_grad and _FUSED_TRAIN:
+            if want_mean:
+                # regulariser configs: one kernel gives sim + the word-mean attention of every pair (+ the per-word
+                # scalars); their backward is the recompute kernel, which takes d(attn_mean) next to dsim
+                nbytes = L.gloria_b200_tc_mean_workspace(Bi, Bc, D, S, lcap)
+                ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+                if need_grad:
+                    stats = torch.empty((Bi, Bc, 2, L.gloria_b200_tc_lpad(lcap)), dtype=torch.float32, device=dev)
+                rc = L.gloria_b200_tc_local_sim_fwd_mean(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(),
+                                                         packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
+                                                         cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg, eps,
+                                                         sim.data_ptr(), mean.data_ptr(), _ptr(stats), ws.data_ptr(),
+                                                         nbytes, _stream(ctx))
+                _lib.check(rc, "tc_local_sim_fwd_mean")
+                fused = True
+            elif need_grad and _FUSED_TRAIN:
                 # fused training forward: sim AND the backward's operand rows (for dsim = 1) in one kernel; the state
                 # tensor is the workspace the backward consumes.  Falls back to forward + recompute-backward when the
                 # workspace does not fit.
@@ -196,13 +209,13 @@ def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
     st = _stream(ctx)
     with torch.cuda.device(dev):
         all_pairs = dsim is not None or d_mean is not None
-        diag_separately = d_diag is not None and (not all_pairs or (mode == MODE_BF16 and d_mean is None))
+        diag_separately = d_diag is not None and (not all_pairs or mode == MODE_BF16)
         if all_pairs:
             if dsim is None:
                 dsim = torch.zeros((Bi, Bc), dtype=torch.float32, device=dev)
-            if mode == MODE_BF16 and d_mean is None:
-                tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp2, agg, eps, dsim, d_ctx,
-                                 d_words)
+            if mode == MODE_BF16:
+                tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp2, agg, eps, dsim, d_mean,
+                                 d_ctx, d_words)
             else:
                 nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
                 ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
@@ -224,7 +237,8 @@ def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
     return d_ctx, d_words
 
 
-def tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp2, agg, eps, dsim, d_ctx, d_words):
+def tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp2, agg, eps, dsim, d_mean, d_ctx,
+                     d_words):
     """bf16 tensor-core backward: prepack, then the fused recompute kernel + accumulation GEMMs behind the C ABI."""
     Bi, D, S = ctx.shape
     Bc, _, Lw = words.shape
@@ -253,7 +267,8 @@ def tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp
                                         packed.words_h.data_ptr(), packed.words_t.data_ptr(), packed.wnorm.data_ptr(),
                                         cap_lens.data_ptr(), stats.data_ptr() if have else None,
                                         Bi, Bc, D, S, Lw, lcap, word_off, temp1, temp2, agg, eps, dsim.data_ptr(),
-                                        d_ctx.data_ptr(), d_words.data_ptr(), ws.data_ptr(), nbytes, _stream(ctx))
+                                        _ptr(d_mean), d_ctx.data_ptr(), d_words.data_ptr(), ws.data_ptr(), nbytes,
+                                        _stream(ctx))
     _lib.check(rc, "tc_local_sim_bwd")
 
 

@@ -161,26 +161,39 @@ int gloria_b200_tc_local_sim_fwd(const void* ctx_h, const void* ctx_n, const voi
                                  float temp1, float temp2, int agg, float eps,
                                  float* sim, float* stats, void* stream);
 
-/* Workspace of the backward.  `budget` (0 = unlimited) caps it: captions are then processed in chunks.  The three
- * bf16 operand matrices take 3 * Bi * Spad * Lpad * 2 bytes per caption (about 260 KB per pair at the full sizes:
- * 67.6 GB for B = 512 -- this is what the 180 GB of HBM3e are used for). */
+/* Workspace of the backward.  `budget` (0 = unlimited) caps it: captions are then processed in chunks.  The two
+ * bf16 operand matrices take 2 * Bi * Sp * Lp * 2 bytes per caption (about 153 KB per pair at the full sizes:
+ * 40 GB for B = 512 -- this is what the 180 GB of HBM3e are used for). */
 size_t gloria_b200_tc_bwd_workspace(int Bi, int Bc, int D, int S, int Lcap, int have_stats, size_t budget);
 
 /* Backward (agg = sum / mean).  A fused tcgen05 kernel recomputes scores and both softmaxes per pair, obtains
  * <C_l, R_s> from the image's Gram matrix (one more score-shaped GEMM, K = S) and writes the per-pair operand rows
  * X^T, E^T, (beta/Z^2) E^T; the sums over images / captions are plain GEMMs.  `stats` is the forward's output
  * (NULL: recomputed with one extra forward pass).  d_ctx [Bi, D, S] and d_words [Bc, D, Lw] fp32 in the callers'
- * native layouts are fully overwritten (padded word columns get exactly 0). */
+ * native layouts are fully overwritten (padded word columns get exactly 0).
+ * d_attn_mean (optional, [Bi, Bc, S]): gradient w.r.t. the word-mean attention of every pair
+ * (gloria_b200_tc_local_sim_fwd_mean) -- the entropy / symmetric-KL / no-attn regularisers of
+ * gloria/loss/gloria_loss.py:108-139,173-199 back-propagate through it. */
 int gloria_b200_tc_local_sim_bwd(const void* ctx_h, const void* ctx_t, const void* ctx_n, const void* words_h,
                                  const void* words_t, const float* wnorm, const int32_t* cap_lens, const float* stats, int Bi, int Bc, int D, int S, int Lw,
                                  int Lcap, int word_off, float temp1, float temp2, int agg, float eps,
-                                 const float* dsim, float* d_ctx, float* d_words,
+                                 const float* dsim, const float* d_attn_mean, float* d_ctx, float* d_words,
                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Forward with the word-mean attention of every pair: attn_mean[j, i, s] = (1/L_i) sum_l A[s, l]  ([Bi, Bc, S] fp32;
+ * gloria/loss/gloria_loss.py:125-127 `attn.mean(1)` collected over the caption loop), sim as above, and (optional)
+ * `stats` [Bi, Bc, 2, Lpad] for gloria_b200_tc_local_sim_bwd.  One tcgen05 kernel per call (scores, both softmaxes,
+ * Gram-form |C'|^2, Z from the Gram matrix's row of ones); workspace = Gram matrices. */
+size_t gloria_b200_tc_mean_workspace(int Bi, int Bc, int D, int S, int Lcap);
+int gloria_b200_tc_local_sim_fwd_mean(const void* ctx_h, const void* ctx_t, const void* words_h, const float* wnorm,
+                                      const int32_t* cap_lens, int Bi, int Bc, int D, int S, int Lcap,
+                                      float temp1, float temp2, int agg, float eps, float* sim, float* attn_mean,
+                                      float* stats, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Fused training path (used when the workspace fits): every backward quantity of a pair is linear in
  * g = dsim[j, i], so ONE kernel computes sim and, for g = 1, the backward operand rows (X^T, E^T, f, gamma) during the
  * forward; the backward is a scale by g plus the accumulation GEMMs -- nothing is recomputed.  The same workspace
- * (gloria_b200_tc_train_workspace bytes; 69 GB at B = 512) is passed to both calls and must stay untouched in between;
+ * (gloria_b200_tc_train_workspace bytes; 41.7 GB at B = 512) is passed to both calls and must stay untouched in between;
  * the backward consumes it (X is scaled in place), so it can run once per forward. */
 size_t gloria_b200_tc_train_workspace(int Bi, int Bc, int D, int S, int Lcap);
 int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void* ctx_t, const void* words_h, const float* wnorm,

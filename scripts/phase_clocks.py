@@ -29,7 +29,7 @@ d_ctx, d_words = torch.empty_like(ctx), torch.empty_like(words)
 dbg.zero_()
 for _ in range(2):
     assert lib.gloria_b200_tc_local_sim_bwd(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(), packed.ctx_n.data_ptr(), packed.words_h.data_ptr(), packed.words_t.data_ptr(), packed.wnorm.data_ptr(),
-        lens.data_ptr(), stats.data_ptr(), B, B, 768, 361, 97, L, 0, 4.0, 5.0, 0, 1e-8, dsim.data_ptr(), d_ctx.data_ptr(),
+        lens.data_ptr(), stats.data_ptr(), B, B, 768, 361, 97, L, 0, 4.0, 5.0, 0, 1e-8, dsim.data_ptr(), None, d_ctx.data_ptr(),
         d_words.data_ptr(), ws.data_ptr(), nbytes, st) == 0
 torch.cuda.synchronize()
 d = dbg.cpu().double(); act = d[:, 5] > 0

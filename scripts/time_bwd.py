@@ -34,7 +34,7 @@ lib.gloria_b200_set_timer_events(2, evs[2][0].cuda_event, evs[2][1].cuda_event)
 def bwd():
     rc = lib.gloria_b200_tc_local_sim_bwd(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(), packed.ctx_n.data_ptr(), packed.words_h.data_ptr(), packed.words_t.data_ptr(), packed.wnorm.data_ptr(),
                                           lens.data_ptr(), stats.data_ptr(), B, B, 768, 361, 97, L, 0, 4.0, 5.0, 0, 1e-8,
-                                          dsim.data_ptr(), d_ctx.data_ptr(), d_words.data_ptr(), ws.data_ptr(), nbytes, st)
+                                          dsim.data_ptr(), None, d_ctx.data_ptr(), d_words.data_ptr(), ws.data_ptr(), nbytes, st)
     assert rc == 0, lib.gloria_b200_last_error()
 
 

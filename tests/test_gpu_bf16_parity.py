@@ -187,7 +187,7 @@ def test_backward_chunked_workspace_and_no_stats(gl):
         d_ctx, d_words = torch.empty_like(ctx), torch.empty_like(words)
         _lib.check(L.gloria_b200_tc_local_sim_bwd(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(), packed.ctx_n.data_ptr(), packed.words_h.data_ptr(), packed.words_t.data_ptr(), packed.wnorm.data_ptr(), lens.data_ptr(),
                                                   stats.data_ptr() if use_stats else None, B, B, 768, 361, 97, lcap, 0,
-                                                  4.0, 5.0, 0, 1e-8, dsim.data_ptr(), d_ctx.data_ptr(),
+                                                  4.0, 5.0, 0, 1e-8, dsim.data_ptr(), None, d_ctx.data_ptr(),
                                                   d_words.data_ptr(), ws.data_ptr(), nbytes, st), "bwd")
         torch.cuda.synchronize()
         outs.append((d_ctx, d_words))
@@ -285,7 +285,7 @@ def test_fused_training_path_c_abi(gl):
     _lib.check(L.gloria_b200_tc_local_sim_bwd(pk.ctx_h.data_ptr(), pk.ctx_t.data_ptr(), pk.ctx_n.data_ptr(),
                                               pk.words_h.data_ptr(), pk.words_t.data_ptr(), pk.wnorm.data_ptr(),
                                               lens.data_ptr(), stats.data_ptr(), Bi, Bc, 768, 361, 97, lcap, 0, 4.0, 5.0, 0,
-                                              1e-8, dsim.data_ptr(), d_ctx0.data_ptr(), d_words0.data_ptr(), ws.data_ptr(),
+                                              1e-8, dsim.data_ptr(), None, d_ctx0.data_ptr(), d_words0.data_ptr(), ws.data_ptr(),
                                               nb, st), "bwd")
     torch.cuda.synchronize()
     # the two paths round X differently (fused: bf16(g * bf16(X for g=1))), each must sit inside the gradient gate
@@ -345,8 +345,55 @@ def test_mterm_many_units_per_cta(gl):
     _lib.check(L.gloria_b200_tc_local_sim_bwd(pk.ctx_h.data_ptr(), pk.ctx_t.data_ptr(), pk.ctx_n.data_ptr(),
                                               pk.words_h.data_ptr(), pk.words_t.data_ptr(), pk.wnorm.data_ptr(),
                                               lens.data_ptr(), stats.data_ptr(), B, B, 768, 361, 97, 97, 0, 4.0, 5.0, 0, 1e-8,
-                                              dsim.data_ptr(), g0[0].data_ptr(), g0[1].data_ptr(), ws.data_ptr(), nb, st),
+                                              dsim.data_ptr(), None, g0[0].data_ptr(), g0[1].data_ptr(), ws.data_ptr(), nb, st),
                "bwd")
     torch.cuda.synchronize()
     assert relerr(sim, sim0) < 1e-3
     assert relerr(g1[0], g0[0]) < GRAD_TOL and relerr(g1[1], g0[1]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("B,seed,lens,use_nav,kw", [
+    (5, 21, [97, 41, 17, 5, 2], True,
+     dict(no_attn_loss_weight=0.3, attention_divergence_loss_weight=0.2, attention_entropy_loss_weight=0.1)),
+    (6, 22, [33, 30, 21, 12, 7, 3], False, dict(attention_entropy_loss_weight=1.0, attention_divergence_loss_weight=0.5)),
+    (16, 23, None, True, dict(no_attn_loss_weight=1.0, attention_divergence_loss_weight=1.0,
+                              attention_entropy_loss_weight=1.0, agg="mean")),
+])
+def test_regularisers_tensor_core(gl, B, seed, lens, use_nav, kw):
+    """Regulariser configs (gloria_loss.py:108-139,173-199; `no_attn_vec` column, no-attn / symmetric-KL / entropy
+    terms over the word-mean attention of every pair) on the tensor-core path: the lean forward kernel emits
+    attn_mean [B, B, S(+1)], the recompute backward takes its gradient.  Forward values against the numpy oracle
+    (fp64); gradients against this library's fp32 mode, which is pinned to the reference's autograd on the golden
+    fixtures (test_gpu_fp32_parity.py::test_local_loss_small_golden)."""
+    import gloria_nlp_project_b200 as g
+    img_l, txt_l, _, _, cl = gen_inputs(seed, B, 768, 19, 19, 97, cap_lens=lens, scale=0.05, dtype=np.float32)
+    nav_l = (np.random.default_rng(seed).standard_normal(768) * 0.05).astype(np.float32) if use_nav else None
+
+    def run():
+        img, txt = cu(img_l, True), cu(txt_l, True)
+        nav = cu(nav_l, True) if use_nav else None
+        l0, l1, na, kl, ent, maps = gl.local_loss(img, txt, cl, no_attn_vec=nav, **kw)
+        (l0 + 0.7 * l1 + na + kl + ent).backward()
+        torch.cuda.synchronize()
+        vals = [float(v.detach()) if isinstance(v, torch.Tensor) else float(v) for v in (l0, l1, na, kl, ent)]
+        return vals, img.grad.clone(), txt.grad.clone(), (nav.grad.clone() if use_nav else None)
+
+    vals, d_img, d_txt, d_nav = run()
+    g.set_precision("fp32")
+    try:
+        vals32, r_img, r_txt, r_nav = run()
+    finally:
+        g.set_precision("bf16")
+    o = O.local_loss(img_l.astype(np.float64), txt_l.astype(np.float64), cl,
+                     no_attn_vec=None if nav_l is None else nav_l.astype(np.float64), **kw)
+    for name, v, v32, ref in zip(("loss0", "loss1", "no_attn", "kl", "entropy"), vals, vals32, o[:5]):
+        ref = float(ref)
+        assert abs(v32 - ref) <= 1e-4 * max(1.0, abs(ref)), (name, v32, ref)
+        assert abs(v - ref) <= LOGIT_TOL * max(1.0, abs(ref)), (name, v, ref)
+    e_img, e_txt = relerr(d_img, r_img), relerr(d_txt, r_txt)
+    print(f"bf16 regularisers B={B}: d_img rel err {e_img:.3e}, d_txt rel err {e_txt:.3e}")
+    assert e_img < GRAD_TOL and e_txt < GRAD_TOL
+    if use_nav:
+        assert relerr(d_nav, r_nav) < GRAD_TOL
+    for i, L in enumerate(cl):
+        assert torch.all(d_txt[i, :, L:] == 0)
