@@ -14,7 +14,7 @@ import torch
 from . import _config, ops
 
 __all__ = ["cosine_similarity", "attention_fn", "global_loss", "kl_divergence", "entropy", "local_loss",
-           "local_similarities"]
+           "local_similarities", "diagonal_attention_maps", "supervised_attention_loss"]
 
 
 def _mode(*tensors: torch.Tensor) -> int:
@@ -71,6 +71,49 @@ def local_similarities(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, 
                                            ops.AGG[agg], float(eps), bool(want_attn_maps), bool(want_mean_attn),
                                            mode)
     return sim, (diag if want_attn_maps else None), (mean if want_mean_attn else None), lens
+
+
+def diagonal_attention_maps(img_features, words_emb, cap_lens, temp1=4.0, no_attn_vec=None, word_offset=0):
+    """att_maps of the diagonal pairs only -- the list local_loss returns as its 6th item (gloria_loss.py:141-143,
+    `attn[i:i+1]` of caption i), computed for B pairs instead of B^2.  Differentiable."""
+    if not img_features.is_cuda:
+        raise RuntimeError("gloria_b200 runs on CUDA tensors only (sm_100a); there is no CPU fallback")
+    Bc, _, Lw = words_emb.shape
+    ih, iw = img_features.shape[2], img_features.shape[3]
+    dev_lens, lens = _cap_lens(cap_lens, Bc, word_offset, Lw, img_features.device)
+    ctx = _context(img_features, no_attn_vec)
+    diag = ops.diag_attn_fwd(ctx, words_emb.float(), dev_lens, max(lens), word_offset, float(temp1))
+    s0 = 1 if no_attn_vec is not None else 0
+    return [diag[i:i + 1, :lens[i], s0:].reshape(1, lens[i], ih, iw) for i in range(Bc)]
+
+
+_CELL_INDEX = {}
+
+
+def _cell_index(ih, iw, oh, ow, device):
+    """Source cell of every output pixel under nn.functional.interpolate's default (nearest) rule, taken from
+    interpolate itself so that the index arithmetic is identical by construction."""
+    key = (ih, iw, oh, ow, str(device))
+    if key not in _CELL_INDEX:
+        cells = torch.arange(ih * iw, dtype=torch.float32, device=device).view(1, 1, ih, iw)
+        _CELL_INDEX[key] = torch.nn.functional.interpolate(cells, size=(oh, ow)).view(-1).long()
+    return _CELL_INDEX[key]
+
+
+def supervised_attention_loss(att_maps, segmentation_labels):
+    """The supervised-attention term of GLoRIA.calc_loss (gloria_model.py:143-147) without the upsampled maps:
+    nearest upsampling repeats each grid cell over a fixed set of pixels, so  sum(label * up) / sum(up)  is
+    sum_c map[c] * (#labelled pixels of cell c) / sum_c map[c] * (#pixels of cell c).  Returns the batch mean of
+    -log of that ratio (the caller applies segmentation_loss_weight)."""
+    mean_maps = torch.cat([m.mean(1) for m in att_maps], 0)                  # [B, h, w]  (:144)
+    B, ih, iw = mean_maps.shape
+    oh, ow = segmentation_labels.shape[1:]
+    cell = _cell_index(ih, iw, oh, ow, mean_maps.device)
+    lab = segmentation_labels.reshape(B, -1).to(mean_maps.dtype)
+    inside = torch.zeros((B, ih * iw), dtype=mean_maps.dtype, device=mean_maps.device).index_add_(1, cell, lab)
+    total = torch.bincount(cell, minlength=ih * iw).to(mean_maps.dtype)
+    flat = mean_maps.reshape(B, -1)
+    return -torch.log((flat * inside).sum(-1) / (flat * total).sum(-1)).mean()
 
 
 # --------------------------------------------------------------------------------------------------------------

@@ -47,23 +47,36 @@ class GLoRIALossMixin:
         """gloria_model.py:125-127"""
         return gloria_loss.global_loss(img_emb_g, text_emb_g, temp3=self.temp3)
 
+    def _regularised(self):
+        return any(getattr(self, n, None) is not None for n in
+                   ("no_attn_loss_weight", "attention_divergence_loss_weight", "attention_entropy_loss_weight"))
+
+    def _diagonal_maps(self, img_emb_l, text_emb_l, sents):
+        return gloria_loss.diagonal_attention_maps(img_emb_l, text_emb_l, cap_lens_from_sents(sents), temp1=self.temp1,
+                                                   no_attn_vec=getattr(self, "no_attn_vec", None))
+
     def calc_loss(self, img_emb_l, img_emb_g, text_emb_l, text_emb_g, sents, segmentation_labels=None):
-        """gloria_model.py:132-150 -> (loss, attn_maps)"""
+        """gloria_model.py:132-150 -> (loss, attn_maps).
+
+        The reference always runs local_loss over all B^2 pairs; when the contrastive local term has weight 0 and no
+        regulariser is configured (the attention fine-tune config) only its diagonal attention maps are used, so only
+        the B diagonal pairs are computed here."""
         loss = 0
-        l_loss0, l_loss1, no_attn_loss, kl_loss, entropy_loss, attn_maps = self._calc_local_loss(
-            img_emb_l, text_emb_l, sents)
-        if self.local_loss_weight != 0:
-            loss += (l_loss0 + l_loss1) * self.local_loss_weight
+        no_attn_loss = kl_loss = entropy_loss = 0
+        if self.local_loss_weight != 0 or self._regularised():
+            l_loss0, l_loss1, no_attn_loss, kl_loss, entropy_loss, attn_maps = self._calc_local_loss(
+                img_emb_l, text_emb_l, sents)
+            if self.local_loss_weight != 0:
+                loss += (l_loss0 + l_loss1) * self.local_loss_weight
+        else:
+            attn_maps = self._diagonal_maps(img_emb_l, text_emb_l, sents)
         if self.global_loss_weight != 0:
             g_loss0, g_loss1 = self._calc_global_loss(img_emb_g, text_emb_g)
             loss += (g_loss0 + g_loss1) * self.global_loss_weight
         if segmentation_labels is not None and getattr(self, "segmentation_loss_weight", None):
             # supervised attention (gloria_model.py:143-147): word-mean of each diagonal map, nearest upsample to
-            # the label resolution, normalise to sum 1, -log of the mass inside the label
-            mean_attn_maps = torch.cat([attn_map.mean(1) for attn_map in attn_maps], 0)
-            up = nn.functional.interpolate(mean_attn_maps.unsqueeze(1), size=segmentation_labels.shape[1:]).squeeze(1)
-            up = up / up.sum(-1, keepdims=True).sum(-2, keepdims=True)
-            loss += -torch.log((segmentation_labels * up).sum(-1).sum(-1)).mean() * self.segmentation_loss_weight
+            # the label resolution, normalise to sum 1, -log of the mass inside the label -- in per-cell form
+            loss += gloria_loss.supervised_attention_loss(attn_maps, segmentation_labels) * self.segmentation_loss_weight
         loss += no_attn_loss + kl_loss + entropy_loss
         return loss, attn_maps
 
@@ -83,13 +96,12 @@ class GLoRIALossMixin:
         return sim.cpu()
 
     def get_attn_maps(self, img_emb_l, text_emb_l, sents):
-        """gloria_model.py:209-211"""
-        _, _, _, _, _, attn_maps = self._calc_local_loss(img_emb_l, text_emb_l, sents)
-        return attn_maps
+        """gloria_model.py:209-211 (the reference runs the whole local_loss for these B maps)"""
+        return self._diagonal_maps(img_emb_l, text_emb_l, sents)
 
 
-_METHODS = ["_calc_local_loss", "_calc_global_loss", "calc_loss", "get_global_similarities",
-            "get_local_similarities", "get_attn_maps"]
+_METHODS = ["_calc_local_loss", "_calc_global_loss", "_regularised", "_diagonal_maps", "calc_loss",
+            "get_global_similarities", "get_local_similarities", "get_attn_maps"]
 
 
 def patch_gloria(target):

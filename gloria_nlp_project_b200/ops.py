@@ -300,6 +300,75 @@ local_sim_fwd.register_autograd(_local_backward, setup_context=_local_setup)
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# diagonal pairs only: attention maps of (image i, caption i)  (gloria_loss.py:141-143; gloria_model.py:143-147,209-211)
+# ----------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("gloria_b200::diag_attn_fwd", mutates_args=())
+def diag_attn_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int, temp1: float) -> Tensor:
+    """attn [B, lcap, S] of the B diagonal pairs (rows beyond each caption's length are zero) -- B pairs of work, where
+    the reference's local_loss runs all B^2 to return these maps."""
+    _need_cuda(ctx, words, cap_lens)
+    L = _lib.lib()
+    B, D, S = ctx.shape
+    Bc, D2, Lw = words.shape
+    if Bc != B or D2 != D:
+        raise RuntimeError(f"diagonal attention maps need matching batches / feature dims, got {tuple(ctx.shape)} and "
+                           f"{tuple(words.shape)}")
+    ctx, words, cap_lens = ctx.contiguous(), words.contiguous(), cap_lens.contiguous()
+    diag = torch.empty((B, lcap, S), dtype=torch.float32, device=ctx.device)
+    with torch.cuda.device(ctx.device):
+        nbytes = L.gloria_b200_diag_attn_workspace(B, D, S, Lw, lcap)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=ctx.device)
+        rc = L.gloria_b200_diag_attn_fwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), B, D, S, Lw, lcap,
+                                             word_off, temp1, diag.data_ptr(), ws.data_ptr(), nbytes, _stream(ctx))
+        _lib.check(rc, "diag_attn_fwd_f32")
+    return diag
+
+
+@diag_attn_fwd.register_fake
+def _(ctx, words, cap_lens, lcap, word_off, temp1):
+    return ctx.new_empty((ctx.shape[0], lcap, ctx.shape[2]))
+
+
+@torch.library.custom_op("gloria_b200::diag_attn_bwd", mutates_args=())
+def diag_attn_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int, temp1: float,
+                  d_diag: Tensor) -> Tuple[Tensor, Tensor]:
+    _need_cuda(ctx, words, cap_lens, d_diag)
+    L = _lib.lib()
+    B, D, S = ctx.shape
+    Lw = words.shape[2]
+    ctx, words, cap_lens, d_diag = ctx.contiguous(), words.contiguous(), cap_lens.contiguous(), _f32c(d_diag)
+    d_ctx, d_words = torch.empty_like(ctx), torch.empty_like(words)
+    with torch.cuda.device(ctx.device):
+        nbytes = L.gloria_b200_diag_attn_workspace(B, D, S, Lw, lcap)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=ctx.device)
+        rc = L.gloria_b200_diag_attn_bwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), B, D, S, Lw, lcap,
+                                             word_off, temp1, d_diag.data_ptr(), d_ctx.data_ptr(), d_words.data_ptr(), 0,
+                                             ws.data_ptr(), nbytes, _stream(ctx))
+        _lib.check(rc, "diag_attn_bwd_f32")
+    return d_ctx, d_words
+
+
+@diag_attn_bwd.register_fake
+def _(ctx, words, cap_lens, lcap, word_off, temp1, d_diag):
+    return torch.empty_like(ctx), torch.empty_like(words)
+
+
+def _diag_setup(ctx, inputs, output):
+    feats, words, cap_lens, lcap, word_off, temp1 = inputs
+    ctx.save_for_backward(feats, words, cap_lens)
+    ctx.args = (lcap, word_off, temp1)
+
+
+def _diag_backward(c, d_diag):
+    feats, words, cap_lens = c.saved_tensors
+    d_ctx, d_words = diag_attn_bwd(feats, words, cap_lens, *c.args, d_diag)
+    return d_ctx, d_words, None, None, None, None
+
+
+diag_attn_fwd.register_autograd(_diag_backward, setup_context=_diag_setup)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # global cosine similarity  (gloria_loss.py:75-80, gloria_model.py:164-169)
 # ----------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("gloria_b200::global_sim_fwd", mutates_args=())

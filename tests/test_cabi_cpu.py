@@ -68,3 +68,33 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_supervised_attention_loss_per_cell_form():
+    """gloria_model.py:143-147 (mean over words -> nearest upsample -> normalise -> -log of the labelled mass) against
+    the per-cell form used by the drop-in (pure torch glue, so it runs on CPU tensors)."""
+    import torch
+    from gloria_nlp_project_b200.gloria_loss import supervised_attention_loss
+    gen = torch.Generator().manual_seed(5)
+    B, ih, iw = 4, 19, 19
+    maps = []
+    for L in (7, 3, 1, 11):
+        a = torch.rand(1, L, ih * iw, generator=gen, dtype=torch.float64).softmax(-1).reshape(1, L, ih, iw)
+        maps.append(a.requires_grad_())
+    labels = torch.rand(B, 224, 224, generator=gen) > 0.7
+    mean_maps = torch.cat([m.mean(1) for m in maps], 0)
+    up = torch.nn.functional.interpolate(mean_maps.unsqueeze(1), size=labels.shape[1:]).squeeze(1)
+    up = up / up.sum(-1, keepdims=True).sum(-2, keepdims=True)
+    ref = -torch.log((labels * up).sum(-1).sum(-1)).mean()
+    g_ref = torch.autograd.grad(ref, maps)
+    out = supervised_attention_loss(maps, labels)
+    g_out = torch.autograd.grad(out, maps)
+    assert abs(float(out) - float(ref)) < 1e-12
+    for a, b in zip(g_out, g_ref):
+        assert torch.allclose(a, b, rtol=1e-10, atol=1e-14)
+    # non-square label resolution, as in the golden fixture (24 x 30)
+    labels = torch.rand(B, 24, 30, generator=gen) > 0.5
+    up = torch.nn.functional.interpolate(mean_maps.unsqueeze(1), size=labels.shape[1:]).squeeze(1)
+    up = up / up.sum(-1, keepdims=True).sum(-2, keepdims=True)
+    ref = -torch.log((labels * up).sum(-1).sum(-1)).mean()
+    assert abs(float(supervised_attention_loss(maps, labels)) - float(ref)) < 1e-12

@@ -397,3 +397,36 @@ def test_regularisers_tensor_core(gl, B, seed, lens, use_nav, kw):
         assert relerr(d_nav, r_nav) < GRAD_TOL
     for i, L in enumerate(cl):
         assert torch.all(d_txt[i, :, L:] == 0)
+
+
+def test_attention_finetune_touches_diagonal_pairs_only(gl, monkeypatch):
+    """cfg 5 (imagenome_attn_finetune, B = 32): with the contrastive weights 0 and no regulariser, calc_loss and
+    get_attn_maps never enter the all-pairs op -- B pairs of work instead of the reference's B^2."""
+    from gloria_nlp_project_b200 import ops
+    from gloria_nlp_project_b200.gloria_model import GLoRIALossMixin
+    from tests.util import Holder
+
+    class M(GLoRIALossMixin, Holder):
+        pass
+
+    def boom(*a, **k):
+        raise AssertionError("all-pairs kernel path entered")
+    B = 32
+    img_l, txt_l, img_g, txt_g, cl = gen_inputs(31, B, 768, 19, 19, 97, scale=0.05, dtype=np.float32)
+    seg = torch.tensor(np.random.default_rng(2).random((B, 224, 224)) > 0.7, device="cuda")
+    sents = [["[CLS]"] + ["w"] * (L - 1) + ["[SEP]"] + ["[PAD]"] * (97 - L - 1) for L in cl]
+    full = M(local_loss_weight=1e-30, global_loss_weight=0, segmentation_loss_weight=1.0)     # all-pairs path
+    img, txt = cu(img_l, True), cu(txt_l, True)
+    ref, ref_maps = full.calc_loss(img, cu(img_g), txt, cu(txt_g), sents, seg)
+    ref.backward()
+    r_img, r_txt = img.grad.clone(), txt.grad.clone()
+    monkeypatch.setattr(ops, "local_sim_fwd", boom)
+    m = M(local_loss_weight=0, global_loss_weight=0, segmentation_loss_weight=1.0)
+    img, txt = cu(img_l, True), cu(txt_l, True)
+    loss, maps = m.calc_loss(img, cu(img_g), txt, cu(txt_g), sents, seg)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) < 1e-5 * abs(float(ref.detach()))
+    assert relerr(img.grad, r_img) < 1e-4 and relerr(txt.grad, r_txt) < 1e-4
+    maps2 = m.get_attn_maps(cu(img_l), cu(txt_l), sents)
+    for a, b, c in zip(maps, maps2, ref_maps):
+        assert torch.equal(a, b) and relerr(a, c) < 1e-5

@@ -56,7 +56,7 @@ def test_local_loss_small_golden(gl, small, tag, kw):
     for name, v in (("no_attn_loss", na), ("kl_loss", kl), ("entropy_loss", ent)):
         ref = small[f"local_{tag}_{name}"]
         if isinstance(v, torch.Tensor):
-            assert abs(float(v) - float(ref)) <= 2e-5 * max(1.0, abs(float(ref))), (name, float(v), float(ref))
+            assert abs(float(v.detach()) - float(ref)) <= 2e-5 * max(1.0, abs(float(ref))), (name, float(v.detach()), float(ref))
         else:
             assert v == 0 and float(ref) == 0
     for i, m in enumerate(maps):
