@@ -22,6 +22,7 @@ PROTOTYPES = {
     "gloria_b200_last_error": (C.c_char_p, []),
     "gloria_b200_launch_count": (C.c_longlong, [_i]),
     "gloria_b200_set_timer_events": (_i, [_i, _p, _p]),
+    "gloria_b200_record_event": (_i, [_p, _p]),
     "gloria_b200_debug_phase_clocks": (None, [_p]),
     "gloria_b200_local_f32_workspace": (_z, [_i, _i, _i, _i, _i, _i, _z]),
     "gloria_b200_local_sim_fwd_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p, _z,
@@ -52,6 +53,7 @@ PROTOTYPES = {
     "gloria_b200_tc_train_workspace": (_z, [_i, _i, _i, _i, _i]),
     "gloria_b200_tc_local_sim_fwd_train": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _z, _p]),
     "gloria_b200_tc_local_sim_bwd_train": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p]),
+    "gloria_b200_tc_local_sim_bwd_train_ev": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p, _p]),
     "gloria_b200_global_sim_fwd": (_i, [_p, _p, _i, _i, _i, _f, _p, _p, _p, _p]),
     "gloria_b200_global_sim_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _f, _p, _p, _p]),
     "gloria_b200_ce_bidir_fwd": (_i, [_p, _i, _f, _p, _p, _p, _p]),

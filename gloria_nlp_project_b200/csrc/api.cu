@@ -64,3 +64,11 @@ extern "C" int gloria_b200_set_timer_events(int slot, void* start_event, void* s
   gloria::g_timer[slot][1].store(stop_event);
   return GLORIA_OK;
 }
+
+// cudaEventRecord for callers that hold only raw handles (the Python shim marks "d_ctx is final" on paths that do
+// not go through gloria_b200_tc_local_sim_bwd_train_ev)
+extern "C" int gloria_b200_record_event(void* event, void* stream) {
+  GLORIA_CHECK_ARG(event != nullptr, "null event");
+  GLORIA_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+  return GLORIA_OK;
+}

@@ -1239,10 +1239,13 @@ extern "C" int gloria_b200_tc_local_sim_fwd_mean(const void* ctx_h, const void* 
   return bw::launch_pair_lpad<true>(lpad, rt, wt, gm, gm /* E^T map unused: nothing is stored */, p, sms, st);
 }
 
-extern "C" int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void* words_t, const int32_t* cap_lens,
-                                                  int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
-                                                  const float* dsim, float* d_ctx, float* d_words, void* workspace,
-                                                  size_t workspace_bytes, void* stream) {
+// Order of the backward: everything d_ctx needs first (dR GEMM, M-term, M.R, unpack), then an optional caller-owned
+// event is recorded, then the caption-side gradient (dW GEMM, gamma, unpack).  A caption-sharded caller starts its
+// reduce_scatter of d_ctx on that event, so the collective overlaps the dW GEMM (distributed.py).
+extern "C" int gloria_b200_tc_local_sim_bwd_train_ev(const void* ctx_t, const void* words_t, const int32_t* cap_lens,
+                                                     int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                                     const float* dsim, float* d_ctx, float* d_words, void* workspace,
+                                                     size_t workspace_bytes, void* d_ctx_ready_event, void* stream) {
   GLORIA_CHECK_ARG(ctx_t && words_t && cap_lens && dsim && d_ctx && d_words && workspace, "null pointer");
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
@@ -1260,19 +1263,51 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void*
   GLORIA_CUBLAS(cublasSetWorkspace(h, ws + pl.off_cublas, bw::CUBLAS_WS));
   const int R1 = Bc * lp;
   const dim3 sgrid((unsigned)((R1 / 8 + 255) / 256), (unsigned)(sp / bw::SCALE_ROWS), (unsigned)Bi);
+  const float one = 1.f, zero = 0.f;
+  const int K1 = Bi * sp;
+  const __nv_bfloat16* Rt = (const __nv_bfloat16*)ctx_t;
+  const __nv_bfloat16* Wt = (const __nv_bfloat16*)words_t;
+  float* dWt = (float*)(ws + pl.off_dwt);
+  float* dRt = (float*)(ws + pl.off_drt);
+  float* Mf = (float*)(ws + pl.off_m);
+  __nv_bfloat16* Mb = (__nv_bfloat16*)(ws + pl.off_mb);
   timer_record(GLORIA_TIMER_TC_BWD_GEMM, 0, st);
   // everything the forward stored is for g = 1 and linear in g = dsim[j, i]: apply it now
   bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, sp, Bc, 0, lp);
   GLORIA_LAUNCHED("scale_x");
+  // ---- image side.  dRt[(j,s), d] = sum_(i,l) X^T[(j,s),(i,l)] Wt[(i,l), d]   (column-major: [D, K1] = Wt^T . X^T)
+  GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, K1, R1, &one, Wt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1, &zero,
+                             dRt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+  // M_j[a, b] = sum_(i,l) E^T[(j,a),(i,l)] g[j,i] f[j,(i,l)] E^T[(j,b),(i,l)]   (own tcgen05 kernel, tc_mterm.cu)
+  int rc;
+  if ((rc = launch_mterm(E, (const float*)(ws + pl.off_fo), dsim, Mf, Bi, Bc, 0, R1, lp, sp, false, st))) return rc;
+  // dRt_j += M_j Rt_j   (M_j symmetric up to rounding; column-major: [D, sp] = Rt_j^T . M_j)
+  const size_t nm = (size_t)Bi * sp * sp;
+  bw::f32_to_bf16<<<(unsigned)((nm / 4 + 255) / 256), 256, 0, st>>>(Mf, Mb, nm);
+  GLORIA_LAUNCHED("f32_to_bf16");
+  GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, sp, sp, &one, Rt, CUDA_R_16BF, D,
+                                           (long long)sp * D, Mb, CUDA_R_16BF, sp, (long long)sp * sp, &one, dRt,
+                                           CUDA_R_32F, D, (long long)sp * D, Bi, CUBLAS_COMPUTE_32F,
+                                           CUBLAS_GEMM_DEFAULT));
+  bw::unpack_dctx<<<dim3((S + 31) / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(dRt, d_ctx, D, S, sp);
+  GLORIA_LAUNCHED("unpack_dctx");
+  if (d_ctx_ready_event) GLORIA_CUDA(cudaEventRecord((cudaEvent_t)d_ctx_ready_event, st));
+  // ---- caption side.  dWt[(i,l), d] = sum_(j,s) X^T[(j,s),(i,l)] Rt[(j,s), d]   (column-major: [D, R1] = Rt^T . (X^T)^T)
+  GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, R1, K1, &one, Rt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1, &zero,
+                             dWt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+  timer_record(GLORIA_TIMER_TC_BWD_GEMM, 1, st);
   bw::gamma_sum<<<(R1 + 255) / 256, 256, 0, st>>>((const float*)(ws + pl.off_go), dsim, gamma, Bi, R1, Bc, 0, lp);
   GLORIA_LAUNCHED("gamma_sum");
-  int rc;
-  if ((rc = bw::accumulate_chunk(h, (const __nv_bfloat16*)ctx_t, (const __nv_bfloat16*)words_t, X, E,
-                                 (const float*)(ws + pl.off_fo), dsim, (float*)(ws + pl.off_dwt),
-                                 (float*)(ws + pl.off_drt), (float*)(ws + pl.off_m), Bi, Bc, D, sp, lp, 0, Bc, true, st)))
-    return rc;
-  return bw::finish_backward(h, (const __nv_bfloat16*)ctx_t, (const __nv_bfloat16*)words_t, cap_lens,
-                             (float*)(ws + pl.off_dwt), (float*)(ws + pl.off_drt), (float*)(ws + pl.off_m),
-                             (__nv_bfloat16*)(ws + pl.off_mb), gamma, d_ctx, d_words, Bi, Bc, D, S, sp, Lw, lp, Lcap,
-                             word_off, st);
+  bw::unpack_dwords_tc<<<dim3((Lw + 31) / 32, D / 32, Bc), dim3(32, 8), 0, st>>>(dWt, gamma, Wt, cap_lens, d_words, D,
+                                                                               Lw, lp, Lcap, word_off);
+  GLORIA_LAUNCHED("unpack_dwords_tc");
+  return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void* words_t, const int32_t* cap_lens,
+                                                  int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                                  const float* dsim, float* d_ctx, float* d_words, void* workspace,
+                                                  size_t workspace_bytes, void* stream) {
+  return gloria_b200_tc_local_sim_bwd_train_ev(ctx_t, words_t, cap_lens, Bi, Bc, D, S, Lw, Lcap, word_off, dsim, d_ctx,
+                                               d_words, workspace, workspace_bytes, nullptr, stream);
 }

@@ -152,28 +152,39 @@ constexpr int KBLK = 64;                 // bf16 per 128-byte swizzle row
 constexpr int TILE = 128;                // regions per score tile == words per context tile == channels per chunk
 constexpr int MAX_NT = 3;                // Spad <= 384
 
-// Static unit schedule shared by all warp roles.  Captions are dealt to CTAs in blocks of gridDim.x; in a block
-// with fewer captions than CTAs, several CTAs split one caption's images.  All CTAs sweep the images in step, so
-// the region tiles of an image are read from L2 by every SM at about the same time.
+// Static unit schedule shared by all warp roles.  A unit is (caption i, chunk of `c` consecutive images); units are
+// numbered chunk-major (u = chunk * Bc + caption) and dealt round-robin to the CTAs, so in every round all CTAs sweep
+// the same two or three image chunks in step and an image's region tiles are L2 hits for every SM but the first.
+// The chunk length minimises rounds * (c + 1/4): the quarter pair is the cost of a unit switch (the operand pipeline
+// runs across units; only the SIMT warps re-read the caption's masks).  At Bc = 64 captions x 512 images per rank
+// (8-GPU shard of B = 512) this is 7 rounds of 32 images = 224 pair slots against 221.4 ideal (one caption per CTA
+// with the images split in two would be 256).
 struct Units {
-  int Bi, Bc, ncta, cta;
-  int blk, i, j, j_end;
-  __device__ Units(int Bi_, int Bc_) : Bi(Bi_), Bc(Bc_), ncta(gridDim.x), cta(blockIdx.x), blk(-1), i(0), j(0), j_end(0) {}
-  __device__ bool next_caption() {
-    while (true) {
-      ++blk;
-      const int base = blk * ncta;
-      if (base >= Bc) return false;
-      const int nb = min(ncta, Bc - base);
-      const int g = ncta / nb;
-      if (cta < nb * g) {
-        i = base + cta % nb;
-        const int sl = cta / nb;
-        j = (int)((long long)sl * Bi / g);
-        j_end = (int)((long long)(sl + 1) * Bi / g);
-        if (j < j_end) return true;
-      }
+  int Bi, Bc, ncta, c, nunits, u;
+  int i, j, j_end;
+  __device__ Units(int Bi_, int Bc_) : Bi(Bi_), Bc(Bc_), ncta(gridDim.x), i(0), j(0), j_end(0) {
+    int best_c = Bi > 0 ? Bi : 1, best_n = 1;
+    long long best = -1;
+    const int kmax = Bi < 128 ? Bi : 128;
+    for (int k = 1; k <= kmax; ++k) {
+      const int cc = (Bi + k - 1) / k;
+      const int nch = (Bi + cc - 1) / cc;
+      const long long rounds = ((long long)Bc * nch + ncta - 1) / ncta;
+      const long long cost = rounds * (4 * cc + 1);
+      if (best < 0 || cost < best) { best = cost; best_c = cc; best_n = nch; }
     }
+    c = best_c;
+    nunits = Bc * best_n;
+    u = (int)blockIdx.x - ncta;
+  }
+  __device__ bool next_caption() {
+    u += ncta;
+    if (u >= nunits) return false;
+    const int ch = u / Bc;
+    i = u - ch * Bc;
+    j = ch * c;
+    j_end = min(Bi, j + c);
+    return true;
   }
 };
 

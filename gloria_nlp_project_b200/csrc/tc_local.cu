@@ -367,32 +367,44 @@ __global__ void pack_ctx(const float* __restrict__ ctx, __nv_bfloat16* __restric
   }
 }
 
-// words [Bc, D, Lw] -> Wt [Bc, LPAD, D] (rows >= cap_len zero) and wnorm [Bc, LPAD];  grid (LPAD/32.., 1, Bc), block (32, 8)
+// words [Bc, D, Lw] -> Wt [Bc, lpb, D] bf16 and Wh [Bc, LPAD, D] fp16 (rows >= cap_len zero);
+// grid (ceil(LPAD/32), D/32, Bc), block (32, 8): one 32 x 32 transpose tile per block
 __global__ void pack_words(const float* __restrict__ words, const int* __restrict__ cap_lens,
-                           __nv_bfloat16* __restrict__ Wt, __half* __restrict__ Wh, float* __restrict__ wnorm, int D,
-                           int Lw, int lpad, int lpb, int lcap, int off) {
+                           __nv_bfloat16* __restrict__ Wt, __half* __restrict__ Wh, int D, int Lw, int lpad, int lpb,
+                           int lcap, int off) {
   __shared__ float t[32][33];
-  __shared__ float part[8][32];
-  const int i = blockIdx.z, l0 = blockIdx.x * 32;
+  const int i = blockIdx.z, l0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
   const int L = min(max(cap_lens[i], 0), lcap);
   const int lr = l0 + threadIdx.x;                 // word handled by this thread in the read phase
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int d = d0 + r;
+    t[r][threadIdx.x] = (lr < L && d < D) ? words[((size_t)i * D + d) * Lw + off + lr] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int l = l0 + r, d = d0 + threadIdx.x;
+    if (l < lpad && d < D) {
+      if (l < lpb) Wt[((size_t)i * lpb + l) * D + d] = __float2bfloat16_rn(t[threadIdx.x][r]);   // GEMM pitch
+      Wh[((size_t)i * lpad + l) * D + d] = __float2half_rn(t[threadIdx.x][r]);                  // tile pitch
+    }
+  }
+}
+
+// wnorm [Bc, LPAD] = |W_l| from the fp32 input (0 beyond the caption);  grid (ceil(LPAD/32), 1, Bc), block (32, 8):
+// the 8 thread rows split the channels, reads are coalesced along the word axis
+__global__ void word_norms(const float* __restrict__ words, const int* __restrict__ cap_lens, float* __restrict__ wnorm,
+                           int D, int Lw, int lpad, int lcap, int off) {
+  __shared__ float part[8][32];
+  const int i = blockIdx.z, lr = blockIdx.x * 32 + threadIdx.x;
+  const int L = min(max(cap_lens[i], 0), lcap);
   float ss = 0.f;
-  for (int d0 = 0; d0 < D; d0 += 32) {
-    for (int r = threadIdx.y; r < 32; r += 8) {
-      const int d = d0 + r;
-      const float v = (lr < L && d < D) ? words[((size_t)i * D + d) * Lw + off + lr] : 0.f;
+  if (lr < L) {
+    const float* w = words + (size_t)i * D * Lw + off + lr;
+#pragma unroll 8
+    for (int d = threadIdx.y; d < D; d += 8) {
+      const float v = __ldg(w + (size_t)d * Lw);
       ss = fmaf(v, v, ss);
-      t[r][threadIdx.x] = v;
     }
-    __syncthreads();
-    for (int r = threadIdx.y; r < 32; r += 8) {
-      const int l = l0 + r, d = d0 + threadIdx.x;
-      if (l < lpad && d < D) {
-        if (l < lpb) Wt[((size_t)i * lpb + l) * D + d] = __float2bfloat16_rn(t[threadIdx.x][r]);   // GEMM pitch
-        Wh[((size_t)i * lpad + l) * D + d] = __float2half_rn(t[threadIdx.x][r]);                  // tile pitch
-      }
-    }
-    __syncthreads();
   }
   part[threadIdx.y][threadIdx.x] = ss;
   __syncthreads();
@@ -507,10 +519,12 @@ extern "C" int gloria_b200_tc_prepack(const float* ctx, const float* words, cons
   pack_ctx<<<dim3(Spad / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(ctx, (__nv_bfloat16*)ctx_n, (__nv_bfloat16*)ctx_t,
                                                                (__half*)ctx_h, D, S, Spad, gloria_b200_tc_sp(S));
   GLORIA_LAUNCHED("pack_ctx");
-  pack_words<<<dim3((lpad + 31) / 32, 1, Bc), dim3(32, 8), 0, st>>>(words, cap_lens, (__nv_bfloat16*)words_t,
-                                                                    (__half*)words_h, wnorm, D, Lw, lpad,
-                                                                    gloria_b200_tc_lp(Lcap), Lcap, word_off);
+  pack_words<<<dim3((lpad + 31) / 32, D / 32, Bc), dim3(32, 8), 0, st>>>(words, cap_lens, (__nv_bfloat16*)words_t,
+                                                                         (__half*)words_h, D, Lw, lpad,
+                                                                         gloria_b200_tc_lp(Lcap), Lcap, word_off);
   GLORIA_LAUNCHED("pack_words");
+  word_norms<<<dim3((lpad + 31) / 32, 1, Bc), dim3(32, 8), 0, st>>>(words, cap_lens, wnorm, D, Lw, lpad, Lcap, word_off);
+  GLORIA_LAUNCHED("word_norms");
   return GLORIA_OK;
 }
 

@@ -52,6 +52,23 @@ def tc_prepack(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off
     return Packed(ctx_h, ctx_t, ctx_n, words_h, words_t, wnorm)
 
 
+_TOTAL_MEM: "dict[int, int]" = {}
+
+
+def _available_bytes(dev: torch.device, want: int) -> int:
+    """Bytes a new allocation could get on `dev`.  cudaMemGetInfo costs ~2 ms of host time per call (more than a whole
+    B=48 step), so it is only asked when the request is large against what the caching allocator's own counters say
+    is left; small requests are answered from those counters (a wrong guess surfaces as torch's OOM error)."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _TOTAL_MEM:
+        _TOTAL_MEM[idx] = torch.cuda.get_device_properties(idx).total_memory
+    optimistic = _TOTAL_MEM[idx] - torch.cuda.memory_allocated(idx)
+    if want * 4 <= optimistic:
+        return optimistic
+    free, _ = torch.cuda.mem_get_info(idx)
+    return free + torch.cuda.memory_reserved(idx) - torch.cuda.memory_allocated(idx)
+
+
 def _need_cuda(*ts: Tensor) -> None:
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -133,9 +150,7 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                 # tensor is the workspace the backward consumes.  Falls back to forward + recompute-backward when the
                 # workspace does not fit.
                 nbytes = L.gloria_b200_tc_train_workspace(Bi, Bc, D, S, lcap)
-                free, _ = torch.cuda.mem_get_info(dev)
-                avail = free + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-                if 0 < nbytes <= min(_TC_WS_BUDGET, int(avail * 0.92)):
+                if 0 < nbytes <= min(_TC_WS_BUDGET, int(_available_bytes(dev, nbytes) * 0.92)):
                     stats = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
                     rc = L.gloria_b200_tc_local_sim_fwd_train(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(),
                                                               packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
@@ -190,11 +205,14 @@ def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, w
 @torch.library.custom_op("gloria_b200::local_sim_bwd", mutates_args=())
 def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int, temp1: float,
                   temp2: float, agg: int, eps: float, dsim: Optional[Tensor], d_diag: Optional[Tensor],
-                  d_mean: Optional[Tensor], stats: Optional[Tensor], mode: int) -> Tuple[Tensor, Tensor]:
+                  d_mean: Optional[Tensor], stats: Optional[Tensor], mode: int,
+                  dctx_event: int = 0) -> Tuple[Tensor, Tensor]:
     """Closed-form backward by recomputation: returns d_ctx [Bi, D, S], d_words [Bc, D, Lw].
 
     dsim None = no gradient reaches the similarity matrix (attention fine-tune with both contrastive weights 0,
-    gloria_model.py:138-147): only the B diagonal pairs are differentiated."""
+    gloria_model.py:138-147): only the B diagonal pairs are differentiated.
+    dctx_event: raw cudaEvent_t handle (0 = none) recorded on the current stream once d_ctx is final -- on the fused
+    training path that is before the caption-side GEMM, so a caption-sharded caller can overlap its reduce_scatter."""
     _need_cuda(ctx, words, cap_lens)
     L = _lib.lib()
     Bi, D, S = ctx.shape
@@ -214,8 +232,10 @@ def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
             if dsim is None:
                 dsim = torch.zeros((Bi, Bc), dtype=torch.float32, device=dev)
             if mode == MODE_BF16:
-                tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp2, agg, eps, dsim, d_mean,
-                                 d_ctx, d_words)
+                ev_done = tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp2, agg, eps, dsim,
+                                           d_mean, d_ctx, d_words, 0 if diag_separately else dctx_event)
+                if ev_done:
+                    dctx_event = 0
             else:
                 nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
                 ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
@@ -234,12 +254,15 @@ def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
         elif not all_pairs:
             d_ctx.zero_()
             d_words.zero_()
+        if dctx_event:
+            _lib.check(L.gloria_b200_record_event(dctx_event, st), "record_event")
     return d_ctx, d_words
 
 
 def tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp2, agg, eps, dsim, d_mean, d_ctx,
-                     d_words):
-    """bf16 tensor-core backward: prepack, then the fused recompute kernel + accumulation GEMMs behind the C ABI."""
+                     d_words, dctx_event=0) -> bool:
+    """bf16 tensor-core backward: prepack, then the fused recompute kernel + accumulation GEMMs behind the C ABI.
+    Returns True when `dctx_event` was recorded by the library (fused training path)."""
     Bi, D, S = ctx.shape
     Bc, _, Lw = words.shape
     have = stats is not None and stats.numel() > 0
@@ -252,12 +275,13 @@ def tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp
         if getattr(stats, "_gloria_consumed", False):
             raise RuntimeError("gloria_b200: the fused training state was already consumed by a backward pass "
                                "(set GLORIA_B200_FUSED_TRAIN=0 to differentiate the same forward twice)")
-        rc = L.gloria_b200_tc_local_sim_bwd_train(packed.ctx_t.data_ptr(), packed.words_t.data_ptr(), cap_lens.data_ptr(),
-                                                  Bi, Bc, D, S, Lw, lcap, word_off, dsim.data_ptr(), d_ctx.data_ptr(),
-                                                  d_words.data_ptr(), stats.data_ptr(), stats.numel(), _stream(ctx))
+        rc = L.gloria_b200_tc_local_sim_bwd_train_ev(packed.ctx_t.data_ptr(), packed.words_t.data_ptr(),
+                                                     cap_lens.data_ptr(), Bi, Bc, D, S, Lw, lcap, word_off,
+                                                     dsim.data_ptr(), d_ctx.data_ptr(), d_words.data_ptr(),
+                                                     stats.data_ptr(), stats.numel(), dctx_event or None, _stream(ctx))
         _lib.check(rc, "tc_local_sim_bwd_train")
         stats._gloria_consumed = True
-        return
+        return bool(dctx_event)
     free, _ = torch.cuda.mem_get_info(ctx.device)
     budget = min(_TC_WS_BUDGET, int(free * 0.9) + torch.cuda.memory_reserved(ctx.device)
                  - torch.cuda.memory_allocated(ctx.device))
@@ -270,10 +294,11 @@ def tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp
                                         _ptr(d_mean), d_ctx.data_ptr(), d_words.data_ptr(), ws.data_ptr(), nbytes,
                                         _stream(ctx))
     _lib.check(rc, "tc_local_sim_bwd")
+    return False
 
 
 @local_sim_bwd.register_fake
-def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim, d_diag, d_mean, stats, mode):
+def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim, d_diag, d_mean, stats, mode, dctx_event=0):
     return torch.empty_like(ctx), torch.empty_like(words)
 
 

@@ -57,6 +57,8 @@ long long gloria_b200_launch_count(int reset);
 #define GLORIA_TIMER_TC_BWD_GEMM 2   /* backward accumulation GEMMs                  */
 #define GLORIA_TIMER_SLOTS 4
 int gloria_b200_set_timer_events(int slot, void* start_event, void* stop_event);
+/* cudaEventRecord(event, stream) for callers that hold only raw handles (see gloria_b200_tc_local_sim_bwd_train_ev). */
+int gloria_b200_record_event(void* event, void* stream);
 /* Development aid (builds with -DGLORIA_PHASE_CLOCKS only): device buffer receiving 8 int64 phase clocks per CTA. */
 void gloria_b200_debug_phase_clocks(void* device_buffer);
 
@@ -204,6 +206,14 @@ int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void* words_t, c
                                        int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
                                        const float* dsim, float* d_ctx, float* d_words,
                                        void* workspace, size_t workspace_bytes, void* stream);
+/* Same, with a caller-owned cudaEvent_t (or NULL) that is recorded on `stream` as soon as d_ctx is final -- before the
+ * caption-side GEMM.  A caption-sharded caller waits on it to start the reduce_scatter of d_ctx while the
+ * rest of the backward still runs. */
+int gloria_b200_tc_local_sim_bwd_train_ev(const void* ctx_t, const void* words_t, const int32_t* cap_lens,
+                                          int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                          const float* dsim, float* d_ctx, float* d_words,
+                                          void* workspace, size_t workspace_bytes, void* d_ctx_ready_event,
+                                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Global similarity (global_loss, gloria_loss.py:75-80; get_global_similarities, gloria_model.py:164-169):
