@@ -70,6 +70,7 @@ struct PairParams {
   int sp;                   // region rows per image in X^T / E^T: round_up(S, 16) <= Spad
   float t1, t1_log2e, t2, eps;
   long long* dbg;           // phase clocks (only read when built with -DGLORIA_PHASE_CLOCKS)
+  int timer_first = 1, timer_last = 1;   // host side only: which ends of the launch the bench timer slot records
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
@@ -946,9 +947,9 @@ int launch_pair(const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap&
   GLORIA_CUDA(cudaFuncSetAttribute(tc_bwd_pair_kernel<LPAD, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    SMEM_BYTES));
   const int slot = FUSED ? GLORIA_TIMER_TC_FWD : GLORIA_TIMER_TC_BWD_PAIR;
-  timer_record(slot, 0, st);
+  if (p.timer_first) timer_record(slot, 0, st);          // a forward launched in image parts is timed first to last
   tc_bwd_pair_kernel<LPAD, FUSED><<<grid, NTHREADS, SMEM_BYTES, st>>>(rt, wt, g, e, p);
-  timer_record(slot, 1, st);
+  if (p.timer_last) timer_record(slot, 1, st);
   GLORIA_LAUNCHED("tc_bwd_pair_kernel");
   return GLORIA_OK;
 }
@@ -1153,12 +1154,17 @@ extern "C" size_t gloria_b200_tc_train_workspace(int Bi, int Bc, int D, int S, i
   return bw::train_plan(Bi, Bc, D, gloria_b200_tc_spad(S), gloria_b200_tc_sp(S), gloria_b200_tc_lp(Lcap)).total;
 }
 
-extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void* ctx_t, const void* words_h,
-                                                  const float* wnorm, const int32_t* cap_lens, int Bi, int Bc, int D,
-                                                  int S, int Lcap, float temp1, float temp2, int agg, float eps,
-                                                  float* sim, void* workspace, size_t workspace_bytes, void* stream) {
+// Image range [j0, j0 + nj) of a (Bi x Bc) training forward: the workspace is laid out for all Bi images, this call
+// fills the rows of the range (X^T / E^T rows, f, gamma, Gram matrices, sim rows).  ctx_h / ctx_t / sim are the base
+// pointers of the full arrays.  A caption-sharded caller launches one part per all_gather chunk (distributed.py).
+extern "C" int gloria_b200_tc_local_sim_fwd_train_part(const void* ctx_h, const void* ctx_t, const void* words_h,
+                                                       const float* wnorm, const int32_t* cap_lens, int Bi, int j0,
+                                                       int nj, int Bc, int D, int S, int Lcap, float temp1, float temp2,
+                                                       int agg, float eps, float* sim, void* workspace,
+                                                       size_t workspace_bytes, void* stream) {
   GLORIA_CHECK_ARG(ctx_h && ctx_t && words_h && wnorm && cap_lens && sim && workspace, "null pointer");
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0, "bad batch sizes %d x %d", Bi, Bc);
+  GLORIA_CHECK_ARG(j0 >= 0 && nj > 0 && j0 + nj <= Bi, "bad image range [%d, %d) of %d", j0, j0 + nj, Bi);
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
   if (agg == GLORIA_AGG_MAX) return fail(GLORIA_ERR_UNSUPPORTED, "agg=max has no backward: use the plain forward");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1167,19 +1173,24 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void*
   const bw::TrainPlan pl = bw::train_plan(Bi, Bc, D, Spad, sp, lp);
   if (workspace_bytes < pl.total) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, pl.total);
   char* ws = (char*)workspace;
-  __nv_bfloat16* gram = (__nv_bfloat16*)(ws + pl.off_gram);
+  const int R1 = Bc * lp;
+  // everything below is addressed relative to image j0
+  const __half* rh = (const __half*)ctx_h + (size_t)j0 * Spad * D;
+  const __nv_bfloat16* rt_ = (const __nv_bfloat16*)ctx_t + (size_t)j0 * sp * D;
+  __nv_bfloat16* gram = (__nv_bfloat16*)(ws + pl.off_gram) + (size_t)j0 * Spad * Spad;
+  __nv_bfloat16* xt = (__nv_bfloat16*)(ws + pl.off_x) + (size_t)j0 * sp * R1;
+  __nv_bfloat16* et = (__nv_bfloat16*)(ws + pl.off_e) + (size_t)j0 * sp * R1;
   cublasHandle_t h = bw::cublas_handle();
   if (!h) return fail(GLORIA_ERR_DRIVER, "cublasCreate failed");
   GLORIA_CUBLAS(cublasSetStream(h, st));
   GLORIA_CUBLAS(cublasSetWorkspace(h, ws + pl.off_cublas, bw::CUBLAS_WS));
   int rc;
-  if ((rc = bw::gram_matrices(h, (const __nv_bfloat16*)ctx_t, gram, Bi, D, S, Spad, sp, st))) return rc;
+  if ((rc = bw::gram_matrices(h, rt_, gram, nj, D, S, Spad, sp, st))) return rc;
   CUtensorMap rt, wt, gm, em;
-  const int R1 = Bc * lp;
-  if ((rc = make_map(&rt, ctx_h, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;
+  if ((rc = make_map(&rt, rh, (uint64_t)D, (uint64_t)nj * Spad, TILE))) return rc;
   if ((rc = make_map(&wt, words_h, (uint64_t)D, (uint64_t)Bc * lpad, (uint32_t)lpad))) return rc;
-  if ((rc = make_map(&gm, gram, (uint64_t)Spad, (uint64_t)Bi * Spad, TILE))) return rc;
-  if ((rc = make_map4(&em, ws + pl.off_e, (uint64_t)lp, (uint64_t)Bc, (uint64_t)sp, (uint64_t)Bi, (uint64_t)lp, (uint64_t)R1,
+  if ((rc = make_map(&gm, gram, (uint64_t)Spad, (uint64_t)nj * Spad, TILE))) return rc;
+  if ((rc = make_map4(&em, et, (uint64_t)lp, (uint64_t)Bc, (uint64_t)sp, (uint64_t)nj, (uint64_t)lp, (uint64_t)R1,
                       (uint64_t)sp * R1, TILE)))
     return rc;
   int dev = 0, sms = 0;
@@ -1187,12 +1198,22 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void*
   GLORIA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   bw::PairParams p{};
   p.wnorm = wnorm; p.cap_lens = cap_lens; p.stats = nullptr; p.dsim = nullptr;
-  p.xt = (__nv_bfloat16*)(ws + pl.off_x); p.et = (__nv_bfloat16*)(ws + pl.off_e);
-  p.fo = (float*)(ws + pl.off_fo); p.go = (float*)(ws + pl.off_go); p.gamma = nullptr; p.sim = sim;
-  p.Bi = Bi; p.Bc = Bc; p.i0 = 0; p.nc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE; p.lp = lp; p.sp = sp;
+  p.xt = xt; p.et = et;
+  p.fo = (float*)(ws + pl.off_fo) + (size_t)j0 * R1; p.go = (float*)(ws + pl.off_go) + (size_t)j0 * R1;
+  p.gamma = nullptr; p.sim = sim + (size_t)j0 * Bc;
+  p.Bi = nj; p.Bc = Bc; p.i0 = 0; p.nc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE; p.lp = lp; p.sp = sp;
   p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps; p.agg = agg;
   p.dbg = (long long*)g_phase_clock_buffer;
+  p.timer_first = j0 == 0; p.timer_last = j0 + nj == Bi;
   return bw::launch_pair_lpad<true>(lpad, rt, wt, gm, em, p, sms, st);
+}
+
+extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void* ctx_t, const void* words_h,
+                                                  const float* wnorm, const int32_t* cap_lens, int Bi, int Bc, int D,
+                                                  int S, int Lcap, float temp1, float temp2, int agg, float eps,
+                                                  float* sim, void* workspace, size_t workspace_bytes, void* stream) {
+  return gloria_b200_tc_local_sim_fwd_train_part(ctx_h, ctx_t, words_h, wnorm, cap_lens, Bi, 0, Bi, Bc, D, S, Lcap, temp1,
+                                                 temp2, agg, eps, sim, workspace, workspace_bytes, stream);
 }
 
 // "lean" forward: sim + word-mean attention (+ the per-word statistics a later recompute backward needs)
@@ -1239,13 +1260,16 @@ extern "C" int gloria_b200_tc_local_sim_fwd_mean(const void* ctx_h, const void* 
   return bw::launch_pair_lpad<true>(lpad, rt, wt, gm, gm /* E^T map unused: nothing is stored */, p, sms, st);
 }
 
-// Order of the backward: everything d_ctx needs first (dR GEMM, M-term, M.R, unpack), then an optional caller-owned
-// event is recorded, then the caption-side gradient (dW GEMM, gamma, unpack).  A caption-sharded caller starts its
-// reduce_scatter of d_ctx on that event, so the collective overlaps the dW GEMM (distributed.py).
-extern "C" int gloria_b200_tc_local_sim_bwd_train_ev(const void* ctx_t, const void* words_t, const int32_t* cap_lens,
-                                                     int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
-                                                     const float* dsim, float* d_ctx, float* d_words, void* workspace,
-                                                     size_t workspace_bytes, void* d_ctx_ready_event, void* stream) {
+// Order of the backward: everything d_ctx needs first (dR GEMM, M-term, M.R, unpack) -- image part by image part, with
+// an optional caller-owned event recorded after each part -- then the caption-side gradient (dW GEMM, gamma, unpack).
+// A caption-sharded caller starts the reduce_scatter of a part's d_ctx rows on that part's event, so the collectives
+// overlap the next part's GEMMs and the dW GEMM (distributed.py).
+extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const void* words_t, const int32_t* cap_lens,
+                                                        int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                                        const float* dsim, float* d_ctx, float* d_words, void* workspace,
+                                                        size_t workspace_bytes, int n_parts, void* const* part_events,
+                                                        void* stream) {
+  GLORIA_CHECK_ARG(n_parts >= 1 && Bi % n_parts == 0, "n_parts=%d must divide Bi=%d", n_parts, Bi);
   GLORIA_CHECK_ARG(ctx_t && words_t && cap_lens && dsim && d_ctx && d_words && workspace, "null pointer");
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
@@ -1275,23 +1299,35 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_ev(const void* ctx_t, const vo
   // everything the forward stored is for g = 1 and linear in g = dsim[j, i]: apply it now
   bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, sp, Bc, 0, lp);
   GLORIA_LAUNCHED("scale_x");
-  // ---- image side.  dRt[(j,s), d] = sum_(i,l) X^T[(j,s),(i,l)] Wt[(i,l), d]   (column-major: [D, K1] = Wt^T . X^T)
-  GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, K1, R1, &one, Wt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1, &zero,
-                             dRt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
-  // M_j[a, b] = sum_(i,l) E^T[(j,a),(i,l)] g[j,i] f[j,(i,l)] E^T[(j,b),(i,l)]   (own tcgen05 kernel, tc_mterm.cu)
-  int rc;
-  if ((rc = launch_mterm(E, (const float*)(ws + pl.off_fo), dsim, Mf, Bi, Bc, 0, R1, lp, sp, false, st))) return rc;
-  // dRt_j += M_j Rt_j   (M_j symmetric up to rounding; column-major: [D, sp] = Rt_j^T . M_j)
-  const size_t nm = (size_t)Bi * sp * sp;
-  bw::f32_to_bf16<<<(unsigned)((nm / 4 + 255) / 256), 256, 0, st>>>(Mf, Mb, nm);
-  GLORIA_LAUNCHED("f32_to_bf16");
-  GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, sp, sp, &one, Rt, CUDA_R_16BF, D,
-                                           (long long)sp * D, Mb, CUDA_R_16BF, sp, (long long)sp * sp, &one, dRt,
-                                           CUDA_R_32F, D, (long long)sp * D, Bi, CUBLAS_COMPUTE_32F,
-                                           CUBLAS_GEMM_DEFAULT));
-  bw::unpack_dctx<<<dim3((S + 31) / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(dRt, d_ctx, D, S, sp);
-  GLORIA_LAUNCHED("unpack_dctx");
-  if (d_ctx_ready_event) GLORIA_CUDA(cudaEventRecord((cudaEvent_t)d_ctx_ready_event, st));
+  // ---- image side, part by part
+  const int nj = Bi / n_parts;
+  const size_t nm = (size_t)nj * sp * sp;
+  for (int part = 0; part < n_parts; ++part) {
+    const size_t j0 = (size_t)part * nj;
+    const __nv_bfloat16* Xp = X + j0 * sp * R1;
+    float* dRp = dRt + j0 * sp * D;
+    float* Mp = Mf + j0 * sp * sp;
+    __nv_bfloat16* Mbp = Mb + j0 * sp * sp;
+    const __nv_bfloat16* Rp = Rt + j0 * sp * D;
+    // dRt[(j,s), d] = sum_(i,l) X^T[(j,s),(i,l)] Wt[(i,l), d]   (column-major: [D, nj*sp] = Wt^T . X^T)
+    GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, nj * sp, R1, &one, Wt, CUDA_R_16BF, D, Xp, CUDA_R_16BF, R1,
+                               &zero, dRp, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+    // M_j[a, b] = sum_(i,l) E^T[(j,a),(i,l)] g[j,i] f[j,(i,l)] E^T[(j,b),(i,l)]   (own tcgen05 kernel, tc_mterm.cu)
+    int rc;
+    if ((rc = launch_mterm(E + j0 * sp * R1, (const float*)(ws + pl.off_fo) + j0 * R1, dsim + j0 * Bc, Mp, nj, Bc, 0, R1,
+                           lp, sp, false, st)))
+      return rc;
+    // dRt_j += M_j Rt_j   (M_j symmetric up to rounding; column-major: [D, sp] = Rt_j^T . M_j)
+    bw::f32_to_bf16<<<(unsigned)((nm / 4 + 255) / 256), 256, 0, st>>>(Mp, Mbp, nm);
+    GLORIA_LAUNCHED("f32_to_bf16");
+    GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, sp, sp, &one, Rp, CUDA_R_16BF, D,
+                                             (long long)sp * D, Mbp, CUDA_R_16BF, sp, (long long)sp * sp, &one, dRp,
+                                             CUDA_R_32F, D, (long long)sp * D, nj, CUBLAS_COMPUTE_32F,
+                                             CUBLAS_GEMM_DEFAULT));
+    bw::unpack_dctx<<<dim3((S + 31) / 32, D / 32, nj), dim3(32, 8), 0, st>>>(dRp, d_ctx + j0 * D * S, D, S, sp);
+    GLORIA_LAUNCHED("unpack_dctx");
+    if (part_events && part_events[part]) GLORIA_CUDA(cudaEventRecord((cudaEvent_t)part_events[part], st));
+  }
   // ---- caption side.  dWt[(i,l), d] = sum_(j,s) X^T[(j,s),(i,l)] Rt[(j,s), d]   (column-major: [D, R1] = Rt^T . (X^T)^T)
   GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, R1, K1, &one, Rt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1, &zero,
                              dWt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
@@ -1302,6 +1338,15 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_ev(const void* ctx_t, const vo
                                                                                Lw, lp, Lcap, word_off);
   GLORIA_LAUNCHED("unpack_dwords_tc");
   return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_tc_local_sim_bwd_train_ev(const void* ctx_t, const void* words_t, const int32_t* cap_lens,
+                                                     int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                                     const float* dsim, float* d_ctx, float* d_words, void* workspace,
+                                                     size_t workspace_bytes, void* d_ctx_ready_event, void* stream) {
+  void* ev[1] = {d_ctx_ready_event};
+  return gloria_b200_tc_local_sim_bwd_train_parts(ctx_t, words_t, cap_lens, Bi, Bc, D, S, Lw, Lcap, word_off, dsim, d_ctx,
+                                                  d_words, workspace, workspace_bytes, 1, ev, stream);
 }
 
 extern "C" int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void* words_t, const int32_t* cap_lens,

@@ -356,7 +356,7 @@ __global__ void pack_ctx(const float* __restrict__ ctx, __nv_bfloat16* __restric
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int d = d0 + r, s = s0 + threadIdx.x;
     const float v = (s < S) ? ctx[((size_t)b * D + d) * S + s] : 0.f;
-    Rn[((size_t)b * D + d) * Spad + s] = __float2bfloat16_rn(v);
+    if (Rn != nullptr) Rn[((size_t)b * D + d) * Spad + s] = __float2bfloat16_rn(v);
     t[r][threadIdx.x] = v;
   }
   __syncthreads();
@@ -508,17 +508,28 @@ extern "C" int gloria_b200_tc_supported(int D, int S, int Lcap) {
   return GLORIA_OK;
 }
 
-extern "C" int gloria_b200_tc_prepack(const float* ctx, const float* words, const int32_t* cap_lens, int Bi, int Bc,
-                                      int D, int S, int Lw, int Lcap, int word_off, void* ctx_h, void* ctx_t,
-                                      void* ctx_n, void* words_h, void* words_t, float* wnorm, void* stream) {
-  GLORIA_CHECK_ARG(ctx && words && cap_lens && ctx_h && ctx_t && ctx_n && words_h && words_t && wnorm, "null pointer");
-  GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
-  if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
+// The two halves of the prepack are separate entry points so that a caption-sharded caller can pack image parts as
+// their all_gather lands (ctx_n = NULL skips the copy only the inference forward / recompute backward read).
+extern "C" int gloria_b200_tc_prepack_ctx(const float* ctx, int Bi, int D, int S, void* ctx_h, void* ctx_t, void* ctx_n,
+                                          void* stream) {
+  GLORIA_CHECK_ARG(ctx && ctx_h && ctx_t, "null pointer");
+  GLORIA_CHECK_ARG(Bi > 0, "bad sizes");
+  if (gloria_b200_tc_supported(D, S, 1)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d", D, S);
   cudaStream_t st = (cudaStream_t)stream;
-  const int Spad = gloria_b200_tc_spad(S), lpad = gloria_b200_tc_lpad(Lcap);
+  const int Spad = gloria_b200_tc_spad(S);
   pack_ctx<<<dim3(Spad / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(ctx, (__nv_bfloat16*)ctx_n, (__nv_bfloat16*)ctx_t,
                                                                (__half*)ctx_h, D, S, Spad, gloria_b200_tc_sp(S));
   GLORIA_LAUNCHED("pack_ctx");
+  return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_tc_prepack_words(const float* words, const int32_t* cap_lens, int Bc, int D, int Lw, int Lcap,
+                                            int word_off, void* words_h, void* words_t, float* wnorm, void* stream) {
+  GLORIA_CHECK_ARG(words && cap_lens && words_h && words_t && wnorm, "null pointer");
+  GLORIA_CHECK_ARG(Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
+  if (gloria_b200_tc_supported(D, 1, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d Lcap=%d", D, Lcap);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int lpad = gloria_b200_tc_lpad(Lcap);
   pack_words<<<dim3((lpad + 31) / 32, D / 32, Bc), dim3(32, 8), 0, st>>>(words, cap_lens, (__nv_bfloat16*)words_t,
                                                                          (__half*)words_h, D, Lw, lpad,
                                                                          gloria_b200_tc_lp(Lcap), Lcap, word_off);
@@ -526,6 +537,17 @@ extern "C" int gloria_b200_tc_prepack(const float* ctx, const float* words, cons
   word_norms<<<dim3((lpad + 31) / 32, 1, Bc), dim3(32, 8), 0, st>>>(words, cap_lens, wnorm, D, Lw, lpad, Lcap, word_off);
   GLORIA_LAUNCHED("word_norms");
   return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_tc_prepack(const float* ctx, const float* words, const int32_t* cap_lens, int Bi, int Bc,
+                                      int D, int S, int Lw, int Lcap, int word_off, void* ctx_h, void* ctx_t,
+                                      void* ctx_n, void* words_h, void* words_t, float* wnorm, void* stream) {
+  GLORIA_CHECK_ARG(ctx && words && cap_lens && ctx_h && ctx_t && ctx_n && words_h && words_t && wnorm, "null pointer");
+  GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
+  if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
+  int rc;
+  if ((rc = gloria_b200_tc_prepack_ctx(ctx, Bi, D, S, ctx_h, ctx_t, ctx_n, stream))) return rc;
+  return gloria_b200_tc_prepack_words(words, cap_lens, Bc, D, Lw, Lcap, word_off, words_h, words_t, wnorm, stream);
 }
 
 extern "C" int gloria_b200_tc_local_sim_fwd(const void* ctx_h, const void* ctx_n, const void* words_h,

@@ -130,15 +130,143 @@ class _ShardedLocalSim(torch.autograd.Function):
                 None, None)
 
 
+_N_PARTS = 2          # image parts per rank shard: gather / reduce_scatter of one part overlap the kernels of the other
+
+
+class _ShardedLocalSimParts(torch.autograd.Function):
+    """bf16 training path of the sharded local similarity, pipelined over image parts.
+
+    Each rank's n images are cut into P parts; part p of every rank is all_gathered into one contiguous block, so the
+    gathered batch is *part-major* ([p][rank][n/P]; a fixed permutation of the natural image order that is undone on
+    the rows of sim).  Forward: gather(p+1) runs on a side stream while part p is packed and its fused training
+    kernel runs.  Backward: the library finishes d_ctx part by part and records an event per part; the
+    reduce_scatter of part p (side stream) overlaps the GEMMs of part p+1 and the caption-side GEMM.
+    Nothing but the 16-bit packed copies and the operand workspace is kept for the backward."""
+
+    @staticmethod
+    def forward(ctx, img_emb_l, text_emb_l, dev_lens, lcap, temp1, temp2, agg, eps, group, P):
+        from . import _lib
+        from .ops import _stream
+        L = _lib.lib()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n, D = img_emb_l.shape[0], img_emb_l.shape[1]
+        x = img_emb_l.reshape(n, D, -1).float().contiguous()
+        S, B, m = x.shape[2], world * n, n // P
+        words = text_emb_l.float().contiguous()
+        Bc, _, Lw = words.shape
+        dev = x.device
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        with torch.cuda.device(dev):
+            spad, sp = L.gloria_b200_tc_spad(S), L.gloria_b200_tc_sp(S)
+            lpad, lp = L.gloria_b200_tc_lpad(lcap), L.gloria_b200_tc_lp(lcap)
+            img_all = x.new_empty((B, D, S))                      # part-major
+            start = torch.cuda.Event()
+            start.record(main)
+            gathered = []
+            for p in range(P):                                    # gather 0 on the main stream, the rest on the side stream
+                st = main if p == 0 else side
+                if p == 1:
+                    side.wait_event(start)
+                with torch.cuda.stream(st):
+                    dist.all_gather_into_tensor(img_all[p * world * m:(p + 1) * world * m], x[p * m:(p + 1) * m],
+                                                group=group)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    gathered.append(ev)
+            ctx_h = torch.empty((B, spad, D), dtype=torch.float16, device=dev)
+            ctx_t = torch.empty((B, sp, D), dtype=torch.bfloat16, device=dev)
+            words_h = torch.empty((Bc, lpad, D), dtype=torch.float16, device=dev)
+            words_t = torch.empty((Bc, lp, D), dtype=torch.bfloat16, device=dev)
+            wnorm = torch.empty((Bc, lpad), dtype=torch.float32, device=dev)
+            nbytes = L.gloria_b200_tc_train_workspace(B, Bc, D, S, lcap)
+            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            sim_pm = torch.empty((B, Bc), dtype=torch.float32, device=dev)
+            s = _stream(x)
+            _lib.check(L.gloria_b200_tc_prepack_words(words.data_ptr(), dev_lens.data_ptr(), Bc, D, Lw, lcap, 0,
+                                                      words_h.data_ptr(), words_t.data_ptr(), wnorm.data_ptr(), s),
+                       "tc_prepack_words")
+            nj = world * m
+            for p in range(P):
+                main.wait_event(gathered[p])
+                j0 = p * nj
+                _lib.check(L.gloria_b200_tc_prepack_ctx(img_all[j0:].data_ptr(), nj, D, S, ctx_h[j0:].data_ptr(),
+                                                        ctx_t[j0:].data_ptr(), None, s), "tc_prepack_ctx")
+                _lib.check(L.gloria_b200_tc_local_sim_fwd_train_part(
+                    ctx_h.data_ptr(), ctx_t.data_ptr(), words_h.data_ptr(), wnorm.data_ptr(), dev_lens.data_ptr(), B, j0,
+                    nj, Bc, D, S, lcap, temp1, temp2, agg, eps, sim_pm.data_ptr(), ws.data_ptr(), nbytes, s),
+                    "tc_local_sim_fwd_train_part")
+            img_all.record_stream(side)
+            # natural image g = r * n + p * m + k  lives at part-major row  p * (world * m) + r * m + k
+            g = torch.arange(B, device=dev)
+            r, q = g // n, g % n
+            perm = (q // m) * (world * m) + r * m + (q % m)
+            sim = sim_pm.index_select(0, perm)
+        ctx.save_for_backward(ctx_t, words_t, dev_lens, ws, perm)
+        ctx.args = (lcap, group, P, S, Lw, img_emb_l.shape, img_emb_l.dtype, text_emb_l.dtype)
+        return sim
+
+    @staticmethod
+    def backward(ctx, dsim):
+        import ctypes
+        from . import _lib
+        from .ops import _stream
+        L = _lib.lib()
+        ctx_t, words_t, dev_lens, ws, perm = ctx.saved_tensors
+        lcap, group, P, S, Lw, img_shape, img_dtype, txt_dtype = ctx.args
+        world = dist.get_world_size(group)
+        B, _, D = ctx_t.shape
+        Bc = words_t.shape[0]
+        n = B // world
+        m = n // P
+        dev = ctx_t.device
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        with torch.cuda.device(dev):
+            dsim_pm = torch.empty((B, Bc), dtype=torch.float32, device=dev)
+            dsim_pm.index_copy_(0, perm, dsim.float().contiguous())
+            d_ctx_all = torch.empty((B, D, S), dtype=torch.float32, device=dev)       # part-major
+            d_words = torch.empty((Bc, D, Lw), dtype=torch.float32, device=dev)
+            d_ctx = torch.empty((n, D, S), dtype=torch.float32, device=dev)
+            events = []
+            for _ in range(P):
+                e = torch.cuda.Event()
+                e.record(main)                                    # materialise the handle; the library re-records it
+                events.append(e)
+            handles = (ctypes.c_void_p * P)(*[e.cuda_event for e in events])
+            _lib.check(L.gloria_b200_tc_local_sim_bwd_train_parts(
+                ctx_t.data_ptr(), words_t.data_ptr(), dev_lens.data_ptr(), B, Bc, D, S, Lw, lcap, 0, dsim_pm.data_ptr(),
+                d_ctx_all.data_ptr(), d_words.data_ptr(), ws.data_ptr(), ws.numel(), P,
+                ctypes.cast(handles, ctypes.c_void_p), _stream(ctx_t)), "tc_local_sim_bwd_train_parts")
+            for p in range(P):
+                side.wait_event(events[p])                        # rows of part p are final; later parts still compute
+                with torch.cuda.stream(side):
+                    dist.reduce_scatter_tensor(d_ctx[p * m:(p + 1) * m], d_ctx_all[p * world * m:(p + 1) * world * m],
+                                               op=dist.ReduceOp.SUM, group=group)
+            main.wait_stream(side)
+        return (d_ctx.reshape(img_shape).to(img_dtype), d_words.to(txt_dtype), None, None, None, None, None, None,
+                None, None)
+
+
 def _sharded_local_sim(img_emb_l, text_emb_l, cap_lens, temp1, temp2, agg, group):
     """Default CUDA path of the sharded local similarity -> sim[:, own captions] ([B, B/G])."""
-    from . import gloria_loss, ops
+    from . import _lib, gloria_loss, ops
     if not img_emb_l.is_cuda:
         raise RuntimeError("gloria_b200 runs on CUDA tensors only (sm_100a); there is no CPU fallback")
-    Bc, _, Lw = text_emb_l.shape
+    Bc, D, Lw = text_emb_l.shape
+    n = img_emb_l.shape[0]
+    S = img_emb_l.shape[2] * img_emb_l.shape[3]
     dev_lens, lens = gloria_loss._cap_lens(cap_lens, Bc, 0, Lw, img_emb_l.device)
     mode = gloria_loss._mode(img_emb_l, text_emb_l)
-    return _ShardedLocalSim.apply(img_emb_l, text_emb_l, dev_lens, max(lens), float(temp1), float(temp2),
+    lcap = max(lens)
+    L = _lib.lib()
+    world = dist.get_world_size(group)
+    P = _N_PARTS if n % _N_PARTS == 0 and n >= 2 * _N_PARTS else 1
+    if (mode == ops.MODE_BF16 and ops._FUSED_TRAIN and agg != "max" and torch.is_grad_enabled()
+            and (img_emb_l.requires_grad or text_emb_l.requires_grad) and L.gloria_b200_tc_supported(D, S, lcap) == 0):
+        nbytes = L.gloria_b200_tc_train_workspace(world * n, Bc, D, S, lcap)
+        if 0 < nbytes <= min(ops._TC_WS_BUDGET, int(ops._available_bytes(img_emb_l.device, nbytes) * 0.92)):
+            return _ShardedLocalSimParts.apply(img_emb_l, text_emb_l, dev_lens, lcap, float(temp1), float(temp2),
+                                               ops.AGG[agg], 1e-8, group, P)
+    return _ShardedLocalSim.apply(img_emb_l, text_emb_l, dev_lens, lcap, float(temp1), float(temp2),
                                   ops.AGG[agg], 1e-8, mode, group)
 
 

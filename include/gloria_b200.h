@@ -153,6 +153,12 @@ int gloria_b200_tc_prepack(const float* ctx, const float* words, const int32_t* 
                            int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
                            void* ctx_h, void* ctx_t, void* ctx_n, void* words_h, void* words_t, float* wnorm,
                            void* stream);
+/* The two halves of the prepack on their own (ctx_n may be NULL: only the inference forward and the recompute backward
+ * read it). */
+int gloria_b200_tc_prepack_ctx(const float* ctx, int Bi, int D, int S, void* ctx_h, void* ctx_t, void* ctx_n,
+                               void* stream);
+int gloria_b200_tc_prepack_words(const float* words, const int32_t* cap_lens, int Bc, int D, int Lw, int Lcap,
+                                 int word_off, void* words_h, void* words_t, float* wnorm, void* stream);
 
 /* Fused forward over all Bi x Bc pairs: scores on tcgen05 (K = D), both softmaxes, attention-weighted context
  * on tcgen05 (K = S), per-word cosine and the temp2 log-sum-exp; only sim[Bi, Bc] reaches HBM -- plus, when
@@ -206,6 +212,22 @@ int gloria_b200_tc_local_sim_bwd_train(const void* ctx_t, const void* words_t, c
                                        int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
                                        const float* dsim, float* d_ctx, float* d_words,
                                        void* workspace, size_t workspace_bytes, void* stream);
+/* Image range [j0, j0 + nj) of a (Bi x Bc) training forward: the workspace is laid out for all Bi images and this call
+ * fills the rows of the range (ctx_h, ctx_t and sim are the base pointers of the full arrays).  One launch per
+ * all_gather chunk lets a caption-sharded caller overlap the gather of the next chunk with this chunk's kernel. */
+int gloria_b200_tc_local_sim_fwd_train_part(const void* ctx_h, const void* ctx_t, const void* words_h,
+                                            const float* wnorm, const int32_t* cap_lens, int Bi, int j0, int nj,
+                                            int Bc, int D, int S, int Lcap, float temp1, float temp2, int agg,
+                                            float eps, float* sim, void* workspace, size_t workspace_bytes,
+                                            void* stream);
+/* Backward with the image side done in n_parts equal image ranges (n_parts divides Bi); part_events[k] (cudaEvent_t or
+ * NULL; the array itself may be NULL) is recorded on `stream` once the d_ctx rows of part k are final.  The
+ * caption-side GEMM runs last. */
+int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const void* words_t, const int32_t* cap_lens,
+                                             int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                             const float* dsim, float* d_ctx, float* d_words,
+                                             void* workspace, size_t workspace_bytes, int n_parts,
+                                             void* const* part_events, void* stream);
 /* Same, with a caller-owned cudaEvent_t (or NULL) that is recorded on `stream` as soon as d_ctx is final -- before the
  * caption-side GEMM.  A caption-sharded caller waits on it to start the reduce_scatter of d_ctx while the
  * rest of the backward still runs. */
