@@ -270,17 +270,29 @@ def run_b200(args):
     sync()
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # inputs smaller than L2 (b48): write a 256 MB buffer between the timed iterations; each step then has its own events
+    small = B * D * S * 4 <= 126e6
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
+    per_step = []
     e0.record()
     for i in range(args.steps):
+        if small:
+            flush_buf.fill_(i & 1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
         arm_timers(i)
         last = step_resident()
+        if small:
+            b.record()
+            per_step.append((a, b))
     e1.record()
     sync()
     t_wall1 = time.time()
     launches = int(lib.gloria_b200_launch_count(1))
     for s in slots.values():
         lib.gloria_b200_set_timer_events(s, None, None)
-    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in per_step) / args.steps if small
+                        else e0.elapsed_time(e1) / args.steps)
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     loss_val = float(last.detach())
 
@@ -364,7 +376,8 @@ def run_b200(args):
                                    "361 regions (19x19), D=768, temps 4/5/10, local+global loss",
                        "parallelism": f"caption-sharded x{world}" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2 (region features %.0f MB per rank)" % (B * D * S * 4 / 1e6)
-                             if B * D * S * 4 > 126e6 else "inputs smaller than L2; steps run back to back",
+                             if B * D * S * 4 > 126e6 else "inputs smaller than L2: a 256 MB buffer is written between "
+                                                           "timed iterations (outside the per-step events)",
                        "loss": loss_val},
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world},

@@ -74,9 +74,17 @@ __global__ void __launch_bounds__(256) global_cos_bwd_side(const float* __restri
   for (int w = 0; w < nwarps; ++w) tot += red[w];
   const float coef = na > 0.f ? tot / na : 0.f;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float acc = coef * xs[d];
-    for (int b = 0; b < Bc; ++b) acc = fmaf(dd[b], y[(long long)b * D + d], acc);
-    dx[(long long)a * D + d] = acc;
+    // four independent chains: with few rows per launch (a caption shard of a large batch) this loop is latency-bound
+    float acc0 = coef * xs[d], acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    int b = 0;
+    for (; b + 4 <= Bc; b += 4) {
+      acc0 = fmaf(dd[b], __ldg(y + (long long)b * D + d), acc0);
+      acc1 = fmaf(dd[b + 1], __ldg(y + (long long)(b + 1) * D + d), acc1);
+      acc2 = fmaf(dd[b + 2], __ldg(y + (long long)(b + 2) * D + d), acc2);
+      acc3 = fmaf(dd[b + 3], __ldg(y + (long long)(b + 3) * D + d), acc3);
+    }
+    for (; b < Bc; ++b) acc0 = fmaf(dd[b], __ldg(y + (long long)b * D + d), acc0);
+    dx[(long long)a * D + d] = (acc0 + acc1) + (acc2 + acc3);
   }
 }
 

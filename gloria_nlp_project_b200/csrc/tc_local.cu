@@ -346,24 +346,29 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
 // prepack: fp32 native layouts -> padded bf16 TMA-legal layouts
 // ---------------------------------------------------------------------------------------------------------------
 // ctx [Bi, D, S] -> Rn [Bi, D, Spad] (bf16), Rt [Bi, Spad, D] (bf16) and Rh [Bi, Spad, D] (fp16)
-// grid (Spad/32, D/32, Bi), block (32, 8).  The score GEMM runs on the fp16 copies: the word softmax amplifies operand
+// grid (Spad/32, D/64, Bi), block (32, 8).  The score GEMM runs on the fp16 copies: the word softmax amplifies operand
 // rounding (scores of unit-variance 768-d features have std 27.7) and fp16 carries 3 more mantissa bits than bf16 at
 // the same tensor rate -- it is also the dtype the reference's AMP runs this bmm in.
 __global__ void pack_ctx(const float* __restrict__ ctx, __nv_bfloat16* __restrict__ Rn, __nv_bfloat16* __restrict__ Rt,
                          __half* __restrict__ Rh, int D, int S, int Spad, int sp) {
-  __shared__ float t[32][33];
-  const int b = blockIdx.z, s0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int d = d0 + r, s = s0 + threadIdx.x;
+  // one 32 (regions) x 64 (channels) tile per block: 128-byte reads along s, 128-byte (2 channels per thread) writes
+  // along d of both transposed copies
+  __shared__ float t[64][33];
+  const int b = blockIdx.z, s0 = blockIdx.x * 32, d0 = blockIdx.y * 64;
+  const int s = s0 + threadIdx.x;
+  for (int r = threadIdx.y; r < 64; r += 8) {
+    const int d = d0 + r;
     const float v = (s < S) ? ctx[((size_t)b * D + d) * S + s] : 0.f;
     if (Rn != nullptr) Rn[((size_t)b * D + d) * Spad + s] = __float2bfloat16_rn(v);
     t[r][threadIdx.x] = v;
   }
   __syncthreads();
+  const int d = d0 + 2 * threadIdx.x;
   for (int r = threadIdx.y; r < 32; r += 8) {
-    const int s = s0 + r, d = d0 + threadIdx.x;
-    if (s < sp) Rt[((size_t)b * sp + s) * D + d] = __float2bfloat16_rn(t[threadIdx.x][r]);   // GEMM pitch
-    Rh[((size_t)b * Spad + s) * D + d] = __float2half_rn(t[threadIdx.x][r]);                // tile pitch
+    const int so = s0 + r;
+    const float v0 = t[2 * threadIdx.x][r], v1 = t[2 * threadIdx.x + 1][r];
+    if (so < sp) *reinterpret_cast<__nv_bfloat162*>(Rt + ((size_t)b * sp + so) * D + d) = __floats2bfloat162_rn(v0, v1);
+    *reinterpret_cast<__half2*>(Rh + ((size_t)b * Spad + so) * D + d) = __floats2half2_rn(v0, v1);
   }
 }
 
@@ -517,7 +522,7 @@ extern "C" int gloria_b200_tc_prepack_ctx(const float* ctx, int Bi, int D, int S
   if (gloria_b200_tc_supported(D, S, 1)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d", D, S);
   cudaStream_t st = (cudaStream_t)stream;
   const int Spad = gloria_b200_tc_spad(S);
-  pack_ctx<<<dim3(Spad / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(ctx, (__nv_bfloat16*)ctx_n, (__nv_bfloat16*)ctx_t,
+  pack_ctx<<<dim3(Spad / 32, D / 64, Bi), dim3(32, 8), 0, st>>>(ctx, (__nv_bfloat16*)ctx_n, (__nv_bfloat16*)ctx_t,
                                                                (__half*)ctx_h, D, S, Spad, gloria_b200_tc_sp(S));
   GLORIA_LAUNCHED("pack_ctx");
   return GLORIA_OK;

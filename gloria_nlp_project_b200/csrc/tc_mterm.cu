@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(bar(B_FULL + s), 1);
-      mbar_init(bar(B_SCALED + s), 128);
+      mbar_init(bar(B_SCALED + s), 256);       // owner group: A' written; other group: phase of `full` observed
       mbar_init(bar(B_EMPTY + s), 1);
     }
     mbar_init(bar(B_ACCF), 1);
@@ -124,8 +124,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
         if (t64 < KBLK && kb < nkb && k < p.R1) w = __ldg(fr + k) * (gr ? __ldg(gr + k / p.lp) : 1.f);
         return w;
       };
-      // Both groups observe EVERY k-block's `full` barrier (parity waits must not skip a phase of a stage), the owner
-      // (k-block parity == group) scales it.
+      // Both groups observe EVERY k-block's `full` barrier: the owner (k-block parity == group) scales it, the other
+      // group only needs to have seen the phase (its next wait on this stage is for the following phase, and a parity
+      // wait cannot tell phase k from phase k+2).  Both arrive on `scaled`, so the MMA of k-block n -- and with it the
+      // refill of its stage -- cannot run before BOTH groups have seen `full`(n): without that, a group coming out of
+      // the epilogue could find its stage already two phases on and wait forever (seen as a launch failure with few
+      // k-blocks per unit).
       int kb_mine = (int)((grp + 2u - (nk & 1u)) & 1u);          // first k-block of this unit owned by this group
       float w_next = load_w(kb_mine);
       for (int kb = 0; kb < nkb; ++kb) {
@@ -140,7 +144,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
         }
         // the stage's previous use has been released (the producer waited for it) once its tiles have landed
         mbar_wait(bar(B_FULL + st), ph);
-        if (!mine) continue;
+        if (!mine) {
+          mbar_arrive(bar(B_SCALED + st));
+          continue;
+        }
         uint8_t* sbase = smem + (size_t)st * STAGE;
         __nv_bfloat16* wsm = reinterpret_cast<__nv_bfloat16*>(sbase + OFF_W);
         if (t64 < KBLK) wsm[t64] = __float2bfloat16_rn(w_cur);

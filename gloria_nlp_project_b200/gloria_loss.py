@@ -14,7 +14,7 @@ import torch
 from . import _config, ops
 
 __all__ = ["cosine_similarity", "attention_fn", "global_loss", "kl_divergence", "entropy", "local_loss",
-           "local_similarities", "diagonal_attention_maps", "supervised_attention_loss"]
+           "local_similarities", "diagonal_attention_maps", "supervised_attention_loss", "plan_length_buckets"]
 
 
 def _mode(*tensors: torch.Tensor) -> int:
@@ -52,6 +52,37 @@ def _context(img_features: torch.Tensor, no_attn_vec: Optional[torch.Tensor]) ->
     return ctx
 
 
+# Length buckets (bf16 tensor-core mode).  The kernels are compiled per padded caption length (multiples of 16 words)
+# and a launch pads every caption to its longest one, so a batch with cap_lens ~ U{5..97} does 112 / 58 of the
+# necessary work in one launch.  Captions are therefore grouped by padded length and each group gets its own launch
+# (and its own fused-training state); groups are merged while that costs less than a launch's fixed overhead.
+BUCKET_OVERHEAD_US = 300.0        # host + launch cost of one more group, independent of the batch
+BUCKET_OVERHEAD_US_PER_IMAGE = 2.4    # prepack + gradient accumulation of one more group, per image
+BUCKET_US_PER_IMAGE_WORD = 3.4e-3     # kernel time per image and padded caption word (98.7 ms / 512 / (512 * 112))
+
+
+def plan_length_buckets(lens: Sequence[int], n_images: int, word_offset: int = 0) -> List[Tuple[List[int], int]]:
+    """Group caption indices by padded length -> [(indices, lcap)], longest group first; one group = no bucketing.
+    Pure host logic (tested on CPU)."""
+    def lpad(n):
+        return (n + 15) // 16 * 16
+    groups = {}
+    for i, n in enumerate(lens):
+        groups.setdefault(lpad(int(n)), []).append(i)
+    keys = sorted(groups, reverse=True)                       # padded lengths, descending
+    merge_cost_words = (BUCKET_OVERHEAD_US + BUCKET_OVERHEAD_US_PER_IMAGE * n_images) / \
+        (BUCKET_US_PER_IMAGE_WORD * max(n_images, 1))
+    # greedy: repeatedly fold the group whose padding to its longer neighbour wastes the fewest caption-words
+    while len(keys) > 1:
+        waste = [(len(groups[keys[k + 1]]) * (keys[k] - keys[k + 1]), k) for k in range(len(keys) - 1)]
+        w, k = min(waste)
+        if w >= merge_cost_words:
+            break
+        groups[keys[k]] = groups[keys[k]] + groups.pop(keys[k + 1])
+        keys.pop(k + 1)
+    return [(sorted(groups[k]), max(int(lens[i]) for i in groups[k])) for k in keys]
+
+
 def local_similarities(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, agg="sum", no_attn_vec=None,
                        word_offset=0, eps=1e-8, want_attn_maps=False, want_mean_attn=False):
     """The [B_img, B_cap] matrix the caption loop of gloria_loss.py:116-162 builds (before the temp3 scale).
@@ -67,6 +98,25 @@ def local_similarities(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, 
     ctx = _context(img_features, no_attn_vec)
     words = words_emb.float()
     mode = _mode(img_features, words_emb)
+    buckets = plan_length_buckets(lens, ctx.shape[0], word_offset) if (mode == ops.MODE_BF16 and not want_mean_attn) \
+        else []
+    if len(buckets) > 1:
+        parts, order = [], []
+        with ops.shared_ctx_pack(ctx):                               # the images are packed once for all groups
+            for idx, lcap_b in buckets:
+                sel = torch.tensor(idx, dtype=torch.long).to(ctx.device, non_blocking=True)
+                sim_b, _, _, _ = ops.local_sim_fwd(ctx, words.index_select(0, sel), dev_lens.index_select(0, sel),
+                                                   lcap_b, word_offset, float(temp1), float(temp2), ops.AGG[agg],
+                                                   float(eps), False, False, mode)
+                parts.append(sim_b)
+                order += idx
+        inv = torch.empty(Bc, dtype=torch.long)
+        inv[torch.tensor(order)] = torch.arange(Bc)
+        sim = torch.cat(parts, 1).index_select(1, inv.to(ctx.device, non_blocking=True))
+        diag = None
+        if want_attn_maps:                                           # B diagonal pairs through the exact fp32 kernels
+            diag = ops.diag_attn_fwd(ctx, words, dev_lens, max(lens), word_offset, float(temp1))
+        return sim, diag, None, lens
     sim, diag, mean, _ = ops.local_sim_fwd(ctx, words, dev_lens, max(lens), word_offset, float(temp1), float(temp2),
                                            ops.AGG[agg], float(eps), bool(want_attn_maps), bool(want_mean_attn),
                                            mode)

@@ -7,7 +7,9 @@ op with CPU tensors raises RuntimeError.
 """
 from __future__ import annotations
 
+import contextlib
 import os
+import threading
 from typing import Optional, Tuple
 
 import torch
@@ -31,6 +33,22 @@ class Packed:
         self.ctx_h, self.ctx_t, self.ctx_n, self.words_h, self.words_t, self.wnorm = t
 
 
+_SHARED = threading.local()
+
+
+@contextlib.contextmanager
+def shared_ctx_pack(ctx: Tensor):
+    """Within the block, every tc_prepack of this very context tensor (same storage, shape and version; the block keeps
+    it alive) reuses one set of packed region copies -- the length-bucketed path launches once per bucket on the same
+    images."""
+    _SHARED.key = (ctx.data_ptr(), tuple(ctx.shape), ctx._version, ctx.device)
+    _SHARED.keep, _SHARED.val = ctx, None
+    try:
+        yield
+    finally:
+        _SHARED.key = _SHARED.keep = _SHARED.val = None
+
+
 def tc_prepack(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int) -> Packed:
     """fp32 native layouts -> ctx_h/ctx_t [Bi,Spad,D] (fp16/bf16), ctx_n [Bi,D,Spad] bf16, words_h/words_t [Bc,Lpad,D]
     (fp16/bf16), wnorm [Bc,Lpad] fp32."""
@@ -39,16 +57,25 @@ def tc_prepack(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off
     Bc, _, Lw = words.shape
     spad, lpad = L.gloria_b200_tc_spad(S), L.gloria_b200_tc_lpad(lcap)
     dev = ctx.device
-    ctx_h = torch.empty((Bi, spad, D), dtype=torch.float16, device=dev)
-    ctx_t = torch.empty((Bi, L.gloria_b200_tc_sp(S), D), dtype=torch.bfloat16, device=dev)
-    ctx_n = torch.empty((Bi, D, spad), dtype=torch.bfloat16, device=dev)
     words_h = torch.empty((Bc, lpad, D), dtype=torch.float16, device=dev)
     words_t = torch.empty((Bc, L.gloria_b200_tc_lp(lcap), D), dtype=torch.bfloat16, device=dev)
     wnorm = torch.empty((Bc, lpad), dtype=torch.float32, device=dev)
-    rc = L.gloria_b200_tc_prepack(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S, Lw, lcap,
-                                  word_off, ctx_h.data_ptr(), ctx_t.data_ptr(), ctx_n.data_ptr(), words_h.data_ptr(),
-                                  words_t.data_ptr(), wnorm.data_ptr(), _stream(ctx))
-    _lib.check(rc, "tc_prepack")
+    key = (ctx.data_ptr(), tuple(ctx.shape), ctx._version, ctx.device)
+    shared = getattr(_SHARED, "key", None) == key
+    if shared and _SHARED.val is not None:
+        ctx_h, ctx_t, ctx_n = _SHARED.val
+    else:
+        ctx_h = torch.empty((Bi, spad, D), dtype=torch.float16, device=dev)
+        ctx_t = torch.empty((Bi, L.gloria_b200_tc_sp(S), D), dtype=torch.bfloat16, device=dev)
+        ctx_n = torch.empty((Bi, D, spad), dtype=torch.bfloat16, device=dev)
+        rc = L.gloria_b200_tc_prepack_ctx(ctx.data_ptr(), Bi, D, S, ctx_h.data_ptr(), ctx_t.data_ptr(), ctx_n.data_ptr(),
+                                          _stream(ctx))
+        _lib.check(rc, "tc_prepack_ctx")
+        if shared:
+            _SHARED.val = (ctx_h, ctx_t, ctx_n)
+    rc = L.gloria_b200_tc_prepack_words(words.data_ptr(), cap_lens.data_ptr(), Bc, D, Lw, lcap, word_off,
+                                        words_h.data_ptr(), words_t.data_ptr(), wnorm.data_ptr(), _stream(ctx))
+    _lib.check(rc, "tc_prepack_words")
     return Packed(ctx_h, ctx_t, ctx_n, words_h, words_t, wnorm)
 
 

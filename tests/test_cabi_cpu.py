@@ -98,3 +98,29 @@ def test_supervised_attention_loss_per_cell_form():
     up = up / up.sum(-1, keepdims=True).sum(-2, keepdims=True)
     ref = -torch.log((labels * up).sum(-1).sum(-1)).mean()
     assert abs(float(supervised_attention_loss(maps, labels)) - float(ref)) < 1e-12
+
+
+def test_length_bucket_plan():
+    """Host logic of the length-bucketed bf16 path: groups partition the captions, each group's lcap is its longest
+    caption, uniform lengths and small batches stay in one launch, a large ragged batch is split by padded length."""
+    import torch
+    from gloria_nlp_project_b200.gloria_loss import plan_length_buckets
+    assert plan_length_buckets([97] * 512, 512) == [(list(range(512)), 97)]
+    gen = torch.Generator().manual_seed(1)
+    small = torch.randint(5, 98, (48,), generator=gen).tolist()
+    assert len(plan_length_buckets(small, 48)) == 1                      # a launch costs more than the padding saves
+    lens = sorted(torch.randint(5, 98, (512,), generator=gen).tolist(), reverse=True)
+    plan = plan_length_buckets(lens, 512)
+    assert len(plan) > 2
+    seen = sorted(i for idx, _ in plan for i in idx)
+    assert seen == list(range(512))
+    for idx, lcap in plan:
+        assert lcap == max(lens[i] for i in idx)
+    pads = [(lcap + 15) // 16 * 16 for _, lcap in plan]
+    assert pads == sorted(pads, reverse=True) and len(set(pads)) == len(pads)
+    work = sum(len(idx) * p for (idx, _), p in zip(plan, pads))
+    assert work < 0.65 * 512 * 112                                       # U{5..97}: ~52 % of the single-launch work
+    # unsorted input: same partition by padded length
+    shuffled = [lens[(7 * i) % 512] for i in range(512)]
+    plan2 = plan_length_buckets(shuffled, 512)
+    assert sorted(len(idx) for idx, _ in plan2) == sorted(len(idx) for idx, _ in plan)

@@ -430,3 +430,59 @@ def test_attention_finetune_touches_diagonal_pairs_only(gl, monkeypatch):
     maps2 = m.get_attn_maps(cu(img_l), cu(txt_l), sents)
     for a, b, c in zip(maps, maps2, ref_maps):
         assert torch.equal(a, b) and relerr(a, c) < 1e-5
+
+
+def test_length_bucketed_training(gl, monkeypatch):
+    """Ragged captions split into one launch per padded length (forced here: the cost model would keep a batch this
+    small in one launch): losses, gradients and attention maps equal the oracle's on the whole batch."""
+    monkeypatch.setattr(gl, "BUCKET_OVERHEAD_US", 0.0)
+    monkeypatch.setattr(gl, "BUCKET_OVERHEAD_US_PER_IMAGE", 0.0)
+    lens = [97, 5, 80, 33, 30, 12, 96, 16]                 # unsorted on purpose: 112 / 16 / 80 / 48 / 32 / 96 groups
+    B = len(lens)
+    assert len(gl.plan_length_buckets(lens, B)) >= 5
+    img_l, txt_l, _, _, cl = gen_inputs(77, B, 768, 19, 19, 97, cap_lens=lens, scale=0.05, dtype=np.float32)
+    img, txt = cu(img_l, True), cu(txt_l, True)
+    l0, l1, _, _, _, maps = gl.local_loss(img, txt, cl)
+    (l0 + 0.5 * l1).backward()
+    i64, t64 = img_l.astype(np.float64), txt_l.astype(np.float64)
+    o0, o1, _, _, _, omaps, _ = O.local_loss(i64, t64, cl)
+    assert relerr(l0, o0) < LOGIT_TOL and relerr(l1, o1) < LOGIT_TOL
+    d_img, d_txt = O.local_loss_bwd(i64, t64, cl, g0=1.0, g1=0.5)
+    assert relerr(img.grad, d_img) < GRAD_TOL
+    assert relerr(txt.grad, d_txt) < GRAD_TOL
+    for k in (0, 1, 5):
+        assert maps[k].shape == (1, lens[k], 19, 19) and relerr(maps[k], omaps[k]) < 1e-3
+    # forward-only (zero-shot style: max aggregation, word offset 1) through the same grouping
+    with torch.no_grad():
+        sim, _, _, _ = gl.local_similarities(img.detach(), txt.detach(), [n - 1 for n in lens[:1]] + [4, 60, 20, 20, 11, 90, 15],
+                                             4.0, 5.0, "max", word_offset=1)
+    ref = O.get_local_similarities(i64, t64, [96, 4, 60, 20, 20, 11, 90, 15])
+    assert relerr(sim, ref) < LOGIT_TOL
+
+
+def test_mterm_short_units_many_per_cta(gl):
+    """Regression: few captions against many images (a length bucket of 3 captions x 512 images: 7 k-blocks per unit,
+    ~10 units per CTA) used to dead-lock the |C|-term kernel now and then -- a scale group coming out of the epilogue
+    found its stage two phases ahead.  Repeated runs must succeed, and because the image-side gradient of image j
+    depends only on (image j, the captions, dsim[j, :]) the first images must reproduce a small separate run."""
+    from gloria_nlp_project_b200 import ops
+    Bi, Bc, small = 512, 3, 6
+    gen = torch.Generator(device="cuda").manual_seed(31)
+    ctx = torch.randn(Bi, 768, 361, device="cuda", generator=gen) * 0.05
+    words = torch.randn(Bc, 768, 97, device="cuda", generator=gen) * 0.05
+    lens = torch.full((Bc,), 97, dtype=torch.int32, device="cuda")
+    G = torch.randn(Bi, Bc, device="cuda", generator=gen) * 0.1
+
+    def run(n):
+        c = ctx[:n].clone().requires_grad_(True)
+        w = words.clone().requires_grad_(True)
+        sim, _, _, _ = ops.local_sim_fwd(c, w, lens, 97, 0, 4.0, 5.0, 0, 1e-8, False, False, ops.MODE_BF16)
+        (sim * G[:n]).sum().backward()
+        torch.cuda.synchronize()
+        return sim.detach(), c.grad
+    sim_s, g_s = run(small)
+    for _ in range(6):
+        sim_l, g_l = run(Bi)
+        assert relerr(sim_l[:small], sim_s) < 1e-5
+        # same arithmetic up to the GEMMs' summation order (cuBLAS picks different tilings for 6 and 512 images)
+        assert relerr(g_l[:small], g_s) < 2e-3
