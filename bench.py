@@ -35,7 +35,7 @@ CPU_SAMPLE = 16          # the CPU arm times a CPU_SAMPLE x CPU_SAMPLE block of 
 # DRAM bytes per launch (read + write) of the dominant kernels at B=512, N=1, from the ncu captures under profiles/
 TRAFFIC_B512 = {("tc_fwd_kernel", False): 2511333120 + 237689344,            # r01_traffic_B512_ncu.csv
                 ("tc_bwd_pair_kernel", False): 5648215808 + 45244279296,
-                ("tc_fwd_kernel", True): 17035313920 + 45348764416}           # r01_final_bench_B512_ncu_launch_list.txt
+                ("tc_fwd_kernel", True): 21674893000 + 42595012000}           # r01_end_fused_train_B512_ncu_summary.txt
 
 
 def parse():
