@@ -44,6 +44,10 @@ PROTOTYPES = {
     "gloria_b200_tc_supported": (_i, [_i, _i, _i]),
     "gloria_b200_tc_prepack": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "gloria_b200_tc_local_sim_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p]),
+    "gloria_b200_tc_packed_groups": (_i, [_i]),
+    "gloria_b200_tc_packed_per": (_i, [_i]),
+    "gloria_b200_tc_prepack_words_packed": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "gloria_b200_tc_local_sim_fwd_packed": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p]),
     "gloria_b200_tc_bwd_workspace": (_z, [_i, _i, _i, _i, _i, _i, _z]),
     "gloria_b200_tc_local_sim_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f,
                                           _p, _p, _p, _p, _p, _z, _p]),

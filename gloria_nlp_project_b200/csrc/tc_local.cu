@@ -35,6 +35,8 @@ struct FwdParams {
   float* sim;                // [Bi, Bc]
   float* stats;              // [Bi, Bc, 2, LPAD] (dot', |C'|^2 of the un-normalised context) or nullptr
   int Bi, Bc, D, S, NT;
+  int n_caps, per;           // SEG > 0 ("packed" mode): Bc counts word tiles; tile g holds captions g*per .. g*per+per-1 (of
+                             // n_caps) in 16-word segments; sim is [Bi, n_caps]
   float t1_log2e;            // temp1 * log2(e)
   float temp2;
   int agg;
@@ -42,7 +44,11 @@ struct FwdParams {
   long long* dbg;            // phase clocks (only read when built with -DGLORIA_PHASE_CLOCKS)
 };
 
-template <int LPAD>
+// SEG = 0: one caption per word tile.  SEG = 16 ("packed" mode, inference only): LPAD / 16 captions of at most 16 words
+// share one word tile -- zero-shot prompts are a handful of words, and the kernel's cost is set by the image tiles it
+// streams per (image, word tile), not by the tile's width.  Softmax #1 and the word aggregation then run per segment;
+// everything in between is per word and does not change.
+template <int LPAD, int SEG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__ CUtensorMap tm_wt,
               const __grid_constant__ CUtensorMap tm_rn, const FwdParams p) {
@@ -208,7 +214,14 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
     uint32_t g1 = 0, nu = 0;
     Units u(p.Bi, p.Bc);
     while (u.next_caption()) {
-      const int L = min(max(p.cap_lens[u.i], 0), LPAD);
+      const int L = SEG ? LPAD : min(max(p.cap_lens[u.i], 0), LPAD);
+      constexpr int NSEG = SEG ? LPAD / (SEG ? SEG : 1) : 1;
+      int Lseg[NSEG];
+#pragma unroll
+      for (int sg = 0; sg < NSEG; ++sg) {
+        const int c = u.i * p.per + sg;
+        Lseg[sg] = (SEG && sg < p.per && c < p.n_caps) ? min(max(p.cap_lens[c], 0), SEG) : 0;
+      }
       for (int j = u.j; j < u.j_end; ++j) {
         for (int t = 0; t < p.NT; ++t) {
           const uint32_t b = g1 & 1;
@@ -221,24 +234,47 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
           tc_fence_before();
           mbar_arrive(bar(B_D1E + b));           // D1 buffer may be overwritten by the next tile's GEMM1
           ++g1;
-          // softmax #1 over the caption's words (gloria_loss.py:42-43), true running max
-          float m = -INFINITY;
-#pragma unroll
-          for (int l = 0; l < LPAD; ++l) m = (l < L) ? fmaxf(m, x[l]) : m;
-          const float mb = m * LOG2E;
-          float sum = 0.f;
-#pragma unroll
-          for (int l = 0; l < LPAD; ++l) {
-            const float e = (l < L) ? ex2(fmaf(x[l], LOG2E, -mb)) : 0.f;
-            x[l] = e;
-            sum += e;
-          }
-          // numerator of softmax #2 (:51-52): exp(temp1 * P); padded regions / words contribute nothing
           const int s_glob = t * TILE + row;
           const bool live_row = s_glob < p.S;
-          const float sc = p.t1_log2e / sum;
+          if constexpr (SEG == 0) {
+            // softmax #1 over the caption's words (gloria_loss.py:42-43), true running max
+            float m = -INFINITY;
 #pragma unroll
-          for (int l = 0; l < LPAD; ++l) x[l] = (live_row && l < L) ? ex2(x[l] * sc) : 0.f;
+            for (int l = 0; l < LPAD; ++l) m = (l < L) ? fmaxf(m, x[l]) : m;
+            const float mb = m * LOG2E;
+            float sum = 0.f;
+#pragma unroll
+            for (int l = 0; l < LPAD; ++l) {
+              const float e = (l < L) ? ex2(fmaf(x[l], LOG2E, -mb)) : 0.f;
+              x[l] = e;
+              sum += e;
+            }
+            // numerator of softmax #2 (:51-52): exp(temp1 * P); padded regions / words contribute nothing
+            const float sc = p.t1_log2e / sum;
+#pragma unroll
+            for (int l = 0; l < LPAD; ++l) x[l] = (live_row && l < L) ? ex2(x[l] * sc) : 0.f;
+          } else {
+            // the same per 16-word segment = per caption of the tile
+#pragma unroll
+            for (int sg = 0; sg < NSEG; ++sg) {
+              const int Ls = Lseg[sg];
+              float* xs = x + sg * SEG;
+              float m = -INFINITY;
+#pragma unroll
+              for (int l = 0; l < SEG; ++l) m = (l < Ls) ? fmaxf(m, xs[l]) : m;
+              const float mb = m * LOG2E;
+              float sum = 0.f;
+#pragma unroll
+              for (int l = 0; l < SEG; ++l) {
+                const float e = (l < Ls) ? ex2(fmaf(xs[l], LOG2E, -mb)) : 0.f;
+                xs[l] = e;
+                sum += e;
+              }
+              const float sc = p.t1_log2e / sum;
+#pragma unroll
+              for (int l = 0; l < SEG; ++l) xs[l] = (live_row && l < Ls) ? ex2(xs[l] * sc) : 0.f;
+            }
+          }
           if (t == 0) mbar_wait(bar(B_EE), (nu & 1) ^ 1);   // previous unit's GEMM2 no longer reads E
           // MN-major SWIZZLE_128B A operand: [word block of 64][region][64 words], 16-B chunk ^= region % 8
           const uint32_t rowaddr = base + OFF_E + (uint32_t)(s_glob >> 3) * 1024u + (uint32_t)(s_glob & 7) * 128u;
@@ -269,8 +305,11 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
     uint32_t g2 = 0;
     Units u(p.Bi, p.Bc);
     while (u.next_caption()) {
-      const int L = min(max(p.cap_lens[u.i], 0), LPAD);
-      const bool live = l < L;
+      // packed mode: word l of the tile is word l % SEG of caption u.i * per + l / SEG
+      const int cap = SEG ? u.i * p.per + l / (SEG ? SEG : 1) : u.i;
+      const bool cap_ok = !SEG || (l < LPAD && l / (SEG ? SEG : 1) < p.per && cap < p.n_caps);
+      const int L = !cap_ok ? 0 : min(max(p.cap_lens[cap], 0), SEG ? SEG : LPAD);
+      const bool live = (SEG ? l % (SEG ? SEG : 1) : l) < L;
       const float nw = (l < LPAD) ? p.wnorm[(size_t)u.i * LPAD + l] : 0.f;
       const uint4* wrow = reinterpret_cast<const uint4*>(p.wt + ((size_t)u.i * LPAD + (l < LPAD ? l : 0)) * p.D);
       for (int j = u.j; j < u.j_end; ++j) {
@@ -312,6 +351,25 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
         // cosine (gloria_loss.py:11-16) and the temp2 aggregation over words (:153-158 / gloria_model.py:198-201)
         const float den = fmaxf(nw * sqrtf(c2), p.eps_s);
         const float v = live ? p.temp2 * (dot / den) : -INFINITY;
+        if constexpr (SEG != 0) {
+          // aggregation over the 16 lanes of this word's segment
+          float mx = v;
+#pragma unroll
+          for (int o = SEG / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          float ex = live ? __expf(v - mx) : 0.f;
+#pragma unroll
+          for (int o = SEG / 2; o > 0; o >>= 1) ex += __shfl_xor_sync(0xffffffffu, ex, o);
+          if (cap_ok && l % SEG == 0) {
+            float r;
+            if (p.agg == GLORIA_AGG_MAX) r = mx;
+            else {
+              r = mx + logf(ex);
+              if (p.agg == GLORIA_AGG_MEAN) r -= logf((float)L);
+            }
+            p.sim[(size_t)j * p.n_caps + cap] = r;
+          }
+          continue;
+        }
         float mx = warp_max(v);
         if (lane == 0) red[q] = mx;
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -367,7 +425,8 @@ __global__ void pack_ctx(const float* __restrict__ ctx, __nv_bfloat16* __restric
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int so = s0 + r;
     const float v0 = t[2 * threadIdx.x][r], v1 = t[2 * threadIdx.x + 1][r];
-    if (so < sp) *reinterpret_cast<__nv_bfloat162*>(Rt + ((size_t)b * sp + so) * D + d) = __floats2bfloat162_rn(v0, v1);
+    if (Rt != nullptr && so < sp)
+      *reinterpret_cast<__nv_bfloat162*>(Rt + ((size_t)b * sp + so) * D + d) = __floats2bfloat162_rn(v0, v1);
     *reinterpret_cast<__half2*>(Rh + ((size_t)b * Spad + so) * D + d) = __floats2half2_rn(v0, v1);
   }
 }
@@ -482,12 +541,12 @@ int make_map4(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t mid, uin
   return GLORIA_OK;
 }
 
-template <int LPAD>
+template <int LPAD, int SEG = 0>
 int launch_fwd(const CUtensorMap& rt, const CUtensorMap& wt, const CUtensorMap& rn, const FwdParams& p, int grid,
                cudaStream_t st) {
-  GLORIA_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<LPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  GLORIA_CUDA(cudaFuncSetAttribute(tc_fwd_kernel<LPAD, SEG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   timer_record(GLORIA_TIMER_TC_FWD, 0, st);
-  tc_fwd_kernel<LPAD><<<grid, NTHREADS, SMEM_BYTES, st>>>(rt, wt, rn, p);
+  tc_fwd_kernel<LPAD, SEG><<<grid, NTHREADS, SMEM_BYTES, st>>>(rt, wt, rn, p);
   timer_record(GLORIA_TIMER_TC_FWD, 1, st);
   GLORIA_LAUNCHED("tc_fwd_kernel");
   return GLORIA_OK;
@@ -514,10 +573,11 @@ extern "C" int gloria_b200_tc_supported(int D, int S, int Lcap) {
 }
 
 // The two halves of the prepack are separate entry points so that a caption-sharded caller can pack image parts as
-// their all_gather lands (ctx_n = NULL skips the copy only the inference forward / recompute backward read).
+// their all_gather lands (ctx_n = NULL skips the copy only the inference forward / recompute backward read, ctx_t = NULL
+// the copy only the training path reads).
 extern "C" int gloria_b200_tc_prepack_ctx(const float* ctx, int Bi, int D, int S, void* ctx_h, void* ctx_t, void* ctx_n,
                                           void* stream) {
-  GLORIA_CHECK_ARG(ctx && ctx_h && ctx_t, "null pointer");
+  GLORIA_CHECK_ARG(ctx && ctx_h, "null pointer");
   GLORIA_CHECK_ARG(Bi > 0, "bad sizes");
   if (gloria_b200_tc_supported(D, S, 1)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d", D, S);
   cudaStream_t st = (cudaStream_t)stream;
@@ -571,7 +631,7 @@ extern "C" int gloria_b200_tc_local_sim_fwd(const void* ctx_h, const void* ctx_n
   if ((rc = make_map(&rn, ctx_n, (uint64_t)Spad, (uint64_t)Bi * D, TILE))) return rc;
   FwdParams p;
   p.wt = (const __half*)words_h; p.wnorm = wnorm; p.cap_lens = cap_lens; p.sim = sim; p.stats = stats;
-  p.Bi = Bi; p.Bc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE;
+  p.Bi = Bi; p.Bc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE; p.n_caps = Bc; p.per = 1;
   p.t1_log2e = temp1 * 1.4426950408889634f; p.temp2 = temp2; p.agg = agg; p.eps_s = eps * (float)S;
   p.dbg = (long long*)g_phase_clock_buffer;
   int dev = 0, sms = 0;
@@ -587,6 +647,99 @@ extern "C" int gloria_b200_tc_local_sim_fwd(const void* ctx_h, const void* ctx_n
     case 96: return launch_fwd<96>(rt, wt, rn, p, grid, st);
     case 112: return launch_fwd<112>(rt, wt, rn, p, grid, st);
     case 128: return launch_fwd<128>(rt, wt, rn, p, grid, st);
+  }
+  return fail(GLORIA_ERR_UNSUPPORTED, "lpad %d", lpad);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Packed prompts (zero-shot scoring, gloria_model.py:171-207 driven by gloria.py:278-306: thousands of images against a
+// few short class prompts).  `per` = 1..8 captions of at most 16 words share one word tile of lpad = 16 * per words.
+// ---------------------------------------------------------------------------------------------------------------
+namespace gloria {
+namespace tc {
+// one block per (caption slot, 64 channels): Wh[g, (slot % per) * 16 + l, d] = words[c, d, off + l] (0 beyond the caption /
+// for empty slots)
+__global__ void pack_words_packed(const float* __restrict__ words, const int* __restrict__ cap_lens,
+                                  __half* __restrict__ Wh, int n_caps, int per, int D, int Lw, int lpad, int off) {
+  const int slot = blockIdx.x, g = slot / per, sg = slot % per;
+  const int d = blockIdx.y * 64 + threadIdx.x;
+  const int L = slot < n_caps ? min(max(cap_lens[slot], 0), 16) : 0;
+  if (d >= D) return;
+  for (int l = 0; l < 16; ++l) {
+    const float v = l < L ? words[((size_t)slot * D + d) * Lw + off + l] : 0.f;
+    Wh[((size_t)g * lpad + sg * 16 + l) * D + d] = __float2half_rn(v);
+  }
+}
+// wnorm[g, (slot % per) * 16 + l] = |words[c, :, off + l]|;  one warp per (slot, l)
+__global__ void word_norms_packed(const float* __restrict__ words, const int* __restrict__ cap_lens,
+                                  float* __restrict__ wnorm, int n_caps, int per, int D, int Lw, int lpad, int off) {
+  const int slot = blockIdx.x, l = threadIdx.y, lane = threadIdx.x;
+  const int L = slot < n_caps ? min(max(cap_lens[slot], 0), 16) : 0;
+  float ss = 0.f;
+  if (l < L)
+    for (int d = lane; d < D; d += 32) {
+      const float v = words[((size_t)slot * D + d) * Lw + off + l];
+      ss = fmaf(v, v, ss);
+    }
+  ss = warp_sum(ss);
+  if (lane == 0) wnorm[(size_t)(slot / per) * lpad + (slot % per) * 16 + l] = sqrtf(ss);
+}
+}  // namespace tc
+}  // namespace gloria
+
+extern "C" int gloria_b200_tc_packed_groups(int Bc) { return Bc <= 0 ? 0 : (Bc + 7) / 8; }
+extern "C" int gloria_b200_tc_packed_per(int Bc) {
+  const int g = gloria_b200_tc_packed_groups(Bc);
+  return g == 0 ? 0 : (Bc + g - 1) / g;
+}
+
+extern "C" int gloria_b200_tc_prepack_words_packed(const float* words, const int32_t* cap_lens, int Bc, int D, int Lw,
+                                                   int word_off, void* words_h, float* wnorm, void* stream) {
+  GLORIA_CHECK_ARG(words && cap_lens && words_h && wnorm, "null pointer");
+  GLORIA_CHECK_ARG(Bc > 0 && word_off >= 0 && word_off + 1 <= Lw, "bad sizes");
+  if (gloria_b200_tc_supported(D, 1, 16)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d", D);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int per = gloria_b200_tc_packed_per(Bc), G = gloria_b200_tc_packed_groups(Bc), lpad = 16 * per;
+  pack_words_packed<<<dim3(G * per, (D + 63) / 64), 64, 0, st>>>(words, cap_lens, (__half*)words_h, Bc, per, D, Lw, lpad,
+                                                               word_off);
+  GLORIA_LAUNCHED("pack_words_packed");
+  word_norms_packed<<<G * per, dim3(32, 16), 0, st>>>(words, cap_lens, wnorm, Bc, per, D, Lw, lpad, word_off);
+  GLORIA_LAUNCHED("word_norms_packed");
+  return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_tc_local_sim_fwd_packed(const void* ctx_h, const void* ctx_n, const void* words_h,
+                                                   const float* wnorm, const int32_t* cap_lens, int Bi, int Bc, int D,
+                                                   int S, float temp1, float temp2, int agg, float eps, float* sim,
+                                                   void* stream) {
+  GLORIA_CHECK_ARG(ctx_h && ctx_n && words_h && wnorm && cap_lens && sim, "null pointer");
+  GLORIA_CHECK_ARG(Bi > 0 && Bc > 0, "bad batch sizes %d x %d", Bi, Bc);
+  if (gloria_b200_tc_supported(D, S, 16)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d", D, S);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int per = gloria_b200_tc_packed_per(Bc), G = gloria_b200_tc_packed_groups(Bc), lpad = 16 * per;
+  const int Spad = gloria_b200_tc_spad(S);
+  CUtensorMap rt, wt, rn;
+  int rc;
+  if ((rc = make_map(&rt, ctx_h, (uint64_t)D, (uint64_t)Bi * Spad, TILE))) return rc;
+  if ((rc = make_map(&wt, words_h, (uint64_t)D, (uint64_t)G * lpad, (uint32_t)lpad))) return rc;
+  if ((rc = make_map(&rn, ctx_n, (uint64_t)Spad, (uint64_t)Bi * D, TILE))) return rc;
+  FwdParams p;
+  p.wt = (const __half*)words_h; p.wnorm = wnorm; p.cap_lens = cap_lens; p.sim = sim; p.stats = nullptr;
+  p.Bi = Bi; p.Bc = G; p.D = D; p.S = S; p.NT = Spad / TILE; p.n_caps = Bc; p.per = per;
+  p.t1_log2e = temp1 * 1.4426950408889634f; p.temp2 = temp2; p.agg = agg; p.eps_s = eps * (float)S;
+  p.dbg = (long long*)g_phase_clock_buffer;
+  int dev = 0, sms = 0;
+  GLORIA_CUDA(cudaGetDevice(&dev));
+  GLORIA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  switch (lpad) {
+    case 16: return launch_fwd<16, 16>(rt, wt, rn, p, sms, st);
+    case 32: return launch_fwd<32, 16>(rt, wt, rn, p, sms, st);
+    case 48: return launch_fwd<48, 16>(rt, wt, rn, p, sms, st);
+    case 64: return launch_fwd<64, 16>(rt, wt, rn, p, sms, st);
+    case 80: return launch_fwd<80, 16>(rt, wt, rn, p, sms, st);
+    case 96: return launch_fwd<96, 16>(rt, wt, rn, p, sms, st);
+    case 112: return launch_fwd<112, 16>(rt, wt, rn, p, sms, st);
+    case 128: return launch_fwd<128, 16>(rt, wt, rn, p, sms, st);
   }
   return fail(GLORIA_ERR_UNSUPPORTED, "lpad %d", lpad);
 }

@@ -22,6 +22,7 @@ MODE_FP32, MODE_BF16 = 0, 1
 
 _WS_BUDGET = int(os.environ.get("GLORIA_B200_WS_BYTES", str(4 << 30)))            # fp32 kernels
 _TC_WS_BUDGET = int(os.environ.get("GLORIA_B200_TC_WS_BYTES", str(96 << 30)))     # bf16 backward operand matrices
+_PACKED_PROMPTS = os.environ.get("GLORIA_B200_PACKED_PROMPTS", "1") != "0"           # packed short-caption inference kernel
 _FUSED_TRAIN = os.environ.get("GLORIA_B200_FUSED_TRAIN", "1") != "0"               # fused forward+backward-operand kernel
 
 
@@ -155,8 +156,12 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
             if L.gloria_b200_tc_supported(D, S, lcap) != 0:
                 raise RuntimeError(f"bf16 tensor-core kernels need D % 128 == 0, S <= 384, cap_len <= 128; got "
                                    f"D={D} S={S} Lcap={lcap} (use set_precision('fp32'))")
-            packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
             need_grad = agg != AGG["max"] and (ctx.requires_grad or words.requires_grad or torch.is_grad_enabled())
+            if not need_grad and not want_mean and not want_diag and lcap <= 16 and Bc >= 2 and _PACKED_PROMPTS:
+                # forward-only scoring of short prompts (zero-shot): up to 8 captions share one word tile
+                _tc_packed_fwd(L, ctx, words, cap_lens, word_off, temp1, temp2, agg, eps, sim)
+                return sim, diag, mean, stats
+            packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
             fused = False
             if want_mean:
                 # regulariser configs: one kernel gives sim + the word-mean attention of every pair (+ the per-word
@@ -207,6 +212,27 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
     if mode == MODE_BF16 and stats.numel() > 0:
         _PACK_CACHE[stats.data_ptr()] = packed          # handed to the backward (same step), dropped there
     return sim, diag, mean, stats
+
+
+def _tc_packed_fwd(L, ctx, words, cap_lens, word_off, temp1, temp2, agg, eps, sim) -> None:
+    """sim[Bi, Bc] through the packed-prompt kernel (gloria_b200_tc_local_sim_fwd_packed)."""
+    Bi, D, S = ctx.shape
+    Bc, _, Lw = words.shape
+    dev = ctx.device
+    per, groups = L.gloria_b200_tc_packed_per(Bc), L.gloria_b200_tc_packed_groups(Bc)
+    spad = L.gloria_b200_tc_spad(S)
+    ctx_h = torch.empty((Bi, spad, D), dtype=torch.float16, device=dev)
+    ctx_n = torch.empty((Bi, D, spad), dtype=torch.bfloat16, device=dev)
+    words_h = torch.empty((groups, 16 * per, D), dtype=torch.float16, device=dev)
+    wnorm = torch.empty((groups, 16 * per), dtype=torch.float32, device=dev)
+    st = _stream(ctx)
+    _lib.check(L.gloria_b200_tc_prepack_ctx(ctx.data_ptr(), Bi, D, S, ctx_h.data_ptr(), None, ctx_n.data_ptr(), st),
+               "tc_prepack_ctx")
+    _lib.check(L.gloria_b200_tc_prepack_words_packed(words.data_ptr(), cap_lens.data_ptr(), Bc, D, Lw, word_off,
+                                                     words_h.data_ptr(), wnorm.data_ptr(), st), "tc_prepack_words_packed")
+    _lib.check(L.gloria_b200_tc_local_sim_fwd_packed(ctx_h.data_ptr(), ctx_n.data_ptr(), words_h.data_ptr(),
+                                                     wnorm.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S, temp1, temp2,
+                                                     agg, eps, sim.data_ptr(), st), "tc_local_sim_fwd_packed")
 
 
 # forward -> backward hand-over of the prepacked 16-bit copies, keyed by the data pointer of the `stats` tensor the

@@ -154,7 +154,7 @@ int gloria_b200_tc_prepack(const float* ctx, const float* words, const int32_t* 
                            void* ctx_h, void* ctx_t, void* ctx_n, void* words_h, void* words_t, float* wnorm,
                            void* stream);
 /* The two halves of the prepack on their own (ctx_n may be NULL: only the inference forward and the recompute backward
- * read it). */
+ * read it; ctx_t may be NULL: only the training path reads it). */
 int gloria_b200_tc_prepack_ctx(const float* ctx, int Bi, int D, int S, void* ctx_h, void* ctx_t, void* ctx_n,
                                void* stream);
 int gloria_b200_tc_prepack_words(const float* words, const int32_t* cap_lens, int Bc, int D, int Lw, int Lcap,
@@ -168,6 +168,20 @@ int gloria_b200_tc_local_sim_fwd(const void* ctx_h, const void* ctx_n, const voi
                                  const int32_t* cap_lens, int Bi, int Bc, int D, int S, int Lcap,
                                  float temp1, float temp2, int agg, float eps,
                                  float* sim, float* stats, void* stream);
+
+/* Packed prompts (zero-shot scoring: gloria_model.py:171-207 as driven by gloria.py:278-306 -- thousands of images
+ * against a few short class prompts).  Up to 8 captions of at most 16 words (after word_off) share one word tile: the
+ * kernel's cost is set by the image tiles it streams per (image, word tile), so 25 prompts cost 4 tiles instead of 25.
+ * Bc captions -> gloria_b200_tc_packed_groups(Bc) tiles of 16 * gloria_b200_tc_packed_per(Bc) words;
+ * words_h [groups, 16 * per, D] fp16 and wnorm [groups, 16 * per] fp32 come from gloria_b200_tc_prepack_words_packed.
+ * Forward only (agg = sum / mean / max); sim [Bi, Bc]. */
+int gloria_b200_tc_packed_groups(int Bc);
+int gloria_b200_tc_packed_per(int Bc);
+int gloria_b200_tc_prepack_words_packed(const float* words, const int32_t* cap_lens, int Bc, int D, int Lw,
+                                        int word_off, void* words_h, float* wnorm, void* stream);
+int gloria_b200_tc_local_sim_fwd_packed(const void* ctx_h, const void* ctx_n, const void* words_h, const float* wnorm,
+                                        const int32_t* cap_lens, int Bi, int Bc, int D, int S,
+                                        float temp1, float temp2, int agg, float eps, float* sim, void* stream);
 
 /* Workspace of the backward.  `budget` (0 = unlimited) caps it: captions are then processed in chunks.  The two
  * bf16 operand matrices take 2 * Bi * Sp * Lp * 2 bytes per caption (about 153 KB per pair at the full sizes:

@@ -486,3 +486,33 @@ def test_mterm_short_units_many_per_cta(gl):
         assert relerr(sim_l[:small], sim_s) < 1e-5
         # same arithmetic up to the GEMMs' summation order (cuBLAS picks different tilings for 6 and 512 images)
         assert relerr(g_l[:small], g_s) < 2e-3
+
+
+@pytest.mark.parametrize("n_img,n_txt,agg,off,seed", [
+    (40, 25, "max", 1, 51),       # the zero-shot grid: 5 classes x 5 prompts -> 4 word tiles of 7 prompts
+    (5, 2, "max", 1, 52),         # one tile, two segments
+    (33, 9, "sum", 0, 53),        # 2 tiles of 5 slots, one slot empty
+    (150, 17, "mean", 0, 54),     # 3 tiles of 6 slots, one empty; more images than CTAs
+    (12, 8, "max", 0, 55),        # a full 128-word tile
+])
+def test_packed_prompts_forward(gl, monkeypatch, n_img, n_txt, agg, off, seed):
+    """Forward-only scoring of short prompts (<= 16 words): several prompts share one word tile (segmented word softmax
+    and aggregation).  Against the oracle, and against the one-prompt-per-tile kernel."""
+    from gloria_nlp_project_b200 import ops
+    rng = np.random.default_rng(seed)
+    lens = [int(v) for v in rng.integers(1, 17, size=n_txt)]
+    lens[0] = 16
+    img_l, _, _, _, _ = gen_inputs(seed, n_img, 768, 19, 19, 97, dtype=np.float32)
+    txt_l = rng.standard_normal((n_txt, 768, 18)).astype(np.float32)
+    img64, txt64 = img_l.astype(np.float64), txt_l.astype(np.float64)
+    if off == 1:
+        ref = O.get_local_similarities(img64, txt64, lens)
+    else:
+        ref = O.local_similarities(img64, txt64[:, :, :16], lens, agg=agg)
+    with torch.no_grad():
+        sim, _, _, _ = gl.local_similarities(cu(img_l), cu(txt_l), lens, 4.0, 5.0, agg, word_offset=off)
+        monkeypatch.setattr(ops, "_PACKED_PROMPTS", False)
+        sim1, _, _, _ = gl.local_similarities(cu(img_l), cu(txt_l), lens, 4.0, 5.0, agg, word_offset=off)
+    assert sim.shape == (n_img, n_txt)
+    assert relerr(sim, ref) < LOGIT_TOL
+    assert relerr(sim, sim1) < 1e-4
