@@ -700,3 +700,81 @@ def _rc_backward(c, g, gstats):
 
 
 row_cosine_fwd.register_autograd(_rc_backward, setup_context=_rc_setup)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# word-piece aggregation of the text encoder (text_model.py:32-90) -- the step right before the loss path
+# ----------------------------------------------------------------------------------------------------------------
+_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+def word_ranges(caption_ids: Tensor, is_continuation: Tensor, sep_id: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """caption_ids [B, T] int64, is_continuation [vocab] uint8 (1 = the entry starts with "##") ->
+    word_range [B, T, 2] int32, token_word [B, T] int32, n_words [B] int32 (all on the device, no sync)."""
+    _need_cuda(caption_ids, is_continuation)
+    L = _lib.lib()
+    ids = caption_ids.to(torch.int64).contiguous()
+    B, T = ids.shape
+    dev = ids.device
+    wr = torch.empty((B, T, 2), dtype=torch.int32, device=dev)
+    tw = torch.empty((B, T), dtype=torch.int32, device=dev)
+    nw = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.gloria_b200_word_ranges(ids.data_ptr(), is_continuation.data_ptr(), is_continuation.numel(), int(sep_id), B,
+                                       T, wr.data_ptr(), tw.data_ptr(), nw.data_ptr(), _stream(ids))
+    _lib.check(rc, "word_ranges")
+    return wr, tw, nw
+
+
+@torch.library.custom_op("gloria_b200::aggregate_tokens", mutates_args=())
+def aggregate_tokens(embeddings: Tensor, word_range: Tensor, token_word: Tensor) -> Tensor:
+    """out[b, layer, w, :] = sum of embeddings[b, layer, t, :] over the tokens of word w ([B, layers, T, D], zero rows
+    beyond each caption's words).  token_word is only carried for the backward."""
+    _need_cuda(embeddings, word_range, token_word)
+    if embeddings.dtype not in _DTYPES:
+        raise RuntimeError(f"aggregate_tokens: unsupported dtype {embeddings.dtype}")
+    L = _lib.lib()
+    emb = embeddings.contiguous()
+    B, layers, T, D = emb.shape
+    out = torch.empty_like(emb)
+    with torch.cuda.device(emb.device):
+        rc = L.gloria_b200_aggregate_tokens_fwd(emb.data_ptr(), _DTYPES[emb.dtype], word_range.data_ptr(), B, layers, T, D,
+                                                out.data_ptr(), _stream(emb))
+    _lib.check(rc, "aggregate_tokens_fwd")
+    return out
+
+
+@aggregate_tokens.register_fake
+def _(embeddings, word_range, token_word):
+    return torch.empty_like(embeddings)
+
+
+@torch.library.custom_op("gloria_b200::aggregate_tokens_bwd", mutates_args=())
+def aggregate_tokens_bwd(d_out: Tensor, token_word: Tensor) -> Tensor:
+    _need_cuda(d_out, token_word)
+    L = _lib.lib()
+    g = d_out.contiguous()
+    B, layers, T, D = g.shape
+    d_emb = torch.empty_like(g)
+    with torch.cuda.device(g.device):
+        rc = L.gloria_b200_aggregate_tokens_bwd(g.data_ptr(), _DTYPES[g.dtype], token_word.data_ptr(), B, layers, T, D,
+                                                d_emb.data_ptr(), _stream(g))
+    _lib.check(rc, "aggregate_tokens_bwd")
+    return d_emb
+
+
+@aggregate_tokens_bwd.register_fake
+def _(d_out, token_word):
+    return torch.empty_like(d_out)
+
+
+def _agg_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[2])
+
+
+def _agg_backward(ctx, d_out):
+    (token_word,) = ctx.saved_tensors
+    return aggregate_tokens_bwd(d_out, token_word), None, None
+
+
+aggregate_tokens.register_autograd(_agg_backward, setup_context=_agg_setup)

@@ -1,0 +1,105 @@
+"""Drop-in for the word-piece aggregation of the reference text encoder
+(gloria/models/text_model.py:32-90, `BertEncoder.aggregate_tokens`) and for the caption lengths the loss derives from
+its sentences (gloria/models/gloria_model.py:107-109).
+
+The reference walks every token of every caption in Python with `word_id.item()` -- B x T device syncs per step -- and
+stacks / sums the word pieces one word at a time.  Here the token ids are read back once (B x T integers, needed anyway
+for the returned word strings), the word boundaries are derived on the device from a "starts with ##" vocabulary table,
+and the aggregation is one streaming kernel with autograd (`ops.aggregate_tokens`).  SURVEY.md section 8f, row 3.
+
+    from gloria.models.text_model import BertEncoder
+    from gloria_nlp_project_b200.text_model import patch_bert_encoder
+    patch_bert_encoder(BertEncoder)          # aggregate_tokens now runs on the device
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+__all__ = ["aggregate_tokens", "AggregateTokensMixin", "patch_bert_encoder", "cap_lens_from_sents", "VocabTable"]
+
+
+class VocabTable:
+    """Device-side view of `idxtoword`: which ids continue a word ("##...") and which id is "[SEP]"."""
+
+    def __init__(self, idxtoword: Dict[int, str]):
+        self.idxtoword = idxtoword
+        self.size = max(idxtoword) + 1
+        cont = torch.zeros(self.size, dtype=torch.uint8)
+        for i, w in idxtoword.items():
+            if w.startswith("##"):
+                cont[i] = 1
+        self._cont_cpu = cont
+        self._cont = {}
+        seps = [i for i, w in idxtoword.items() if w == "[SEP]"]
+        self.sep_id = seps[0] if seps else -1
+
+    def is_continuation(self, device: torch.device) -> torch.Tensor:
+        key = str(device)
+        if key not in self._cont:
+            self._cont[key] = self._cont_cpu.to(device)
+        return self._cont[key]
+
+
+def _sentences(ids: Sequence[Sequence[int]], idxtoword: Dict[int, str]) -> List[List[str]]:
+    """The word strings of text_model.py:43-82 from the token ids (host side, no tensors involved)."""
+    out = []
+    for row in ids:
+        words, bank, n_tok = [], [], len(row)
+        for v in row:
+            word = idxtoword[int(v)]
+            if word == "[SEP]":
+                words.append("".join(bank))
+                words.append(word)
+                break
+            if not word.startswith("##"):
+                if bank:
+                    words.append("".join(bank))
+                bank = [word]
+            else:
+                bank.append(word[2:])
+        out.append(words + ["[PAD]"] * (n_tok - len(words)))
+    return out
+
+
+def aggregate_tokens(embeddings: torch.Tensor, caption_ids: torch.Tensor, vocab: VocabTable
+                     ) -> Tuple[torch.Tensor, List[List[str]]]:
+    """embeddings [B, layers, T, D] (CUDA; fp32 / fp16 / bf16), caption_ids [B, T] -> (aggregated [B, layers, T, D],
+    sentences) exactly as BertEncoder.aggregate_tokens returns them; differentiable w.r.t. the embeddings."""
+    if not embeddings.is_cuda:
+        raise RuntimeError("gloria_b200 runs on CUDA tensors only (sm_100a); there is no CPU fallback")
+    ids_dev = caption_ids.to(embeddings.device, non_blocking=True)
+    wr, tw, _ = ops.word_ranges(ids_dev, vocab.is_continuation(embeddings.device), vocab.sep_id)
+    agg = ops.aggregate_tokens(embeddings, wr, tw)
+    sentences = _sentences(caption_ids.tolist(), vocab.idxtoword)          # one read-back instead of B x T .item() syncs
+    return agg, sentences
+
+
+def cap_lens_from_sents(sents) -> List[int]:
+    """gloria_model.py:107-109: words not starting with '[' plus one."""
+    return [len([w for w in sent if not w.startswith("[")]) + 1 for sent in sents]
+
+
+class AggregateTokensMixin:
+    """Place before the reference BertEncoder in an MRO, or use patch_bert_encoder()."""
+
+    def aggregate_tokens(self, embeddings, caption_ids):
+        table = getattr(self, "_gloria_b200_vocab", None)
+        if table is None or table.idxtoword is not self.idxtoword:
+            table = VocabTable(self.idxtoword)
+            object.__setattr__(self, "_gloria_b200_vocab", table)
+        return aggregate_tokens(embeddings, caption_ids, table)
+
+
+def patch_bert_encoder(target):
+    """Monkey-patch the reference BertEncoder class (or an instance) so aggregate_tokens runs on the device."""
+    import types
+    fn = AggregateTokensMixin.aggregate_tokens
+    if isinstance(target, type):
+        target.aggregate_tokens = fn
+    else:
+        object.__setattr__(target, "aggregate_tokens", types.MethodType(fn, target))
+    return target

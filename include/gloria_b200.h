@@ -271,6 +271,28 @@ int gloria_b200_ce_bidir_fwd(const float* m, int B, float scale, float* losses, 
 int gloria_b200_ce_bidir_bwd(const float* m, int B, float scale, const float* row_lse, const float* col_lse,
                              const float* g, float* dm, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Word-piece aggregation of the text encoder (BertEncoder.aggregate_tokens, gloria/models/text_model.py:32-90): the
+ * step right before the loss path.  caption_ids [B, T] int64 (device); is_continuation [vocab] = 1 where the
+ * vocabulary entry starts with "##"; sep_id = id of "[SEP]".
+ *   gloria_b200_word_ranges: word_range [B, T, 2] (first token, one past the last token of word w; (0,0) beyond the
+ *     caption's words), token_word [B, T] (word of token t, -1 if the token belongs to no emitted word), n_words [B].
+ *   gloria_b200_aggregate_tokens_fwd: out[b, layer, w, :] = sum of embeddings[b, layer, t, :] over the tokens of word w,
+ *     zero rows beyond n_words[b]; embeddings / out [B, layers, T, D] contiguous, dtype one of GLORIA_DTYPE_*
+ *     (fp32 accumulation, one rounding).
+ *   gloria_b200_aggregate_tokens_bwd: d_embeddings[b, layer, t, :] = d_out[b, layer, token_word[b, t], :] (or 0).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define GLORIA_DTYPE_F32 0
+#define GLORIA_DTYPE_F16 1
+#define GLORIA_DTYPE_BF16 2
+int gloria_b200_word_ranges(const long long* caption_ids, const unsigned char* is_continuation, int vocab,
+                            long long sep_id, int B, int T, int32_t* word_range, int32_t* token_word,
+                            int32_t* n_words, void* stream);
+int gloria_b200_aggregate_tokens_fwd(const void* embeddings, int dtype, const int32_t* word_range, int B, int layers,
+                                     int T, int D, void* out, void* stream);
+int gloria_b200_aggregate_tokens_bwd(const void* d_out, int dtype, const int32_t* token_word, int B, int layers,
+                                     int T, int D, void* d_embeddings, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

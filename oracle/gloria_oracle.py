@@ -350,3 +350,73 @@ def segmentation_attention_loss(att_maps, segmentation_labels):
     up = up / up.sum(-1, keepdims=True).sum(-2, keepdims=True)
     lab = segmentation_labels.astype(mean_maps.dtype)
     return np.mean(-np.log((lab * up).sum(-1).sum(-1)))
+
+
+# ---------------------------------------------------------------------------------------------
+# zero-shot driver (gloria/gloria.py:186-275)
+# ---------------------------------------------------------------------------------------------
+def get_similarities(img_emb_l, img_emb_g, text_emb_l, text_emb_g, cap_lens, similarity_type="both"):
+    """gloria.py:224-237 on embeddings: local (gloria_model.py:171-207), global (:164-169) or their mean."""
+    g = get_global_similarities(img_emb_g, text_emb_g)
+    loc = get_local_similarities(img_emb_l, text_emb_l, cap_lens)
+    if similarity_type == "global":
+        return g
+    if similarity_type == "local":
+        return loc
+    if similarity_type == "both":
+        return (loc + g) / 2
+    raise RuntimeError("similarity type should be one of ['global', 'local', 'both']")
+
+
+def zero_shot_classification(img_emb_l, img_emb_g, text_emb_l, text_emb_g, cap_lens, class_sizes):
+    """gloria.py:240-275: per class, "both" similarities of every image with the class prompts, max over the prompts
+    (:262), stacked to [N_img, n_classes]; z-scored over the images (utils.py:12-15, numpy std, ddof = 0) when there is
+    more than one image (:268).  Prompts of class k are rows sum(class_sizes[:k]) ... of the text embeddings."""
+    cols, o = [], 0
+    for n in class_sizes:
+        n = int(n)
+        s = get_similarities(img_emb_l, img_emb_g, text_emb_l[o:o + n], text_emb_g[o:o + n], list(cap_lens[o:o + n]))
+        cols.append(s.max(axis=1))
+        o += n
+    cs = np.stack(cols, axis=1)
+    if cs.shape[0] > 1:
+        cs = (cs - cs.mean(axis=0)) / cs.std(axis=0)
+    return cs
+
+
+# ---------------------------------------------------------------------------------------------
+# word-piece aggregation (gloria/models/text_model.py:32-90)
+# ---------------------------------------------------------------------------------------------
+def aggregate_tokens(embeddings, caption_ids, idxtoword):
+    """BertEncoder.aggregate_tokens: embeddings [B, layers, T, D], caption_ids [B, T] ->
+    (agg [B, layers, T, D], sentences).  Word pieces ("##...") are summed into the word they continue; "[SEP]" closes
+    the open word, is kept as a word of its own and ends the caption (:50-58); without "[SEP]" the word still open at
+    the end is never emitted; rows beyond the caption's words are zero, sentences are padded with "[PAD]" (:77-82)."""
+    B, layers, T, D = embeddings.shape
+    out = np.zeros_like(embeddings)
+    sentences = []
+    for b in range(B):
+        words, bank, bank_words, n = [], [], [], 0
+        for t in range(T):
+            word = idxtoword[int(caption_ids[b, t])]
+            if word == "[SEP]":
+                out[b, :, n] = np.sum([embeddings[b, :, k] for k in bank], axis=0) if bank else 0
+                words.append("".join(bank_words))
+                n += 1
+                out[b, :, n] = embeddings[b, :, t]
+                words.append(word)
+                n += 1
+                break
+            if not word.startswith("##"):
+                if len(bank_words) == 0:
+                    bank, bank_words = [t], [word]
+                else:
+                    out[b, :, n] = np.sum([embeddings[b, :, k] for k in bank], axis=0)
+                    words.append("".join(bank_words))
+                    n += 1
+                    bank, bank_words = [t], [word]
+            else:
+                bank.append(t)
+                bank_words.append(word[2:])
+        sentences.append(words + ["[PAD]"] * (T - n))
+    return out, sentences

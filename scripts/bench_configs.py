@@ -139,5 +139,33 @@ def main():
              precision="fp32 diagonal kernels", ms_per_step=ms, pairs_touched=B, l2="flushed between iterations")
 
 
+def text_side():
+    """word-piece aggregation of the text encoder (B=48 / 512 captions x 4 layers x 97 tokens x 768)."""
+    from gloria_nlp_project_b200 import text_model
+    pk = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "MEASURED_PEAKS.json")
+    hbm_peak = (json.load(open(pk)) if os.path.exists(pk) else {}).get("hbm_gbs", 6650.0)
+    vocab = ["[PAD]", "[CLS]", "[SEP]"] + [f"w{i}" for i in range(1000)] + [f"##p{i}" for i in range(400)]
+    table = text_model.VocabTable(dict(enumerate(vocab)))
+    g = torch.Generator().manual_seed(7)
+    for B in (48, 512):
+        ids = torch.randint(3, len(vocab), (B, 97), generator=g)
+        ids[:, 0] = 1
+        for b in range(B):
+            ids[b, int(torch.randint(5, 97, (1,), generator=g))] = 2
+        emb = torch.randn(B, 4, 97, 768, device=dev)
+        ids_dev = ids.to(dev)
+        ms_all = timed(lambda: text_model.aggregate_tokens(emb, ids, table), 10, 3, flush=True)
+        wr, tw, _ = text_model.ops.word_ranges(ids_dev, table.is_continuation(dev), table.sep_id)
+        ms_k = timed(lambda: text_model.ops.aggregate_tokens(emb, wr, tw), 10, 3, flush=True)
+        nbytes = 2 * emb.numel() * 4
+        emit(config=f"8f-3 aggregate_tokens B={B} x 4 layers x 97 tokens x 768 fp32", ms_call_incl_host_sentences=ms_all,
+             ms_kernel=ms_k, algorithmic_GB=nbytes / 1e9, kernel_GBps=nbytes / ms_k / 1e6,
+             frac_of_hbm_peak=nbytes / ms_k / 1e6 / hbm_peak, l2="flushed between iterations")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "text":
+        text_side()
+    else:
+        main()
+        text_side()

@@ -201,3 +201,50 @@ def test_torch_port_matches_reference(small):
     wc, at = T.attention_fn(q, torch.tensor(small["img_l"]), 4.0)
     close(wc.numpy(), small["attn_wctx"])
     close(at.numpy(), small["attn_map"])
+
+
+# ---------------------------------------------------------------------------------------------
+# zero-shot driver (gloria/gloria.py:186-275); golden written by oracle/make_golden_zero_shot.py
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def zs(golden_dir):
+    return dict(np.load(os.path.join(golden_dir, "zero_shot_fp64.npz")))
+
+
+def test_zero_shot_get_similarities(zs):
+    sl = slice(2, 5)                                   # prompts of the second class
+    cl = [int(v) for v in zs["cap_lens"][sl]]
+    for kind in ("both", "local", "global"):
+        got = O.get_similarities(zs["img_l"], zs["img_g"], zs["txt_l"][sl], zs["txt_g"][sl], cl, kind)
+        # the reference rounds the global matrix to float32 (`torch.Tensor(...)`, gloria_model.py:169)
+        close(got, zs[f"sim_{kind}_class1"], 1e-10 if kind == "local" else 1e-6)
+
+
+def test_zero_shot_classification(zs):
+    cl = [int(v) for v in zs["cap_lens"]]
+    got = O.zero_shot_classification(zs["img_l"], zs["img_g"], zs["txt_l"], zs["txt_g"], cl, zs["class_sizes"])
+    close(got, zs["class_similarities"], 1e-5)        # z-scores of values carrying that float32 rounding
+    one = O.zero_shot_classification(zs["img_l"][:1], zs["img_g"][:1], zs["txt_l"], zs["txt_g"], cl, zs["class_sizes"])
+    close(one, zs["class_similarities_one_image"], 1e-6)     # a single image is not normalised (gloria.py:268)
+
+
+# ---------------------------------------------------------------------------------------------
+# word-piece aggregation (text_model.py:32-90); golden written by oracle/make_golden_text.py
+# ---------------------------------------------------------------------------------------------
+def test_aggregate_tokens(golden_dir):
+    g = np.load(os.path.join(golden_dir, "aggregate_tokens.npz"))
+    idxtoword = {i: str(w) for i, w in enumerate(g["vocab"])}
+    agg, sents = O.aggregate_tokens(g["embeddings"], g["caption_ids"], idxtoword)
+    close(agg, g["agg"], 1e-14)
+    assert [list(s) for s in sents] == [[str(w) for w in s] for s in g["sentences"]]
+
+
+def test_aggregate_tokens_host_sentences(golden_dir):
+    """The drop-in builds the word strings on the host from one read-back of the ids (no tensors): same strings, and the
+    caption lengths the loss derives from them (gloria_model.py:107-109)."""
+    from gloria_nlp_project_b200.text_model import _sentences, cap_lens_from_sents
+    g = np.load(os.path.join(golden_dir, "aggregate_tokens.npz"))
+    idxtoword = {i: str(w) for i, w in enumerate(g["vocab"])}
+    sents = _sentences(g["caption_ids"].tolist(), idxtoword)
+    assert sents == [[str(w) for w in s] for s in g["sentences"]]
+    assert cap_lens_from_sents(sents)[:3] == [6, 2, 4]
