@@ -59,6 +59,33 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
+// L2 eviction-priority policies for the bulk copies of the fused training kernel: its 45 GB write stream (X^T, E^T rows)
+// would otherwise push the re-used region / Gram tiles out of L2 (22 GB of DRAM re-reads against 0.5 GB of inputs)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap* tm, int x, int y, uint32_t bar,
+                                                 uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+      "[%4], %5;"
+      ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3,
+                                                  uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+               : "memory");
+}
+
 // shared memory (SWIZZLE_128B box) -> global, 3-D tensor map; elements outside the tensor's extents are not written
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
