@@ -80,11 +80,12 @@ def lib() -> C.CDLL:
     if _lib is None:
         with _lock:
             if _lib is None:
-                if not os.path.exists(LIB_PATH):
+                path = os.environ.get("GLORIA_B200_LIB", LIB_PATH)      # development: A/B two builds on one box
+                if not os.path.exists(path):
                     raise RuntimeError(
-                        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(nvcc, sm_100a). There is no CPU fallback for this path.")
-                h = C.CDLL(LIB_PATH)
+                h = C.CDLL(path)
                 for name, (res, args) in PROTOTYPES.items():
                     fn = getattr(h, name)      # AttributeError if a declared symbol is not exported
                     fn.restype, fn.argtypes = res, args

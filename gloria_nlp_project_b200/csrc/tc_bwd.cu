@@ -37,8 +37,8 @@ constexpr int E_BYTES = 2 * MAX_NT * TILE * 128;
 constexpr int NCOL = 144;                                // per-column arrays: 3 groups x 6 chunks x 8 (phantom chunks included)
 constexpr int OFF_COEFA = OFF_E + E_BYTES;               // float4 (a, b, c', -) per word: dP = E (a S_ + b T' + c')
 constexpr int OFF_COEFX = OFF_COEFA + NCOL * 16;         // float e per word (X = e E + dS)
-constexpr int OFF_COEFF = OFF_COEFX + NCOL * 4;          // bf16 f per word (Bo = f E)
-constexpr int OFF_NEGM = OFF_COEFF + NCOL * 2 + 32;      // float 0 / -inf per word (beyond the caption)
+constexpr int OFF_COEFAX = OFF_COEFX + NCOL * 4;         // float a per word again, dense (the S_ half of the element pass)
+constexpr int OFF_NEGM = OFF_COEFAX + NCOL * 4;          // float 0 / -inf per word (beyond the caption)
 constexpr int OFF_CMASK = OFF_NEGM + NCOL * 4;           // uint16 0xFFFF / 0 per word
 constexpr int OFF_ZBUF = OFF_CMASK + NCOL * 2 + 32;      // Z per word
 constexpr int OFF_RED = OFF_ZBUF + 128 * 4;              // 32 floats of reduction scratch
@@ -165,6 +165,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
   float* accs = reinterpret_cast<float*>(smem + OFF_ACCS);
   float4* coefA = reinterpret_cast<float4*>(smem + OFF_COEFA);
   float* coefX = reinterpret_cast<float*>(smem + OFF_COEFX);
+  float* coefAx = reinterpret_cast<float*>(smem + OFF_COEFAX);
   float* negm = reinterpret_cast<float*>(smem + OFF_NEGM);
   uint32_t* cmask = reinterpret_cast<uint32_t*>(smem + OFF_CMASK);
   auto bar = [&](int idx) { return bars + 8u * (uint32_t)idx; };
@@ -376,6 +377,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
     const size_t e_blk = (size_t)Spad * 128u;      // bytes between the two 64-word blocks of E
     const float4* cA = coefA + col0;
     const float* cX = coefX + col0;
+    const float* cAx = coefAx + col0;
     const float* nM = negm + col0;
     const uint32_t* cM = cmask + (col0 >> 1);
     uint32_t n = 0, ttc = 0, xc = 0;
@@ -547,11 +549,12 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
               const uint8_t* erow = smem + OFF_E + (size_t)(s_glob >> 3) * 1024u + (size_t)sw * 128u;
               const uint32_t ts = tmem + lane_addr + (uint32_t)(t * LPAD + col0);
               const uint32_t tt = tmem + lane_addr + TT_COL + (uint32_t)col0;
+              // T' half first, so that its single TMEM buffer goes back to the tensor pipe as early as possible (the next
+              // GEMM-T tile then runs under the S_ half below)
 #pragma unroll
               for (int c = 0; c < CW; ++c) {
                 if (c_lo + c < NCH) {
-                  float sv[8], tv[8];
-                  tmem_ld8(ts + c * 8, sv);
+                  float tv[8];
                   tmem_ld8(tt + c * 8, tv);
                   const int ch = c_lo + c;
                   const uint4 ev = *reinterpret_cast<const uint4*>(erow + (size_t)(ch >> 3) * e_blk +
@@ -565,7 +568,6 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
 #pragma unroll
                   for (int k = 0; k < 8; ++k) {
                     const float e = (k & 1) ? bf_hi(ew[k >> 1]) : bf_lo(ew[k >> 1]);   // 0 in padded rows / words
-                    a1[c * 8 + k] = fmaf(e, sv[k], a1[c * 8 + k]);
                     a2[c * 8 + k] = fmaf(e, tv[k], a2[c * 8 + k]);
                   }
                 }
@@ -573,6 +575,23 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
               if (idx < NT - 1) {                    // (the last tile's T' is kept: pass B starts with it)
                 tc_fence_before();
                 mbar_arrive(bar(B_TTE));             // T' buffer may be overwritten by the next GEMM-T tile
+              }
+#pragma unroll
+              for (int c = 0; c < CW; ++c) {
+                if (c_lo + c < NCH) {
+                  float sv[8];
+                  tmem_ld8(ts + c * 8, sv);
+                  const int ch = c_lo + c;
+                  const uint4 ev = *reinterpret_cast<const uint4*>(erow + (size_t)(ch >> 3) * e_blk +
+                                                                   (size_t)((((uint32_t)ch & 7u) ^ sw) << 4));
+                  tmem_ld_wait();
+                  const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const float e = (k & 1) ? bf_hi(ew[k >> 1]) : bf_lo(ew[k >> 1]);
+                    a1[c * 8 + k] = fmaf(e, sv[k], a1[c * 8 + k]);
+                  }
+                }
               }
             }
           }
@@ -646,6 +665,7 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
                 coefA[wl] = live ? make_float4(p.t1 * ddot * iz, p.t1 * beta * iz * iz, -p.t1 * rs * iz - wm * qt, wm)
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                 coefX[wl] = live ? ddot * iz : 0.f;
+                coefAx[wl] = live ? p.t1 * ddot * iz : 0.f;
               }
               if (p.fo != nullptr && wl < p.lp) p.fo[((size_t)j * p.nc + u.i) * p.lp + wl] = live ? beta * iz * iz : 0.f;
               if (FUSED) {
@@ -703,21 +723,45 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             float dp[WG];
             uint32_t pp[WG / 2];
             float ug = 0.f;
-            // pass 1 (one chunk at a time): dP = E (a S_ + b T' + c'), partial u = sum_l P dP
+            // pass 1a (T' half): dp = b T' + c'.  The T' buffer goes back to the tensor pipe right after it, so the next
+            // tile's GEMM-T runs under pass 1b and pass 2 of this tile.
 #pragma unroll
             for (int c = 0; c < CW; ++c) {
-              float sv[8], tv[8];
+              float tv[8];
               if (c_lo + c < NCH) {
-                tmem_ld8(ts + c * 8, sv);
                 tmem_ld8(tt + c * 8, tv);
               } else {                                         // phantom chunk: finite inputs, zero coefficients
 #pragma unroll
-                for (int k = 0; k < 8; ++k) sv[k] = tv[k] = 0.f;
+                for (int k = 0; k < 8; ++k) tv[k] = 0.f;
+              }
+              tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int o = c * 8 + k;
+                const float4 f0 = cA[o];
+                const float c0 = FUSED ? f0.z : fmaf(f0.w, msv, f0.z);
+                dp[o] = fmaf(f0.y, tv[k], c0);
+              }
+            }
+            tc_fence_before();
+            mbar_arrive(bar(B_TTE));                 // T' buffer may be overwritten by the next tile's GEMM-T
+            // pass 1b (S_ half, one chunk at a time): dP = E (a S_ + dp), partial u = sum_l P dP
+#pragma unroll
+            for (int c = 0; c < CW; ++c) {
+              float sv[8];
+              if (c_lo + c < NCH) {
+                tmem_ld8(ts + c * 8, sv);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sv[k] = 0.f;
               }
               const int ch = min(c_lo + c, NCH - 1);           // phantom chunk: any valid address
               const uint4 ev = *reinterpret_cast<const uint4*>(erow + (size_t)(ch >> 3) * e_blk +
                                                                (size_t)((((uint32_t)ch & 7u) ^ sw) << 4));
               const uint4 cm = *reinterpret_cast<const uint4*>(cM + c * 4);
+              const float4 a0 = *reinterpret_cast<const float4*>(cAx + c * 8);
+              const float4 a1v = *reinterpret_cast<const float4*>(cAx + c * 8 + 4);
+              const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1v.x, a1v.y, a1v.z, a1v.w};
               tmem_ld_wait();
               const uint32_t ew[4] = {ev.x, ev.y, ev.z, ev.w};
               const uint32_t mk[4] = {cm.x, cm.y, cm.z, cm.w};
@@ -725,11 +769,9 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
               for (int k = 0; k < 8; k += 2) {
                 const int o = c * 8 + k;
                 const float e0 = bf_lo(ew[k >> 1]), e1 = bf_hi(ew[k >> 1]);
-                const float4 f0 = cA[o], f1 = cA[o + 1];
                 const float P0 = ex2(fmaf(sv[k], LOG2E, nmbv)) * rinv, P1 = ex2(fmaf(sv[k + 1], LOG2E, nmbv)) * rinv;
-                const float c0 = FUSED ? f0.z : fmaf(f0.w, msv, f0.z), c1 = FUSED ? f1.z : fmaf(f1.w, msv, f1.z);
-                const float d0 = e0 * fmaf(f0.x, sv[k], fmaf(f0.y, tv[k], c0));
-                const float d1 = e1 * fmaf(f1.x, sv[k + 1], fmaf(f1.y, tv[k + 1], c1));
+                const float d0 = e0 * fmaf(av[k], sv[k], dp[o]);
+                const float d1 = e1 * fmaf(av[k + 1], sv[k + 1], dp[o + 1]);
                 const uint32_t pk = pack_bf16(P0, P1) & mk[k >> 1];   // P = 0 beyond the caption (so dS = 0 there)
                 dp[o] = d0;
                 dp[o + 1] = d1;
@@ -739,7 +781,6 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
               }
             }
             tc_fence_before();
-            mbar_arrive(bar(B_TTE));                 // T' buffer may be overwritten by the next tile's GEMM-T
             mbar_arrive(bar(B_D1E + t));             // S_ tile may be overwritten by the next pair's GEMM1
             float2* xb = xch + (xc & 1) * (NGROUP * 128);
             ++xc;
