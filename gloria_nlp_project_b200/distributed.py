@@ -23,7 +23,7 @@ from typing import Callable, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-__all__ = ["sharded_loss", "gather_cat", "gather_reduce_scatter"]
+__all__ = ["sharded_loss", "gather_cat", "gather_reduce_scatter", "part_major_rows"]
 
 
 class _GatherSliceGrad(torch.autograd.Function):
@@ -133,6 +133,16 @@ class _ShardedLocalSim(torch.autograd.Function):
 _N_PARTS = 2          # image parts per rank shard: gather / reduce_scatter of one part overlap the kernels of the other
 
 
+def part_major_rows(n_per_rank: int, world: int, parts: int) -> torch.Tensor:
+    """Row of every image in the part-major gathered batch: image g = r * n + p * m + k (rank r, part p of `parts`,
+    k < m = n / parts) is gathered to row  p * (world * m) + r * m + k,  because part p of every rank lands in one
+    contiguous block of the all_gather output.  Returns the int64 index [world * n] (CPU)."""
+    m = n_per_rank // parts
+    g = torch.arange(world * n_per_rank)
+    r, q = g // n_per_rank, g % n_per_rank
+    return (q // m) * (world * m) + r * m + (q % m)
+
+
 class _ShardedLocalSimParts(torch.autograd.Function):
     """bf16 training path of the sharded local similarity, pipelined over image parts.
 
@@ -196,10 +206,7 @@ class _ShardedLocalSimParts(torch.autograd.Function):
                     nj, Bc, D, S, lcap, temp1, temp2, agg, eps, sim_pm.data_ptr(), ws.data_ptr(), nbytes, s),
                     "tc_local_sim_fwd_train_part")
             img_all.record_stream(side)
-            # natural image g = r * n + p * m + k  lives at part-major row  p * (world * m) + r * m + k
-            g = torch.arange(B, device=dev)
-            r, q = g // n, g % n
-            perm = (q // m) * (world * m) + r * m + (q % m)
+            perm = part_major_rows(n, world, P).to(dev, non_blocking=True)
             sim = sim_pm.index_select(0, perm)
         ctx.save_for_backward(ctx_t, words_t, dev_lens, ws, perm)
         ctx.args = (lcap, group, P, S, Lw, img_emb_l.shape, img_emb_l.dtype, text_emb_l.dtype)

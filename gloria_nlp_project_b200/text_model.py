@@ -36,6 +36,13 @@ class VocabTable:
         self._cont = {}
         seps = [i for i, w in idxtoword.items() if w == "[SEP]"]
         self.sep_id = seps[0] if seps else -1
+        # host tables for the word strings: the piece text ("##" stripped) and the continuation flag per id
+        self.piece = [""] * self.size
+        self.cont = [False] * self.size
+        for i, w in idxtoword.items():
+            c = w.startswith("##")
+            self.cont[i] = c
+            self.piece[i] = w[2:] if c else w
 
     def is_continuation(self, device: torch.device) -> torch.Tensor:
         key = str(device)
@@ -44,23 +51,30 @@ class VocabTable:
         return self._cont[key]
 
 
-def _sentences(ids: Sequence[Sequence[int]], idxtoword: Dict[int, str]) -> List[List[str]]:
-    """The word strings of text_model.py:43-82 from the token ids (host side, no tensors involved)."""
+def _sentences(ids: Sequence[Sequence[int]], vocab) -> List[List[str]]:
+    """The word strings of text_model.py:43-82 from the token ids (host side, no tensors involved).  `vocab` is a
+    VocabTable or a plain idxtoword dict."""
+    if not isinstance(vocab, VocabTable):
+        vocab = VocabTable(vocab)
+    piece, cont, sep = vocab.piece, vocab.cont, vocab.sep_id
     out = []
     for row in ids:
-        words, bank, n_tok = [], [], len(row)
-        for v in row:
-            word = idxtoword[int(v)]
-            if word == "[SEP]":
-                words.append("".join(bank))
-                words.append(word)
-                break
-            if not word.startswith("##"):
-                if bank:
-                    words.append("".join(bank))
-                bank = [word]
+        n_tok = len(row)
+        try:
+            p = row.index(sep)
+        except ValueError:
+            p = -1
+        words, cur = [], None
+        for v in (row[:p] if p >= 0 else row):
+            if cont[v] and cur is not None:
+                cur.append(piece[v])
             else:
-                bank.append(word[2:])
+                if cur is not None:
+                    words.append("".join(cur))
+                cur = [piece[v]]
+        if p >= 0:                                   # [SEP] closes the open word and is a word of its own (:50-58);
+            words.append("".join(cur) if cur is not None else "")
+            words.append("[SEP]")                    # without it the word still open is never emitted
         out.append(words + ["[PAD]"] * (n_tok - len(words)))
     return out
 
@@ -74,7 +88,7 @@ def aggregate_tokens(embeddings: torch.Tensor, caption_ids: torch.Tensor, vocab:
     ids_dev = caption_ids.to(embeddings.device, non_blocking=True)
     wr, tw, _ = ops.word_ranges(ids_dev, vocab.is_continuation(embeddings.device), vocab.sep_id)
     agg = ops.aggregate_tokens(embeddings, wr, tw)
-    sentences = _sentences(caption_ids.tolist(), vocab.idxtoword)          # one read-back instead of B x T .item() syncs
+    sentences = _sentences(caption_ids.tolist(), vocab)                   # one read-back instead of B x T .item() syncs
     return agg, sentences
 
 

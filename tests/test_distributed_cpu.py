@@ -96,3 +96,22 @@ def test_single_process_path_matches():
     q0, q1 = T.global_loss(t[2], t[3])
     np.testing.assert_allclose([float(l0), float(l1), float(g0), float(g1)], [float(r0), float(r1), float(q0), float(q1)],
                                rtol=1e-12)
+
+
+def test_part_major_rows():
+    """Index math of the part-pipelined sharded path: simulate the per-part all_gathers of image ids and check that
+    `part_major_rows` finds every image where the gathers put it (and that reduce_scatter blocks are rank-major)."""
+    import torch
+    from gloria_nlp_project_b200.distributed import part_major_rows
+    for world, n, parts in [(2, 4, 2), (8, 64, 2), (4, 6, 3), (3, 5, 1)]:
+        m = n // parts
+        own = [torch.arange(r * n, (r + 1) * n) for r in range(world)]          # image ids held by each rank
+        gathered = torch.cat([torch.cat([own[r][p * m:(p + 1) * m] for r in range(world)]) for p in range(parts)])
+        rows = part_major_rows(n, world, parts)
+        assert sorted(rows.tolist()) == list(range(world * n))
+        assert torch.equal(gathered[rows], torch.arange(world * n))
+        # reduce_scatter of part p hands rank r the block [p*world*m + r*m, +m) = its own images p*m .. (p+1)*m
+        for p in range(parts):
+            for r in range(world):
+                blk = gathered[p * world * m + r * m: p * world * m + (r + 1) * m]
+                assert torch.equal(blk, own[r][p * m:(p + 1) * m])
