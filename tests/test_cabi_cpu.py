@@ -124,3 +124,35 @@ def test_length_bucket_plan():
     shuffled = [lens[(7 * i) % 512] for i in range(512)]
     plan2 = plan_length_buckets(shuffled, 512)
     assert sorted(len(idx) for idx, _ in plan2) == sorted(len(idx) for idx, _ in plan)
+
+
+def test_new_entry_points_validate_arguments(libpath):
+    """Packed prompts, part-wise training calls and the word aggregation: host-side arithmetic and argument checks
+    (no device work is reached)."""
+    import torch
+    from gloria_nlp_project_b200 import _lib, text_model, zero_shot
+    L = _lib.lib()
+    # 25 prompts -> 4 word tiles of 7 prompts (16 words each); 8 -> one full tile; 9 -> 2 tiles of 5
+    assert (L.gloria_b200_tc_packed_groups(25), L.gloria_b200_tc_packed_per(25)) == (4, 7)
+    assert (L.gloria_b200_tc_packed_groups(8), L.gloria_b200_tc_packed_per(8)) == (1, 8)
+    assert (L.gloria_b200_tc_packed_groups(9), L.gloria_b200_tc_packed_per(9)) == (2, 5)
+    assert L.gloria_b200_tc_packed_groups(0) == 0
+    assert L.gloria_b200_tc_local_sim_fwd_packed(None, None, None, None, None, 4, 4, 768, 361, 4.0, 5.0, 2, 1e-8, None,
+                                                 None) == 1
+    # the image parts of the backward must divide the batch
+    one = 1 << 20
+    rc = L.gloria_b200_tc_local_sim_bwd_train_parts(one, one, one, 6, 2, 768, 361, 97, 97, 0, one, one, one, one, 1 << 30,
+                                                    4, None, None)
+    assert rc == 1 and b"n_parts" in L.gloria_b200_last_error()
+    rc = L.gloria_b200_tc_local_sim_fwd_train_part(one, one, one, one, one, 8, 6, 4, 2, 768, 361, 97, 4.0, 5.0, 0, 1e-8,
+                                                   one, one, 1 << 30, None)
+    assert rc == 1 and b"image range" in L.gloria_b200_last_error()
+    assert L.gloria_b200_aggregate_tokens_fwd(None, 0, None, 2, 4, 16, 24, None, None) == 1
+    assert L.gloria_b200_word_ranges(None, None, 10, 2, 2, 16, None, None, None, None) == 1
+    # no CPU fallback in the callers on either side of the path
+    table = text_model.VocabTable({0: "[PAD]", 1: "[CLS]", 2: "[SEP]", 3: "a", 4: "##b"})
+    assert table.sep_id == 2 and table.cont[4] and table.piece[4] == "b"
+    with pytest.raises(RuntimeError, match="CUDA"):
+        text_model.aggregate_tokens(torch.randn(1, 2, 4, 8), torch.tensor([[1, 3, 4, 2]]), table)
+    with pytest.raises(RuntimeError):
+        zero_shot.get_similarities(object(), torch.zeros(1), {"caption_ids": None}, similarity_type="cosine")
