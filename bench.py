@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     return ap.parse_args()
 
 
@@ -120,41 +121,123 @@ def cpu_sample_inputs(B_sample):
 
 
 def cpu_arm(B, steps, warmup):
-    """Time `steps` passes of the reference's CPU loss on a CPU_SAMPLE^2 block of the B^2 pair grid; scale to B."""
+    """Time `steps` passes of the reference's CPU loss at batch CPU_SAMPLE (= BASELINE.json configs[0]: batch 16, 97
+    words, 361 regions, D=768, fwd+bwd) after `warmup` passes on the SAME shape.  That step is exactly a
+    CPU_SAMPLE x CPU_SAMPLE block of the B x B pair grid, so the batch-B figure is the measured time x (B/16)^2
+    (the reference cannot hold B = 512 at all: O(B^2 S L) autograd storage)."""
     import torch
     from oracle import gloria_oracle_torch as T
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     inp = cpu_sample_inputs(CPU_SAMPLE)
     for _ in range(warmup):
-        T.loss_step(*cpu_sample_inputs(4))
-    t0 = time.perf_counter()
-    for _ in range(steps):
         T.loss_step(*inp)
-    dt = (time.perf_counter() - t0) / steps
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        T.loss_step(*inp)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    dt = times[len(times) // 2]                          # median pass
     pair_s = dt / (CPU_SAMPLE * CPU_SAMPLE)              # seconds per (image, caption) grid cell
     t_step = pair_s * B * B                              # extrapolated full step at batch B
     return dict(value=B / t_step, ms_per_step=t_step * 1e3, cores=torch.get_num_threads(), sample_s=dt,
-                sample=f"{CPU_SAMPLE}x{CPU_SAMPLE} block of the {B}x{B} pair grid (97 words, 361 regions, D=768), "
-                       f"fwd+bwd, torch {torch.__version__} CPU, {steps} timed passes; extrapolated x{(B * B) // (CPU_SAMPLE ** 2)}")
+                cfg1={"batch": CPU_SAMPLE, "ms_per_step": dt * 1e3, "pairs_per_s": CPU_SAMPLE / dt, "passes": steps,
+                      "warmup_passes": warmup, "note": "measured, not extrapolated: BASELINE.json configs[0]"},
+                extrapolation=f"x{(B * B) // (CPU_SAMPLE ** 2)} pair-grid cells (batch {B} = {(B // CPU_SAMPLE) ** 2} "
+                              f"blocks of {CPU_SAMPLE}x{CPU_SAMPLE})",
+                sample=f"{CPU_SAMPLE}x{CPU_SAMPLE} block of the {B}x{B} pair grid = one full batch-{CPU_SAMPLE} step "
+                       f"(97 words, 361 regions, D=768), fwd+bwd, torch {torch.__version__} CPU, median of {steps} "
+                       f"timed passes after {warmup} warm-up passes on the same shape; value extrapolated "
+                       f"x{(B * B) // (CPU_SAMPLE ** 2)}")
 
 
 def run_reference(args):
     B = WORKLOADS[args.workload]
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    r = cpu_arm(B, steps, min(args.warmup, 1))
+    steps = max(5, min(args.steps, 10))
+    warm = max(1, min(args.warmup, 2))
+    r = cpu_arm(B, steps, warm)
     line = {"impl": "reference", "metric": "image-text pairs/s, GLoRIA local+global loss fwd+bwd", "value": r["value"],
-            "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+            "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: global batch {B}, 97 words, 361 regions, D=768 (CPU sample)"},
             "cpu_baseline": {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
-                             "sample": r["sample"]},
+                             "sample": r["sample"], "cfg1_measured": r["cfg1"], "extrapolation": r["extrapolation"]},
             "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# pre-timing parity check (every N): the same public API the timed steps call, at batch 32, against the numpy oracle
+# ------------------------------------------------------------------------------------------------------------------
+PARITY_B = 32
+
+
+def parity_check(world, rank, dev, loss_of_factory):
+    """Loss and gradients of a batch-32 step (ragged captions) computed through the SAME code path the timed steps
+    take at this N (single-GPU API, or distributed.sharded_loss over NCCL), compared with the numpy oracle (fp64, run
+    on rank 0 only; the checker, never the thing measured).  Unit-variance features rounded to 16-bit-representable
+    values so that kernel and oracle see identical operands.  Gates: loss 2e-3, gradients 1e-2."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    B = PARITY_B
+    if B % world:
+        return {"skipped": f"batch {B} not divisible by {world} ranks"}
+    n = B // world
+    rng = np.random.default_rng(4242)
+    img_l = torch.from_numpy(rng.standard_normal((B, D, H, W), dtype=np.float32)).to(torch.bfloat16).float()
+    txt_l = torch.from_numpy(rng.standard_normal((B, D, LW), dtype=np.float32)).to(torch.bfloat16).float()
+    img_g = torch.from_numpy(rng.standard_normal((B, D), dtype=np.float32))
+    txt_g = torch.from_numpy(rng.standard_normal((B, D), dtype=np.float32))
+    lens = [int(v) for v in rng.integers(5, LW + 1, size=B)]
+    for r in range(world):
+        lens[r * n] = LW                                  # every shard holds one full-length caption
+    for i, L in enumerate(lens):
+        txt_l[i, :, L:] = 0
+    sl = slice(rank * n, (rank + 1) * n)
+    t = {k: v[sl].to(dev).requires_grad_(True) for k, v in
+         (("img_l", img_l), ("txt_l", txt_l), ("img_g", img_g), ("txt_g", txt_g))}
+    loss = loss_of_factory(lens[sl])(t)
+    loss.backward()
+    torch.cuda.synchronize()
+    got = float(loss.detach())
+    ref = {}
+    if rank == 0:
+        from oracle import gloria_oracle as O
+        t0 = time.perf_counter()
+        i64, w64, g64, y64 = (a.numpy().astype(np.float64) for a in (img_l, txt_l, img_g, txt_g))
+        o = O.local_loss(i64, w64, lens)
+        og = O.global_loss(g64, y64)
+        ref["loss"] = float(o[0] + o[1] + og[0] + og[1])
+        d_img, d_txt = O.local_loss_bwd(i64, w64, lens)
+        d_ig, d_tg = O.global_loss_bwd(g64, y64)
+        ref["grads"] = [torch.tensor(a, dtype=torch.float32) for a in (d_img, d_txt, d_ig, d_tg)]
+        ref["oracle_s"] = time.perf_counter() - t0
+    names = ("img_l", "txt_l", "img_g", "txt_g")
+    shapes = ((B, D, H, W), (B, D, LW), (B, D), (B, D))
+    errs = {}
+    for k, (name, shp) in enumerate(zip(names, shapes)):
+        full = ref["grads"][k].to(dev) if rank == 0 else torch.empty(shp, dtype=torch.float32, device=dev)
+        if world > 1:
+            dist.broadcast(full, 0)
+        num = (t[name].grad.float() - full[sl]).abs().max().reshape(1)
+        if world > 1:
+            dist.all_reduce(num, op=dist.ReduceOp.MAX)
+        errs["d_" + name] = float(num.item() / full.abs().max().item())
+    if rank != 0:
+        return None
+    loss_err = abs(got - ref["loss"]) / abs(ref["loss"])
+    ok = loss_err < 2e-3 and all(v < 1e-2 for v in errs.values())
+    return {"batch": B, "n_ranks": world, "path": "distributed.sharded_loss (NCCL)" if world > 1 else
+            "gloria_loss.local_loss + global_loss", "loss": got, "loss_oracle": ref["loss"], "loss_rel_err": loss_err,
+            "grad_rel_err_maxnorm": errs, "tol": {"loss": 2e-3, "grad": 1e-2}, "ok": bool(ok),
+            "oracle": "oracle/gloria_oracle.py (numpy fp64, rank 0), %.1f s" % ref["oracle_s"],
+            "inputs": "seeded unit-variance features rounded to bf16-representable values, cap_lens ~ U{5..97}"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -182,6 +265,20 @@ def run_b200(args):
     lib = _lib.lib()                                       # raises if the CUDA library is missing: no fallback
     G.set_precision(args.precision)
 
+    def loss_factory(lens):
+        def f(t):
+            if world == 1:
+                l0, l1, _, _, _, _ = gloria_loss.local_loss(t["img_l"], t["txt_l"], lens)
+                g0, g1 = gloria_loss.global_loss(t["img_g"], t["txt_g"])
+            else:
+                l0, l1, g0, g1 = distributed.sharded_loss(t["img_l"], t["txt_l"], t["img_g"], t["txt_g"], lens)
+            return l0 + l1 + g0 + g1
+        return f
+
+    parity = None
+    if not args.no_parity_check and args.precision == "bf16":
+        parity = parity_check(world, rank, dev, loss_factory)
+
     B = WORKLOADS[args.workload]
     if B % world:
         raise SystemExit(f"global batch {B} is not divisible by {world} ranks")
@@ -196,13 +293,7 @@ def run_b200(args):
     names = ("img_l", "txt_l", "img_g", "txt_g")
     h2d = sum(host[k].numel() * host[k].element_size() for k in names)
 
-    def loss_of(t):
-        if world == 1:
-            l0, l1, _, _, _, _ = gloria_loss.local_loss(t["img_l"], t["txt_l"], cap_lens)
-            g0, g1 = gloria_loss.global_loss(t["img_g"], t["txt_g"])
-        else:
-            l0, l1, g0, g1 = distributed.sharded_loss(t["img_l"], t["txt_l"], t["img_g"], t["txt_g"], cap_lens)
-        return l0 + l1 + g0 + g1
+    loss_of = loss_factory(cap_lens)
 
     resident = {k: host[k].to(dev).requires_grad_(True) for k in names}
 
@@ -369,8 +460,9 @@ def run_b200(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_arm(B, 2, 1)
-        cpu = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        r = cpu_arm(B, 5, 1)
+        cpu = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "cfg1_measured": r["cfg1"], "extrapolation": r["extrapolation"]}
 
     line = {"metric": "image-text pairs/s, GLoRIA local+global loss fwd+bwd", "value": B / (ms * 1e-3), "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -384,7 +476,8 @@ def run_b200(args):
                        "loss": loss_val},
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "parity_check": parity}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -31,6 +31,7 @@ __all__ = [
     "local_loss",
     "local_sim_pair_bwd",
     "local_loss_bwd",
+    "local_loss_full_bwd",
     "get_local_similarities",
     "get_global_similarities",
     "segmentation_attention_loss",
@@ -314,6 +315,66 @@ def local_loss_bwd(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, temp
         dctx += dc
         dwords[i, :, :L] = dw
     return dctx.reshape(img_features.shape), dwords
+
+
+def local_loss_full_bwd(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, temp3=10.0, agg="sum", g0=1.0, g1=1.0,
+                        no_attn_vec=None, no_attn_loss_weight=None, attention_divergence_loss_weight=None,
+                        attention_entropy_loss_weight=None):
+    """Gradient of  g0*loss0 + g1*loss1 + no_attn_loss + kl_loss + entropy_loss  (the five scalars of
+    gloria_loss.py:99-201, each as the reference returns it) w.r.t. img_features, words_emb and no_attn_vec.
+
+    The regularisers (:129-139, 173-197) are functions of the attention maps only, so their gradient enters the closed
+    form as the extra `d_attn_ext` of `local_sim_pair_bwd`; with `no_attn_vec` the context carries the learned column
+    (:31-34) and its gradient is the sum of column 0 of d_ctx over the images.  Pinned to the reference's autograd on
+    the `local_reg_*` / `local_ent_only_*` goldens (tests/test_oracle_golden.py).
+    Returns (d_img, d_words, d_no_attn_vec or None).
+    """
+    Bi, D = img_features.shape[:2]
+    Bc = words_emb.shape[0]
+    dt = img_features.dtype
+    has_v = no_attn_vec is not None
+    ctx = img_features.reshape(Bi, D, -1)
+    if has_v:
+        ctx = np.concatenate([np.broadcast_to(no_attn_vec.reshape(1, D, 1), (Bi, D, 1)), ctx], axis=2)
+    sim, attns = local_similarities(img_features, words_emb, cap_lens, temp1, temp2, agg, no_attn_vec=no_attn_vec,
+                                    want_attn=True)
+    logits = sim * temp3
+    dsim = temp3 * (g0 * _cross_entropy_arange_grad(logits) + g1 * _cross_entropy_arange_grad(logits.T).T)
+    s0 = 1 if has_v else 0
+    S = ctx.shape[2] - s0
+    # word-mean attention of every pair and what the regularisers see of it (:132-135)
+    fret = np.stack([a[:, :, s0:].mean(1) for a in attns], 1)                  # [Bi, Bc, S]
+    f = np.concatenate([1 - fret.sum(-1, keepdims=True), fret], -1) if has_v else fret
+    df = np.zeros_like(f)                                                      # dLoss / d f
+    if attention_entropy_loss_weight is not None:                              # mean over all pairs of -sum f log f
+        df += -(np.log(f) + 1.0) / (Bi * Bc)
+    if attention_divergence_loss_weight is not None:                           # -w * mean_{c != i} sym_kl(f[i,i], f[i,c])
+        wkl = -attention_divergence_loss_weight / (Bi * (Bc - 1))
+        for i in range(Bi):
+            pcur = f[i, i][None]                                               # [1, K]
+            q = f[i]                                                           # [Bc, K]
+            lr = np.log(pcur) - np.log(q)
+            dq = 0.5 * (-lr - (pcur - q) / q)
+            dp = 0.5 * (lr + (pcur - q) / pcur)
+            off = np.ones(Bc, dtype=bool)
+            off[i] = False
+            df[i, off] += wkl * dq[off]
+            df[i, i] += wkl * dp[off].sum(0)
+    dfret = (df[:, :, 1:] - df[:, :, :1]) if has_v else df                     # through f = [1 - sum, fret]
+    dctx = np.zeros_like(ctx)
+    dwords = np.zeros_like(words_emb)
+    for i in range(Bc):
+        L = int(cap_lens[i])
+        ext = np.zeros((Bi, L, ctx.shape[2]), dtype=dt)
+        ext[:, :, s0:] = dfret[:, i][:, None, :] / L                           # f = mean over the caption's words
+        if no_attn_loss_weight is not None and i < Bi:                         # w * mean_i log(1 - mean_l sum_s a_ret) (:129-130,173-177)
+            m = attns[i][i, :, s0:].sum(-1).mean()
+            ext[i, :, s0:] += no_attn_loss_weight / Bi * (-1.0 / L) / (1.0 - m)
+        dc, dw = local_sim_pair_bwd(ctx, words_emb[i, :, :L], temp1, temp2, dsim[:, i], agg, ext)
+        dctx += dc
+        dwords[i, :, :L] = dw
+    d_nav = dctx[:, :, 0].sum(0) if has_v else None
+    return dctx[:, :, s0:].reshape(img_features.shape), dwords, d_nav
 
 
 # --------------------------------------------------------------------------------------

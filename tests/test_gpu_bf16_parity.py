@@ -363,8 +363,7 @@ def test_regularisers_tensor_core(gl, B, seed, lens, use_nav, kw):
     """Regulariser configs (gloria_loss.py:108-139,173-199; `no_attn_vec` column, no-attn / symmetric-KL / entropy
     terms over the word-mean attention of every pair) on the tensor-core path: the lean forward kernel emits
     attn_mean [B, B, S(+1)], the recompute backward takes its gradient.  Forward values against the numpy oracle
-    (fp64); gradients against this library's fp32 mode, which is pinned to the reference's autograd on the golden
-    fixtures (test_gpu_fp32_parity.py::test_local_loss_small_golden)."""
+    (fp64); gradients of BOTH modes against the oracle's closed form with the regulariser terms."""
     import gloria_nlp_project_b200 as g
     img_l, txt_l, _, _, cl = gen_inputs(seed, B, 768, 19, 19, 97, cap_lens=lens, scale=0.05, dtype=np.float32)
     nav_l = (np.random.default_rng(seed).standard_normal(768) * 0.05).astype(np.float32) if use_nav else None
@@ -390,11 +389,17 @@ def test_regularisers_tensor_core(gl, B, seed, lens, use_nav, kw):
         ref = float(ref)
         assert abs(v32 - ref) <= 1e-4 * max(1.0, abs(ref)), (name, v32, ref)
         assert abs(v - ref) <= LOGIT_TOL * max(1.0, abs(ref)), (name, v, ref)
-    e_img, e_txt = relerr(d_img, r_img), relerr(d_txt, r_txt)
-    print(f"bf16 regularisers B={B}: d_img rel err {e_img:.3e}, d_txt rel err {e_txt:.3e}")
+    # gradients: both modes against the ORACLE's closed form (pinned to the reference's autograd incl. the regularisers:
+    # test_oracle_golden.py::test_local_loss_full_backward_with_regularisers)
+    o_img, o_txt, o_nav = O.local_loss_full_bwd(img_l.astype(np.float64), txt_l.astype(np.float64), cl, g0=1.0, g1=0.7,
+                                                no_attn_vec=None if nav_l is None else nav_l.astype(np.float64), **kw)
+    e_img, e_txt = relerr(d_img, o_img), relerr(d_txt, o_txt)
+    e32_img, e32_txt = relerr(r_img, o_img), relerr(r_txt, o_txt)
+    print(f"regularisers B={B} vs oracle: bf16 d_img {e_img:.3e} d_txt {e_txt:.3e}; fp32 d_img {e32_img:.3e} d_txt {e32_txt:.3e}")
     assert e_img < GRAD_TOL and e_txt < GRAD_TOL
+    assert e32_img < 1e-3 and e32_txt < 1e-3
     if use_nav:
-        assert relerr(d_nav, r_nav) < GRAD_TOL
+        assert relerr(d_nav, o_nav) < GRAD_TOL and relerr(r_nav, o_nav) < 1e-3
     for i, L in enumerate(cl):
         assert torch.all(d_txt[i, :, L:] == 0)
 

@@ -81,6 +81,25 @@ def test_local_loss_backward_closed_form(small, tag, kw):
         assert np.all(d_txt[i, :, L:] == 0)
 
 
+@pytest.mark.parametrize("tag,use_nav,kw", [
+    ("reg", True, dict(no_attn_loss_weight=0.3, attention_divergence_loss_weight=0.2, attention_entropy_loss_weight=0.1)),
+    ("ent_only", False, dict(attention_entropy_loss_weight=1.0, attention_divergence_loss_weight=0.5)),
+    ("sum", False, dict()),
+])
+def test_local_loss_full_backward_with_regularisers(small, tag, use_nav, kw):
+    """Closed-form gradient INCLUDING the no-attn / symmetric-KL / entropy regularisers (and d no_attn_vec) equals the
+    real reference's autograd (goldens local_reg_* / local_ent_only_* written by oracle/make_golden.py)."""
+    nav = small["nav"] if use_nav else None
+    d_img, d_txt, d_nav = O.local_loss_full_bwd(small["img_l"], small["txt_l"], small["cap_lens"].tolist(), g0=1.0, g1=0.7,
+                                                no_attn_vec=nav, **kw)
+    close(d_img, small[f"local_{tag}_d_img"], 1e-9)
+    close(d_txt, small[f"local_{tag}_d_txt"], 1e-9)
+    if use_nav:
+        close(d_nav, small["local_reg_d_nav"], 1e-9)
+    else:
+        assert d_nav is None
+
+
 def test_zero_word_vector(small):
     txt = small["txt_l"].copy()
     txt[2, :, 3] = 0.0
