@@ -21,6 +21,7 @@
 // library GEMM is used) and a per-image [S x S] x [S x D] product; see DESIGN.md for the byte / FLOP accounting.
 #include <cublas_v2.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -995,6 +996,23 @@ int l2_hints_mode() {
   return mode;
 }
 
+// How the two accumulation GEMMs of the training backward run (GLORIA_B200_BWD_GEMM):
+//   0 "inflight": own CTA-pair tcgen05 GEMMs (tc_gemm.cu) that apply g = dsim[j,i] to the A operand on the fly
+//   1 "scale"   : one streaming pass X *= g, then the own GEMMs in their plain mode
+//   2 "cublas"  : the streaming pass, then cuBLAS -- the default: a plain library GEMM that runs the same tile at the same
+//                 tensor-pipe occupancy but ~25% fewer L2 sector reads and therefore higher clocks under the 1000 W cap
+//                 (measured: DESIGN.md section 5b); the own kernels stay under test and one environment variable away
+int bwd_gemm_mode() {
+  static const int mode = [] {
+    const char* e = getenv("GLORIA_B200_BWD_GEMM");
+    if (!e) return 2;
+    if (!strcmp(e, "inflight") || !strcmp(e, "0")) return 0;
+    if (!strcmp(e, "scale") || !strcmp(e, "1")) return 1;
+    return 2;
+  }();
+  return mode;
+}
+
 #define GLORIA_CUBLAS(expr)                                                                       \
   do {                                                                                            \
     cublasStatus_t _s = (expr);                                                                   \
@@ -1074,15 +1092,21 @@ int gram_matrices(cublasHandle_t h, const __nv_bfloat16* Rt, __nv_bfloat16* gram
 int accumulate_chunk(cublasHandle_t h, const __nv_bfloat16* Rt, const __nv_bfloat16* Wt, const __nv_bfloat16* X,
                      const __nv_bfloat16* E, const float* f, const float* g, float* dWt, float* dRt, float* Mf, int Bi,
                      int Bc, int D, int sp, int lp, int i0, int nc, bool first, cudaStream_t st) {
-  const float one = 1.f, zero = 0.f;
-  const float beta = first ? 0.f : 1.f;
   const int K1 = Bi * sp, R1 = nc * lp;
-  // dWt[(i,l), d] = sum_(j,s) X^T[(j,s),(i,l)] Rt[(j,s), d]            (column-major: [D, R1] = Rt^T . (X^T)^T)
-  GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, R1, K1, &one, Rt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1, &zero,
-                             dWt + (size_t)i0 * lp * D, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
-  // dRt[(j,s), d] (+)= sum_(i,l) X^T[(j,s),(i,l)] Wt[(i,l), d]         (column-major: [D, K1] = Wt^T . X^T)
-  GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, K1, R1, &one, Wt + (size_t)i0 * lp * D, CUDA_R_16BF, D, X,
-                             CUDA_R_16BF, R1, &beta, dRt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+  int rc;
+  if (bwd_gemm_mode() != 2) {
+    // dWt[(i,l), d] = sum_(j,s) X^T[(j,s),(i,l)] Rt[(j,s), d]      (A^T = X^T in memory)
+    if ((rc = acc_gemm(X, Rt, dWt + (size_t)i0 * lp * D, R1, D, K1, D, false, 1, false, nullptr, 0, 0, 1, 1, false, st))) return rc;
+    // dRt[(j,s), d] (+)= sum_(i,l) X^T[(j,s),(i,l)] Wt[(i,l), d]
+    if ((rc = acc_gemm(X, Wt + (size_t)i0 * lp * D, dRt, K1, D, R1, D, true, 1, !first, nullptr, 0, 0, 1, 1, false, st))) return rc;
+  } else {
+    const float one = 1.f, zero = 0.f;
+    const float beta = first ? 0.f : 1.f;
+    GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, R1, K1, &one, Rt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1, &zero,
+                               dWt + (size_t)i0 * lp * D, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+    GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, K1, R1, &one, Wt + (size_t)i0 * lp * D, CUDA_R_16BF, D, X,
+                               CUDA_R_16BF, R1, &beta, dRt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+  }
   // M_j[a, b] (+)= sum_(i,l) E^T[(j,a),(i,l)] g[j,i] f[j,(i,l)] E^T[(j,b),(i,l)]   (own tcgen05 kernel, tc_mterm.cu)
   return launch_mterm(E, f, g, Mf, Bi, Bc, i0, R1, lp, sp, !first, st);
 }
@@ -1358,9 +1382,13 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const
   float* Mf = (float*)(ws + pl.off_m);
   __nv_bfloat16* Mb = (__nv_bfloat16*)(ws + pl.off_mb);
   timer_record(GLORIA_TIMER_TC_BWD_GEMM, 0, st);
-  // everything the forward stored is for g = 1 and linear in g = dsim[j, i]: apply it now
-  bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, sp, Bc, 0, lp);
-  GLORIA_LAUNCHED("scale_x");
+  const int gmode = bw::bwd_gemm_mode();
+  // everything the forward stored is for g = 1 and linear in g = dsim[j, i]: the own GEMMs apply it to their A operand in
+  // flight (mode 0); otherwise one streaming pass scales X in place first
+  if (gmode != 0) {
+    bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, sp, Bc, 0, lp);
+    GLORIA_LAUNCHED("scale_x");
+  }
   // ---- image side, part by part
   const int nj = Bi / n_parts;
   const size_t nm = (size_t)nj * sp * sp;
@@ -1371,11 +1399,17 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const
     float* Mp = Mf + j0 * sp * sp;
     __nv_bfloat16* Mbp = Mb + j0 * sp * sp;
     const __nv_bfloat16* Rp = Rt + j0 * sp * D;
-    // dRt[(j,s), d] = sum_(i,l) X^T[(j,s),(i,l)] Wt[(i,l), d]   (column-major: [D, nj*sp] = Wt^T . X^T)
-    GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, nj * sp, R1, &one, Wt, CUDA_R_16BF, D, Xp, CUDA_R_16BF, R1,
-                               &zero, dRp, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
-    // M_j[a, b] = sum_(i,l) E^T[(j,a),(i,l)] g[j,i] f[j,(i,l)] E^T[(j,b),(i,l)]   (own tcgen05 kernel, tc_mterm.cu)
+    // dRt[(j,s), d] = sum_(i,l) g[j,i] X^T[(j,s),(i,l)] Wt[(i,l), d]
     int rc;
+    if (gmode == 0) {
+      if ((rc = acc_gemm(Xp, Wt, dRp, nj * sp, D, R1, D, true, 1, false, dsim + j0 * Bc, Bc, 1, sp, lp, false, st))) return rc;
+    } else if (gmode == 1) {
+      if ((rc = acc_gemm(Xp, Wt, dRp, nj * sp, D, R1, D, true, 1, false, nullptr, 0, 0, 1, 1, false, st))) return rc;
+    } else {
+      GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, nj * sp, R1, &one, Wt, CUDA_R_16BF, D, Xp, CUDA_R_16BF, R1,
+                                 &zero, dRp, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+    }
+    // M_j[a, b] = sum_(i,l) E^T[(j,a),(i,l)] g[j,i] f[j,(i,l)] E^T[(j,b),(i,l)]   (own tcgen05 kernel, tc_mterm.cu)
     if ((rc = launch_mterm(E + j0 * sp * R1, (const float*)(ws + pl.off_fo) + j0 * R1, dsim + j0 * Bc, Mp, nj, Bc, 0, R1,
                            lp, sp, false, st)))
       return rc;
@@ -1390,9 +1424,18 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const
     GLORIA_LAUNCHED("unpack_dctx");
     if (part_events && part_events[part]) GLORIA_CUDA(cudaEventRecord((cudaEvent_t)part_events[part], st));
   }
-  // ---- caption side.  dWt[(i,l), d] = sum_(j,s) X^T[(j,s),(i,l)] Rt[(j,s), d]   (column-major: [D, R1] = Rt^T . (X^T)^T)
-  GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, R1, K1, &one, Rt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1, &zero,
-                             dWt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+  // ---- caption side.  dWt[(i,l), d] = sum_(j,s) g[j,i] X^T[(j,s),(i,l)] Rt[(j,s), d]   (A^T = X^T in memory)
+  {
+    int rc;
+    if (gmode == 0) {
+      if ((rc = acc_gemm(X, Rt, dWt, R1, D, K1, D, false, 1, false, dsim, 1, Bc, lp, sp, false, st))) return rc;
+    } else if (gmode == 1) {
+      if ((rc = acc_gemm(X, Rt, dWt, R1, D, K1, D, false, 1, false, nullptr, 0, 0, 1, 1, false, st))) return rc;
+    } else {
+      GLORIA_CUBLAS(cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, D, R1, K1, &one, Rt, CUDA_R_16BF, D, X, CUDA_R_16BF, R1, &zero,
+                                 dWt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+    }
+  }
   timer_record(GLORIA_TIMER_TC_BWD_GEMM, 1, st);
   bw::gamma_sum<<<(R1 + 255) / 256, 256, 0, st>>>((const float*)(ws + pl.off_go), dsim, gamma, Bi, R1, Bc, 0, lp);
   GLORIA_LAUNCHED("gamma_sum");

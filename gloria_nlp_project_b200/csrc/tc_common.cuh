@@ -237,6 +237,10 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uin
 // tc_mterm.cu: M[j] (+)= Eo_j^T diag(g[j,i] f[j,k]) Eo_j for all images (g may be null)
 int launch_mterm(const void* Et, const float* f, const float* g, float* M, int Bi, int Bc, int i0, int R1, int lp, int sp,
                  bool accumulate, cudaStream_t st);
+// tc_gemm.cu: C[M, N] (fp32, row pitch ldc) = or += A B on the CTA-pair tcgen05 GEMM; see the definition for the arguments
+int acc_gemm(const void* A, const void* B, float* C, int M, int N, int K, int ldc, bool a_kmajor, int ksplit,
+             bool accumulate, const float* g, int g_sm, int g_sk, int m_div, int k_div, bool force_scaled_path,
+             cudaStream_t st);
 // 4-D bf16 tensor [imgs, rows, mid, inner] (pitches in elements), box [1, box_rows, 1, 64], SWIZZLE_128B (TMA stores
 // of E^T rows: clipped at `inner` columns per caption and at `rows` region rows per image)
 int make_map4(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t mid, uint64_t rows, uint64_t imgs,

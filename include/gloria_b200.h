@@ -252,6 +252,24 @@ int gloria_b200_tc_local_sim_bwd_train_ev(const void* ctx_t, const void* words_t
                                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Accumulation GEMM of the backward (the sums over images / captions that autograd forms for the two bmm's of
+ * attention_fn, gloria_loss.py:40,59): C[M, N] (fp32, row-major) = or += A B, bf16 operands in device memory, on a
+ * persistent CTA-pair tcgen05 kernel (csrc/tc_gemm.cu).  Exported for the parity tests and for callers that want the
+ * primitive alone; the training backward calls it internally.
+ *   a_kmajor != 0: A is [M, K] row-major; else A is given transposed, [K, M] row-major.  B is [K, N] row-major.
+ *   N % 16 == 0, K % 8 == 0 (and M % 8 == 0 for a transposed A).
+ *   ksplit: 0 = library's choice, k > 1 cuts K in k parts whose tiles are added with red.global.add.
+ *   accumulate != 0: C += A B (C holds the value to add to); otherwise C is overwritten.
+ *   g (may be NULL): A[m, k] is multiplied by g[(m / m_div) * g_sm + (k / k_div) * g_sk] in fp32 and rounded to bf16 on
+ *     its way to the tensor cores (through tensor memory for a row-major A, in place in shared memory for a transposed
+ *     A); the divisor along the contiguous axis of A (k_div, resp. m_div) must be a multiple of 8.
+ *   force_scaled_path: route an unscaled A through the scaling pipeline as well (weight 1; test hook).
+ * ---------------------------------------------------------------------------------------------------------- */
+int gloria_b200_acc_gemm(const void* A, const void* B, float* C, int M, int N, int K, int a_kmajor, int ksplit,
+                         int accumulate, const float* g, int g_sm, int g_sk, int m_div, int k_div,
+                         int force_scaled_path, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Global similarity (global_loss, gloria_loss.py:75-80; get_global_similarities, gloria_model.py:164-169):
  *   cosm[a, b] = <x_a, y_b> / max(|x_a| |y_b|, eps),  x [Bi, D], y [Bc, D];  xn [Bi], yn [Bc] are saved norms.
  * ---------------------------------------------------------------------------------------------------------- */
