@@ -1108,7 +1108,7 @@ int accumulate_chunk(cublasHandle_t h, const __nv_bfloat16* Rt, const __nv_bfloa
                                CUDA_R_16BF, R1, &beta, dRt, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
   }
   // M_j[a, b] (+)= sum_(i,l) E^T[(j,a),(i,l)] g[j,i] f[j,(i,l)] E^T[(j,b),(i,l)]   (own tcgen05 kernel, tc_mterm.cu)
-  return launch_mterm(E, f, g, Mf, Bi, Bc, i0, R1, lp, sp, !first, st);
+  return launch_mterm(E, f, g, Mf, nullptr, Bi, Bc, i0, R1, lp, sp, !first, st);
 }
 
 int finish_backward(cublasHandle_t h, const __nv_bfloat16* Rt, const __nv_bfloat16* Wt, const int32_t* cap_lens,
@@ -1391,7 +1391,6 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const
   }
   // ---- image side, part by part
   const int nj = Bi / n_parts;
-  const size_t nm = (size_t)nj * sp * sp;
   for (int part = 0; part < n_parts; ++part) {
     const size_t j0 = (size_t)part * nj;
     const __nv_bfloat16* Xp = X + j0 * sp * R1;
@@ -1410,12 +1409,11 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const
                                  &zero, dRp, CUDA_R_32F, D, CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
     }
     // M_j[a, b] = sum_(i,l) E^T[(j,a),(i,l)] g[j,i] f[j,(i,l)] E^T[(j,b),(i,l)]   (own tcgen05 kernel, tc_mterm.cu)
-    if ((rc = launch_mterm(E + j0 * sp * R1, (const float*)(ws + pl.off_fo) + j0 * R1, dsim + j0 * Bc, Mp, nj, Bc, 0, R1,
-                           lp, sp, false, st)))
+    // (the epilogue writes the bf16 operand of the M.R GEMM directly: no fp32 M, no conversion pass)
+    if ((rc = launch_mterm(E + j0 * sp * R1, (const float*)(ws + pl.off_fo) + j0 * R1, dsim + j0 * Bc, Mp, Mbp, nj, Bc, 0,
+                           R1, lp, sp, false, st)))
       return rc;
     // dRt_j += M_j Rt_j   (M_j symmetric up to rounding; column-major: [D, sp] = Rt_j^T . M_j)
-    bw::f32_to_bf16<<<(unsigned)((nm / 4 + 255) / 256), 256, 0, st>>>(Mp, Mbp, nm);
-    GLORIA_LAUNCHED("f32_to_bf16");
     GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, sp, sp, &one, Rp, CUDA_R_16BF, D,
                                              (long long)sp * D, Mbp, CUDA_R_16BF, sp, (long long)sp * sp, &one, dRp,
                                              CUDA_R_32F, D, (long long)sp * D, nj, CUBLAS_COMPUTE_32F,

@@ -234,9 +234,10 @@ struct UnitIter {
 
 // host side (tc_local.cu): 2-D bf16 tensor map [rows, inner] (inner contiguous), box [box_rows, 64], SWIZZLE_128B
 int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uint32_t box_rows);
-// tc_mterm.cu: M[j] (+)= Eo_j^T diag(g[j,i] f[j,k]) Eo_j for all images (g may be null)
-int launch_mterm(const void* Et, const float* f, const float* g, float* M, int Bi, int Bc, int i0, int R1, int lp, int sp,
-                 bool accumulate, cudaStream_t st);
+// tc_mterm.cu: M[j] (+)= Eo_j^T diag(g[j,i] f[j,k]) Eo_j for all images (g may be null); Mb != null (and !accumulate):
+// the result is written as bf16 to Mb instead of fp32 to M
+int launch_mterm(const void* Et, const float* f, const float* g, float* M, void* Mb, int Bi, int Bc, int i0, int R1, int lp,
+                 int sp, bool accumulate, cudaStream_t st);
 // tc_gemm.cu: C[M, N] (fp32, row pitch ldc) = or += A B on the CTA-pair tcgen05 GEMM; see the definition for the arguments
 int acc_gemm(const void* A, const void* B, float* C, int M, int N, int K, int ldc, bool a_kmajor, int ksplit,
              bool accumulate, const float* g, int g_sm, int g_sk, int m_div, int k_div, bool force_scaled_path,

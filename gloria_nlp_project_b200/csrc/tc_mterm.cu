@@ -27,10 +27,38 @@ struct Params {
   const float* f;        // [Bi, R1]
   const float* g;        // [Bi, Bc] or nullptr (f already carries dsim)
   float* M;              // [Bi, sp, sp]
+  __nv_bfloat16* Mb;     // [Bi, sp, sp] bf16 output instead of M (final, non-accumulating launch), or null
   int Bi, Bc, i0, R1, lp, sp, NT, accumulate;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constant__ CUtensorMap tm_e, const Params p) {
+// Per image the symmetric M_j needs the blocks (a, b >= a) of its NT x NT tile grid.  A CLUSTER OF TWO CTAs takes one image
+// at a time and walks its K range once, in step: rank 0 owns row tile 0 (blocks (0, b)), rank 1 the row tiles 1..NT-1
+// (blocks (1,1), (1,2), (2,2) at NT = 3) -- three 128 x 128 accumulators each at NT = 3, so the pair stays balanced and the
+// E^T rows of the image are fetched from HBM once (the second CTA's tiles are L2 hits of the first's; before, the row
+// tiles of an image were separate units that drifted apart and read E^T twice: 38.7 GB per step for 20 GB of operand).
+struct Role {
+  int t0, nl, ns;            // first tile loaded, tiles loaded (slots 0..nl-1), tiles scaled (slot s -> slot 3 - s)
+  int nm;                    // MMAs per k-step: (a slot, b slot) -> accumulator m; block (ra[m], rb[m]) of the tile grid
+  int sa[3], sb[3], ra[3], rb[3];
+};
+__device__ __forceinline__ Role make_role(int rank, int NT) {
+  Role r{};
+  if (rank == 0) {
+    r.t0 = 0; r.nl = NT; r.ns = 1; r.nm = NT;
+    for (int b = 0; b < NT; ++b) { r.sa[b] = 3; r.sb[b] = b; r.ra[b] = 0; r.rb[b] = b; }
+  } else {
+    r.t0 = 1; r.nl = NT - 1; r.ns = NT - 1; r.nm = 0;
+    for (int a = 1; a < NT; ++a)
+      for (int b = a; b < NT; ++b) {
+        r.sa[r.nm] = 3 - (a - 1); r.sb[r.nm] = b - 1; r.ra[r.nm] = a; r.rb[r.nm] = b;
+        ++r.nm;
+      }
+  }
+  return r;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+mterm_kernel(const __grid_constant__ CUtensorMap tm_e, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -40,7 +68,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NT = p.NT;
   const int nkb = (p.R1 + KBLK - 1) / KBLK;
-  const int nunits = p.Bi * NT;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const Role role = make_role((int)rank, NT);
+  const int ncl = gridDim.x >> 1, cl = blockIdx.x >> 1;
+  const bool idle = role.nm == 0;                                  // NT = 1: the second CTA of the pair has no block
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -59,18 +91,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
+  if (idle) {
+    // nothing to do
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int st = 0; uint32_t ph = 0;
-      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-        const int j = u / NT, a = u % NT;
-        const int nb = NT - a;                                   // region tiles a .. NT-1
+      for (int j = cl; j < p.Bi; j += ncl) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(bar(B_EMPTY + st), ph ^ 1);
-          mbar_expect_tx(bar(B_FULL + st), (uint32_t)nb * TILE_BYTES);
-          for (int b = 0; b < nb; ++b)
-            tma_load_2d(base + st * STAGE + b * TILE_BYTES, &tm_e, kb * KBLK, j * p.sp + (a + b) * TILE, bar(B_FULL + st));
+          mbar_expect_tx(bar(B_FULL + st), (uint32_t)role.nl * TILE_BYTES);
+          for (int b = 0; b < role.nl; ++b)
+            tma_load_2d(base + st * STAGE + b * TILE_BYTES, &tm_e, kb * KBLK, j * p.sp + (role.t0 + b) * TILE, bar(B_FULL + st));
           if (++st == NSTAGE) { st = 0; ph ^= 1; }
         }
       }
@@ -81,20 +113,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
       constexpr uint32_t idesc = make_idesc(TILE, TILE, 0, 0);   // A' (K-major) x raw tile (K-major)
       const uint64_t d0 = make_smem_desc(base, 16, 1024);
       int st = 0; uint32_t ph = 0, nu = 0;
-      for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-        const int nb = NT - u % NT;
-        mbar_wait(bar(B_ACCE), (nu & 1) ^ 1);                    // previous unit's accumulators have been read
+      for (int j = cl; j < p.Bi; j += ncl) {
+        mbar_wait(bar(B_ACCE), (nu & 1) ^ 1);                    // previous image's accumulators have been read
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(bar(B_SCALED + st), ph);                     // tiles landed and A' written
           tc_fence_after();
           const uint64_t ds = d0 + (uint64_t)((st * STAGE) >> 4);
-          const uint64_t da = ds + (uint64_t)(OFF_AS >> 4);
-          for (int b = 0; b < nb; ++b) {
-            const uint64_t db = ds + (uint64_t)((b * TILE_BYTES) >> 4);
+          for (int m = 0; m < role.nm; ++m) {
+            const uint64_t da = ds + (uint64_t)((role.sa[m] * TILE_BYTES) >> 4);
+            const uint64_t db = ds + (uint64_t)((role.sb[m] * TILE_BYTES) >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem + (uint32_t)(b * TILE), da + 2 * k, db + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+              umma_bf16(tmem + (uint32_t)(m * TILE), da + 2 * k, db + 2 * k, idesc, (uint32_t)((kb | k) != 0));
           }
           umma_commit(bar(B_EMPTY + st));
           if (++st == NSTAGE) { st = 0; ph ^= 1; }
@@ -111,10 +142,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
     const int row = q * 32 + lane;
     const int t64 = (threadIdx.x - 128) & 127;                   // 0..127 inside the group
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    uint32_t nk = 0, nu = 0;                                     // running k-block / unit counters of this CTA
-    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-      const int j = u / NT, a = u % NT;
-      const int nb = NT - a;
+    uint32_t nk = 0, nu = 0;                                     // running k-block / image counters of this CTA
+    for (int j = cl; j < p.Bi; j += ncl) {
       const float* fr = p.f + (size_t)j * p.R1;
       const float* gr = p.g ? p.g + (size_t)j * p.Bc + p.i0 : nullptr;
       // weight of column t64 of a k-block; loaded one k-block (of this group) ahead: its L2 latency is off the chain
@@ -130,7 +159,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
       // refill of its stage -- cannot run before BOTH groups have seen `full`(n): without that, a group coming out of
       // the epilogue could find its stage already two phases on and wait forever (seen as a launch failure with few
       // k-blocks per unit).
-      int kb_mine = (int)((grp + 2u - (nk & 1u)) & 1u);          // first k-block of this unit owned by this group
+      int kb_mine = (int)((grp + 2u - (nk & 1u)) & 1u);          // first k-block of this image owned by this group
       float w_next = load_w(kb_mine);
       for (int kb = 0; kb < nkb; ++kb) {
         const uint32_t n = nk + (uint32_t)kb;
@@ -153,55 +182,71 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
         if (t64 < KBLK) wsm[t64] = __float2bfloat16_rn(w_cur);
         if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
         else asm volatile("bar.sync 3, 128;" ::: "memory");
-        // A' = (tile a) * w per column; tile a is the stage's first tile; 128-byte swizzle: chunk c of row r sits at c ^ (r & 7)
-        const uint8_t* src = sbase + (size_t)row * 128;
-        uint8_t* dst = sbase + OFF_AS + (size_t)row * 128;
+        // A' = (loaded tile s) * w per column -> slot 3 - s; 128-byte swizzle: chunk c of row r sits at c ^ (r & 7)
+        for (int s = 0; s < role.ns; ++s) {
+          const uint8_t* src = sbase + (size_t)s * TILE_BYTES + (size_t)row * 128;
+          uint8_t* dst = sbase + (size_t)(3 - s) * TILE_BYTES + (size_t)row * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int pc = (c ^ (row & 7)) << 4;
-          const uint4 v = *reinterpret_cast<const uint4*>(src + pc);
-          const uint4 wv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(wsm) + c * 16);
-          const uint32_t vi[4] = {v.x, v.y, v.z, v.w}, wi[4] = {wv.x, wv.y, wv.z, wv.w};
-          uint32_t oi[4];
+          for (int c = 0; c < 8; ++c) {
+            const int pc = (c ^ (row & 7)) << 4;
+            const uint4 v = *reinterpret_cast<const uint4*>(src + pc);
+            const uint4 wv = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(wsm) + c * 16);
+            const uint32_t vi[4] = {v.x, v.y, v.z, v.w}, wi[4] = {wv.x, wv.y, wv.z, wv.w};
+            uint32_t oi[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const __nv_bfloat162 r2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&vi[k]),
-                                              *reinterpret_cast<const __nv_bfloat162*>(&wi[k]));
-            oi[k] = *reinterpret_cast<const uint32_t*>(&r2);
+            for (int k = 0; k < 4; ++k) {
+              const __nv_bfloat162 r2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&vi[k]),
+                                                *reinterpret_cast<const __nv_bfloat162*>(&wi[k]));
+              oi[k] = *reinterpret_cast<const uint32_t*>(&r2);
+            }
+            *reinterpret_cast<uint4*>(dst + pc) = make_uint4(oi[0], oi[1], oi[2], oi[3]);
           }
-          *reinterpret_cast<uint4*>(dst + pc) = make_uint4(oi[0], oi[1], oi[2], oi[3]);
         }
         fence_proxy_async_smem();
         mbar_arrive(bar(B_SCALED + st));
       }
       nk += (uint32_t)nkb;
       if (grp == 0) {
-        // ---- epilogue: blocks (a, a+b) from TMEM, mirrored to (a+b, a)
+        // ---- epilogue: this CTA's blocks from TMEM, each mirrored across the diagonal
         mbar_wait(bar(B_ACCF), nu & 1);
         tc_fence_after();
-        const int r_glob = a * TILE + row;
         float* Mj = p.M + (size_t)j * p.sp * p.sp;
-        for (int b = 0; b < nb; ++b) {
+        __nv_bfloat16* Mbj = p.Mb ? p.Mb + (size_t)j * p.sp * p.sp : nullptr;
+        for (int m = 0; m < role.nm; ++m) {
+          const int a = role.ra[m], b = role.rb[m];
+          const int r_glob = a * TILE + row;
 #pragma unroll 1
           for (int c = 0; c < TILE / 16; ++c) {
             float v[16];
-            tmem_ld16(tmem + lane_addr + (uint32_t)(b * TILE + c * 16), v);
+            tmem_ld16(tmem + lane_addr + (uint32_t)(m * TILE + c * 16), v);
             tmem_ld_wait();
-            const int col0 = (a + b) * TILE + c * 16;
-            if (r_glob < p.sp) {
-              if (col0 + 16 <= p.sp) {                           // sp is a multiple of 16: whole group in or out
-                float4* d1 = reinterpret_cast<float4*>(Mj + (size_t)r_glob * p.sp + col0);
+            const int col0 = b * TILE + c * 16;
+            if (r_glob < p.sp && col0 + 16 <= p.sp) {            // sp is a multiple of 16: whole group in or out
+              float4* d1 = reinterpret_cast<float4*>(Mj + (size_t)r_glob * p.sp + col0);
+              if (p.accumulate) {
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
-                  float4 o = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
-                  if (p.accumulate) { const float4 t = d1[k4]; o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-                  d1[k4] = o;
+                  const float4 t = d1[k4];
+                  v[4 * k4] += t.x; v[4 * k4 + 1] += t.y; v[4 * k4 + 2] += t.z; v[4 * k4 + 3] += t.w;
                 }
-                if (b > 0) {                                     // mirror (lanes write consecutive floats: coalesced)
+              }
+              if (Mbj != nullptr) {                              // bf16 copy for the M.R GEMM (final values only)
+                uint4* o = reinterpret_cast<uint4*>(Mbj + (size_t)r_glob * p.sp + col0);
+                o[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                o[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+              } else {
 #pragma unroll
-                  for (int k = 0; k < 16; ++k) {
-                    float* d2 = Mj + (size_t)(col0 + k) * p.sp + r_glob;
-                    *d2 = p.accumulate ? *d2 + v[k] : v[k];
+                for (int k4 = 0; k4 < 4; ++k4) d1[k4] = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+              }
+              if (b > a) {                                       // mirror (lanes write consecutive elements: coalesced)
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                  const size_t o2 = (size_t)(col0 + k) * p.sp + r_glob;
+                  if (Mbj != nullptr) {
+                    Mbj[o2] = __float2bfloat16_rn(v[k]);
+                  } else {
+                    // (with accumulate the mirror holds the same running value as the block itself: write, do not re-add)
+                    Mj[o2] = v[k];
                   }
                 }
               }
@@ -225,18 +270,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) mterm_kernel(const __grid_constan
 }  // namespace mt
 
 // M[j] (+)= Eo_j^T diag(w_j) Eo_j  for all images; Et is the [Bi*sp, R1] bf16 operand matrix (row-major)
-int launch_mterm(const void* Et, const float* f, const float* g, float* M, int Bi, int Bc, int i0, int R1, int lp, int sp,
-                 bool accumulate, cudaStream_t st) {
+int launch_mterm(const void* Et, const float* f, const float* g, float* M, void* Mb, int Bi, int Bc, int i0, int R1, int lp,
+                 int sp, bool accumulate, cudaStream_t st) {
   CUtensorMap em;
   int rc;
   if ((rc = make_map(&em, Et, (uint64_t)R1, (uint64_t)Bi * sp, TILE))) return rc;
   mt::Params p;
-  p.f = f; p.g = g; p.M = M; p.Bi = Bi; p.Bc = Bc; p.i0 = i0; p.R1 = R1; p.lp = lp; p.sp = sp;
+  p.f = f; p.g = g; p.M = M; p.Mb = (__nv_bfloat16*)Mb; p.Bi = Bi; p.Bc = Bc; p.i0 = i0; p.R1 = R1; p.lp = lp; p.sp = sp;
   p.NT = (sp + TILE - 1) / TILE; p.accumulate = accumulate ? 1 : 0;
   int dev = 0, sms = 0;
   GLORIA_CUDA(cudaGetDevice(&dev));
   GLORIA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int grid = min(sms, Bi * p.NT);
+  const int grid = 2 * min(sms / 2, Bi);                     // clusters of two: one image per cluster at a time
   GLORIA_CUDA(cudaFuncSetAttribute(mt::mterm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mt::SMEM_BYTES));
   mt::mterm_kernel<<<grid, mt::NTHREADS, mt::SMEM_BYTES, st>>>(em, p);
   GLORIA_LAUNCHED("mterm_kernel");
