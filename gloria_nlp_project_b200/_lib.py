@@ -66,6 +66,7 @@ PROTOTYPES = {
     "gloria_b200_tc_local_sim_bwd_train_ev": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p, _p]),
     "gloria_b200_acc_gemm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
     "gloria_b200_word_ranges": (_i, [_p, _p, _i, C.c_longlong, _i, _i, _p, _p, _p, _p]),
+    "gloria_b200_word_ranges_cap_lens": (_i, [_p, _p, _p, _i, C.c_longlong, _i, _i, _p, _p, _p, _p, _p]),
     "gloria_b200_aggregate_tokens_fwd": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p]),
     "gloria_b200_aggregate_tokens_bwd": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p]),
     "gloria_b200_global_sim_fwd": (_i, [_p, _p, _i, _i, _i, _f, _p, _p, _p, _p]),

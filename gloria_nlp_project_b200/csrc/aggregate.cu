@@ -23,9 +23,12 @@ namespace {
 // word_range [B, T, 2] = (first token, one past the last token) of word w, (0, 0) for w >= n_words[b];
 // token_word [B, T] = word index of token t, or -1 if the token is not part of any emitted word.
 // One warp per caption (T <= 1024).
+// cap_lens (optional, with is_bracket [vocab] = 1 where the entry's text, "##" stripped, starts with '['):
+// gloria_model.py:107-109 on the device -- 1 + the number of emitted words whose string does not start with '['.
 __global__ void word_ranges(const long long* __restrict__ ids, const unsigned char* __restrict__ is_cont, int vocab,
                             long long sep_id, int B, int T, int* __restrict__ word_range, int* __restrict__ token_word,
-                            int* __restrict__ n_words) {
+                            int* __restrict__ n_words, const unsigned char* __restrict__ is_bracket,
+                            int* __restrict__ cap_lens) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -37,11 +40,17 @@ __global__ void word_ranges(const long long* __restrict__ ids, const unsigned ch
   if (lane != 0) return;                       // the walk itself is sequential and tiny (T <= ~100 tokens)
   int w = -1, start = 0;
   bool closed = false;
+  int plain = 0;                               // emitted words that do not start with '['
+  auto is_plain = [&](int t0) {
+    const long long v0 = id[t0];
+    return !(is_bracket != nullptr && v0 >= 0 && v0 < vocab && is_bracket[v0] != 0);
+  };
   for (int t = 0; t < T; ++t) {
     const long long v = id[t];
     const bool cont = v >= 0 && v < vocab && is_cont[v] != 0;
     if (v == sep_id) {
-      if (w >= 0) { wr[2 * w] = start; wr[2 * w + 1] = t; }            // close the open word
+      if (w >= 0) { wr[2 * w] = start; wr[2 * w + 1] = t; plain += is_plain(start); }   // close the open word
+      else ++plain;                            // [SEP] first: the reference appends an empty word string before it
       ++w;
       wr[2 * w] = t; wr[2 * w + 1] = t + 1;                           // [SEP] is a word of its own
       tw[t] = w;
@@ -49,7 +58,7 @@ __global__ void word_ranges(const long long* __restrict__ ids, const unsigned ch
       break;
     }
     if (!cont || w < 0) {                      // starts a word (a leading "##" piece starts the first word)
-      if (w >= 0) { wr[2 * w] = start; wr[2 * w + 1] = t; }
+      if (w >= 0) { wr[2 * w] = start; wr[2 * w + 1] = t; plain += is_plain(start); }
       ++w;
       start = t;
     }
@@ -62,6 +71,7 @@ __global__ void word_ranges(const long long* __restrict__ ids, const unsigned ch
     n = w;
   }
   n_words[b] = n;
+  if (cap_lens != nullptr) cap_lens[b] = plain + 1;
 }
 
 template <typename T> __device__ __forceinline__ float to_f(T v);
@@ -186,7 +196,21 @@ extern "C" int gloria_b200_word_ranges(const long long* caption_ids, const unsig
   GLORIA_CHECK_ARG(B > 0 && T > 0 && vocab > 0, "bad sizes B=%d T=%d vocab=%d", B, T, vocab);
   cudaStream_t st = (cudaStream_t)stream;
   word_ranges<<<(B + 3) / 4, 128, 0, st>>>(caption_ids, is_continuation, vocab, sep_id, B, T, word_range, token_word,
-                                          n_words);
+                                          n_words, nullptr, nullptr);
+  GLORIA_LAUNCHED("word_ranges");
+  return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_word_ranges_cap_lens(const long long* caption_ids, const unsigned char* is_continuation,
+                                                const unsigned char* is_bracket, int vocab, long long sep_id, int B,
+                                                int T, int32_t* word_range, int32_t* token_word, int32_t* n_words,
+                                                int32_t* cap_lens, void* stream) {
+  GLORIA_CHECK_ARG(caption_ids && is_continuation && is_bracket && word_range && token_word && n_words && cap_lens,
+                   "null pointer");
+  GLORIA_CHECK_ARG(B > 0 && T > 0 && vocab > 0, "bad sizes B=%d T=%d vocab=%d", B, T, vocab);
+  cudaStream_t st = (cudaStream_t)stream;
+  word_ranges<<<(B + 3) / 4, 128, 0, st>>>(caption_ids, is_continuation, vocab, sep_id, B, T, word_range, token_word,
+                                          n_words, is_bracket, cap_lens);
   GLORIA_LAUNCHED("word_ranges");
   return GLORIA_OK;
 }

@@ -851,12 +851,15 @@ __global__ void gram_ones_row(__nv_bfloat16* __restrict__ G, int S, int Spad) {
 constexpr int SCALE_ROWS = 16;
 // X[(j,s), (i,l)] *= g[j, i]  in place (fused training path: X was produced for g = 1).
 // grid (ceil(R1/8/256), sp/SCALE_ROWS, Bi): each thread owns 8 columns of one image and streams SCALE_ROWS rows
+// `consumed` (device flag in the training state, may be null): set once a backward has scaled X in place; a second
+// backward over the same state would scale twice, so it poisons its result with NaN instead of returning wrong numbers
 __global__ void __launch_bounds__(256) scale_x(__nv_bfloat16* __restrict__ X, const float* __restrict__ g, int R1,
-                                               int Spad, int Bc, int i0, int lpad) {
+                                               int Spad, int Bc, int i0, int lpad, const int* __restrict__ consumed) {
   const int c8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (c8 >= R1) return;
   const int j = blockIdx.z;
-  const float gs = g[(size_t)j * Bc + i0 + c8 / lpad];
+  float gs = g[(size_t)j * Bc + i0 + c8 / lpad];
+  if (consumed != nullptr && *consumed != 0) gs = __int_as_float(0x7fc00000);
   const size_t row0 = (size_t)j * Spad + (size_t)blockIdx.y * SCALE_ROWS;
 #pragma unroll 4
   for (int r = 0; r < SCALE_ROWS; ++r) {
@@ -869,6 +872,8 @@ __global__ void __launch_bounds__(256) scale_x(__nv_bfloat16* __restrict__ X, co
     *ptr = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
+
+__global__ void mark_consumed(int* flag) { *flag = 1; }
 
 // gamma[i, l] = sum_j g[j, i] * go[j, (i,l)]   (fused training path);  one thread per column
 __global__ void gamma_sum(const float* __restrict__ go, const float* __restrict__ g, float* __restrict__ gamma, int Bi,
@@ -1051,7 +1056,7 @@ int launch_pair_lpad(int lpad, const CUtensorMap& rt, const CUtensorMap& wt, con
 
 // ---- fused training path: one workspace shared by the forward (gram, X, E, fo, go) and the backward (the rest)
 struct TrainPlan {
-  size_t off_gram, off_x, off_e, off_fo, off_go, off_dwt, off_drt, off_m, off_mb, off_gamma, off_cublas, total;
+  size_t off_gram, off_x, off_e, off_fo, off_go, off_dwt, off_drt, off_m, off_mb, off_gamma, off_cublas, off_flag, total;
 };
 TrainPlan train_plan(int Bi, int Bc, int D, int Spad, int sp, int lpad) {
   TrainPlan t{};
@@ -1069,6 +1074,7 @@ TrainPlan train_plan(int Bi, int Bc, int D, int Spad, int sp, int lpad) {
   t.off_mb = take((size_t)Bi * sp * sp * 2);
   t.off_gamma = take((size_t)Bc * lpad * 4);
   t.off_cublas = take(CUBLAS_WS);
+  t.off_flag = take(1024);
   t.total = o;
   return t;
 }
@@ -1270,6 +1276,7 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train_part(const void* ctx_h, const 
   GLORIA_CUBLAS(cublasSetStream(h, st));
   GLORIA_CUBLAS(cublasSetWorkspace(h, ws + pl.off_cublas, bw::CUBLAS_WS));
   int rc;
+  if (j0 == 0) GLORIA_CUDA(cudaMemsetAsync(ws + pl.off_flag, 0, 1024, st));       // fresh state: not consumed yet
   if ((rc = bw::gram_matrices(h, rt_, gram, nj, D, S, Spad, sp, st))) return rc;
   CUtensorMap rt, wt, gm, em;
   if ((rc = make_map(&rt, rh, (uint64_t)D, (uint64_t)nj * Spad, TILE))) return rc;
@@ -1386,8 +1393,10 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const
   // everything the forward stored is for g = 1 and linear in g = dsim[j, i]: the own GEMMs apply it to their A operand in
   // flight (mode 0); otherwise one streaming pass scales X in place first
   if (gmode != 0) {
-    bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, sp, Bc, 0, lp);
+    bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, sp, Bc, 0, lp, (const int*)(ws + pl.off_flag));
     GLORIA_LAUNCHED("scale_x");
+    bw::mark_consumed<<<1, 1, 0, st>>>((int*)(ws + pl.off_flag));
+    GLORIA_LAUNCHED("mark_consumed");
   }
   // ---- image side, part by part
   const int nj = Bi / n_parts;

@@ -99,12 +99,9 @@ class _ShardedLocalSim(torch.autograd.Function):
         img_all = x.new_empty((world * n, D, x.shape[2]))
         dist.all_gather_into_tensor(img_all, x, group=group)
         words = text_emb_l.float().contiguous()
-        if any(ctx.needs_input_grad[:2]):
-            # tells the op (called here with autograd off) to run the fused training forward and keep its state
-            words = words.detach().requires_grad_(True)
         sim, _, _, stats = ops.local_sim_fwd(img_all, words, dev_lens, lcap, 0, temp1, temp2, agg, eps, False, False,
-                                             mode)
-        ctx.save_for_backward(img_all, words.detach(), dev_lens, stats)
+                                             mode, bool(any(ctx.needs_input_grad[:2])))
+        ctx.save_for_backward(img_all, words, dev_lens, stats)
         ctx.args = (lcap, temp1, temp2, agg, eps, mode, group, img_emb_l.shape, img_emb_l.dtype, text_emb_l.dtype)
         return sim
 
@@ -115,6 +112,7 @@ class _ShardedLocalSim(torch.autograd.Function):
         lcap, temp1, temp2, agg, eps, mode, group, img_shape, img_dtype, txt_dtype = ctx.args
         world = dist.get_world_size(group)
         dev = img_all.device
+        ops.check_state_unconsumed(ctx, img_all, words, lcap, stats, mode)
         ready = torch.cuda.Event()
         ready.record()                                   # materialise the handle; the op re-records it
         d_ctx_all, d_words = ops.local_sim_bwd(img_all, words, dev_lens, lcap, 0, temp1, temp2, agg, eps,
@@ -218,8 +216,13 @@ class _ShardedLocalSimParts(torch.autograd.Function):
         from . import _lib
         from .ops import _stream
         L = _lib.lib()
+        from . import ops
         ctx_t, words_t, dev_lens, ws, perm = ctx.saved_tensors
         lcap, group, P, S, Lw, img_shape, img_dtype, txt_dtype = ctx.args
+        if ops._BWD_MUTATES:
+            if getattr(ctx, "_gloria_consumed", False):
+                raise RuntimeError("gloria_b200: the fused training state was already consumed by a backward pass")
+            ctx._gloria_consumed = True
         world = dist.get_world_size(group)
         B, _, D = ctx_t.shape
         Bc = words_t.shape[0]
@@ -253,7 +256,17 @@ class _ShardedLocalSimParts(torch.autograd.Function):
                 None, None)
 
 
-def _sharded_local_sim(img_emb_l, text_emb_l, cap_lens, temp1, temp2, agg, group):
+def _agree(dev, lcap: int, parts_ok: bool, group):
+    """Every rank must issue the same sequence of collectives: the pipelined path runs P all_gathers / reduce_scatters of
+    n / P rows, the fallback one of n rows, and the choice depends on rank-local facts (free memory, the longest local
+    caption).  One small all_reduce makes it global: lcap = max over ranks, parts path only if every rank can take it."""
+    t = torch.tensor([int(lcap), -int(bool(parts_ok))], dtype=torch.int32, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    lcap_all, neg_ok = (int(v) for v in t.tolist())
+    return lcap_all, neg_ok == -1
+
+
+def _sharded_local_sim(img_emb_l, text_emb_l, cap_lens, temp1, temp2, agg, group, eps=1e-8):
     """Default CUDA path of the sharded local similarity -> sim[:, own captions] ([B, B/G])."""
     from . import _lib, gloria_loss, ops
     if not img_emb_l.is_cuda:
@@ -263,18 +276,23 @@ def _sharded_local_sim(img_emb_l, text_emb_l, cap_lens, temp1, temp2, agg, group
     S = img_emb_l.shape[2] * img_emb_l.shape[3]
     dev_lens, lens = gloria_loss._cap_lens(cap_lens, Bc, 0, Lw, img_emb_l.device)
     mode = gloria_loss._mode(img_emb_l, text_emb_l)
-    lcap = max(lens)
+    lcap = max(lens) if lens is not None else Lw
     L = _lib.lib()
     world = dist.get_world_size(group)
     P = _N_PARTS if n % _N_PARTS == 0 and n >= 2 * _N_PARTS else 1
-    if (mode == ops.MODE_BF16 and ops._FUSED_TRAIN and agg != "max" and torch.is_grad_enabled()
-            and (img_emb_l.requires_grad or text_emb_l.requires_grad) and L.gloria_b200_tc_supported(D, S, lcap) == 0):
-        nbytes = L.gloria_b200_tc_train_workspace(world * n, Bc, D, S, lcap)
-        if 0 < nbytes <= min(ops._TC_WS_BUDGET, int(ops._available_bytes(img_emb_l.device, nbytes) * 0.92)):
-            return _ShardedLocalSimParts.apply(img_emb_l, text_emb_l, dev_lens, lcap, float(temp1), float(temp2),
-                                               ops.AGG[agg], 1e-8, group, P)
+    want_parts = (mode == ops.MODE_BF16 and ops._FUSED_TRAIN and agg != "max" and torch.is_grad_enabled()
+                  and (img_emb_l.requires_grad or text_emb_l.requires_grad))
+    parts_ok = False
+    if want_parts and L.gloria_b200_tc_supported(D, S, Lw) == 0:
+        # sized for the longest caption any rank may hold (Lw), so the answer cannot flip when lcap is agreed below
+        nbytes = L.gloria_b200_tc_train_workspace(world * n, Bc, D, S, Lw)
+        parts_ok = 0 < nbytes <= min(ops._TC_WS_BUDGET, int(ops._available_bytes(img_emb_l.device, nbytes) * 0.92))
+    lcap, parts_ok = _agree(img_emb_l.device, lcap, parts_ok, group)
+    if parts_ok:
+        return _ShardedLocalSimParts.apply(img_emb_l, text_emb_l, dev_lens, lcap, float(temp1), float(temp2),
+                                           ops.AGG[agg], float(eps), group, P)
     return _ShardedLocalSim.apply(img_emb_l, text_emb_l, dev_lens, lcap, float(temp1), float(temp2),
-                                  ops.AGG[agg], 1e-8, mode, group)
+                                  ops.AGG[agg], float(eps), mode, group)
 
 
 def _default_local_sim(img_all, words_local, cap_lens_local, temp1, temp2, agg):
@@ -304,6 +322,11 @@ def sharded_loss(img_emb_l: torch.Tensor, text_emb_l: torch.Tensor, img_emb_g: t
 
     All ranks must hold the same number of pairs.  Equals `local_loss` / `global_loss` of the reference
     (gloria_loss.py:99-170, 66-88) evaluated on the concatenation of all ranks' shards.
+
+    Gradient scale under DDP: every rank gets the gradient of the FULL-batch loss w.r.t. its own shard of the inputs.
+    DistributedDataParallel then AVERAGES parameter gradients over ranks, which leaves them at 1 / world_size of the
+    single-device full-batch gradient: multiply the returned loss by world_size (or register a SUM communication
+    hook) to reproduce single-device training exactly.
     """
     local_sim_fn = local_sim_fn or _default_local_sim
     global_cos_fn = global_cos_fn or _default_global_cos
@@ -314,7 +337,7 @@ def sharded_loss(img_emb_l: torch.Tensor, text_emb_l: torch.Tensor, img_emb_g: t
         return (*ce_fn(sim, temp3), *ce_fn(cosm, temp3))
     img_g_all = gather_reduce_scatter(img_emb_g, group)              # [B, D]
     if local_sim_fn is _default_local_sim:
-        sim_blk = _sharded_local_sim(img_emb_l, text_emb_l, cap_lens, temp1, temp2, agg, group)   # [B, B/G]
+        sim_blk = _sharded_local_sim(img_emb_l, text_emb_l, cap_lens, temp1, temp2, agg, group, eps)   # [B, B/G]
     else:
         img_all = gather_reduce_scatter(img_emb_l, group)            # [B, D, H, W]
         sim_blk = local_sim_fn(img_all, text_emb_l, cap_lens, temp1, temp2, agg)      # [B, B/G]

@@ -14,7 +14,8 @@ import torch
 from . import _config, ops
 
 __all__ = ["cosine_similarity", "attention_fn", "global_loss", "kl_divergence", "entropy", "local_loss",
-           "local_similarities", "diagonal_attention_maps", "supervised_attention_loss", "plan_length_buckets"]
+           "local_similarities", "diagonal_attention_maps", "supervised_attention_loss", "plan_length_buckets",
+           "DeviceCapLens", "LazyAttnMaps"]
 
 
 def _mode(*tensors: torch.Tensor) -> int:
@@ -25,9 +26,64 @@ def _mode(*tensors: torch.Tensor) -> int:
     return ops.MODE_BF16 if p == "bf16" else ops.MODE_FP32
 
 
-def _cap_lens(cap_lens: Union[Sequence[int], torch.Tensor], n: int, word_off: int, Lw: int,
-              device: torch.device) -> Tuple[torch.Tensor, List[int]]:
-    """The reference indexes cap_lens[i] as Python ints (list, or tensor -> implicit sync); do the same once."""
+class DeviceCapLens:
+    """Caption lengths that exist on the device only (e.g. from `text_model.aggregate_tokens`, which derives them from
+    the token ids in its word-boundary kernel).  Passing one as `cap_lens` keeps the whole loss step free of host
+    round trips: no `.tolist()`, no H2D copy, one launch padded to the word axis of `words_emb` (the kernels clamp
+    each caption's length to [0, Lw - word_offset] themselves; no length buckets), and the attention maps are sliced
+    per caption only when somebody reads them (`LazyAttnMaps`).  A plain CUDA int tensor is NOT treated this way: the
+    reference reads `cap_lens[i]` as Python ints, and a tensor argument keeps that meaning."""
+
+    def __init__(self, lens: torch.Tensor):
+        self.tensor = lens.reshape(-1).to(torch.int32).contiguous()
+        self._host = None
+
+    def __len__(self):
+        return self.tensor.numel()
+
+    def tolist(self) -> List[int]:
+        if self._host is None:
+            self._host = [int(v) for v in self.tensor.tolist()]          # the one sync, only on demand
+        return self._host
+
+
+class LazyAttnMaps(Sequence):
+    """`att_maps` of local_loss (gloria_loss.py:141-143: a list of [1, L_i, H, W] maps of the diagonal pairs) over the
+    padded [B, Lcap, S] tensor the kernel wrote; element i is sliced to its caption's length when it is read (the
+    lengths are then fetched from the device once).  `stacked` gives the padded tensor without any sync."""
+
+    def __init__(self, diag: torch.Tensor, lens: "DeviceCapLens", s0: int, ih: int, iw: int):
+        self.stacked, self._lens, self._s0, self._hw = diag, lens, s0, (ih, iw)
+
+    def __len__(self):
+        return self.stacked.shape[0]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        L = min(self._lens.tolist()[i], self.stacked.shape[1])
+        return self.stacked[i:i + 1, :L, self._s0:].reshape(1, L, *self._hw)
+
+
+def _att_maps(diag, lens, dev_lens_obj, s0, ih, iw, n):
+    if lens is None:
+        return LazyAttnMaps(diag, dev_lens_obj, s0, ih, iw)
+    return [diag[i:i + 1, :lens[i], s0:].reshape(1, lens[i], ih, iw) for i in range(n)]
+
+
+def _cap_lens(cap_lens: Union[Sequence[int], torch.Tensor, "DeviceCapLens"], n: int, word_off: int, Lw: int,
+              device: torch.device) -> Tuple[torch.Tensor, Optional[List[int]]]:
+    """The reference indexes cap_lens[i] as Python ints (list, or tensor -> implicit sync); do the same once.
+    A `DeviceCapLens` skips the host side altogether: returns (device int32 tensor, None)."""
+    if isinstance(cap_lens, DeviceCapLens):
+        if len(cap_lens) < n:
+            raise RuntimeError(f"cap_lens has {len(cap_lens)} entries for {n} captions")
+        t = cap_lens.tensor if cap_lens.tensor.device == device else cap_lens.tensor.to(device)
+        return (t if len(cap_lens) == n else t[:n].contiguous()), None
     if isinstance(cap_lens, torch.Tensor):
         lens = [int(v) for v in cap_lens.reshape(-1).tolist()]
     else:
@@ -98,8 +154,11 @@ def local_similarities(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, 
     ctx = _context(img_features, no_attn_vec)
     words = words_emb.float()
     mode = _mode(img_features, words_emb)
-    buckets = plan_length_buckets(lens, ctx.shape[0], word_offset) if (mode == ops.MODE_BF16 and not want_mean_attn) \
-        else []
+    need_grad = torch.is_grad_enabled() and (img_features.requires_grad or words_emb.requires_grad
+                                             or (no_attn_vec is not None and no_attn_vec.requires_grad))
+    lcap = max(lens) if lens is not None else Lw - word_offset       # device-only lengths: pad to the word axis
+    buckets = plan_length_buckets(lens, ctx.shape[0], word_offset) \
+        if (mode == ops.MODE_BF16 and not want_mean_attn and lens is not None) else []
     if len(buckets) > 1:
         parts, order = [], []
         with ops.shared_ctx_pack(ctx):                               # the images are packed once for all groups
@@ -107,7 +166,7 @@ def local_similarities(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, 
                 sel = torch.tensor(idx, dtype=torch.long).to(ctx.device, non_blocking=True)
                 sim_b, _, _, _ = ops.local_sim_fwd(ctx, words.index_select(0, sel), dev_lens.index_select(0, sel),
                                                    lcap_b, word_offset, float(temp1), float(temp2), ops.AGG[agg],
-                                                   float(eps), False, False, mode)
+                                                   float(eps), False, False, mode, need_grad)
                 parts.append(sim_b)
                 order += idx
         inv = torch.empty(Bc, dtype=torch.long)
@@ -117,9 +176,9 @@ def local_similarities(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, 
         if want_attn_maps:                                           # B diagonal pairs through the exact fp32 kernels
             diag = ops.diag_attn_fwd(ctx, words, dev_lens, max(lens), word_offset, float(temp1))
         return sim, diag, None, lens
-    sim, diag, mean, _ = ops.local_sim_fwd(ctx, words, dev_lens, max(lens), word_offset, float(temp1), float(temp2),
+    sim, diag, mean, _ = ops.local_sim_fwd(ctx, words, dev_lens, lcap, word_offset, float(temp1), float(temp2),
                                            ops.AGG[agg], float(eps), bool(want_attn_maps), bool(want_mean_attn),
-                                           mode)
+                                           mode, need_grad)
     return sim, (diag if want_attn_maps else None), (mean if want_mean_attn else None), lens
 
 
@@ -132,9 +191,10 @@ def diagonal_attention_maps(img_features, words_emb, cap_lens, temp1=4.0, no_att
     ih, iw = img_features.shape[2], img_features.shape[3]
     dev_lens, lens = _cap_lens(cap_lens, Bc, word_offset, Lw, img_features.device)
     ctx = _context(img_features, no_attn_vec)
-    diag = ops.diag_attn_fwd(ctx, words_emb.float(), dev_lens, max(lens), word_offset, float(temp1))
+    lcap = max(lens) if lens is not None else Lw - word_offset
+    diag = ops.diag_attn_fwd(ctx, words_emb.float(), dev_lens, lcap, word_offset, float(temp1))
     s0 = 1 if no_attn_vec is not None else 0
-    return [diag[i:i + 1, :lens[i], s0:].reshape(1, lens[i], ih, iw) for i in range(Bc)]
+    return _att_maps(diag, lens, cap_lens, s0, ih, iw, Bc)
 
 
 _CELL_INDEX = {}
@@ -155,7 +215,14 @@ def supervised_attention_loss(att_maps, segmentation_labels):
     nearest upsampling repeats each grid cell over a fixed set of pixels, so  sum(label * up) / sum(up)  is
     sum_c map[c] * (#labelled pixels of cell c) / sum_c map[c] * (#pixels of cell c).  Returns the batch mean of
     -log of that ratio (the caller applies segmentation_loss_weight)."""
-    mean_maps = torch.cat([m.mean(1) for m in att_maps], 0)                  # [B, h, w]  (:144)
+    if isinstance(att_maps, LazyAttnMaps):
+        # word-mean of each map from the padded tensor (rows beyond a caption's length are zero): sum / length, no sync
+        ih, iw = att_maps._hw
+        d = att_maps.stacked[:, :, att_maps._s0:]
+        n = att_maps._lens.tensor[:d.shape[0]].clamp(1, d.shape[1]).to(d.dtype)
+        mean_maps = (d.sum(1) / n[:, None]).reshape(d.shape[0], ih, iw)
+    else:
+        mean_maps = torch.cat([m.mean(1) for m in att_maps], 0)              # [B, h, w]  (:144)
     B, ih, iw = mean_maps.shape
     oh, ow = segmentation_labels.shape[1:]
     cell = _cell_index(ih, iw, oh, ow, mean_maps.device)
@@ -228,7 +295,7 @@ def local_loss(
     sim, diag, mean, lens = local_similarities(img_features, words_emb, cap_lens, temp1, temp2, agg, no_attn_vec,
                                                word_offset=0, want_attn_maps=True, want_mean_attn=want_mean)
     s0 = 1 if has_v else 0                                          # returned maps drop the no-attn column (:60-61)
-    att_maps = [diag[i:i + 1, :lens[i], s0:].reshape(1, lens[i], ih, iw) for i in range(words_emb.shape[0])]
+    att_maps = _att_maps(diag, lens, cap_lens, s0, ih, iw, words_emb.shape[0])
 
     losses, _, _ = ops.ce_bidir_fwd(sim, float(temp3))              # :164-170
     loss0, loss1 = losses[0], losses[1]

@@ -22,7 +22,13 @@ __all__ = ["GLoRIALossMixin", "patch_gloria", "cap_lens_from_sents"]
 
 
 def cap_lens_from_sents(sents):
-    """gloria_model.py:107-109: number of words not starting with '[' plus one ([CLS] kept, [SEP] dropped)."""
+    """gloria_model.py:107-109: number of words not starting with '[' plus one ([CLS] kept, [SEP] dropped).
+    Sentences that come from this package's `text_model.aggregate_tokens` carry the same numbers as a device tensor
+    (`sents.cap_lens`, computed by the word-boundary kernel): they are used as they are, and neither the strings nor
+    a host copy of the lengths is ever built on the training path."""
+    dev = getattr(sents, "cap_lens", None)
+    if isinstance(dev, gloria_loss.DeviceCapLens):
+        return dev
     return [len([w for w in sent if not w.startswith("[")]) + 1 for sent in sents]
 
 

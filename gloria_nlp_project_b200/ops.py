@@ -1,8 +1,9 @@
 """torch custom ops (with autograd) over the C ABI of libgloria_b200.so.
 
 PyTorch is plumbing here: it owns device memory and streams and records the autograd graph; every number is
-computed by the CUDA kernels behind `include/gloria_b200.h`.  The ops are opaque to torch.compile / CUDA graphs
-(`torch.library.custom_op` + `register_fake` + `register_autograd`).  There is no CPU implementation: calling an
+computed by the CUDA kernels behind `include/gloria_b200.h`.  The ops are opaque to torch.compile
+(`torch.library.custom_op` + `register_fake` + `register_autograd`; the byte state the bf16 forward hands to its
+backward has a data-dependent length, declared as such in the fake) and hold no process-global state.  There is no CPU implementation: calling an
 op with CPU tensors raises RuntimeError.
 """
 from __future__ import annotations
@@ -50,26 +51,41 @@ def shared_ctx_pack(ctx: Tensor):
         _SHARED.key = _SHARED.keep = _SHARED.val = None
 
 
-def tc_prepack(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int) -> Packed:
+def tc_prepack(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int, ctx_t: Optional[Tensor] = None,
+               words_t: Optional[Tensor] = None) -> Packed:
     """fp32 native layouts -> ctx_h/ctx_t [Bi,Spad,D] (fp16/bf16), ctx_n [Bi,D,Spad] bf16, words_h/words_t [Bc,Lpad,D]
-    (fp16/bf16), wnorm [Bc,Lpad] fp32."""
+    (fp16/bf16), wnorm [Bc,Lpad] fp32.  ctx_t / words_t may be given as uint8 views to write into (the training state
+    carries them to the backward); ctx_n is then not produced (only the inference / recompute kernels read it)."""
     L = _lib.lib()
     Bi, D, S = ctx.shape
     Bc, _, Lw = words.shape
     spad, lpad = L.gloria_b200_tc_spad(S), L.gloria_b200_tc_lpad(lcap)
     dev = ctx.device
     words_h = torch.empty((Bc, lpad, D), dtype=torch.float16, device=dev)
-    words_t = torch.empty((Bc, L.gloria_b200_tc_lp(lcap), D), dtype=torch.bfloat16, device=dev)
+    lean = ctx_t is not None
+    if words_t is None:
+        words_t = torch.empty((Bc, L.gloria_b200_tc_lp(lcap), D), dtype=torch.bfloat16, device=dev)
+    else:
+        words_t = words_t[:Bc * L.gloria_b200_tc_lp(lcap) * D * 2].view(torch.bfloat16).view(Bc, L.gloria_b200_tc_lp(lcap), D)
     wnorm = torch.empty((Bc, lpad), dtype=torch.float32, device=dev)
     key = (ctx.data_ptr(), tuple(ctx.shape), ctx._version, ctx.device)
     shared = getattr(_SHARED, "key", None) == key
+    sp = L.gloria_b200_tc_sp(S)
     if shared and _SHARED.val is not None:
-        ctx_h, ctx_t, ctx_n = _SHARED.val
+        ctx_h, ctx_t0, ctx_n = _SHARED.val
+        if lean:      # the state needs its own copy of the (shared) ctx_t: one device copy instead of a second pack
+            ctx_t = ctx_t[:Bi * sp * D * 2].view(torch.bfloat16).view(Bi, sp, D)
+            ctx_t.copy_(ctx_t0)
+        else:
+            ctx_t = ctx_t0
     else:
         ctx_h = torch.empty((Bi, spad, D), dtype=torch.float16, device=dev)
-        ctx_t = torch.empty((Bi, L.gloria_b200_tc_sp(S), D), dtype=torch.bfloat16, device=dev)
-        ctx_n = torch.empty((Bi, D, spad), dtype=torch.bfloat16, device=dev)
-        rc = L.gloria_b200_tc_prepack_ctx(ctx.data_ptr(), Bi, D, S, ctx_h.data_ptr(), ctx_t.data_ptr(), ctx_n.data_ptr(),
+        if lean:
+            ctx_t = ctx_t[:Bi * sp * D * 2].view(torch.bfloat16).view(Bi, sp, D)
+        else:
+            ctx_t = torch.empty((Bi, sp, D), dtype=torch.bfloat16, device=dev)
+        ctx_n = None if (lean and not shared) else torch.empty((Bi, D, spad), dtype=torch.bfloat16, device=dev)
+        rc = L.gloria_b200_tc_prepack_ctx(ctx.data_ptr(), Bi, D, S, ctx_h.data_ptr(), ctx_t.data_ptr(), _ptr(ctx_n),
                                           _stream(ctx))
         _lib.check(rc, "tc_prepack_ctx")
         if shared:
@@ -121,9 +137,14 @@ def _f32c(t: Tensor) -> Tensor:
 @torch.library.custom_op("gloria_b200::local_sim_fwd", mutates_args=())
 def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int, temp1: float,
                   temp2: float, agg: int, eps: float, want_diag: bool, want_mean: bool,
-                  mode: int) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-    """sim [Bi, Bc], attn_diag [Bc, lcap, S] (or empty), attn_mean [Bi, Bc, S] (or empty), stats (bf16 mode:
-    per-word scalars saved for the backward, else empty).
+                  mode: int, need_grad: bool = True) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """sim [Bi, Bc], attn_diag [Bc, lcap, S] (or empty), attn_mean [Bi, Bc, S] (or empty), state (uint8 [n]: what the
+    bf16 backward needs -- the fused training workspace followed by the 16-bit operand copies, or the per-word
+    scalars of the recompute path; empty in fp32 mode and when need_grad is false).
+
+    need_grad is the CALLER's statement that a backward will follow (the host wrappers pass
+    `torch.is_grad_enabled() and an input requires grad`): only then is the training forward run and its state
+    (41.7 GB at B = 512) allocated.
 
     ctx [Bi, D, S] fp32, words [Bc, D, Lw] fp32, cap_lens int32 [Bc] on the same device.
     Replaces the caption loop of gloria_loss.py:116-162 (attention_fn + cosine_similarity + aggregation).
@@ -141,7 +162,7 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
     sim = torch.empty((Bi, Bc), dtype=torch.float32, device=dev)
     diag = torch.empty((Bc, lcap, S) if want_diag else (0,), dtype=torch.float32, device=dev)
     mean = torch.empty((Bi, Bc, S) if want_mean else (0,), dtype=torch.float32, device=dev)
-    stats = torch.empty((0,), dtype=torch.float32, device=dev)
+    stats = torch.empty((0,), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         if mode == MODE_FP32:
             nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
@@ -156,34 +177,24 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
             if L.gloria_b200_tc_supported(D, S, lcap) != 0:
                 raise RuntimeError(f"bf16 tensor-core kernels need D % 128 == 0, S <= 384, cap_len <= 128; got "
                                    f"D={D} S={S} Lcap={lcap} (use set_precision('fp32'))")
-            need_grad = agg != AGG["max"] and (ctx.requires_grad or words.requires_grad or torch.is_grad_enabled())
+            need_grad = bool(need_grad) and agg != AGG["max"]
             if not need_grad and not want_mean and not want_diag and lcap <= 16 and Bc >= 2 and _PACKED_PROMPTS:
                 # forward-only scoring of short prompts (zero-shot): up to 8 captions share one word tile
                 _tc_packed_fwd(L, ctx, words, cap_lens, word_off, temp1, temp2, agg, eps, sim)
                 return sim, diag, mean, stats
-            packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
             fused = False
-            if want_mean:
-                # regulariser configs: one kernel gives sim + the word-mean attention of every pair (+ the per-word
-                # scalars); their backward is the recompute kernel, which takes d(attn_mean) next to dsim
-                nbytes = L.gloria_b200_tc_mean_workspace(Bi, Bc, D, S, lcap)
-                ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-                if need_grad:
-                    stats = torch.empty((Bi, Bc, 2, L.gloria_b200_tc_lpad(lcap)), dtype=torch.float32, device=dev)
-                rc = L.gloria_b200_tc_local_sim_fwd_mean(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(),
-                                                         packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
-                                                         cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg, eps,
-                                                         sim.data_ptr(), mean.data_ptr(), _ptr(stats), ws.data_ptr(),
-                                                         nbytes, _stream(ctx))
-                _lib.check(rc, "tc_local_sim_fwd_mean")
-                fused = True
-            elif need_grad and _FUSED_TRAIN:
-                # fused training forward: sim AND the backward's operand rows (for dsim = 1) in one kernel; the state
-                # tensor is the workspace the backward consumes.  Falls back to forward + recompute-backward when the
-                # workspace does not fit.
+            lpad = L.gloria_b200_tc_lpad(lcap)
+            if need_grad and not want_mean and _FUSED_TRAIN:
+                # fused training forward: sim AND the backward's operand rows (for dsim = 1) in one kernel.  The state
+                # tensor is [workspace | ctx_t | words_t]: the backward needs nothing else (no global hand-over cache).
+                # Falls back to forward + recompute-backward when the workspace does not fit.
                 nbytes = L.gloria_b200_tc_train_workspace(Bi, Bc, D, S, lcap)
-                if 0 < nbytes <= min(_TC_WS_BUDGET, int(_available_bytes(dev, nbytes) * 0.92)):
-                    stats = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+                n_ct, n_wt = _ctx_t_bytes(L, Bi, D, S), _words_t_bytes(L, Bc, D, lcap)
+                total = nbytes + n_ct + n_wt
+                if 0 < nbytes and total <= min(_TC_WS_BUDGET, int(_available_bytes(dev, total) * 0.92)):
+                    stats = torch.empty((total,), dtype=torch.uint8, device=dev)
+                    packed = tc_prepack(ctx, words, cap_lens, lcap, word_off, ctx_t=stats[nbytes:nbytes + n_ct],
+                                        words_t=stats[nbytes + n_ct:])
                     rc = L.gloria_b200_tc_local_sim_fwd_train(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(),
                                                               packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
                                                               cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg,
@@ -192,13 +203,28 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                     _lib.check(rc, "tc_local_sim_fwd_train")
                     fused = True
             if not fused:
-                if need_grad:
-                    stats = torch.empty((Bi, Bc, 2, L.gloria_b200_tc_lpad(lcap)), dtype=torch.float32, device=dev)
-                rc = L.gloria_b200_tc_local_sim_fwd(packed.ctx_h.data_ptr(), packed.ctx_n.data_ptr(),
-                                                    packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
-                                                    cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg, eps,
-                                                    sim.data_ptr(), _ptr(stats), _stream(ctx))
-                _lib.check(rc, "tc_local_sim_fwd")
+                packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
+                fstats = None
+                if need_grad:           # per-word scalars for the recompute backward, carried as bytes
+                    stats = torch.empty((Bi * Bc * 2 * lpad * 4,), dtype=torch.uint8, device=dev)
+                    fstats = stats.view(torch.float32)
+                if want_mean:
+                    # regulariser configs: one kernel gives sim + the word-mean attention of every pair (+ the per-word
+                    # scalars); their backward is the recompute kernel, which takes d(attn_mean) next to dsim
+                    nbytes = L.gloria_b200_tc_mean_workspace(Bi, Bc, D, S, lcap)
+                    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+                    rc = L.gloria_b200_tc_local_sim_fwd_mean(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(),
+                                                             packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
+                                                             cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg,
+                                                             eps, sim.data_ptr(), mean.data_ptr(), _ptr(fstats),
+                                                             ws.data_ptr(), nbytes, _stream(ctx))
+                    _lib.check(rc, "tc_local_sim_fwd_mean")
+                else:
+                    rc = L.gloria_b200_tc_local_sim_fwd(packed.ctx_h.data_ptr(), packed.ctx_n.data_ptr(),
+                                                        packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
+                                                        cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg, eps,
+                                                        sim.data_ptr(), _ptr(fstats), _stream(ctx))
+                    _lib.check(rc, "tc_local_sim_fwd")
             if want_diag:
                 if Bi != Bc:
                     raise RuntimeError(f"diagonal attention maps need as many images as captions, got {Bi} x {Bc}")
@@ -209,9 +235,15 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                                                      Lw, lcap, word_off, temp1, diag.data_ptr(), ws.data_ptr(),
                                                      nbytes, _stream(ctx))
                 _lib.check(rc, "diag_attn_fwd_f32")
-    if mode == MODE_BF16 and stats.numel() > 0:
-        _PACK_CACHE[stats.data_ptr()] = packed          # handed to the backward (same step), dropped there
     return sim, diag, mean, stats
+
+
+def _ctx_t_bytes(L, Bi, D, S) -> int:
+    return (Bi * L.gloria_b200_tc_sp(S) * D * 2 + 1023) // 1024 * 1024
+
+
+def _words_t_bytes(L, Bc, D, lcap) -> int:
+    return (Bc * L.gloria_b200_tc_lp(lcap) * D * 2 + 1023) // 1024 * 1024
 
 
 def _tc_packed_fwd(L, ctx, words, cap_lens, word_off, temp1, temp2, agg, eps, sim) -> None:
@@ -235,24 +267,19 @@ def _tc_packed_fwd(L, ctx, words, cap_lens, word_off, temp1, temp2, agg, eps, si
                                                      agg, eps, sim.data_ptr(), st), "tc_local_sim_fwd_packed")
 
 
-# forward -> backward hand-over of the prepacked 16-bit copies, keyed by the data pointer of the `stats` tensor the
-# autograd context saves (so the backward does not repeat the prepack).  Entries are popped by the backward; a
-# forward that is never differentiated leaves at most a few entries, evicted FIFO.
-_PACK_CACHE: "dict[int, Packed]" = {}
-
-
-def _pack_cache_trim(limit: int = 8) -> None:
-    while len(_PACK_CACHE) > limit:
-        _PACK_CACHE.pop(next(iter(_PACK_CACHE)))
-
-
 @local_sim_fwd.register_fake
-def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, want_mean, mode):
+def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, want_mean, mode, need_grad=True):
     Bi, D, S = ctx.shape
     Bc = words.shape[0]
+    if mode == MODE_BF16 and need_grad and agg != AGG["max"]:
+        # fused-training workspace or recompute statistics: which one is decided from free memory at run time, so the
+        # length of the byte state is a data-dependent size
+        n = torch.library.get_ctx().new_dynamic_size()
+        state = ctx.new_empty((n,), dtype=torch.uint8)
+    else:
+        state = ctx.new_empty((0,), dtype=torch.uint8)
     return (ctx.new_empty((Bi, Bc)), ctx.new_empty((Bc, lcap, S) if want_diag else (0,)),
-            ctx.new_empty((Bi, Bc, S) if want_mean else (0,)),
-            ctx.new_empty((Bi, Bc, 2, (lcap + 15) // 16 * 16) if mode == MODE_BF16 else (0,)))
+            ctx.new_empty((Bi, Bc, S) if want_mean else (0,)), state)
 
 
 @torch.library.custom_op("gloria_b200::local_sim_bwd", mutates_args=())
@@ -271,6 +298,8 @@ def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
     Bi, D, S = ctx.shape
     Bc, _, Lw = words.shape
     ctx, words, cap_lens = ctx.contiguous(), words.contiguous(), cap_lens.contiguous()
+    if stats is not None and stats.numel() == 0:
+        stats = None
     dsim = None if dsim is None else _f32c(dsim)
     d_diag = None if d_diag is None else _f32c(d_diag)
     d_mean = None if d_mean is None else _f32c(d_mean)
@@ -314,27 +343,29 @@ def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
 
 def tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp2, agg, eps, dsim, d_mean, d_ctx,
                      d_words, dctx_event=0) -> bool:
-    """bf16 tensor-core backward: prepack, then the fused recompute kernel + accumulation GEMMs behind the C ABI.
-    Returns True when `dctx_event` was recorded by the library (fused training path)."""
+    """bf16 tensor-core backward behind the C ABI: from the fused training state, or by recomputation (prepack, fused
+    recompute kernel, accumulation GEMMs).  Returns True when `dctx_event` was recorded by the library."""
     Bi, D, S = ctx.shape
     Bc, _, Lw = words.shape
     have = stats is not None and stats.numel() > 0
-    packed = _PACK_CACHE.pop(stats.data_ptr(), None) if have else None
-    _pack_cache_trim()
-    if packed is None or packed.ctx_h.shape[0] != Bi or packed.words_h.shape[0] != Bc:
-        packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
-    if have and stats.dtype == torch.uint8:
-        # state of the fused training forward: scale by dsim + accumulation GEMMs, nothing is recomputed
-        if getattr(stats, "_gloria_consumed", False):
-            raise RuntimeError("gloria_b200: the fused training state was already consumed by a backward pass "
-                               "(set GLORIA_B200_FUSED_TRAIN=0 to differentiate the same forward twice)")
-        rc = L.gloria_b200_tc_local_sim_bwd_train_ev(packed.ctx_t.data_ptr(), packed.words_t.data_ptr(),
+    lpad = L.gloria_b200_tc_lpad(lcap)
+    n_stats = Bi * Bc * 2 * lpad * 4
+    if have and stats.numel() != n_stats:
+        # state of the fused training forward = [workspace | ctx_t | words_t]: scale by dsim + accumulation GEMMs, nothing
+        # is recomputed or re-packed.  (A second backward over the same state is caught on the device: the library
+        # poisons its result with NaN rather than scaling the operands twice.)
+        nbytes = L.gloria_b200_tc_train_workspace(Bi, Bc, D, S, lcap)
+        n_ct = _ctx_t_bytes(L, Bi, D, S)
+        if stats.numel() != nbytes + n_ct + _words_t_bytes(L, Bc, D, lcap):
+            raise RuntimeError(f"gloria_b200: unexpected training-state size {stats.numel()}")
+        rc = L.gloria_b200_tc_local_sim_bwd_train_ev(stats[nbytes:].data_ptr(), stats[nbytes + n_ct:].data_ptr(),
                                                      cap_lens.data_ptr(), Bi, Bc, D, S, Lw, lcap, word_off,
                                                      dsim.data_ptr(), d_ctx.data_ptr(), d_words.data_ptr(),
-                                                     stats.data_ptr(), stats.numel(), dctx_event or None, _stream(ctx))
+                                                     stats.data_ptr(), nbytes, dctx_event or None, _stream(ctx))
         _lib.check(rc, "tc_local_sim_bwd_train")
-        stats._gloria_consumed = True
         return bool(dctx_event)
+    packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
+    fstats = stats.view(torch.float32) if have else None
     free, _ = torch.cuda.mem_get_info(ctx.device)
     budget = min(_TC_WS_BUDGET, int(free * 0.9) + torch.cuda.memory_reserved(ctx.device)
                  - torch.cuda.memory_allocated(ctx.device))
@@ -342,7 +373,7 @@ def tc_local_sim_bwd(L, ctx, words, cap_lens, stats, lcap, word_off, temp1, temp
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=ctx.device)
     rc = L.gloria_b200_tc_local_sim_bwd(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(), packed.ctx_n.data_ptr(),
                                         packed.words_h.data_ptr(), packed.words_t.data_ptr(), packed.wnorm.data_ptr(),
-                                        cap_lens.data_ptr(), stats.data_ptr() if have else None,
+                                        cap_lens.data_ptr(), fstats.data_ptr() if have else None,
                                         Bi, Bc, D, S, Lw, lcap, word_off, temp1, temp2, agg, eps, dsim.data_ptr(),
                                         _ptr(d_mean), d_ctx.data_ptr(), d_words.data_ptr(), ws.data_ptr(), nbytes,
                                         _stream(ctx))
@@ -355,8 +386,28 @@ def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim, d_diag
     return torch.empty_like(ctx), torch.empty_like(words)
 
 
+_BWD_MUTATES = os.environ.get("GLORIA_B200_BWD_GEMM", "cublas") not in ("inflight", "0")
+
+
+def check_state_unconsumed(node, ctx: Tensor, words: Tensor, lcap: int, stats: Optional[Tensor], mode: int) -> None:
+    """The fused training backward scales its operand state in place (unless GLORIA_B200_BWD_GEMM=inflight), so a second
+    backward through the same forward (retain_graph=True) must not run: the flag lives on the autograd node of that
+    forward -- per graph, nothing process-wide.  (The library additionally poisons such a result with NaN on the
+    device, for callers of the C ABI.)"""
+    if mode != MODE_BF16 or stats is None or stats.numel() == 0 or not _BWD_MUTATES:
+        return
+    lpad = (lcap + 15) // 16 * 16
+    if stats.numel() == ctx.shape[0] * words.shape[0] * 2 * lpad * 4:
+        return                                        # per-word statistics of the recompute path: re-usable
+    if getattr(node, "_gloria_consumed", False):
+        raise RuntimeError("gloria_b200: the fused training state was already consumed by a backward pass (set "
+                           "GLORIA_B200_FUSED_TRAIN=0 or GLORIA_B200_BWD_GEMM=inflight to differentiate the same "
+                           "forward twice)")
+    node._gloria_consumed = True
+
+
 def _local_setup(ctx, inputs, output):
-    feats, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, want_mean, mode = inputs
+    feats, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, want_mean, mode = inputs[:12]
     ctx.save_for_backward(feats, words, cap_lens, output[3])
     ctx.args = (lcap, word_off, temp1, temp2, agg, eps, mode)
     ctx.set_materialize_grads(False)
@@ -369,9 +420,12 @@ def _local_backward(c, dsim, d_diag, d_mean, d_stats):
         d_diag = None
     if d_mean is not None and d_mean.numel() == 0:
         d_mean = None
+    if not torch.compiler.is_compiling():            # (host-side guard; the traced backward keeps the device-side one)
+        check_state_unconsumed(c, ctx, words, lcap, stats, mode)
+    # the state goes in as it is (its length is data dependent under tracing); the op treats an empty one as absent
     d_ctx, d_words = local_sim_bwd(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim, d_diag,
-                                   d_mean, stats if stats.numel() > 0 else None, mode)
-    return d_ctx, d_words, None, None, None, None, None, None, None, None, None, None
+                                   d_mean, stats, mode)
+    return d_ctx, d_words, None, None, None, None, None, None, None, None, None, None, None
 
 
 local_sim_fwd.register_autograd(_local_backward, setup_context=_local_setup)
@@ -708,9 +762,11 @@ row_cosine_fwd.register_autograd(_rc_backward, setup_context=_rc_setup)
 _DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 
 
-def word_ranges(caption_ids: Tensor, is_continuation: Tensor, sep_id: int) -> Tuple[Tensor, Tensor, Tensor]:
+def word_ranges(caption_ids: Tensor, is_continuation: Tensor, sep_id: int, is_bracket: Optional[Tensor] = None):
     """caption_ids [B, T] int64, is_continuation [vocab] uint8 (1 = the entry starts with "##") ->
-    word_range [B, T, 2] int32, token_word [B, T] int32, n_words [B] int32 (all on the device, no sync)."""
+    word_range [B, T, 2] int32, token_word [B, T] int32, n_words [B] int32 (all on the device, no sync).
+    With is_bracket [vocab] uint8 (1 = the entry's text starts with '[') a fourth tensor follows: cap_lens [B] int32,
+    the caption lengths of gloria_model.py:107-109."""
     _need_cuda(caption_ids, is_continuation)
     L = _lib.lib()
     ids = caption_ids.to(torch.int64).contiguous()
@@ -720,10 +776,17 @@ def word_ranges(caption_ids: Tensor, is_continuation: Tensor, sep_id: int) -> Tu
     tw = torch.empty((B, T), dtype=torch.int32, device=dev)
     nw = torch.empty((B,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        rc = L.gloria_b200_word_ranges(ids.data_ptr(), is_continuation.data_ptr(), is_continuation.numel(), int(sep_id), B,
-                                       T, wr.data_ptr(), tw.data_ptr(), nw.data_ptr(), _stream(ids))
-    _lib.check(rc, "word_ranges")
-    return wr, tw, nw
+        if is_bracket is None:
+            rc = L.gloria_b200_word_ranges(ids.data_ptr(), is_continuation.data_ptr(), is_continuation.numel(),
+                                           int(sep_id), B, T, wr.data_ptr(), tw.data_ptr(), nw.data_ptr(), _stream(ids))
+            _lib.check(rc, "word_ranges")
+            return wr, tw, nw
+        cl = torch.empty((B,), dtype=torch.int32, device=dev)
+        rc = L.gloria_b200_word_ranges_cap_lens(ids.data_ptr(), is_continuation.data_ptr(), is_bracket.data_ptr(),
+                                                is_continuation.numel(), int(sep_id), B, T, wr.data_ptr(), tw.data_ptr(),
+                                                nw.data_ptr(), cl.data_ptr(), _stream(ids))
+    _lib.check(rc, "word_ranges_cap_lens")
+    return wr, tw, nw, cl
 
 
 @torch.library.custom_op("gloria_b200::aggregate_tokens", mutates_args=())

@@ -13,13 +13,15 @@ and the aggregation is one streaming kernel with autograd (`ops.aggregate_tokens
 """
 from __future__ import annotations
 
+from collections.abc import Sequence as _SequenceABC
 from typing import Dict, List, Sequence, Tuple
 
 import torch
 
-from . import ops
+from . import gloria_loss, ops
 
-__all__ = ["aggregate_tokens", "AggregateTokensMixin", "patch_bert_encoder", "cap_lens_from_sents", "VocabTable"]
+__all__ = ["aggregate_tokens", "AggregateTokensMixin", "patch_bert_encoder", "cap_lens_from_sents", "VocabTable",
+           "LazySentences"]
 
 
 class VocabTable:
@@ -39,16 +41,29 @@ class VocabTable:
         # host tables for the word strings: the piece text ("##" stripped) and the continuation flag per id
         self.piece = [""] * self.size
         self.cont = [False] * self.size
+        brk = torch.zeros(self.size, dtype=torch.uint8)
         for i, w in idxtoword.items():
             c = w.startswith("##")
             self.cont[i] = c
             self.piece[i] = w[2:] if c else w
+            if self.piece[i].startswith("["):
+                brk[i] = 1
+        self._brk_cpu = brk
+        self._brk = {}
 
     def is_continuation(self, device: torch.device) -> torch.Tensor:
         key = str(device)
         if key not in self._cont:
             self._cont[key] = self._cont_cpu.to(device)
         return self._cont[key]
+
+    def is_bracket(self, device: torch.device) -> torch.Tensor:
+        """1 where a word that STARTS with this entry starts with '[' ([CLS], [SEP], [PAD], ...): what the caption
+        length of gloria_model.py:107-109 skips."""
+        key = str(device)
+        if key not in self._brk:
+            self._brk[key] = self._brk_cpu.to(device)
+        return self._brk[key]
 
 
 def _sentences(ids: Sequence[Sequence[int]], vocab) -> List[List[str]]:
@@ -79,21 +94,58 @@ def _sentences(ids: Sequence[Sequence[int]], vocab) -> List[List[str]]:
     return out
 
 
+class LazySentences(_SequenceABC):
+    """The `sentences` BertEncoder.aggregate_tokens returns (a list of word-string lists), built only when somebody
+    reads them (logging, attention plots): the training step needs just the caption lengths, and those arrive as
+    `cap_lens` -- a `gloria_loss.DeviceCapLens` computed by the word-boundary kernel -- so a step involves no read-back
+    of the token ids and no Python string work at all (5.9 ms of host time per step at B = 512 before)."""
+
+    def __init__(self, caption_ids: torch.Tensor, vocab: "VocabTable", cap_lens: torch.Tensor, n_words: torch.Tensor):
+        self._ids, self._vocab, self._built = caption_ids, vocab, None
+        self.cap_lens = gloria_loss.DeviceCapLens(cap_lens)
+        self.n_words = n_words
+
+    def _materialise(self) -> List[List[str]]:
+        if self._built is None:
+            self._built = _sentences(self._ids.tolist(), self._vocab)   # one read-back instead of B x T .item() syncs
+        return self._built
+
+    def __len__(self):
+        return self._ids.shape[0]
+
+    def __getitem__(self, i):
+        return self._materialise()[i]
+
+    def __iter__(self):
+        return iter(self._materialise())
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __repr__(self):
+        return repr(self._materialise())
+
+
 def aggregate_tokens(embeddings: torch.Tensor, caption_ids: torch.Tensor, vocab: VocabTable
-                     ) -> Tuple[torch.Tensor, List[List[str]]]:
+                     ) -> Tuple[torch.Tensor, "LazySentences"]:
     """embeddings [B, layers, T, D] (CUDA; fp32 / fp16 / bf16), caption_ids [B, T] -> (aggregated [B, layers, T, D],
-    sentences) exactly as BertEncoder.aggregate_tokens returns them; differentiable w.r.t. the embeddings."""
+    sentences) as BertEncoder.aggregate_tokens returns them; differentiable w.r.t. the embeddings.  `sentences` behaves
+    like the reference's list of word lists but is built lazily, and carries `.cap_lens` for the loss (see
+    LazySentences)."""
     if not embeddings.is_cuda:
         raise RuntimeError("gloria_b200 runs on CUDA tensors only (sm_100a); there is no CPU fallback")
-    ids_dev = caption_ids.to(embeddings.device, non_blocking=True)
-    wr, tw, _ = ops.word_ranges(ids_dev, vocab.is_continuation(embeddings.device), vocab.sep_id)
+    dev = embeddings.device
+    ids_dev = caption_ids.to(dev, non_blocking=True)
+    wr, tw, nw, cl = ops.word_ranges(ids_dev, vocab.is_continuation(dev), vocab.sep_id, vocab.is_bracket(dev))
     agg = ops.aggregate_tokens(embeddings, wr, tw)
-    sentences = _sentences(caption_ids.tolist(), vocab)                   # one read-back instead of B x T .item() syncs
-    return agg, sentences
+    return agg, LazySentences(caption_ids, vocab, cl, nw)
 
 
-def cap_lens_from_sents(sents) -> List[int]:
-    """gloria_model.py:107-109: words not starting with '[' plus one."""
+def cap_lens_from_sents(sents):
+    """gloria_model.py:107-109: words not starting with '[' plus one (the device tensor of a LazySentences as it is)."""
+    dev = getattr(sents, "cap_lens", None)
+    if isinstance(dev, gloria_loss.DeviceCapLens):
+        return dev
     return [len([w for w in sent if not w.startswith("[")]) + 1 for sent in sents]
 
 

@@ -306,6 +306,13 @@ int gloria_b200_ce_bidir_bwd(const float* m, int B, float scale, const float* ro
 int gloria_b200_word_ranges(const long long* caption_ids, const unsigned char* is_continuation, int vocab,
                             long long sep_id, int B, int T, int32_t* word_range, int32_t* token_word,
                             int32_t* n_words, void* stream);
+/* Same, plus the caption lengths the loss derives from the word strings (gloria_model.py:107-109: words that do not
+ * start with '[' plus one) computed on the device: is_bracket [vocab] = 1 where the entry's text ("##" stripped) starts
+ * with '['.  cap_lens [B] feeds local_loss / calc_loss without a host round trip. */
+int gloria_b200_word_ranges_cap_lens(const long long* caption_ids, const unsigned char* is_continuation,
+                                     const unsigned char* is_bracket, int vocab, long long sep_id, int B, int T,
+                                     int32_t* word_range, int32_t* token_word, int32_t* n_words, int32_t* cap_lens,
+                                     void* stream);
 int gloria_b200_aggregate_tokens_fwd(const void* embeddings, int dtype, const int32_t* word_range, int B, int layers,
                                      int T, int D, void* out, void* stream);
 int gloria_b200_aggregate_tokens_bwd(const void* d_out, int dtype, const int32_t* token_word, int B, int layers,

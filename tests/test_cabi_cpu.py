@@ -156,3 +156,26 @@ def test_new_entry_points_validate_arguments(libpath):
         text_model.aggregate_tokens(torch.randn(1, 2, 4, 8), torch.tensor([[1, 3, 4, 2]]), table)
     with pytest.raises(RuntimeError):
         zero_shot.get_similarities(object(), torch.zeros(1), {"caption_ids": None}, similarity_type="cosine")
+
+
+def test_lazy_containers_host_logic():
+    """LazySentences / LazyAttnMaps / DeviceCapLens are plain host containers over tensors: their list behaviour is
+    testable on CPU tensors (the kernels that fill them are covered by the `-m gpu` tests)."""
+    import torch
+    from gloria_nlp_project_b200 import gloria_loss, text_model
+    vocab = ["[PAD]", "[CLS]", "[SEP]", "heart", "##s", "is", "[UNK]", "normal"]
+    table = text_model.VocabTable(dict(enumerate(vocab)))
+    assert table._brk_cpu.tolist() == [1, 1, 1, 0, 0, 0, 1, 0]
+    ids = torch.tensor([[1, 3, 4, 5, 7, 2, 0, 0], [1, 6, 5, 2, 0, 0, 0, 0]])
+    ref = text_model._sentences(ids.tolist(), table)
+    lens = [len([w for w in s if not w.startswith("[")]) + 1 for s in ref]
+    lazy = text_model.LazySentences(ids, table, torch.tensor(lens, dtype=torch.int32), torch.tensor([5, 4]))
+    assert lazy._built is None and len(lazy) == 2
+    assert text_model.cap_lens_from_sents(lazy) is lazy.cap_lens and lazy._built is None
+    assert lazy == ref and ref == lazy and lazy[0][1] == "hearts" and [len(s) for s in lazy] == [8, 8]
+    assert lazy.cap_lens.tolist() == lens == [4, 2]
+    diag = torch.arange(2 * 6 * 5, dtype=torch.float32).reshape(2, 6, 5)
+    maps = gloria_loss.LazyAttnMaps(diag, lazy.cap_lens, 1, 2, 2)
+    assert len(maps) == 2 and maps[0].shape == (1, 4, 2, 2) and maps[-1].shape == (1, 2, 2, 2)
+    assert torch.equal(maps[1], diag[1:2, :2, 1:].reshape(1, 2, 2, 2))
+    assert [m.shape[1] for m in maps] == [4, 2]

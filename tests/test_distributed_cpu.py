@@ -115,3 +115,35 @@ def test_part_major_rows():
             for r in range(world):
                 blk = gathered[p * world * m + r * m: p * world * m + (r + 1) * m]
                 assert torch.equal(blk, own[r][p * m:(p + 1) * m])
+
+
+def _agree_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gloria_nlp_project_b200 import distributed as D
+        # rank 0: short captions, workspace fits;  rank 1: a 97-word caption and (say) no room for the workspace
+        out = [D._agree(torch.device("cpu"), 50 if rank == 0 else 97, rank == 0, None),
+               D._agree(torch.device("cpu"), 30 + rank, True, None)]
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_ranks_agree_on_the_collective_schedule():
+    """The pipelined (P-part) and the single-gather paths issue different collectives, so the choice must not depend
+    on rank-local state: one rank that cannot take the pipelined path moves every rank to the fallback, and the padded
+    caption length is the maximum over ranks."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_agree_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0] == res[1] == [(97, False), (31, True)]

@@ -124,10 +124,23 @@ def test_gradients_tensor_core_backward(gl, B, seed, scale, lens, kw, exact):
     d_img, d_txt = O.local_loss_bwd(img_l.astype(np.float64), txt_l.astype(np.float64), cl, g0=1.0, g1=0.7, **kw)
     e_img, e_txt = relerr(img.grad, d_img), relerr(txt.grad, d_txt)
     print(f"bf16 backward B={B} scale={scale}: d_img rel err {e_img:.3e}, d_txt rel err {e_txt:.3e}")
-    # raw (not 16-bit-representable) unit-variance features: the gate is the inherent fp16 operand rounding of the
-    # score GEMM (~1 %, quantified in test_unit_variance_operand_rounding), hence 2e-2 there and 1e-2 everywhere else
-    tol = 2 * GRAD_TOL if (scale == 1.0 and not exact) else GRAD_TOL
-    assert e_img < tol and e_txt < tol
+    if scale == 1.0 and not exact:
+        # Raw (not 16-bit-representable) unit-variance features: the fp16 operand rounding of the score GEMM is amplified
+        # by the word softmax (test_unit_variance_operand_rounding).  The gate is the REAL reference's own behaviour on
+        # these very inputs: tests/golden/amp_unit.json (oracle/make_golden_amp.py) holds how far its fp16-autocast
+        # gradients are from its fp32 gradients (2.0 - 2.7 %); this mode must be at least that close to fp32, and
+        # within 1.5e-2 in any case.
+        import json
+        import os
+        amp = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "amp_unit.json")))["cases"][f"B{B}"]
+        assert amp["seed"] == seed and amp["cap_lens"] == [int(v) for v in cl]
+        assert abs(float(np.float64(img_l).sum() + np.float64(txt_l).sum()) - amp["input_checksum"]) < 1e-6
+        print(f"   reference under fp16 autocast vs its fp32: d_img {amp['amp_d_img_rel_err']:.3e}, "
+              f"d_txt {amp['amp_d_txt_rel_err']:.3e}")
+        assert e_img <= max(GRAD_TOL, amp["amp_d_img_rel_err"]) and e_txt <= max(GRAD_TOL, amp["amp_d_txt_rel_err"])
+        assert e_img < 1.5 * GRAD_TOL and e_txt < 1.5 * GRAD_TOL
+    else:
+        assert e_img < GRAD_TOL and e_txt < GRAD_TOL
     for i, L in enumerate(cl):                                   # padded word columns: exactly zero
         assert torch.all(txt.grad[i, :, L:] == 0)
 

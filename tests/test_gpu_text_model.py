@@ -27,6 +27,8 @@ def test_aggregate_tokens_golden(golden_dir):
     assert agg.shape == emb.shape
     assert relerr(agg, g["agg"]) < 1e-6
     assert sents == [[str(w) for w in s] for s in g["sentences"]]
+    assert text_model.cap_lens_from_sents(sents).tolist() == \
+        [len([w for w in s if not str(w).startswith("[")]) + 1 for s in g["sentences"]]
     # backward = gather: compare with autograd through a dense torch restatement of the same sums
     wgt = torch.randn(agg.shape, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
     (agg * wgt).sum().backward()
@@ -82,5 +84,8 @@ def test_aggregate_tokens_random_streams(dtype, tol):
     agg, sents = text_model.aggregate_tokens(emb_t, torch.tensor(ids), table)        # ids on the host, as the loader has them
     ref, ref_sents = O.aggregate_tokens(emb_t.float().cpu().numpy().astype(np.float64), ids, idxtoword)
     assert relerr(agg.float(), ref) < tol
+    # caption lengths straight from the word-boundary kernel (no strings involved) == gloria_model.py:107-109 on the strings
+    dev_lens = text_model.cap_lens_from_sents(sents)
+    assert dev_lens.tensor.is_cuda and sents._built is None            # nothing was materialised on the host so far
+    assert dev_lens.tolist() == [len([w for w in s if not w.startswith("[")]) + 1 for s in ref_sents]
     assert sents == ref_sents
-    assert text_model.cap_lens_from_sents(sents) == [len([w for w in s if not w.startswith("[")]) + 1 for s in ref_sents]
