@@ -19,6 +19,7 @@ _i, _f, _p, _z = C.c_int, C.c_float, C.c_void_p, C.c_size_t
 # name -> (restype, argtypes); mirrors include/gloria_b200.h one to one
 PROTOTYPES = {
     "gloria_b200_version": (_i, []),
+    "gloria_b200_build_id": (C.c_char_p, []),
     "gloria_b200_last_error": (C.c_char_p, []),
     "gloria_b200_launch_count": (C.c_longlong, [_i]),
     "gloria_b200_set_timer_events": (_i, [_i, _p, _p]),
@@ -91,6 +92,13 @@ def lib() -> C.CDLL:
                 for name, (res, args) in PROTOTYPES.items():
                     fn = getattr(h, name)      # AttributeError if a declared symbol is not exported
                     fn.restype, fn.argtypes = res, args
+                if "GLORIA_B200_LIB" not in os.environ and os.environ.get("GLORIA_B200_SKIP_ID_CHECK") != "1":
+                    from .build import source_id
+                    built, now = h.gloria_b200_build_id().decode(), source_id()
+                    if built != now:
+                        raise RuntimeError(
+                            f"{path} was built from other sources (library id {built}, sources on disk {now}): rebuild "
+                            "with `python -c 'import __graft_entry__ as g; g.build()'`")
                 _lib = h
     return _lib
 

@@ -14,12 +14,28 @@ NVCC_FLAGS = [
 ]
 
 
+ID_PATH = LIB_PATH + ".id"
+
+
+def source_id() -> str:
+    """sha256 over every file the library is compiled from (csrc/* and the public header), in name order.  It is baked
+    into the library (`gloria_b200_build_id()`), so a loaded .so can be tied to the sources beside it."""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h")))
+    files.append(os.path.join(PKG_DIR, "..", "include", "gloria_b200.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:24]
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(ID_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(PKG_DIR, "..", "include", "gloria_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    with open(ID_PATH) as fh:
+        return fh.read().strip() != source_id()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -28,7 +44,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = os.environ.get("GLORIA_B200_NVCC_EXTRA", "").split()      # e.g. -DGLORIA_PHASE_CLOCKS (development)
-    cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-lcublas"], *extra, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES], "-lcublas"]
+    sid = source_id()
+    cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-lcublas"], *extra, f'-DGLORIA_BUILD_ID="{sid}"', "-o", LIB_PATH,
+           *[os.path.join(CSRC, s) for s in SOURCES], "-lcublas"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -37,6 +55,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+    with open(ID_PATH, "w") as fh:
+        fh.write(sid + "\n")
     return LIB_PATH
 
 

@@ -50,7 +50,14 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 }  // namespace gloria
 
-extern "C" int gloria_b200_version(void) { return 100; }
+extern "C" int gloria_b200_version(void) { return 200; }
+
+#ifndef GLORIA_BUILD_ID
+#define GLORIA_BUILD_ID "unknown"
+#endif
+// sha256 prefix of the sources this binary was compiled from (build.py: source_id()); _lib.py compares it with the
+// sources on disk, so a stale prebuilt library is refused instead of silently used
+extern "C" const char* gloria_b200_build_id(void) { return GLORIA_BUILD_ID; }
 
 extern "C" const char* gloria_b200_last_error(void) { return gloria::err_buf(); }
 

@@ -45,6 +45,10 @@ typedef enum gloria_status {
 #define GLORIA_AGG_MAX 2
 
 int gloria_b200_version(void);
+/* sha256 prefix (24 hex digits) of the sources this binary was built from: csrc/* and this header, as hashed by
+ * gloria_nlp_project_b200/build.py::source_id().  The Python loader refuses a library whose id differs from the
+ * sources beside it. */
+const char* gloria_b200_build_id(void);
 const char* gloria_b200_last_error(void);
 /* number of kernels launched by this thread's calls since the last reset (bench.py's gpu_launches) */
 long long gloria_b200_launch_count(int reset);
