@@ -1246,14 +1246,17 @@ extern "C" size_t gloria_b200_tc_train_workspace(int Bi, int Bc, int D, int S, i
 }
 
 // Image range [j0, j0 + nj) of a (Bi x Bc) training forward: the workspace is laid out for all Bi images, this call
-// fills the rows of the range (X^T / E^T rows, f, gamma, Gram matrices, sim rows).  ctx_h / ctx_t / sim are the base
-// pointers of the full arrays.  A caption-sharded caller launches one part per all_gather chunk (distributed.py).
-extern "C" int gloria_b200_tc_local_sim_fwd_train_part(const void* ctx_h, const void* ctx_t, const void* words_h,
-                                                       const float* wnorm, const int32_t* cap_lens, int Bi, int j0,
-                                                       int nj, int Bc, int D, int S, int Lcap, float temp1, float temp2,
-                                                       int agg, float eps, float* sim, void* workspace,
-                                                       size_t workspace_bytes, void* stream) {
-  GLORIA_CHECK_ARG(ctx_h && ctx_t && words_h && wnorm && cap_lens && sim && workspace, "null pointer");
+// fills the rows of the range (X^T / E^T rows, f, gamma, Gram matrices, sim rows).  range_h / range_t point at the packed
+// copies of the FIRST image of the range (they need not live in the arrays of the other images: a caption-sharded
+// caller runs its own images from a private buffer while the gather of the others is in flight); sim is the base of
+// the full [Bi, Bc] matrix.  flags: 1 = record the bench timer's start before, 2 = its stop after the launch,
+// 4 = this is the first launch of a forward (resets the state's consumed flag).
+extern "C" int gloria_b200_tc_local_sim_fwd_train_range(const void* range_h, const void* range_t, const void* words_h,
+                                                        const float* wnorm, const int32_t* cap_lens, int Bi, int j0,
+                                                        int nj, int Bc, int D, int S, int Lcap, float temp1, float temp2,
+                                                        int agg, float eps, float* sim, void* workspace,
+                                                        size_t workspace_bytes, int flags, void* stream) {
+  GLORIA_CHECK_ARG(range_h && range_t && words_h && wnorm && cap_lens && sim && workspace, "null pointer");
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0, "bad batch sizes %d x %d", Bi, Bc);
   GLORIA_CHECK_ARG(j0 >= 0 && nj > 0 && j0 + nj <= Bi, "bad image range [%d, %d) of %d", j0, j0 + nj, Bi);
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
@@ -1266,8 +1269,8 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train_part(const void* ctx_h, const 
   char* ws = (char*)workspace;
   const int R1 = Bc * lp;
   // everything below is addressed relative to image j0
-  const __half* rh = (const __half*)ctx_h + (size_t)j0 * Spad * D;
-  const __nv_bfloat16* rt_ = (const __nv_bfloat16*)ctx_t + (size_t)j0 * sp * D;
+  const __half* rh = (const __half*)range_h;
+  const __nv_bfloat16* rt_ = (const __nv_bfloat16*)range_t;
   __nv_bfloat16* gram = (__nv_bfloat16*)(ws + pl.off_gram) + (size_t)j0 * Spad * Spad;
   __nv_bfloat16* xt = (__nv_bfloat16*)(ws + pl.off_x) + (size_t)j0 * sp * R1;
   __nv_bfloat16* et = (__nv_bfloat16*)(ws + pl.off_e) + (size_t)j0 * sp * R1;
@@ -1276,7 +1279,7 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train_part(const void* ctx_h, const 
   GLORIA_CUBLAS(cublasSetStream(h, st));
   GLORIA_CUBLAS(cublasSetWorkspace(h, ws + pl.off_cublas, bw::CUBLAS_WS));
   int rc;
-  if (j0 == 0) GLORIA_CUDA(cudaMemsetAsync(ws + pl.off_flag, 0, 1024, st));       // fresh state: not consumed yet
+  if (flags & 4) GLORIA_CUDA(cudaMemsetAsync(ws + pl.off_flag, 0, 1024, st));       // fresh state: not consumed yet
   if ((rc = bw::gram_matrices(h, rt_, gram, nj, D, S, Spad, sp, st))) return rc;
   CUtensorMap rt, wt, gm, em;
   if ((rc = make_map(&rt, rh, (uint64_t)D, (uint64_t)nj * Spad, TILE))) return rc;
@@ -1296,9 +1299,25 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train_part(const void* ctx_h, const 
   p.Bi = nj; p.Bc = Bc; p.i0 = 0; p.nc = Bc; p.D = D; p.S = S; p.NT = Spad / TILE; p.lp = lp; p.sp = sp;
   p.t1 = temp1; p.t1_log2e = temp1 * 1.4426950408889634f; p.t2 = temp2; p.eps = eps; p.agg = agg;
   p.dbg = (long long*)g_phase_clock_buffer;
-  p.timer_first = j0 == 0; p.timer_last = j0 + nj == Bi;
+  p.timer_first = (flags & 1) != 0; p.timer_last = (flags & 2) != 0;
   p.l2_hints = bw::l2_hints_mode();
   return bw::launch_pair_lpad<true>(lpad, rt, wt, gm, em, p, sms, st);
+}
+
+// Same with ctx_h / ctx_t given as the bases of the full arrays; the timer brackets the first to the last range.
+extern "C" int gloria_b200_tc_local_sim_fwd_train_part(const void* ctx_h, const void* ctx_t, const void* words_h,
+                                                       const float* wnorm, const int32_t* cap_lens, int Bi, int j0,
+                                                       int nj, int Bc, int D, int S, int Lcap, float temp1, float temp2,
+                                                       int agg, float eps, float* sim, void* workspace,
+                                                       size_t workspace_bytes, void* stream) {
+  GLORIA_CHECK_ARG(ctx_h && ctx_t, "null pointer");
+  GLORIA_CHECK_ARG(j0 >= 0 && nj > 0 && j0 + nj <= Bi, "bad image range [%d, %d) of %d", j0, j0 + nj, Bi);
+  const int Spad = gloria_b200_tc_spad(S), sp = gloria_b200_tc_sp(S);
+  const int flags = (j0 == 0 ? 1 | 4 : 0) | (j0 + nj == Bi ? 2 : 0);
+  return gloria_b200_tc_local_sim_fwd_train_range((const __half*)ctx_h + (size_t)j0 * Spad * D,
+                                                  (const __nv_bfloat16*)ctx_t + (size_t)j0 * sp * D, words_h, wnorm, cap_lens,
+                                                  Bi, j0, nj, Bc, D, S, Lcap, temp1, temp2, agg, eps, sim, workspace,
+                                                  workspace_bytes, flags, stream);
 }
 
 extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void* ctx_t, const void* words_h,

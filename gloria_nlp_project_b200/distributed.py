@@ -146,8 +146,9 @@ class _ShardedLocalSimParts(torch.autograd.Function):
 
     Each rank's n images are cut into P parts; part p of every rank is all_gathered into one contiguous block, so the
     gathered batch is *part-major* ([p][rank][n/P]; a fixed permutation of the natural image order that is undone on
-    the rows of sim).  Forward: gather(p+1) runs on a side stream while part p is packed and its fused training
-    kernel runs.  Backward: the library finishes d_ctx part by part and records an event per part; the
+    the rows of sim).  Forward: each rank packs its own images and the 16-bit copies are gathered on a side stream
+    while the fused training kernel already runs on the rank's own images (from the local pack); the other ranks' images
+    follow part by part as their gathers land.  Backward: the library finishes d_ctx part by part and records an event per part; the
     reduce_scatter of part p (side stream) overlaps the GEMMs of part p+1 and the caption-side GEMM.
     Nothing but the 16-bit packed copies and the operand workspace is kept for the backward."""
 
@@ -167,43 +168,52 @@ class _ShardedLocalSimParts(torch.autograd.Function):
         with torch.cuda.device(dev):
             spad, sp = L.gloria_b200_tc_spad(S), L.gloria_b200_tc_sp(S)
             lpad, lp = L.gloria_b200_tc_lpad(lcap), L.gloria_b200_tc_lp(lcap)
-            img_all = x.new_empty((B, D, S))                      # part-major
-            start = torch.cuda.Event()
-            start.record(main)
-            gathered = []
-            for p in range(P):                                    # gather 0 on the main stream, the rest on the side stream
-                st = main if p == 0 else side
-                if p == 1:
-                    side.wait_event(start)
-                with torch.cuda.stream(st):
-                    dist.all_gather_into_tensor(img_all[p * world * m:(p + 1) * world * m], x[p * m:(p + 1) * m],
-                                                group=group)
-                    ev = torch.cuda.Event()
-                    ev.record(st)
-                    gathered.append(ev)
+            s = _stream(x)
+            # 1. every rank packs ITS OWN images only (before: all B images on every rank) ...
+            own_h = torch.empty((n, spad, D), dtype=torch.float16, device=dev)
+            own_t = torch.empty((n, sp, D), dtype=torch.bfloat16, device=dev)
+            _lib.check(L.gloria_b200_tc_prepack_ctx(x.data_ptr(), n, D, S, own_h.data_ptr(), own_t.data_ptr(), None, s),
+                       "tc_prepack_ctx")
+            packed = torch.cuda.Event()
+            packed.record(main)
+            # 2. ... and the 16-bit copies are what is gathered (the same bytes as the fp32 features), part by part on the
+            # side stream, into the part-major arrays the kernels and the backward read
             ctx_h = torch.empty((B, spad, D), dtype=torch.float16, device=dev)
             ctx_t = torch.empty((B, sp, D), dtype=torch.bfloat16, device=dev)
+            nj = world * m
+            gathered = []
+            side.wait_event(packed)
+            with torch.cuda.stream(side):
+                for p in range(P):
+                    dist.all_gather_into_tensor(ctx_h[p * nj:(p + 1) * nj], own_h[p * m:(p + 1) * m], group=group)
+                    dist.all_gather_into_tensor(ctx_t[p * nj:(p + 1) * nj], own_t[p * m:(p + 1) * m], group=group)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    gathered.append(ev)
             words_h = torch.empty((Bc, lpad, D), dtype=torch.float16, device=dev)
             words_t = torch.empty((Bc, lp, D), dtype=torch.bfloat16, device=dev)
             wnorm = torch.empty((Bc, lpad), dtype=torch.float32, device=dev)
             nbytes = L.gloria_b200_tc_train_workspace(B, Bc, D, S, lcap)
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
             sim_pm = torch.empty((B, Bc), dtype=torch.float32, device=dev)
-            s = _stream(x)
             _lib.check(L.gloria_b200_tc_prepack_words(words.data_ptr(), dev_lens.data_ptr(), Bc, D, Lw, lcap, 0,
                                                       words_h.data_ptr(), words_t.data_ptr(), wnorm.data_ptr(), s),
                        "tc_prepack_words")
-            nj = world * m
+
+            def launch(h, t, j0, cnt, flags):
+                _lib.check(L.gloria_b200_tc_local_sim_fwd_train_range(
+                    h.data_ptr(), t.data_ptr(), words_h.data_ptr(), wnorm.data_ptr(), dev_lens.data_ptr(), B, j0, cnt, Bc,
+                    D, S, lcap, temp1, temp2, agg, eps, sim_pm.data_ptr(), ws.data_ptr(), nbytes, flags, s),
+                    "tc_local_sim_fwd_train_range")
+
+            # 3. one launch per part as its gather lands (part 0's gather is the only exposed one).  Running the rank's own
+            # images first from the local pack was tried and is slower: it takes 3 P launches instead of P, and at 8 ranks a
+            # launch over 32 images x 64 captions fills the 148 CTAs for 14 pair slots only.
             for p in range(P):
                 main.wait_event(gathered[p])
-                j0 = p * nj
-                _lib.check(L.gloria_b200_tc_prepack_ctx(img_all[j0:].data_ptr(), nj, D, S, ctx_h[j0:].data_ptr(),
-                                                        ctx_t[j0:].data_ptr(), None, s), "tc_prepack_ctx")
-                _lib.check(L.gloria_b200_tc_local_sim_fwd_train_part(
-                    ctx_h.data_ptr(), ctx_t.data_ptr(), words_h.data_ptr(), wnorm.data_ptr(), dev_lens.data_ptr(), B, j0,
-                    nj, Bc, D, S, lcap, temp1, temp2, agg, eps, sim_pm.data_ptr(), ws.data_ptr(), nbytes, s),
-                    "tc_local_sim_fwd_train_part")
-            img_all.record_stream(side)
+                launch(ctx_h[p * nj:], ctx_t[p * nj:], p * nj, nj, (5 if p == 0 else 0) | (2 if p == P - 1 else 0))
+            for t in (own_h, own_t):
+                t.record_stream(side)
             perm = part_major_rows(n, world, P).to(dev, non_blocking=True)
             sim = sim_pm.index_select(0, perm)
         ctx.save_for_backward(ctx_t, words_t, dev_lens, ws, perm)
@@ -256,6 +266,9 @@ class _ShardedLocalSimParts(torch.autograd.Function):
                 None, None)
 
 
+_AGREED: "dict[tuple, bool]" = {}
+
+
 def _agree(dev, lcap: int, parts_ok: bool, group):
     """Every rank must issue the same sequence of collectives: the pipelined path runs P all_gathers / reduce_scatters of
     n / P rows, the fallback one of n rows, and the choice depends on rank-local facts (free memory, the longest local
@@ -264,6 +277,16 @@ def _agree(dev, lcap: int, parts_ok: bool, group):
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     lcap_all, neg_ok = (int(v) for v in t.tolist())
     return lcap_all, neg_ok == -1
+
+
+def _agree_cached(key, dev, lcap: int, parts_ok: bool, group):
+    """`_agree` costs a host synchronisation, so the answer is asked once per configuration (shapes, world size, padded
+    caption length) and reused: the sharded path pads to the word axis, which is the same on every rank, and the
+    workspace question has the same answer every step unless memory runs out (which then fails loudly, not silently)."""
+    if key not in _AGREED:
+        _, ok = _agree(dev, lcap, parts_ok, group)
+        _AGREED[key] = ok
+    return _AGREED[key]
 
 
 def _sharded_local_sim(img_emb_l, text_emb_l, cap_lens, temp1, temp2, agg, group, eps=1e-8):
@@ -276,7 +299,7 @@ def _sharded_local_sim(img_emb_l, text_emb_l, cap_lens, temp1, temp2, agg, group
     S = img_emb_l.shape[2] * img_emb_l.shape[3]
     dev_lens, lens = gloria_loss._cap_lens(cap_lens, Bc, 0, Lw, img_emb_l.device)
     mode = gloria_loss._mode(img_emb_l, text_emb_l)
-    lcap = max(lens) if lens is not None else Lw
+    lcap = Lw          # pad to the word axis: the same on every rank without asking (the kernels mask per caption)
     L = _lib.lib()
     world = dist.get_world_size(group)
     P = _N_PARTS if n % _N_PARTS == 0 and n >= 2 * _N_PARTS else 1
@@ -287,7 +310,8 @@ def _sharded_local_sim(img_emb_l, text_emb_l, cap_lens, temp1, temp2, agg, group
         # sized for the longest caption any rank may hold (Lw), so the answer cannot flip when lcap is agreed below
         nbytes = L.gloria_b200_tc_train_workspace(world * n, Bc, D, S, Lw)
         parts_ok = 0 < nbytes <= min(ops._TC_WS_BUDGET, int(ops._available_bytes(img_emb_l.device, nbytes) * 0.92))
-    lcap, parts_ok = _agree(img_emb_l.device, lcap, parts_ok, group)
+    if want_parts:
+        parts_ok = _agree_cached((world, n, Bc, D, S, Lw, id(group)), img_emb_l.device, lcap, parts_ok, group)
     if parts_ok:
         return _ShardedLocalSimParts.apply(img_emb_l, text_emb_l, dev_lens, lcap, float(temp1), float(temp2),
                                            ops.AGG[agg], float(eps), group, P)

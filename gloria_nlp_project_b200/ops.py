@@ -394,10 +394,13 @@ def check_state_unconsumed(node, ctx: Tensor, words: Tensor, lcap: int, stats: O
     backward through the same forward (retain_graph=True) must not run: the flag lives on the autograd node of that
     forward -- per graph, nothing process-wide.  (The library additionally poisons such a result with NaN on the
     device, for callers of the C ABI.)"""
-    if mode != MODE_BF16 or stats is None or stats.numel() == 0 or not _BWD_MUTATES:
+    if mode != MODE_BF16 or stats is None or not _BWD_MUTATES:
+        return
+    n = stats.numel()
+    if not isinstance(n, int) or n == 0:              # symbolic under tracing: the device-side guard remains
         return
     lpad = (lcap + 15) // 16 * 16
-    if stats.numel() == ctx.shape[0] * words.shape[0] * 2 * lpad * 4:
+    if n == ctx.shape[0] * words.shape[0] * 2 * lpad * 4:
         return                                        # per-word statistics of the recompute path: re-usable
     if getattr(node, "_gloria_consumed", False):
         raise RuntimeError("gloria_b200: the fused training state was already consumed by a backward pass (set "
@@ -420,8 +423,7 @@ def _local_backward(c, dsim, d_diag, d_mean, d_stats):
         d_diag = None
     if d_mean is not None and d_mean.numel() == 0:
         d_mean = None
-    if not torch.compiler.is_compiling():            # (host-side guard; the traced backward keeps the device-side one)
-        check_state_unconsumed(c, ctx, words, lcap, stats, mode)
+    check_state_unconsumed(c, ctx, words, lcap, stats, mode)
     # the state goes in as it is (its length is data dependent under tracing); the op treats an empty one as absent
     d_ctx, d_words = local_sim_bwd(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim, d_diag,
                                    d_mean, stats, mode)

@@ -238,6 +238,15 @@ int gloria_b200_tc_local_sim_fwd_train_part(const void* ctx_h, const void* ctx_t
                                             int Bc, int D, int S, int Lcap, float temp1, float temp2, int agg,
                                             float eps, float* sim, void* workspace, size_t workspace_bytes,
                                             void* stream);
+/* Same for callers whose images of the range live in a buffer of their own: range_h / range_t point at the packed copies of
+ * image j0 (nj images follow contiguously).  flags: 1 = record the bench timer's start before the launch, 2 = its stop
+ * after it, 4 = first launch of this forward (resets the state's consumed flag).  A caption-sharded caller computes its
+ * own images from its local pack while the all_gather of the other ranks' packed copies is in flight. */
+int gloria_b200_tc_local_sim_fwd_train_range(const void* range_h, const void* range_t, const void* words_h,
+                                             const float* wnorm, const int32_t* cap_lens, int Bi, int j0, int nj,
+                                             int Bc, int D, int S, int Lcap, float temp1, float temp2, int agg,
+                                             float eps, float* sim, void* workspace, size_t workspace_bytes,
+                                             int flags, void* stream);
 /* Backward with the image side done in n_parts equal image ranges (n_parts divides Bi); part_events[k] (cudaEvent_t or
  * NULL; the array itself may be NULL) is recorded on `stream` once the d_ctx rows of part k are final.  The
  * caption-side GEMM runs last. */

@@ -132,7 +132,7 @@ def test_step_is_cuda_graph_capturable():
         torch.cuda.synchronize()
         assert abs(float(loss_g) - float(loss_e)) < 1e-6 * abs(float(loss_e))
         for a, b in zip(grads_g, grads_e):
-            assert torch.isfinite(a).all() and relerr(a, b) < 1e-4
+            assert torch.isfinite(a).all() and relerr(a, b) < 1e-3
     finally:
         g.set_precision("auto")
 
