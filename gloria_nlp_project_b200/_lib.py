@@ -63,7 +63,9 @@ PROTOTYPES = {
     "gloria_b200_tc_local_sim_fwd_train_part": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p,
                                                      _p, _z, _p]),
     "gloria_b200_tc_local_sim_fwd_train_range": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p,
-                                                      _p, _z, _i, _p]),
+                                                      _p, _z, _i, _p, _i, _p]),
+    "gloria_b200_tc_local_sim_fwd_train_diag": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _z,
+                                                     _p, _i, _p]),
     "gloria_b200_tc_local_sim_bwd_train_parts": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _i,
                                                       _p, _p]),
     "gloria_b200_tc_local_sim_bwd_train_ev": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p, _p]),

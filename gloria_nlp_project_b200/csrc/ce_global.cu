@@ -39,17 +39,26 @@ __global__ void __launch_bounds__(256) global_cos_fwd(const float* __restrict__ 
 
 // Gradient w.r.t. the "row side" of cos[a,b] = <x_a, y_b> / max(|x_a||y_b|, eps); dcos is addressed through
 // (rs, cs) so the same kernel serves both sides.  dynamic smem: (D + Bc) floats.
-__global__ void __launch_bounds__(256) global_cos_bwd_side(const float* __restrict__ x, const float* __restrict__ y,
-                                                           const float* __restrict__ xn,
-                                                           const float* __restrict__ yn,
-                                                           const float* __restrict__ dcos, long long rs,
-                                                           long long cs, int Bc, int D, float eps,
-                                                           float* __restrict__ dx) {
+__global__ void __launch_bounds__(256) global_cos_bwd_side(const float* __restrict__ x_, const float* __restrict__ y_,
+                                                           const float* __restrict__ xn_,
+                                                           const float* __restrict__ yn_,
+                                                           const float* __restrict__ dcos, int Bi, int Bc_, int D,
+                                                           float eps, float* __restrict__ dx_, float* __restrict__ dy_) {
+  // one launch for both sides: blocks [0, Bi) differentiate w.r.t. x (rows of dcos), blocks [Bi, Bi + Bc) w.r.t. y
+  // (columns of dcos); the roles of the two matrices swap for the second group
+  const bool side_y = (int)blockIdx.x >= Bi;
+  const float* x = side_y ? y_ : x_;
+  const float* y = side_y ? x_ : y_;
+  const float* xn = side_y ? yn_ : xn_;
+  const float* yn = side_y ? xn_ : yn_;
+  const long long rs = side_y ? 1 : Bc_, cs = side_y ? Bc_ : 1;
+  const int Bc = side_y ? Bi : Bc_;
+  float* dx = side_y ? dy_ : dx_;
   extern __shared__ float smem[];
   float* xs = smem;
   float* dd = smem + D;
   __shared__ float red[8];
-  const int a = blockIdx.x;
+  const int a = side_y ? (int)blockIdx.x - Bi : (int)blockIdx.x;
   for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = x[(long long)a * D + d];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -166,10 +175,9 @@ extern "C" int gloria_b200_global_sim_bwd(const float* x, const float* y, const 
   GLORIA_CHECK_ARG((size_t)(D + (Bi > Bc ? Bi : Bc)) * sizeof(float) <= 48 * 1024,
                    "global_sim_bwd: D + B = %d exceeds the 48 KB shared-memory tile", D + (Bi > Bc ? Bi : Bc));
   cudaStream_t st = (cudaStream_t)stream;
-  global_cos_bwd_side<<<Bi, 256, (D + Bc) * sizeof(float), st>>>(x, y, xn, yn, dcos, Bc, 1, Bc, D, eps, dx);
-  GLORIA_LAUNCHED("global_cos_bwd_side(x)");
-  global_cos_bwd_side<<<Bc, 256, (D + Bi) * sizeof(float), st>>>(y, x, yn, xn, dcos, 1, Bc, Bi, D, eps, dy);
-  GLORIA_LAUNCHED("global_cos_bwd_side(y)");
+  global_cos_bwd_side<<<Bi + Bc, 256, (D + (Bi > Bc ? Bi : Bc)) * sizeof(float), st>>>(x, y, xn, yn, dcos, Bi, Bc, D, eps,
+                                                                                        dx, dy);
+  GLORIA_LAUNCHED("global_cos_bwd_side");
   return GLORIA_OK;
 }
 

@@ -74,6 +74,11 @@ struct PairParams {
   long long* dbg;           // phase clocks (only read when built with -DGLORIA_PHASE_CLOCKS)
   int timer_first = 1, timer_last = 1;   // host side only: which ends of the launch the bench timer slot records
   int l2_hints = 0;         // bit 0: X^T / E^T stores evict-first; bit 1: operand tile loads evict-last
+  // FUSED: attention maps of the diagonal pairs (att_maps of local_loss, gloria_loss.py:141-143).  The softmax warps of the
+  // pair (image diag_j0 + j == caption i0 + i) store their fp32 numerators E[s,l] = exp(temp1 P) here, [Bc, diag_lcap, S];
+  // `normalise_diag` then divides each row by its sum.  null = not wanted.
+  float* diag_raw = nullptr;
+  int diag_lcap = 0, diag_j0 = 0;
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
@@ -489,14 +494,25 @@ tc_bwd_pair_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_const
             inv[idx] = rinv;
             const float sc = p.t1_log2e * rinv * ex2(mg - mbv);       // P = e * ex2(mg - mb) / tot
             if (idx == 0) STIMED(sw_ee, mbar_wait(bar(B_EE), (n & 1) ^ 1));   // previous pair's GEMM-T done with E
+            // diagonal pair whose attention map is wanted: this row's fp32 numerators go out as they are computed
+            float* drow = nullptr;
+            if (FUSED && p.diag_raw != nullptr && p.diag_j0 + j == i && s_glob < p.S)
+              drow = p.diag_raw + (size_t)i * p.diag_lcap * p.S + s_glob;
 #pragma unroll
             for (int c = 0; c < CW; ++c) {
               const uint4 cm = *reinterpret_cast<const uint4*>(cM + c * 4);
               const uint32_t mk[4] = {cm.x & rowmask, cm.y & rowmask, cm.z & rowmask, cm.w & rowmask};
               uint32_t w[4];
 #pragma unroll
-              for (int k = 0; k < 8; k += 2)
-                w[k >> 1] = pack_bf16(ex2(x[c * 8 + k] * sc), ex2(x[c * 8 + k + 1] * sc)) & mk[k >> 1];
+              for (int k = 0; k < 8; k += 2) {
+                const float e0 = ex2(x[c * 8 + k] * sc), e1 = ex2(x[c * 8 + k + 1] * sc);
+                w[k >> 1] = pack_bf16(e0, e1) & mk[k >> 1];
+                if (drow != nullptr) {                       // (lanes = consecutive regions: 128-byte rows per word)
+                  const int l = col0 + c * 8 + k;
+                  if (l < L && l < p.diag_lcap) drow[(size_t)l * p.S] = e0;
+                  if (l + 1 < L && l + 1 < p.diag_lcap) drow[(size_t)(l + 1) * p.S] = e1;
+                }
+              }
               const int ch = c_lo + c;
               if (ch < NCH)
                 *reinterpret_cast<uint4*>(erow + (size_t)(ch >> 3) * e_blk + (size_t)((((uint32_t)ch & 7u) ^ sw) << 4)) =
@@ -874,6 +890,23 @@ __global__ void __launch_bounds__(256) scale_x(__nv_bfloat16* __restrict__ X, co
 }
 
 __global__ void mark_consumed(int* flag) { *flag = 1; }
+
+// attn[i, l, :] = raw[i, l, :] / sum_s raw[i, l, s] for l < cap_len (rows beyond: zero); one warp per (caption, word)
+__global__ void normalise_diag(float* __restrict__ a, const int* __restrict__ cap_lens, int Bc, int lcap, int S) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= Bc * lcap) return;
+  const int lane = threadIdx.x & 31;
+  const int i = row / lcap, l = row - i * lcap;
+  float* r = a + (size_t)row * S;
+  if (l >= min(max(cap_lens[i], 0), lcap)) {
+    for (int s = lane; s < S; s += 32) r[s] = 0.f;
+    return;
+  }
+  float z = 0.f;
+  for (int s = lane; s < S; s += 32) z += r[s];
+  z = 1.f / warp_sum(z);
+  for (int s = lane; s < S; s += 32) r[s] *= z;
+}
 
 // gamma[i, l] = sum_j g[j, i] * go[j, (i,l)]   (fused training path);  one thread per column
 __global__ void gamma_sum(const float* __restrict__ go, const float* __restrict__ g, float* __restrict__ gamma, int Bi,
@@ -1255,7 +1288,8 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train_range(const void* range_h, con
                                                         const float* wnorm, const int32_t* cap_lens, int Bi, int j0,
                                                         int nj, int Bc, int D, int S, int Lcap, float temp1, float temp2,
                                                         int agg, float eps, float* sim, void* workspace,
-                                                        size_t workspace_bytes, int flags, void* stream) {
+                                                        size_t workspace_bytes, int flags, float* attn_diag_raw,
+                                                        int diag_lcap, void* stream) {
   GLORIA_CHECK_ARG(range_h && range_t && words_h && wnorm && cap_lens && sim && workspace, "null pointer");
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0, "bad batch sizes %d x %d", Bi, Bc);
   GLORIA_CHECK_ARG(j0 >= 0 && nj > 0 && j0 + nj <= Bi, "bad image range [%d, %d) of %d", j0, j0 + nj, Bi);
@@ -1301,6 +1335,7 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train_range(const void* range_h, con
   p.dbg = (long long*)g_phase_clock_buffer;
   p.timer_first = (flags & 1) != 0; p.timer_last = (flags & 2) != 0;
   p.l2_hints = bw::l2_hints_mode();
+  p.diag_raw = attn_diag_raw; p.diag_lcap = diag_lcap; p.diag_j0 = j0;      // pair (j0 + j, i) is diagonal when equal
   return bw::launch_pair_lpad<true>(lpad, rt, wt, gm, em, p, sms, st);
 }
 
@@ -1317,7 +1352,7 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train_part(const void* ctx_h, const 
   return gloria_b200_tc_local_sim_fwd_train_range((const __half*)ctx_h + (size_t)j0 * Spad * D,
                                                   (const __nv_bfloat16*)ctx_t + (size_t)j0 * sp * D, words_h, wnorm, cap_lens,
                                                   Bi, j0, nj, Bc, D, S, Lcap, temp1, temp2, agg, eps, sim, workspace,
-                                                  workspace_bytes, flags, stream);
+                                                  workspace_bytes, flags, nullptr, 0, stream);
 }
 
 extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void* ctx_t, const void* words_h,
@@ -1326,6 +1361,26 @@ extern "C" int gloria_b200_tc_local_sim_fwd_train(const void* ctx_h, const void*
                                                   float* sim, void* workspace, size_t workspace_bytes, void* stream) {
   return gloria_b200_tc_local_sim_fwd_train_part(ctx_h, ctx_t, words_h, wnorm, cap_lens, Bi, 0, Bi, Bc, D, S, Lcap, temp1,
                                                  temp2, agg, eps, sim, workspace, workspace_bytes, stream);
+}
+
+// Training forward that also returns the attention maps of the diagonal pairs (Bi == Bc): attn_diag [Bc, diag_lcap, S],
+// rows beyond each caption's length zero.  The maps come out of the fused kernel's own softmax (fp32 numerators stored by
+// the diagonal pairs, one normalising launch after it) instead of a second, B-pair pass over the features.
+extern "C" int gloria_b200_tc_local_sim_fwd_train_diag(const void* ctx_h, const void* ctx_t, const void* words_h,
+                                                       const float* wnorm, const int32_t* cap_lens, int Bi, int Bc,
+                                                       int D, int S, int Lcap, float temp1, float temp2, int agg,
+                                                       float eps, float* sim, void* workspace, size_t workspace_bytes,
+                                                       float* attn_diag, int diag_lcap, void* stream) {
+  GLORIA_CHECK_ARG(attn_diag != nullptr && diag_lcap >= Lcap, "attn_diag buffer missing or shorter than Lcap");
+  GLORIA_CHECK_ARG(Bi == Bc, "diagonal attention maps need as many images as captions, got %d x %d", Bi, Bc);
+  int rc = gloria_b200_tc_local_sim_fwd_train_range(ctx_h, ctx_t, words_h, wnorm, cap_lens, Bi, 0, Bi, Bc, D, S, Lcap, temp1,
+                                                    temp2, agg, eps, sim, workspace, workspace_bytes, 7, attn_diag,
+                                                    diag_lcap, stream);
+  if (rc) return rc;
+  const int rows = Bc * diag_lcap;
+  bw::normalise_diag<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(attn_diag, cap_lens, Bc, diag_lcap, S);
+  GLORIA_LAUNCHED("normalise_diag");
+  return GLORIA_OK;
 }
 
 // "lean" forward: sim + word-mean attention (+ the per-word statistics a later recompute backward needs)

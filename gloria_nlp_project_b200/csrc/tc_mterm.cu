@@ -33,28 +33,54 @@ struct Params {
 
 // Per image the symmetric M_j needs the blocks (a, b >= a) of its NT x NT tile grid.  A CLUSTER OF TWO CTAs takes one image
 // at a time and walks its K range once, in step: rank 0 owns row tile 0 (blocks (0, b)), rank 1 the row tiles 1..NT-1
-// (blocks (1,1), (1,2), (2,2) at NT = 3) -- three 128 x 128 accumulators each at NT = 3, so the pair stays balanced and the
-// E^T rows of the image are fetched from HBM once (the second CTA's tiles are L2 hits of the first's; before, the row
-// tiles of an image were separate units that drifted apart and read E^T twice: 38.7 GB per step for 20 GB of operand).
+// (blocks (1,1), (1,2), (2,2) at NT = 3) -- three 128 x 128 accumulators each at NT = 3, so the pair stays balanced.
+// The tiles both CTAs need (1 .. NT-1) are loaded ONCE by rank 0's producer and MULTICAST into both CTAs' stages, so the
+// E^T rows of an image cross L2 -> SM once per CTA but HBM -> L2 exactly once and the pair cannot drift apart: rank 0
+// refills a stage only when BOTH CTAs' MMAs have released it (its `empty` barrier counts rank 1's commit too).  Before, the
+// row tiles of an image were separate units (38.7 GB of DRAM reads per step for 20 GB of operand), then two unsynchronised
+// CTAs (33.7 GB).
 struct Role {
-  int t0, nl, ns;            // first tile loaded, tiles loaded (slots 0..nl-1), tiles scaled (slot s -> slot 3 - s)
+  int t0, nl, ns;            // first tile held, tiles held (tile t lives in slot t in BOTH CTAs), tiles scaled
+  int ssrc[2], sdst[2];      // scale pass s: slot ssrc[s] -> slot sdst[s]
   int nm;                    // MMAs per k-step: (a slot, b slot) -> accumulator m; block (ra[m], rb[m]) of the tile grid
   int sa[3], sb[3], ra[3], rb[3];
 };
 __device__ __forceinline__ Role make_role(int rank, int NT) {
   Role r{};
-  if (rank == 0) {
+  if (rank == 0) {           // row tile 0: A' = tile 0 scaled -> slot 3
     r.t0 = 0; r.nl = NT; r.ns = 1; r.nm = NT;
+    r.ssrc[0] = 0; r.sdst[0] = 3;
     for (int b = 0; b < NT; ++b) { r.sa[b] = 3; r.sb[b] = b; r.ra[b] = 0; r.rb[b] = b; }
-  } else {
+  } else {                   // row tiles 1..NT-1: tile 1 scaled -> slot 3, tile 2 scaled -> slot 0 (tile 0 is not held here)
     r.t0 = 1; r.nl = NT - 1; r.ns = NT - 1; r.nm = 0;
-    for (int a = 1; a < NT; ++a)
+    for (int a = 1; a < NT; ++a) {
+      r.ssrc[a - 1] = a; r.sdst[a - 1] = a == 1 ? 3 : 0;
       for (int b = a; b < NT; ++b) {
-        r.sa[r.nm] = 3 - (a - 1); r.sb[r.nm] = b - 1; r.ra[r.nm] = a; r.rb[r.nm] = b;
+        r.sa[r.nm] = r.sdst[a - 1]; r.sb[r.nm] = b; r.ra[r.nm] = a; r.rb[r.nm] = b;
         ++r.nm;
       }
+    }
   }
   return r;
+}
+
+// One TMA load delivered to the same shared-memory offset (and signalled on the mbarrier at the same offset) of every CTA
+// in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, int x, int y, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], "
+      "[%4], %5;"
+      ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
@@ -78,7 +104,7 @@ mterm_kernel(const __grid_constant__ CUtensorMap tm_e, const Params p) {
     for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(bar(B_FULL + s), 1);
       mbar_init(bar(B_SCALED + s), 256);       // owner group: A' written; other group: phase of `full` observed
-      mbar_init(bar(B_EMPTY + s), 1);
+      mbar_init(bar(B_EMPTY + s), (rank == 0 && NT > 1) ? 2 : 1);   // rank 0: its own MMAs' commit and its peer's
     }
     mbar_init(bar(B_ACCF), 1);
     mbar_init(bar(B_ACCE), 128);
@@ -88,6 +114,7 @@ mterm_kernel(const __grid_constant__ CUtensorMap tm_e, const Params p) {
   if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                           // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -99,10 +126,14 @@ mterm_kernel(const __grid_constant__ CUtensorMap tm_e, const Params p) {
       int st = 0; uint32_t ph = 0;
       for (int j = cl; j < p.Bi; j += ncl) {
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(bar(B_EMPTY + st), ph ^ 1);
+          mbar_wait(bar(B_EMPTY + st), ph ^ 1);           // rank 0: released by both CTAs; rank 1: by its own MMAs
           mbar_expect_tx(bar(B_FULL + st), (uint32_t)role.nl * TILE_BYTES);
-          for (int b = 0; b < role.nl; ++b)
-            tma_load_2d(base + st * STAGE + b * TILE_BYTES, &tm_e, kb * KBLK, j * p.sp + (role.t0 + b) * TILE, bar(B_FULL + st));
+          if (rank == 0) {
+            // tile 0 is rank 0's alone; tiles 1 .. NT-1 go to both CTAs with one load each
+            tma_load_2d(base + st * STAGE, &tm_e, kb * KBLK, j * p.sp, bar(B_FULL + st));
+            for (int t = 1; t < NT; ++t)
+              tma_load_2d_mc(base + st * STAGE + t * TILE_BYTES, &tm_e, kb * KBLK, j * p.sp + t * TILE, bar(B_FULL + st), 3);
+          }
           if (++st == NSTAGE) { st = 0; ph ^= 1; }
         }
       }
@@ -127,7 +158,8 @@ mterm_kernel(const __grid_constant__ CUtensorMap tm_e, const Params p) {
             for (int k = 0; k < 4; ++k)
               umma_bf16(tmem + (uint32_t)(m * TILE), da + 2 * k, db + 2 * k, idesc, (uint32_t)((kb | k) != 0));
           }
-          umma_commit(bar(B_EMPTY + st));
+          if (rank == 0) umma_commit(bar(B_EMPTY + st));
+          else umma_commit_mc(bar(B_EMPTY + st), 3);           // frees the stage here AND tells rank 0's producer
           if (++st == NSTAGE) { st = 0; ph ^= 1; }
         }
         umma_commit(bar(B_ACCF));
@@ -182,10 +214,10 @@ mterm_kernel(const __grid_constant__ CUtensorMap tm_e, const Params p) {
         if (t64 < KBLK) wsm[t64] = __float2bfloat16_rn(w_cur);
         if (grp == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
         else asm volatile("bar.sync 3, 128;" ::: "memory");
-        // A' = (loaded tile s) * w per column -> slot 3 - s; 128-byte swizzle: chunk c of row r sits at c ^ (r & 7)
+        // A' = (held tile) * w per column; 128-byte swizzle: chunk c of row r sits at c ^ (r & 7)
         for (int s = 0; s < role.ns; ++s) {
-          const uint8_t* src = sbase + (size_t)s * TILE_BYTES + (size_t)row * 128;
-          uint8_t* dst = sbase + (size_t)(3 - s) * TILE_BYTES + (size_t)row * 128;
+          const uint8_t* src = sbase + (size_t)role.ssrc[s] * TILE_BYTES + (size_t)row * 128;
+          uint8_t* dst = sbase + (size_t)role.sdst[s] * TILE_BYTES + (size_t)row * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const int pc = (c ^ (row & 7)) << 4;
@@ -261,6 +293,7 @@ mterm_kernel(const __grid_constant__ CUtensorMap tm_e, const Params p) {
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                           // no CTA leaves while its peer may still multicast to it or signal it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);

@@ -23,7 +23,7 @@ from typing import Callable, Optional, Sequence
 import torch
 import torch.distributed as dist
 
-__all__ = ["sharded_loss", "gather_cat", "gather_reduce_scatter", "part_major_rows"]
+__all__ = ["sharded_loss", "sharded_calc_loss", "gather_cat", "gather_reduce_scatter", "part_major_rows"]
 
 
 class _GatherSliceGrad(torch.autograd.Function):
@@ -203,7 +203,7 @@ class _ShardedLocalSimParts(torch.autograd.Function):
             def launch(h, t, j0, cnt, flags):
                 _lib.check(L.gloria_b200_tc_local_sim_fwd_train_range(
                     h.data_ptr(), t.data_ptr(), words_h.data_ptr(), wnorm.data_ptr(), dev_lens.data_ptr(), B, j0, cnt, Bc,
-                    D, S, lcap, temp1, temp2, agg, eps, sim_pm.data_ptr(), ws.data_ptr(), nbytes, flags, s),
+                    D, S, lcap, temp1, temp2, agg, eps, sim_pm.data_ptr(), ws.data_ptr(), nbytes, flags, None, 0, s),
                     "tc_local_sim_fwd_train_range")
 
             # 3. one launch per part as its gather lands (part 0's gather is the only exposed one).  Running the rank's own
@@ -372,3 +372,56 @@ def sharded_loss(img_emb_l: torch.Tensor, text_emb_l: torch.Tensor, img_emb_g: t
     sim = both_all[:, 0].t()                                         # [B_img, B_cap]
     cosm = both_all[:, 1].t()
     return (*ce_fn(sim.contiguous(), temp3), *ce_fn(cosm.contiguous(), temp3))
+
+
+def _global_mean(local_mean: torch.Tensor, group) -> torch.Tensor:
+    """Mean over the global batch of a per-rank mean (equal shard sizes): the VALUE is the all-reduced one, the
+    gradient that flows back is this rank's share of it (1 / world of its local mean)."""
+    world = dist.get_world_size(group)
+    tot = local_mean.detach().clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    return local_mean / world + (tot - local_mean.detach()) / world
+
+
+def sharded_calc_loss(model, img_emb_l: torch.Tensor, img_emb_g: torch.Tensor, text_emb_l: torch.Tensor,
+                      text_emb_g: torch.Tensor, sents, segmentation_labels: Optional[torch.Tensor] = None, group=None,
+                      attn_maps_fn: Optional[Callable] = None, seg_loss_fn: Optional[Callable] = None, **loss_fns):
+    """`GLoRIA.calc_loss` (gloria/models/gloria_model.py:132-150) from per-rank shards -> (loss, attn_maps).
+
+    `model` supplies the attributes the reference's __init__ sets (temp1/2/3, local_loss_weight, global_loss_weight,
+    segmentation_loss_weight, no_attn_vec).  The contrastive terms are `sharded_loss` (full-batch negatives); the
+    attention maps of the diagonal pairs and the supervised-attention term (:143-147) are local by nature -- pair (i, i)
+    lives on the rank that owns image and caption i -- so they are computed on the rank's own pairs, and the term's
+    batch mean is all-reduced (value) while its gradient stays with the owner.  `attn_maps` holds the maps of THIS
+    rank's pairs.  The optional no-attention / KL / entropy regularisers (gloria_loss.py:108-139) compare every image's
+    own map with its maps under all other captions; they are not sharded: configure them on a single device.
+    """
+    from . import gloria_loss
+    from .gloria_model import cap_lens_from_sents
+    if any(getattr(model, k, None) is not None for k in
+           ("no_attn_loss_weight", "attention_divergence_loss_weight", "attention_entropy_loss_weight")):
+        raise RuntimeError("sharded_calc_loss: the attention regularisers need every pair's word-mean attention on one "
+                           "device; run calc_loss unsharded for these configurations")
+    if isinstance(sents, gloria_loss.DeviceCapLens) or (len(sents) and isinstance(sents[0], int)):
+        cap_lens = sents                       # caption lengths given directly
+    else:
+        cap_lens = cap_lens_from_sents(sents)  # word lists (or this package's LazySentences)
+    nav = getattr(model, "no_attn_vec", None)
+    sharded = dist.is_initialized() and dist.get_world_size(group) > 1
+    loss = 0
+    lw, gw = model.local_loss_weight, model.global_loss_weight
+    if lw != 0 or gw != 0:
+        if nav is not None and lw != 0:
+            raise RuntimeError("sharded_calc_loss: no_attn_vec is not supported on the sharded contrastive path")
+        l0, l1, g0, g1 = sharded_loss(img_emb_l, text_emb_l, img_emb_g, text_emb_g, cap_lens, temp1=model.temp1,
+                                      temp2=model.temp2, temp3=model.temp3, group=group, **loss_fns)
+        loss = (l0 + l1) * lw + (g0 + g1) * gw
+    attn_maps_fn = attn_maps_fn or (lambda i, t, c: gloria_loss.diagonal_attention_maps(i, t, c, temp1=model.temp1,
+                                                                                       no_attn_vec=nav))
+    attn_maps = attn_maps_fn(img_emb_l, text_emb_l, cap_lens)
+    if segmentation_labels is not None and getattr(model, "segmentation_loss_weight", None):
+        seg = (seg_loss_fn or gloria_loss.supervised_attention_loss)(attn_maps, segmentation_labels)
+        if sharded:
+            seg = _global_mean(seg, group)
+        loss = loss + seg * model.segmentation_loss_weight
+    return loss, attn_maps

@@ -25,6 +25,7 @@ _WS_BUDGET = int(os.environ.get("GLORIA_B200_WS_BYTES", str(4 << 30)))          
 _TC_WS_BUDGET = int(os.environ.get("GLORIA_B200_TC_WS_BYTES", str(96 << 30)))     # bf16 backward operand matrices
 _PACKED_PROMPTS = os.environ.get("GLORIA_B200_PACKED_PROMPTS", "1") != "0"           # packed short-caption inference kernel
 _FUSED_TRAIN = os.environ.get("GLORIA_B200_FUSED_TRAIN", "1") != "0"               # fused forward+backward-operand kernel
+_FUSED_DIAG = os.environ.get("GLORIA_B200_FUSED_DIAG", "1") != "0"                 # ... which also emits the diagonal attention maps
 
 
 class Packed:
@@ -182,7 +183,7 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                 # forward-only scoring of short prompts (zero-shot): up to 8 captions share one word tile
                 _tc_packed_fwd(L, ctx, words, cap_lens, word_off, temp1, temp2, agg, eps, sim)
                 return sim, diag, mean, stats
-            fused = False
+            fused = diag_done = False
             lpad = L.gloria_b200_tc_lpad(lcap)
             if need_grad and not want_mean and _FUSED_TRAIN:
                 # fused training forward: sim AND the backward's operand rows (for dsim = 1) in one kernel.  The state
@@ -195,12 +196,21 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                     stats = torch.empty((total,), dtype=torch.uint8, device=dev)
                     packed = tc_prepack(ctx, words, cap_lens, lcap, word_off, ctx_t=stats[nbytes:nbytes + n_ct],
                                         words_t=stats[nbytes + n_ct:])
-                    rc = L.gloria_b200_tc_local_sim_fwd_train(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(),
-                                                              packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
-                                                              cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg,
-                                                              eps, sim.data_ptr(), stats.data_ptr(), nbytes,
-                                                              _stream(ctx))
-                    _lib.check(rc, "tc_local_sim_fwd_train")
+                    if want_diag and Bi == Bc and _FUSED_DIAG:
+                        # the attention maps of the diagonal pairs come out of the same kernel (its softmax stores them)
+                        rc = L.gloria_b200_tc_local_sim_fwd_train_diag(
+                            packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(), packed.words_h.data_ptr(),
+                            packed.wnorm.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg, eps,
+                            sim.data_ptr(), stats.data_ptr(), nbytes, diag.data_ptr(), lcap, _stream(ctx))
+                        _lib.check(rc, "tc_local_sim_fwd_train_diag")
+                        diag_done = True
+                    else:
+                        rc = L.gloria_b200_tc_local_sim_fwd_train(packed.ctx_h.data_ptr(), packed.ctx_t.data_ptr(),
+                                                                  packed.words_h.data_ptr(), packed.wnorm.data_ptr(),
+                                                                  cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2,
+                                                                  agg, eps, sim.data_ptr(), stats.data_ptr(), nbytes,
+                                                                  _stream(ctx))
+                        _lib.check(rc, "tc_local_sim_fwd_train")
                     fused = True
             if not fused:
                 packed = tc_prepack(ctx, words, cap_lens, lcap, word_off)
@@ -225,7 +235,7 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                                                         cap_lens.data_ptr(), Bi, Bc, D, S, lcap, temp1, temp2, agg, eps,
                                                         sim.data_ptr(), _ptr(fstats), _stream(ctx))
                     _lib.check(rc, "tc_local_sim_fwd")
-            if want_diag:
+            if want_diag and not diag_done:
                 if Bi != Bc:
                     raise RuntimeError(f"diagonal attention maps need as many images as captions, got {Bi} x {Bc}")
                 # diagonal attention maps: B pairs (not B^2) through the exact fp32 kernels

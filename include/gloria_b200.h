@@ -246,7 +246,17 @@ int gloria_b200_tc_local_sim_fwd_train_range(const void* range_h, const void* ra
                                              const float* wnorm, const int32_t* cap_lens, int Bi, int j0, int nj,
                                              int Bc, int D, int S, int Lcap, float temp1, float temp2, int agg,
                                              float eps, float* sim, void* workspace, size_t workspace_bytes,
-                                             int flags, void* stream);
+                                             int flags, float* attn_diag_raw, int diag_lcap, void* stream);
+/* Training forward that also returns the attention maps of the diagonal pairs (att_maps of local_loss,
+ * gloria_loss.py:141-143; needs Bi == Bc): attn_diag [Bc, diag_lcap, S] (diag_lcap >= Lcap), rows beyond each caption's
+ * length zero.  The maps come out of the fused kernel's own softmax -- the diagonal pairs store their fp32 numerators,
+ * one small launch normalises them -- instead of a second pass over the features.  (attn_diag_raw / diag_lcap of the
+ * range variant above: the un-normalised buffer, or NULL.) */
+int gloria_b200_tc_local_sim_fwd_train_diag(const void* ctx_h, const void* ctx_t, const void* words_h,
+                                            const float* wnorm, const int32_t* cap_lens, int Bi, int Bc, int D, int S,
+                                            int Lcap, float temp1, float temp2, int agg, float eps, float* sim,
+                                            void* workspace, size_t workspace_bytes, float* attn_diag, int diag_lcap,
+                                            void* stream);
 /* Backward with the image side done in n_parts equal image ranges (n_parts divides Bi); part_events[k] (cudaEvent_t or
  * NULL; the array itself may be NULL) is recorded on `stream` once the d_ctx rows of part k are final.  The
  * caption-side GEMM runs last. */

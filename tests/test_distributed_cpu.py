@@ -147,3 +147,72 @@ def test_ranks_agree_on_the_collective_schedule():
         p.join(60)
         assert p.exitcode == 0
     assert res[0] == res[1] == [(97, False), (31, True)]
+
+
+class _Model:
+    temp1, temp2, temp3 = 4.0, 5.0, 10.0
+    local_loss_weight, global_loss_weight, segmentation_loss_weight = 1.0, 0.5, 2.0
+    no_attn_vec = None
+
+
+def _maps_fn(img, txt, cl):
+    return T.local_loss(img, txt, cl)[2]             # att_maps of the (local) diagonal pairs, differentiable
+
+
+def _calc_inputs():
+    B, Dm, H, W, Lw = 4, 32, 3, 4, 9
+    img_l, txt_l, img_g, txt_g, cl = gen_inputs(33, B, Dm, H, W, Lw, cap_lens=[9, 7, 4, 2])
+    labels = (np.random.default_rng(3).random((B, 6, 8)) > 0.6).astype(np.float64)
+    labels[:, 0, 0] = 1.0
+    return B, img_l, txt_l, img_g, txt_g, cl, labels
+
+
+def _calc_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gloria_nlp_project_b200 import distributed as D
+        torch.set_num_threads(2)
+        B, img_l, txt_l, img_g, txt_g, cl, labels = _calc_inputs()
+        n = B // world
+        sl = slice(rank * n, (rank + 1) * n)
+        leaves = [torch.tensor(a[sl]).requires_grad_(True) for a in (img_l, txt_l, img_g, txt_g)]
+        loss, maps = D.sharded_calc_loss(_Model(), leaves[0], leaves[2], leaves[1], leaves[3], cl[sl],
+                                         segmentation_labels=torch.tensor(labels[sl]), attn_maps_fn=_maps_fn,
+                                         **_oracle_fns())
+        loss.backward()
+        q.put((rank, float(loss), [t.grad.numpy() for t in leaves], [tuple(m.shape) for m in maps]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_calc_loss_equals_unsharded():
+    """GLoRIA.calc_loss (contrastive terms + supervised attention on the diagonal pairs) from two shards == the same
+    terms on the whole batch: loss value on every rank, gradients on each rank's shard."""
+    from gloria_nlp_project_b200 import gloria_loss
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_calc_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    B, img_l, txt_l, img_g, txt_g, cl, labels = _calc_inputs()
+    leaves = [torch.tensor(a).requires_grad_(True) for a in (img_l, txt_l, img_g, txt_g)]
+    l0, l1, maps, _ = T.local_loss(leaves[0], leaves[1], cl)
+    g0, g1 = T.global_loss(leaves[2], leaves[3])
+    m = _Model()
+    want = (l0 + l1) * m.local_loss_weight + (g0 + g1) * m.global_loss_weight + \
+        gloria_loss.supervised_attention_loss(maps, torch.tensor(labels)) * m.segmentation_loss_weight
+    want.backward()
+    n = B // world
+    for rank, loss, grads, shapes in res:
+        assert abs(loss - float(want)) < 1e-12 * abs(float(want))
+        assert shapes == [(1, L, 3, 4) for L in cl[rank * n:(rank + 1) * n]]
+        for gsh, leaf in zip(grads, leaves):
+            np.testing.assert_allclose(gsh, leaf.grad.numpy()[rank * n:(rank + 1) * n], rtol=1e-9, atol=1e-14)

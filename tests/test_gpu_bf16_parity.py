@@ -446,8 +446,10 @@ def test_attention_finetune_touches_diagonal_pairs_only(gl, monkeypatch):
     assert abs(float(loss.detach()) - float(ref.detach())) < 1e-5 * abs(float(ref.detach()))
     assert relerr(img.grad, r_img) < 1e-4 and relerr(txt.grad, r_txt) < 1e-4
     maps2 = m.get_attn_maps(cu(img_l), cu(txt_l), sents)
+    # (the all-pairs path takes its maps from the fused kernel's own softmax -- fp16-operand scores -- the diagonal-only
+    # path from the exact fp32 kernels)
     for a, b, c in zip(maps, maps2, ref_maps):
-        assert torch.equal(a, b) and relerr(a, c) < 1e-5
+        assert torch.equal(a, b) and relerr(a, c) < 1e-4
 
 
 def test_length_bucketed_training(gl, monkeypatch):

@@ -84,3 +84,71 @@ def test_sharded_two_gpus(precision, tol, gtol):
         sl = slice(rank * n, (rank + 1) * n)
         for got, ref in zip(grads, (d_img, d_txt, d_ig, d_tg)):
             assert rel(got.astype(np.float64), ref[sl]) < gtol
+
+
+def _calc_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import gloria_nlp_project_b200 as G
+        from gloria_nlp_project_b200 import distributed as D
+        from tests.util import Holder
+        G.set_precision("bf16")
+        B, img_l, txt_l, img_g, txt_g, cl = _inputs()
+        labels = (np.random.default_rng(5).random((B, 64, 64)) > 0.7).astype(np.float32)
+        n = B // world
+        sl = slice(rank * n, (rank + 1) * n)
+        m = Holder(local_loss_weight=1.0, global_loss_weight=0.5, segmentation_loss_weight=2.0)
+        leaves = [torch.tensor(a[sl], device="cuda").requires_grad_(True) for a in (img_l, txt_l, img_g, txt_g)]
+        loss, maps = D.sharded_calc_loss(m, leaves[0], leaves[2], leaves[1], leaves[3], cl[sl],
+                                         segmentation_labels=torch.tensor(labels[sl], device="cuda"))
+        loss.backward()
+        torch.cuda.synchronize()
+        q.put((rank, float(loss), [t.grad.cpu().numpy() for t in leaves], [tuple(x.shape) for x in maps]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_calc_loss_two_gpus():
+    """calc_loss (contrastive terms + supervised attention, gloria_model.py:132-150) from two NCCL ranks == the
+    single-GPU drop-in on the whole batch (which is pinned to the reference's goldens `ft_*` / `calc_*`)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import gloria_nlp_project_b200 as G
+    from gloria_nlp_project_b200.gloria_model import GLoRIALossMixin
+    from tests.util import Holder
+
+    class M(GLoRIALossMixin, Holder):
+        pass
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_calc_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    B, img_l, txt_l, img_g, txt_g, cl = _inputs()
+    labels = (np.random.default_rng(5).random((B, 64, 64)) > 0.7).astype(np.float32)
+    G.set_precision("bf16")
+    try:
+        m = M(local_loss_weight=1.0, global_loss_weight=0.5, segmentation_loss_weight=2.0)
+        leaves = [torch.tensor(a, device="cuda").requires_grad_(True) for a in (img_l, txt_l, img_g, txt_g)]
+        sents = [["[CLS]"] + ["w"] * (L - 1) + ["[SEP]"] for L in cl]
+        want, _ = m.calc_loss(leaves[0], leaves[2], leaves[1], leaves[3], sents,
+                              segmentation_labels=torch.tensor(labels, device="cuda"))
+        want.backward()
+    finally:
+        G.set_precision("auto")
+    n = B // world
+    for rank, loss, grads, shapes in res:
+        assert abs(loss - float(want)) < 2e-4 * abs(float(want))
+        assert shapes == [(1, L, 19, 19) for L in cl[rank * n:(rank + 1) * n]]
+        for got, leaf in zip(grads, leaves):
+            ref = leaf.grad.cpu().numpy()[rank * n:(rank + 1) * n]
+            assert float(np.abs(got - ref).max() / np.abs(ref).max()) < 2e-3
