@@ -29,6 +29,7 @@ rows = list(csv.reader(src.splitlines()))
 hdr = rows[1]; data = rows[2:]
 iS, iSrc = hdr.index("# Samples"), hdr.index("Source")
 cols = {k: hdr.index(k) for k in ("stall_long_sb", "stall_short_sb", "stall_wait", "stall_barrier", "stall_math", "stall_mio", "stall_lg", "stall_not_selected", "stall_selected") if k in hdr}
+data = [r for r in data if len(r) > iS and r[iS].isdigit()]
 tot = sum(int(r[iS] or 0) for r in data)
 print(f"# source page: {tot} warp-stall samples; totals by reason:", {k: sum(int(r[i] or 0) for r in data) for k, i in cols.items()})
 for r in sorted(data, key=lambda r: -int(r[iS] or 0))[:int(sys.argv[2]) if len(sys.argv) > 2 else 20]:
