@@ -30,6 +30,12 @@ PROTOTYPES = {
                                            _p]),
     "gloria_b200_local_sim_bwd_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p, _p,
                                            _p, _z, _p]),
+    "gloria_b200_f32tc_supported": (_i, [_i, _i, _i]),
+    "gloria_b200_local_f32tc_workspace": (_z, [_i, _i, _i, _i, _i, _i, _z, _i]),
+    "gloria_b200_local_sim_fwd_f32tc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p, _z,
+                                             _p]),
+    "gloria_b200_local_sim_bwd_f32tc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p, _p,
+                                             _p, _z, _p]),
     "gloria_b200_diag_attn_workspace": (_z, [_i, _i, _i, _i, _i]),
     "gloria_b200_diag_attn_fwd_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p, _z, _p]),
     "gloria_b200_diag_attn_bwd_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p, _z, _p]),
@@ -70,6 +76,7 @@ PROTOTYPES = {
                                                       _p, _p]),
     "gloria_b200_tc_local_sim_bwd_train_ev": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p, _p]),
     "gloria_b200_acc_gemm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
+    "gloria_b200_acc_gemm_planes": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "gloria_b200_word_ranges": (_i, [_p, _p, _i, C.c_longlong, _i, _i, _p, _p, _p, _p]),
     "gloria_b200_word_ranges_cap_lens": (_i, [_p, _p, _p, _i, C.c_longlong, _i, _i, _p, _p, _p, _p, _p]),
     "gloria_b200_aggregate_tokens_fwd": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p]),

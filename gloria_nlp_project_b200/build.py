@@ -7,7 +7,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libgloria_b200.so")
-SOURCES = ["api.cu", "simt_f32.cu", "ce_global.cu", "tc_local.cu", "tc_bwd.cu", "tc_mterm.cu", "tc_gemm.cu", "aggregate.cu"]
+SOURCES = ["api.cu", "simt_f32.cu", "ce_global.cu", "tc_local.cu", "tc_bwd.cu", "tc_mterm.cu", "tc_gemm.cu", "tc_f32.cu", "aggregate.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-lcublas",

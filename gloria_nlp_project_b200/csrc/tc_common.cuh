@@ -238,6 +238,21 @@ int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t rows, uin
 // the result is written as bf16 to Mb instead of fp32 to M
 int launch_mterm(const void* Et, const float* f, const float* g, float* M, void* Mb, int Bi, int Bc, int i0, int R1, int lp,
                  int sp, bool accumulate, cudaStream_t st);
+// tc_gemm.cu, general form.  Plain modes take batches and operand planes: the operands are dense 2-D bf16 arrays of
+// a_rows / b_rows rows in all ([rows, K] for row-major A, [rows, M] for transposed A, [rows, N] for B); batch b starts
+// a_brows / b_brows rows further down (C: c_bstride elements further on), plane q a_prows / b_prows rows further down.
+// nterms = 3 / 6: operands are given as bf16 pieces of fp32 values (plane 0 = leading piece, 1 / 2 = residuals) and the
+// products hi.lo + lo.hi + hi.hi (3) or all products down to 2^-24 (6) are accumulated into one fp32 result.
+struct GemmEx {
+  const void* A; const void* B; float* C;
+  int M, N, K, ldc;
+  bool a_kmajor; int ksplit; bool accumulate;
+  const float* g; int g_sm, g_sk, m_div, k_div; bool force_scaled_path;
+  int nb; long long a_brows, b_brows, c_bstride;
+  int nterms; long long a_prows, b_prows;
+  long long a_rows, b_rows;          // tensor-map extents (0: one plane, one batch)
+};
+int acc_gemm_ex(const GemmEx& e, cudaStream_t st);
 // tc_gemm.cu: C[M, N] (fp32, row pitch ldc) = or += A B on the CTA-pair tcgen05 GEMM; see the definition for the arguments
 int acc_gemm(const void* A, const void* B, float* C, int M, int N, int K, int ldc, bool a_kmajor, int ksplit,
              bool accumulate, const float* g, int g_sm, int g_sk, int m_div, int k_div, bool force_scaled_path,

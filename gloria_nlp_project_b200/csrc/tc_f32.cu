@@ -1,0 +1,731 @@
+// fp32 mode of the GLoRIA local similarity ON THE TENSOR CORES (sm_100a): every bmm of the reference op graph
+// (gloria/loss/gloria_loss.py:40,59 and their autograd) runs on the CTA-pair tcgen05 GEMM of tc_gemm.cu with
+// SPLIT-PRECISION operands, the softmaxes / cosine / aggregation are streaming fp32 kernels in between.
+//
+// Split precision: an fp32 value x is carried as three bf16 pieces x = p0 + p1 + p2 (p0 = bf16(x), p1 = bf16(x - p0),
+// p2 = bf16(x - p0 - p1): 24 significant bits, every piece product is exact in the fp32 accumulator).  A GEMM sums
+//   6 terms  p2.q0 + p1.q1 + p0.q2 + p1.q0 + p0.q1 + p0.q0      (everything down to 2^-24: the forward, 1e-5 gate) or
+//   3 terms  p1.q0 + p0.q1 + p0.q0                              (2^-16: gradient GEMMs)
+// as runs of k-blocks into ONE accumulator, smallest term first -- tensor memory accumulates round-toward-zero
+// (profiles/r02_tmem_accumulation_rounding_probe.txt), so the large term must come last: K = 768 then lands at
+// 9e-7 rms of the exact result, the same as an fp32 FFMA loop.
+//
+// Layout (chunk of nc captions [i0, i0+nc), all Bi images; Sq = round_up(S, 64), Lp = round_up(Lcap, 8),
+// NC = round_up(nc * Lp, 64)): the big matrices have rows (j, s) and columns (ii, l), like X^T of the bf16 backward.
+//   Rt_p  [3][Bi*Sq, D]  bf16   region features, rows (j, s)            (A of the score GEMM, B of GEMMs 2 and 5)
+//   Rn_p  [3][Bi*D, Sq]  bf16   region features, rows (j, d)            (B of GEMM 3)
+//   Wn_p  [3][D, NC]     bf16   words of the chunk, columns (ii, l)     (B of the score GEMM)
+//   Wt_p  [3][NC, D]     bf16   words of the chunk, rows (ii, l)        (B of GEMM 6)
+//   SC    [Bi*Sq, NC]    fp32   scores, then P (word softmax)           GEMM 1:  SC = Rt Wn
+//   AT_p  [3][Bi*Sq, NC] bf16   attention A (region softmax)
+//   CX    [Bi][NC, D]    fp32   context                                 GEMM 2:  CX_j = AT_j^T Rt_j          (batched over j)
+//   dC_p  [3][Bi*NC, D]  bf16   dL/dC                                   (cosine backward)
+//   DAt   [Bi][NC, Sq]   fp32   dL/dA, transposed blocks                GEMM 3:  DAt_j = dC_j Rn_j           (batched)
+//   dRt   [Bi*Sq, D]     fp32   region gradient                         GEMM 4:  dRt_j += AT_j dC_j          (batched)
+//   DS_p  [3][Bi*Sq, NC] bf16   dL/dscores                              (softmax backward)
+//   dWc   [NC, D]        fp32   word gradient of the chunk              GEMM 5:  dWc = DS^T Rt
+//                                                                       GEMM 6:  dRt += DS Wt
+// Everything inside the tensor-map extents is written (padding = exact zeros): the GEMM reads whole tiles.
+#include <math.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace gloria {
+namespace f32tc {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void split3(float x, bf16& p0, bf16& p1, bf16& p2) {
+  p0 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(p0);
+  p1 = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(p1);
+  p2 = __float2bfloat16_rn(r2);
+}
+__device__ __forceinline__ float join3(bf16 p0, bf16 p1, bf16 p2) {
+  return (__bfloat162float(p2) + __bfloat162float(p1)) + __bfloat162float(p0);     // exact: the pieces do not overlap
+}
+
+// ctx [Bi, D, S] fp32 -> Rt_p [3][Bi*Sq, D] (transposed; rows s >= S zero) and Rn_p [3][Bi*D, Sq] (columns s >= S zero; or null)
+__global__ void split_ctx(const float* __restrict__ ctx, bf16* __restrict__ rt, bf16* __restrict__ rn, int Bi, int D, int S, int Sq) {
+  __shared__ float t[32][33];
+  const int j = blockIdx.z, s0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const size_t rt_plane = (size_t)Bi * Sq * D, rn_plane = (size_t)Bi * D * Sq;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int d = d0 + r, s = s0 + threadIdx.x;
+    const float v = (s < S) ? ctx[((size_t)j * D + d) * S + s] : 0.f;
+    t[r][threadIdx.x] = v;
+    if (rn != nullptr) {
+      bf16 p0, p1, p2;
+      split3(v, p0, p1, p2);
+      const size_t o = ((size_t)j * D + d) * Sq + s;
+      rn[o] = p0; rn[rn_plane + o] = p1; rn[2 * rn_plane + o] = p2;
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int s = s0 + r, d = d0 + threadIdx.x;
+    bf16 p0, p1, p2;
+    split3(t[threadIdx.x][r], p0, p1, p2);
+    const size_t o = ((size_t)j * Sq + s) * D + d;
+    rt[o] = p0; rt[rt_plane + o] = p1; rt[2 * rt_plane + o] = p2;
+  }
+}
+
+// words [Bc, D, Lw] -> Wt32 [Bc, Lw, D]
+__global__ void transpose_words(const float* __restrict__ in, float* __restrict__ out, int D, int L) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const float* ib = in + (size_t)b * D * L;
+  float* ob = out + (size_t)b * D * L;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int d = d0 + r, l = l0 + threadIdx.x;
+    t[r][threadIdx.x] = (d < D && l < L) ? ib[(size_t)d * L + l] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int l = l0 + r, d = d0 + threadIdx.x;
+    if (l < L && d < D) ob[(size_t)l * D + d] = t[threadIdx.x][r];
+  }
+}
+__global__ void word_norms(const float* __restrict__ x, float* __restrict__ n, long long rows, int D) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * D;
+  float s = 0.f;
+  for (int d = lane; d < D; d += 32) s = fmaf(xr[d], xr[d], s);
+  s = warp_sum(s);
+  if (lane == 0) n[row] = sqrtf(s);
+}
+
+// Wt32 rows of the chunk -> Wt_p [3][NC, D] (or null) and Wn_p [3][D, NC]; column c = ii * Lp + l, zero beyond the caption
+__global__ void split_words(const float* __restrict__ wt32, const int* __restrict__ cap_lens, bf16* __restrict__ wnp,
+                            bf16* __restrict__ wtp, int i0, int nc, int Lw, int Lcap, int Lp, int off, int D, int NC) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const size_t plane = (size_t)NC * D;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, d = d0 + threadIdx.x;
+    const int ii = c / Lp, l = c - ii * Lp;
+    float v = 0.f;
+    if (ii < nc) {
+      const int L = min(max(cap_lens[i0 + ii], 0), Lcap);
+      if (l < L) v = wt32[((size_t)(i0 + ii) * Lw + off + l) * D + d];
+    }
+    t[r][threadIdx.x] = v;
+    if (wtp != nullptr) {
+      bf16 p0, p1, p2;
+      split3(v, p0, p1, p2);
+      const size_t o = (size_t)c * D + d;
+      wtp[o] = p0; wtp[plane + o] = p1; wtp[2 * plane + o] = p2;
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int d = d0 + r, c = c0 + threadIdx.x;
+    bf16 p0, p1, p2;
+    split3(t[threadIdx.x][r], p0, p1, p2);
+    const size_t o = (size_t)d * NC + c;
+    wnp[o] = p0; wnp[plane + o] = p1; wnp[2 * plane + o] = p2;
+  }
+}
+
+// Double softmax of one (image, caption) block (gloria_loss.py:42-53).  SC block: scores on entry, P (word softmax) on exit.
+// AT_p block: A = softmax_s(temp1 P) as bf16 pieces, zero in padded rows / columns.  dynamic smem: S * (Lp + 1) + 3 * 128 floats
+__global__ void __launch_bounds__(256) softmax_fwd(float* __restrict__ sc, bf16* __restrict__ atp, const int* __restrict__ cap_lens,
+                                                   int i0, int nc, int Bi, int Bc, int S, int Sq, int Lcap, int Lp, int NC,
+                                                   float temp1, float* __restrict__ attn_diag, float* __restrict__ attn_mean) {
+  extern __shared__ float sm[];
+  const int LP1 = Lp + 1;
+  float* tile = sm;                          // E[s][l]
+  float* zpart = sm + (size_t)S * LP1;       // [2][128]
+  float* invz = zpart + 256;                 // [128]
+  const int p = blockIdx.x, j = p / nc, ii = p - j * nc, i = i0 + ii;
+  const int L = min(max(cap_lens[i], 0), Lcap);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  float* scb = sc + (size_t)j * Sq * NC + (size_t)ii * Lp;
+  // softmax #1 over the caption's words, warp per region row (coalesced along l)
+  for (int s = warp; s < S; s += nwarps) {
+    float* row = scb + (size_t)s * NC;
+    float m = -INFINITY;
+    for (int l = lane; l < L; l += 32) m = fmaxf(m, row[l]);
+    m = warp_max(m);
+    float den = 0.f;
+    for (int l = lane; l < L; l += 32) den += expf(row[l] - m);
+    den = warp_sum(den);
+    const float inv = 1.f / den;
+    for (int l = lane; l < Lp; l += 32) {
+      const float P = (l < L) ? expf(row[l] - m) * inv : 0.f;
+      row[l] = P;
+      tile[(size_t)s * LP1 + l] = (l < L) ? expf(temp1 * P) : 0.f;
+    }
+  }
+  __syncthreads();
+  // softmax #2 over the regions: Z_l (two threads per word, rows interleaved)
+  {
+    const int l = tid & 127, half = tid >> 7;
+    float z = 0.f;
+    if (l < Lp)
+      for (int s = half; s < S; s += 2) z += tile[(size_t)s * LP1 + l];
+    zpart[half * 128 + l] = z;
+  }
+  __syncthreads();
+  if (tid < 128) invz[tid] = (tid < L) ? 1.f / (zpart[tid] + zpart[128 + tid]) : 0.f;
+  __syncthreads();
+  // A as bf16 pieces, two words per thread
+  const size_t plane = (size_t)Bi * Sq * NC;
+  const int half_lp = Lp >> 1;
+  bf16* ab = atp + (size_t)j * Sq * NC + (size_t)ii * Lp;
+  for (int idx = tid; idx < Sq * half_lp; idx += blockDim.x) {
+    const int s = idx / half_lp, l = (idx - s * half_lp) * 2;
+    float a0 = 0.f, a1 = 0.f;
+    if (s < S) {
+      a0 = tile[(size_t)s * LP1 + l] * invz[l];
+      a1 = tile[(size_t)s * LP1 + l + 1] * invz[l + 1];
+    }
+    bf16 x0, x1, x2, y0, y1, y2;
+    split3(a0, x0, x1, x2);
+    split3(a1, y0, y1, y2);
+    const size_t o = (size_t)s * NC + l;
+    *reinterpret_cast<__nv_bfloat162*>(ab + o) = __nv_bfloat162(x0, y0);
+    *reinterpret_cast<__nv_bfloat162*>(ab + plane + o) = __nv_bfloat162(x1, y1);
+    *reinterpret_cast<__nv_bfloat162*>(ab + 2 * plane + o) = __nv_bfloat162(x2, y2);
+  }
+  if (attn_diag != nullptr && j == i) {       // att_maps of the diagonal pair, [Bc, Lcap, S] (gloria_loss.py:141-143)
+    float* dg = attn_diag + (size_t)i * Lcap * S;
+    for (int idx = tid; idx < Lcap * S; idx += blockDim.x) {
+      const int l = idx / S, s = idx - l * S;
+      dg[idx] = (l < L) ? tile[(size_t)s * LP1 + l] * invz[l] : 0.f;
+    }
+  }
+  if (attn_mean != nullptr) {                 // word-mean attention (gloria_loss.py:132), [Bi, Bc, S]
+    float* mo = attn_mean + ((size_t)j * Bc + i) * S;
+    const float invL = L > 0 ? 1.f / (float)L : 0.f;
+    for (int s = tid; s < S; s += blockDim.x) {
+      float acc = 0.f;
+      for (int l = 0; l < L; ++l) acc += tile[(size_t)s * LP1 + l] * invz[l];
+      mo[s] = acc * invL;
+    }
+  }
+}
+
+// Per-word cosine (gloria_loss.py:11-16,150) + aggregation over words (:153-158); in backward mode also the per-word
+// coefficients ddot, beta = dnc / nc, gamma = dnw / nw of the closed-form backward.  One CTA per pair; smem 3 * Lp floats.
+__global__ void __launch_bounds__(256) cosine_agg(const float* __restrict__ cx, const float* __restrict__ wt32,
+                                                  const float* __restrict__ wn, const int* __restrict__ cap_lens, int i0, int nc,
+                                                  int Bc, int Lcap, int Lp, int NC, int Lw, int off, int D, float temp2, int agg,
+                                                  float eps, float* __restrict__ sim, const float* __restrict__ dsim,
+                                                  float* __restrict__ coef) {
+  extern __shared__ float sm[];
+  float* r_s = sm;
+  float* dot_s = sm + Lp;
+  float* nc_s = sm + 2 * Lp;
+  const int p = blockIdx.x, j = p / nc, ii = p - j * nc, i = i0 + ii;
+  const int L = min(max(cap_lens[i], 0), Lcap);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int l = warp; l < L; l += nwarps) {
+    const float* w = wt32 + ((size_t)i * Lw + off + l) * D;
+    const float* c = cx + ((size_t)j * NC + (size_t)ii * Lp + l) * D;
+    float dot = 0.f, c2 = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float cv = c[d];
+      dot = fmaf(w[d], cv, dot);
+      c2 = fmaf(cv, cv, c2);
+    }
+    dot = warp_sum(dot);
+    c2 = warp_sum(c2);
+    if (lane == 0) {
+      const float ncv = sqrtf(c2);
+      const float den = fmaxf(wn[(size_t)i * Lw + off + l] * ncv, eps);
+      r_s[l] = dot / den;
+      dot_s[l] = dot;
+      nc_s[l] = ncv;
+    }
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  float m = -INFINITY;
+  for (int l = lane; l < L; l += 32) m = fmaxf(m, r_s[l]);
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int l = lane; l < L; l += 32) sum += expf(temp2 * (r_s[l] - m));
+  sum = warp_sum(sum);
+  if (lane == 0 && sim != nullptr) {
+    float v;
+    if (agg == GLORIA_AGG_MAX) v = temp2 * m;
+    else {
+      v = temp2 * m + logf(sum);
+      if (agg == GLORIA_AGG_MEAN) v -= logf((float)L);
+    }
+    sim[(size_t)j * Bc + i] = v;
+  }
+  if (dsim == nullptr) return;
+  const float g = dsim[(size_t)j * Bc + i];
+  float* cf = coef + (size_t)p * 3 * Lp;
+  for (int l = lane; l < Lp; l += 32) {
+    float ddot = 0.f, beta = 0.f, gamma = 0.f;
+    if (l < L) {
+      const float q = expf(temp2 * (r_s[l] - m)) / sum;
+      const float dr = g * temp2 * q;
+      const float nwv = wn[(size_t)i * Lw + off + l], ncv = nc_s[l], dot = dot_s[l];
+      const float prod = nwv * ncv;
+      const float den = fmaxf(prod, eps);
+      ddot = dr / den;
+      const float dden = (prod >= eps) ? -dr * dot / (den * den) : 0.f;
+      beta = ncv > 0.f ? dden * nwv / ncv : 0.f;      // (dL/d|C|) / |C|
+      gamma = nwv > 0.f ? dden * ncv / nwv : 0.f;     // (dL/d|W|) / |W|
+    }
+    cf[l] = ddot;
+    cf[Lp + l] = beta;
+    cf[2 * Lp + l] = gamma;
+  }
+}
+
+// dC = ddot W + beta C as bf16 pieces (zero rows beyond the caption), and the direct word gradient
+// dWt32[i][off+l][:] = sum_j ddot C + gamma W.   grid (Lp, nc): one CTA owns word l of caption i0 + ii.
+__global__ void __launch_bounds__(256) context_grad(const float* __restrict__ cx, const float* __restrict__ wt32,
+                                                    float* __restrict__ dwt32, const float* __restrict__ coef,
+                                                    const int* __restrict__ cap_lens, bf16* __restrict__ dcp, int i0, int nc,
+                                                    int Bi, int Lcap, int Lp, int NC, int Lw, int off, int D) {
+  const int l = blockIdx.x, ii = blockIdx.y, i = i0 + ii;
+  const int L = min(max(cap_lens[i], 0), Lcap);
+  const bool live = l < L;
+  const float* w = wt32 + ((size_t)i * Lw + off + l) * D;
+  float* dw = dwt32 + ((size_t)i * Lw + off + l) * D;
+  const size_t plane = (size_t)Bi * NC * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float wv = live ? w[d] : 0.f;
+    float acc = 0.f;
+    for (int j = 0; j < Bi; ++j) {
+      const size_t row = (size_t)j * NC + (size_t)ii * Lp + l;
+      float dc = 0.f;
+      if (live) {
+        const float* cf = coef + ((size_t)j * nc + ii) * 3 * Lp;
+        const float ddot = cf[l], beta = cf[Lp + l], gamma = cf[2 * Lp + l];
+        const float cv = cx[row * D + d];
+        dc = fmaf(ddot, wv, beta * cv);
+        acc += fmaf(ddot, cv, gamma * wv);
+      }
+      bf16 p0, p1, p2;
+      split3(dc, p0, p1, p2);
+      const size_t o = row * D + d;
+      dcp[o] = p0; dcp[plane + o] = p1; dcp[2 * plane + o] = p2;
+    }
+    if (live) dw[d] = acc;
+  }
+}
+
+// Backward of the two softmaxes for one (image, caption) block.  DAt block [Lp, Sq]: dL/dA (transposed); AT_p: A;
+// SC block: P.  Output DS_p block: dL/dscores as bf16 pieces (zero in padded rows / columns).
+// dynamic smem: S * (Lp + 1) + 3 * 128 floats
+__global__ void __launch_bounds__(256) softmax_bwd(const float* __restrict__ dat, const bf16* __restrict__ atp,
+                                                   const float* __restrict__ sc, bf16* __restrict__ dsp,
+                                                   const int* __restrict__ cap_lens, int i0, int nc, int Bi, int Bc, int S, int Sq,
+                                                   int Lcap, int Lp, int NC, float temp1, const float* __restrict__ d_attn_diag,
+                                                   const float* __restrict__ d_attn_mean) {
+  extern __shared__ float sm[];
+  const int LP1 = Lp + 1;
+  float* tile = sm;                          // g[s][l]
+  float* zpart = sm + (size_t)S * LP1;       // [2][128]
+  float* rs = zpart + 256;                   // [128]
+  const int p = blockIdx.x, j = p / nc, ii = p - j * nc, i = i0 + ii;
+  const int L = min(max(cap_lens[i], 0), Lcap);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const float* db = dat + ((size_t)j * NC + (size_t)ii * Lp) * Sq;
+  const float* ed = (d_attn_diag != nullptr && j == i) ? d_attn_diag + (size_t)i * Lcap * S : nullptr;
+  const float* em = (d_attn_mean != nullptr) ? d_attn_mean + ((size_t)j * Bc + i) * S : nullptr;
+  const float invL = L > 0 ? 1.f / (float)L : 0.f;
+  for (int idx = tid; idx < L * S; idx += blockDim.x) {
+    const int l = idx / S, s = idx - l * S;
+    float v = db[(size_t)l * Sq + s];
+    if (ed) v += ed[idx];
+    if (em) v += em[s] * invL;
+    tile[(size_t)s * LP1 + l] = v;
+  }
+  __syncthreads();
+  // softmax #2 backward: dZ = A (dA - sum_s A dA);  dP = temp1 dZ      (two threads per word, rows interleaved)
+  const size_t plane = (size_t)Bi * Sq * NC;
+  const bf16* ab = atp + (size_t)j * Sq * NC + (size_t)ii * Lp;
+  const int lc = tid & 127, half = tid >> 7;
+  {
+    float acc = 0.f;
+    if (lc < L)
+      for (int s = half; s < S; s += 2) {
+        const size_t o = (size_t)s * NC + lc;
+        acc = fmaf(join3(ab[o], ab[plane + o], ab[2 * plane + o]), tile[(size_t)s * LP1 + lc], acc);
+      }
+    zpart[half * 128 + lc] = acc;
+  }
+  __syncthreads();
+  if (tid < 128) rs[tid] = zpart[tid] + zpart[128 + tid];
+  __syncthreads();
+  if (lc < L) {
+    const float r = rs[lc];
+    for (int s = half; s < S; s += 2) {
+      const size_t o = (size_t)s * NC + lc;
+      const float a = join3(ab[o], ab[plane + o], ab[2 * plane + o]);
+      float* t = tile + (size_t)s * LP1 + lc;
+      *t = temp1 * a * (*t - r);
+    }
+  }
+  __syncthreads();
+  // softmax #1 backward: dS = P (dP - sum_l P dP), warp per region row; bf16 pieces out
+  const float* pb = sc + (size_t)j * Sq * NC + (size_t)ii * Lp;
+  bf16* ob = dsp + (size_t)j * Sq * NC + (size_t)ii * Lp;
+  for (int s = warp; s < Sq; s += nwarps) {
+    const size_t ro = (size_t)s * NC;
+    float t = 0.f;
+    if (s < S) {
+      for (int l = lane; l < L; l += 32) t = fmaf(pb[ro + l], tile[(size_t)s * LP1 + l], t);
+      t = warp_sum(t);
+    }
+    for (int l = lane; l < Lp; l += 32) {
+      float v = 0.f;
+      if (s < S && l < L) v = pb[ro + l] * (tile[(size_t)s * LP1 + l] - t);
+      bf16 p0, p1, p2;
+      split3(v, p0, p1, p2);
+      ob[ro + l] = p0; ob[plane + ro + l] = p1; ob[2 * plane + ro + l] = p2;
+    }
+  }
+}
+
+// dWt32[i0+ii][off+l][:] += dWc[ii*Lp + l][:]  for the live words of the chunk
+__global__ void add_word_grad(const float* __restrict__ dwc, float* __restrict__ dwt32, const int* __restrict__ cap_lens, int i0,
+                              int Lcap, int Lp, int Lw, int off, int D) {
+  const int l = blockIdx.x, ii = blockIdx.y, i = i0 + ii;
+  const int L = min(max(cap_lens[i], 0), Lcap);
+  if (l >= L) return;
+  const float* src = dwc + ((size_t)ii * Lp + l) * D;
+  float* dst = dwt32 + ((size_t)i * Lw + off + l) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) dst[d] += src[d];
+}
+
+// dRt [Bi*Sq, D] -> d_ctx [Bi, D, S]
+__global__ void unpack_dctx(const float* __restrict__ drt, float* __restrict__ d_ctx, int D, int S, int Sq) {
+  __shared__ float t[32][33];
+  const int j = blockIdx.z, s0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int s = s0 + r, d = d0 + threadIdx.x;
+    t[r][threadIdx.x] = drt[((size_t)j * Sq + s) * D + d];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int d = d0 + r, s = s0 + threadIdx.x;
+    if (s < S) d_ctx[((size_t)j * D + d) * S + s] = t[threadIdx.x][r];
+  }
+}
+// dWt32 [Bc, Lw, D] -> d_words [Bc, D, Lw], zero outside [off, off + cap_len)
+__global__ void unpack_dwords(const float* __restrict__ dwt, float* __restrict__ dwords, const int* __restrict__ cap_lens, int D,
+                              int Lw, int Lcap, int off) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, l0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int L = min(max(cap_lens[b], 0), Lcap);
+  const float* ib = dwt + (size_t)b * D * Lw;
+  float* ob = dwords + (size_t)b * D * Lw;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int l = l0 + r, d = d0 + threadIdx.x;
+    t[r][threadIdx.x] = (l < Lw && d < D && l >= off && l < off + L) ? ib[(size_t)l * D + d] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int d = d0 + r, l = l0 + threadIdx.x;
+    if (d < D && l < Lw) ob[(size_t)d * Lw + l] = t[threadIdx.x][r];
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// host orchestration
+// -------------------------------------------------------------------------------------------------------------
+struct Dims {
+  int Bi, Bc, D, S, Sq, Lw, Lcap, Lp, off;
+};
+struct Plan {
+  int nc, NCmax;
+  size_t rt, rn, wt32, wn, dwt32, drt, wnp, wtp, sc, atp, cx, coef, dcp, dat, dsp, dwc, total;
+};
+
+static int round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+static size_t softmax_smem(int S, int Lp) { return ((size_t)S * (Lp + 1) + 3 * 128) * sizeof(float); }
+
+static size_t fixed_bytes(const Dims& d, bool bwd) {
+  size_t f = align_up((size_t)3 * d.Bi * d.Sq * d.D * 2, 256) + align_up((size_t)d.Bc * d.Lw * d.D * 4, 256) +
+             align_up((size_t)d.Bc * d.Lw * 4, 256);
+  if (bwd) f += align_up((size_t)3 * d.Bi * d.D * d.Sq * 2, 256) + align_up((size_t)d.Bc * d.Lw * d.D * 4, 256) +
+                align_up((size_t)d.Bi * d.Sq * d.D * 4, 256);
+  return f + 8192;
+}
+// bytes per column (ii, l) of the chunk matrices
+static size_t column_bytes(const Dims& d, bool bwd) {
+  size_t c = (size_t)6 * d.D + (size_t)d.Bi * d.Sq * 4 + (size_t)d.Bi * d.Sq * 6 + (size_t)d.Bi * d.D * 4;
+  if (bwd) c += (size_t)6 * d.D + (size_t)d.Bi * 12 + (size_t)d.Bi * d.D * 6 + (size_t)d.Bi * d.Sq * 4 + (size_t)d.Bi * d.Sq * 6 +
+                (size_t)d.D * 4;
+  return c;
+}
+static Plan make_plan(const Dims& d, size_t bytes, bool bwd) {
+  Plan pl{};
+  const size_t fixed = fixed_bytes(d, bwd), col = column_bytes(d, bwd);
+  const size_t min_cols = (size_t)round_up(d.Lp, 64);
+  if (bytes < fixed + col * min_cols + 16 * 256) { pl.nc = 0; return pl; }
+  size_t cols = (bytes - fixed - 16 * 256) / col;
+  size_t nc = cols >= 64 ? (cols - 63) / d.Lp : 0;          // NC = round_up(nc * Lp, 64) <= nc * Lp + 63
+  if (nc < 1) nc = 1;
+  if (nc > (size_t)d.Bc) nc = d.Bc;
+  pl.nc = (int)nc;
+  const size_t NC = (size_t)round_up((int)nc * d.Lp, 64);
+  pl.NCmax = (int)NC;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += align_up(n, 256); return r; };
+  pl.rt = take((size_t)3 * d.Bi * d.Sq * d.D * 2);
+  pl.wt32 = take((size_t)d.Bc * d.Lw * d.D * 4);
+  pl.wn = take((size_t)d.Bc * d.Lw * 4);
+  pl.wnp = take((size_t)3 * d.D * NC * 2);
+  pl.sc = take((size_t)d.Bi * d.Sq * NC * 4);
+  pl.atp = take((size_t)3 * d.Bi * d.Sq * NC * 2);
+  pl.cx = take((size_t)d.Bi * NC * d.D * 4);
+  if (bwd) {
+    pl.rn = take((size_t)3 * d.Bi * d.D * d.Sq * 2);
+    pl.dwt32 = take((size_t)d.Bc * d.Lw * d.D * 4);
+    pl.drt = take((size_t)d.Bi * d.Sq * d.D * 4);
+    pl.wtp = take((size_t)3 * NC * d.D * 2);
+    pl.coef = take((size_t)d.Bi * nc * 3 * d.Lp * 4);
+    pl.dcp = take((size_t)3 * d.Bi * NC * d.D * 2);
+    pl.dat = take((size_t)d.Bi * NC * d.Sq * 4);
+    pl.dsp = take((size_t)3 * d.Bi * d.Sq * NC * 2);
+    pl.dwc = take(NC * d.D * 4);
+  }
+  pl.total = o;
+  if (pl.total > bytes) pl.nc = 0;
+  return pl;
+}
+
+static int supported(int D, int S, int Lcap) {
+  if (D <= 0 || S <= 0 || Lcap <= 0) return 1;
+  if (D % 64) return 1;
+  const int Lp = round_up(Lcap, 8);
+  if (Lp > 128) return 1;
+  if (softmax_smem(S, Lp) > 220 * 1024) return 1;
+  return 0;
+}
+
+static int check_common(const void* ctx, const void* words, const void* cap_lens, int Bi, int Bc, int D, int S, int Lw, int Lcap,
+                        int word_off, int agg) {
+  GLORIA_CHECK_ARG(ctx && words && cap_lens, "null input pointer");
+  GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && D > 0 && S > 0 && Lw > 0, "non-positive size (Bi=%d Bc=%d D=%d S=%d Lw=%d)", Bi, Bc, D, S, Lw);
+  GLORIA_CHECK_ARG(word_off >= 0 && Lcap > 0 && word_off + Lcap <= Lw, "caption window [%d, %d) exceeds the word axis (%d)",
+                   word_off, word_off + Lcap, Lw);
+  GLORIA_CHECK_ARG(agg == GLORIA_AGG_SUM || agg == GLORIA_AGG_MEAN || agg == GLORIA_AGG_MAX, "bad agg %d", agg);
+  if (supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "fp32 tensor-core path needs D %% 64 == 0 and cap_len <= 128 (D=%d S=%d Lcap=%d)", D, S, Lcap);
+  if ((long long)Bi * round_up(S, 64) >= (1 << 24)) return fail(GLORIA_ERR_UNSUPPORTED, "too many region rows");
+  return GLORIA_OK;
+}
+
+// pieces of the region features and the fp32 word rows + norms: once per call
+static int prepare(const float* ctx, const float* words, const Dims& d, const Plan& pl, char* ws, bool bwd, cudaStream_t st) {
+  bf16* rt = (bf16*)(ws + pl.rt);
+  bf16* rn = bwd ? (bf16*)(ws + pl.rn) : nullptr;
+  split_ctx<<<dim3(d.Sq / 32, d.D / 32, d.Bi), dim3(32, 8), 0, st>>>(ctx, rt, rn, d.Bi, d.D, d.S, d.Sq);
+  GLORIA_LAUNCHED("f32tc::split_ctx");
+  float* wt32 = (float*)(ws + pl.wt32);
+  transpose_words<<<dim3((d.Lw + 31) / 32, (d.D + 31) / 32, d.Bc), dim3(32, 8), 0, st>>>(words, wt32, d.D, d.Lw);
+  GLORIA_LAUNCHED("f32tc::transpose_words");
+  const long long rows = (long long)d.Bc * d.Lw;
+  word_norms<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(wt32, (float*)(ws + pl.wn), rows, d.D);
+  GLORIA_LAUNCHED("f32tc::word_norms");
+  return GLORIA_OK;
+}
+
+// scores, P, A, C of the chunk [i0, i0 + nc)
+static int chunk_forward(const Dims& d, const Plan& pl, char* ws, const int32_t* cap_lens, int i0, int nc, int NC, float temp1,
+                         int score_terms, int ctx_terms, bool bwd, float* attn_diag, float* attn_mean, cudaStream_t st) {
+  int rc;
+  bf16* rt = (bf16*)(ws + pl.rt);
+  bf16* wnp = (bf16*)(ws + pl.wnp);
+  bf16* wtp = bwd ? (bf16*)(ws + pl.wtp) : nullptr;
+  float* sc = (float*)(ws + pl.sc);
+  bf16* atp = (bf16*)(ws + pl.atp);
+  float* cx = (float*)(ws + pl.cx);
+  split_words<<<dim3(NC / 32, d.D / 32), dim3(32, 8), 0, st>>>((const float*)(ws + pl.wt32), cap_lens, wnp, wtp, i0, nc, d.Lw,
+                                                              d.Lcap, d.Lp, d.off, d.D, NC);
+  GLORIA_LAUNCHED("f32tc::split_words");
+  {  // GEMM 1: SC[(j,s), (ii,l)] = sum_d R[(j,s), d] W[d, (ii,l)]            (bmm #1, gloria_loss.py:40)
+    tc::GemmEx e{};
+    e.A = rt; e.B = wnp; e.C = sc;
+    e.M = d.Bi * d.Sq; e.N = NC; e.K = d.D; e.ldc = NC; e.a_kmajor = true; e.ksplit = 1;
+    e.nb = 1; e.nterms = score_terms;
+    e.a_prows = (long long)d.Bi * d.Sq; e.b_prows = d.D;
+    e.a_rows = 3LL * d.Bi * d.Sq; e.b_rows = 3LL * d.D;
+    if ((rc = tc::acc_gemm_ex(e, st))) return rc;
+  }
+  softmax_fwd<<<(unsigned)(d.Bi * nc), 256, softmax_smem(d.S, d.Lp), st>>>(sc, atp, cap_lens, i0, nc, d.Bi, d.Bc, d.S, d.Sq, d.Lcap,
+                                                                          d.Lp, NC, temp1, attn_diag, attn_mean);
+  GLORIA_LAUNCHED("f32tc::softmax_fwd");
+  if (NC > nc * d.Lp) {      // padding columns of A: exact zeros in every plane
+    GLORIA_CUDA(cudaMemset2DAsync(atp + (size_t)nc * d.Lp, (size_t)NC * 2, 0, (size_t)(NC - nc * d.Lp) * 2, (size_t)3 * d.Bi * d.Sq, st));
+  }
+  {  // GEMM 2: CX_j[(ii,l), d] = sum_s A[(j,s), (ii,l)] R[(j,s), d]           (bmm #2, gloria_loss.py:59)
+    tc::GemmEx e{};
+    e.A = atp; e.B = rt; e.C = cx;
+    e.M = NC; e.N = d.D; e.K = d.Sq; e.ldc = d.D; e.a_kmajor = false; e.ksplit = 1;
+    e.nb = d.Bi; e.a_brows = d.Sq; e.b_brows = d.Sq; e.c_bstride = (long long)NC * d.D;
+    e.nterms = ctx_terms;
+    e.a_prows = (long long)d.Bi * d.Sq; e.b_prows = (long long)d.Bi * d.Sq;
+    e.a_rows = 3LL * d.Bi * d.Sq; e.b_rows = 3LL * d.Bi * d.Sq;
+    if ((rc = tc::acc_gemm_ex(e, st))) return rc;
+  }
+  return GLORIA_OK;
+}
+
+}  // namespace f32tc
+}  // namespace gloria
+
+using namespace gloria;
+using namespace gloria::f32tc;
+
+extern "C" int gloria_b200_f32tc_supported(int D, int S, int Lcap) { return supported(D, S, Lcap); }
+
+extern "C" size_t gloria_b200_local_f32tc_workspace(int Bi, int Bc, int D, int S, int Lw, int Lcap, size_t budget, int backward) {
+  if (Bi <= 0 || Bc <= 0 || D <= 0 || S <= 0 || Lw <= 0 || Lcap <= 0) return 0;
+  Dims d{Bi, Bc, D, S, round_up(S, 64), Lw, Lcap, round_up(Lcap, 8), 0};
+  const bool bwd = backward != 0;
+  const size_t fixed = fixed_bytes(d, bwd), col = column_bytes(d, bwd);
+  size_t want = fixed + col * ((size_t)Bc * d.Lp + 64) + 16 * 256;
+  const size_t least = fixed + col * ((size_t)d.Lp + 64) + 16 * 256;
+  if (budget != 0 && want > budget) want = budget > least ? budget : least;
+  return want;
+}
+
+static int set_smem(const void* fn, size_t bytes) {
+  GLORIA_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_local_sim_fwd_f32tc(const float* ctx, const float* words, const int32_t* cap_lens, int Bi, int Bc, int D,
+                                               int S, int Lw, int Lcap, int word_off, float temp1, float temp2, int agg, float eps,
+                                               float* sim, float* attn_diag, float* attn_mean, void* workspace,
+                                               size_t workspace_bytes, void* stream) {
+  int rc = check_common(ctx, words, cap_lens, Bi, Bc, D, S, Lw, Lcap, word_off, agg);
+  if (rc) return rc;
+  GLORIA_CHECK_ARG(sim != nullptr && workspace != nullptr, "null output / workspace");
+  GLORIA_CHECK_ARG(attn_diag == nullptr || Bi == Bc, "attn_diag needs Bi == Bc (got %d x %d)", Bi, Bc);
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d{Bi, Bc, D, S, round_up(S, 64), Lw, Lcap, round_up(Lcap, 8), word_off};
+  const Plan pl = make_plan(d, workspace_bytes, false);
+  if (pl.nc < 1) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B too small", workspace_bytes);
+  if ((rc = set_smem((const void*)softmax_fwd, softmax_smem(S, d.Lp)))) return rc;
+  char* ws = (char*)workspace;
+  if ((rc = prepare(ctx, words, d, pl, ws, false, st))) return rc;
+  for (int i0 = 0; i0 < Bc; i0 += pl.nc) {
+    const int nc = min(pl.nc, Bc - i0);
+    const int NC = round_up(nc * d.Lp, 64);
+    if ((rc = chunk_forward(d, pl, ws, cap_lens, i0, nc, NC, temp1, 6, 6, false, attn_diag, attn_mean, st))) return rc;
+    cosine_agg<<<(unsigned)(Bi * nc), 256, 3 * d.Lp * sizeof(float), st>>>(
+        (const float*)(ws + pl.cx), (const float*)(ws + pl.wt32), (const float*)(ws + pl.wn), cap_lens, i0, nc, Bc, Lcap, d.Lp, NC, Lw,
+        word_off, D, temp2, agg, eps, sim, nullptr, nullptr);
+    GLORIA_LAUNCHED("f32tc::cosine_agg");
+  }
+  return GLORIA_OK;
+}
+
+extern "C" int gloria_b200_local_sim_bwd_f32tc(const float* ctx, const float* words, const int32_t* cap_lens, int Bi, int Bc, int D,
+                                               int S, int Lw, int Lcap, int word_off, float temp1, float temp2, int agg, float eps,
+                                               const float* dsim, const float* d_attn_diag, const float* d_attn_mean, float* d_ctx,
+                                               float* d_words, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(ctx, words, cap_lens, Bi, Bc, D, S, Lw, Lcap, word_off, agg);
+  if (rc) return rc;
+  GLORIA_CHECK_ARG(dsim && d_ctx && d_words && workspace, "null gradient / workspace pointer");
+  GLORIA_CHECK_ARG(d_attn_diag == nullptr || Bi == Bc, "d_attn_diag needs Bi == Bc (got %d x %d)", Bi, Bc);
+  if (agg == GLORIA_AGG_MAX) return fail(GLORIA_ERR_UNSUPPORTED, "backward of agg=max is not part of the path");
+  cudaStream_t st = (cudaStream_t)stream;
+  Dims d{Bi, Bc, D, S, round_up(S, 64), Lw, Lcap, round_up(Lcap, 8), word_off};
+  const Plan pl = make_plan(d, workspace_bytes, true);
+  if (pl.nc < 1) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B too small", workspace_bytes);
+  if ((rc = set_smem((const void*)softmax_fwd, softmax_smem(S, d.Lp)))) return rc;
+  if ((rc = set_smem((const void*)softmax_bwd, softmax_smem(S, d.Lp)))) return rc;
+  char* ws = (char*)workspace;
+  bf16* rt = (bf16*)(ws + pl.rt);
+  bf16* rn = (bf16*)(ws + pl.rn);
+  float* wt32 = (float*)(ws + pl.wt32);
+  float* wn = (float*)(ws + pl.wn);
+  float* dwt32 = (float*)(ws + pl.dwt32);
+  float* drt = (float*)(ws + pl.drt);
+  bf16* wtp = (bf16*)(ws + pl.wtp);
+  float* sc = (float*)(ws + pl.sc);
+  bf16* atp = (bf16*)(ws + pl.atp);
+  float* cx = (float*)(ws + pl.cx);
+  float* coef = (float*)(ws + pl.coef);
+  bf16* dcp = (bf16*)(ws + pl.dcp);
+  float* dat = (float*)(ws + pl.dat);
+  bf16* dsp = (bf16*)(ws + pl.dsp);
+  float* dwc = (float*)(ws + pl.dwc);
+  if ((rc = prepare(ctx, words, d, pl, ws, true, st))) return rc;
+  GLORIA_CUDA(cudaMemsetAsync(drt, 0, (size_t)Bi * d.Sq * D * sizeof(float), st));
+  GLORIA_CUDA(cudaMemsetAsync(dwt32, 0, (size_t)Bc * Lw * D * sizeof(float), st));
+  for (int i0 = 0; i0 < Bc; i0 += pl.nc) {
+    const int nc = min(pl.nc, Bc - i0);
+    const int NC = round_up(nc * d.Lp, 64);
+    const int tail = NC - nc * d.Lp;
+    // recompute the forward intermediates of the chunk (scores with all six terms: they pass through two softmaxes)
+    if ((rc = chunk_forward(d, pl, ws, cap_lens, i0, nc, NC, temp1, 6, 3, true, nullptr, nullptr, st))) return rc;
+    cosine_agg<<<(unsigned)(Bi * nc), 256, 3 * d.Lp * sizeof(float), st>>>(cx, wt32, wn, cap_lens, i0, nc, Bc, Lcap, d.Lp, NC, Lw,
+                                                                          word_off, D, temp2, agg, eps, nullptr, dsim, coef);
+    GLORIA_LAUNCHED("f32tc::cosine_agg(bwd)");
+    context_grad<<<dim3((unsigned)d.Lp, (unsigned)nc), 256, 0, st>>>(cx, wt32, dwt32, coef, cap_lens, dcp, i0, nc, Bi, Lcap, d.Lp, NC,
+                                                                     Lw, word_off, D);
+    GLORIA_LAUNCHED("f32tc::context_grad");
+    if (tail > 0)            // padding rows of dC: exact zeros in every plane
+      GLORIA_CUDA(cudaMemset2DAsync(dcp + (size_t)nc * d.Lp * D, (size_t)NC * D * 2, 0, (size_t)tail * D * 2, (size_t)3 * Bi, st));
+    {  // GEMM 3: DAt_j[(ii,l), s] = sum_d dC_j[(ii,l), d] R_j[d, s]
+      tc::GemmEx e{};
+      e.A = dcp; e.B = rn; e.C = dat;
+      e.M = NC; e.N = d.Sq; e.K = D; e.ldc = d.Sq; e.a_kmajor = true; e.ksplit = 1;
+      e.nb = Bi; e.a_brows = NC; e.b_brows = D; e.c_bstride = (long long)NC * d.Sq;
+      e.nterms = 3;
+      e.a_prows = (long long)Bi * NC; e.b_prows = (long long)Bi * D;
+      e.a_rows = 3LL * Bi * NC; e.b_rows = 3LL * Bi * D;
+      if ((rc = tc::acc_gemm_ex(e, st))) return rc;
+    }
+    {  // GEMM 4: dRt_j[s, d] += sum_(ii,l) A[(j,s), (ii,l)] dC_j[(ii,l), d]
+      tc::GemmEx e{};
+      e.A = atp; e.B = dcp; e.C = drt;
+      e.M = d.Sq; e.N = D; e.K = NC; e.ldc = D; e.a_kmajor = true; e.ksplit = 1; e.accumulate = true;
+      e.nb = Bi; e.a_brows = d.Sq; e.b_brows = NC; e.c_bstride = (long long)d.Sq * D;
+      e.nterms = 3;
+      e.a_prows = (long long)Bi * d.Sq; e.b_prows = (long long)Bi * NC;
+      e.a_rows = 3LL * Bi * d.Sq; e.b_rows = 3LL * Bi * NC;
+      if ((rc = tc::acc_gemm_ex(e, st))) return rc;
+    }
+    softmax_bwd<<<(unsigned)(Bi * nc), 256, softmax_smem(S, d.Lp), st>>>(dat, atp, sc, dsp, cap_lens, i0, nc, Bi, Bc, S, d.Sq, Lcap, d.Lp,
+                                                                        NC, temp1, d_attn_diag, d_attn_mean);
+    GLORIA_LAUNCHED("f32tc::softmax_bwd");
+    if (tail > 0)
+      GLORIA_CUDA(cudaMemset2DAsync(dsp + (size_t)nc * d.Lp, (size_t)NC * 2, 0, (size_t)tail * 2, (size_t)3 * Bi * d.Sq, st));
+    {  // GEMM 5: dWc[(ii,l), d] = sum_(j,s) DS[(j,s), (ii,l)] R[(j,s), d]
+      tc::GemmEx e{};
+      e.A = dsp; e.B = rt; e.C = dwc;
+      e.M = NC; e.N = D; e.K = Bi * d.Sq; e.ldc = D; e.a_kmajor = false; e.ksplit = 0;
+      e.nb = 1; e.nterms = 3;
+      e.a_prows = (long long)Bi * d.Sq; e.b_prows = (long long)Bi * d.Sq;
+      e.a_rows = 3LL * Bi * d.Sq; e.b_rows = 3LL * Bi * d.Sq;
+      if ((rc = tc::acc_gemm_ex(e, st))) return rc;
+    }
+    add_word_grad<<<dim3((unsigned)d.Lp, (unsigned)nc), 256, 0, st>>>(dwc, dwt32, cap_lens, i0, Lcap, d.Lp, Lw, word_off, D);
+    GLORIA_LAUNCHED("f32tc::add_word_grad");
+    {  // GEMM 6: dRt[(j,s), d] += sum_(ii,l) DS[(j,s), (ii,l)] W[(ii,l), d]
+      tc::GemmEx e{};
+      e.A = dsp; e.B = wtp; e.C = drt;
+      e.M = Bi * d.Sq; e.N = D; e.K = NC; e.ldc = D; e.a_kmajor = true; e.ksplit = 1; e.accumulate = true;
+      e.nb = 1; e.nterms = 3;
+      e.a_prows = (long long)Bi * d.Sq; e.b_prows = NC;
+      e.a_rows = 3LL * Bi * d.Sq; e.b_rows = 3LL * NC;
+      if ((rc = tc::acc_gemm_ex(e, st))) return rc;
+    }
+  }
+  unpack_dctx<<<dim3(d.Sq / 32, D / 32, Bi), dim3(32, 8), 0, st>>>(drt, d_ctx, D, S, d.Sq);
+  GLORIA_LAUNCHED("f32tc::unpack_dctx");
+  unpack_dwords<<<dim3((Lw + 31) / 32, (D + 31) / 32, Bc), dim3(32, 8), 0, st>>>(dwt32, d_words, cap_lens, D, Lw, Lcap, word_off);
+  GLORIA_LAUNCHED("f32tc::unpack_dwords");
+  return GLORIA_OK;
+}

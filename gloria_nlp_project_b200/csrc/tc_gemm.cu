@@ -84,6 +84,14 @@ struct Params {
   const float* g;
   int g_sm, g_sk, m_div, k_div;
   float inv_m_div, inv_k_div;
+  // plain modes only -- batches and operand planes (the split-precision fp32 mode, tc_f32.cu):
+  //   unit = (n tile, row block, batch b); tiles of batch b sit a_brows / b_brows tensor-map rows further down, its C
+  //   c_bstride elements further on.  The k-blocks are nterms runs of nkb_t: run t reads plane pa[t] of A and plane
+  //   pb[t] of B (a_prows / b_prows tensor-map rows per plane), all into the same accumulator.
+  int nb, a_brows, b_brows;
+  long long c_bstride;
+  int nterms, nkb_t, a_prows, b_prows;
+  unsigned char pa[8], pb[8];
   int pf;                 // L2 prefetch distance in k-blocks (0 = off)
   int exp;                // development experiments (GLORIA_B200_GEMM_EXP): 1 = TS without the scale pipeline (static A)
   long long* dbg;         // phase clocks (only read when built with -DGLORIA_PHASE_CLOCKS)
@@ -184,14 +192,19 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // unit u -> (n tile, row block, k-split); the n tiles of a row block are adjacent (they share the A panel)
 struct Unit {
-  int n, m, kb0, kb1;
+  int n, m, b, kb0, kb1;
   __device__ Unit(int u, const Params& p) {
     n = u % p.NN;
     const int r = u / p.NN;
     m = r % p.MT;
     const int s = r / p.MT;
-    kb0 = (int)((long long)p.nkb * s / p.S);
-    kb1 = (int)((long long)p.nkb * (s + 1) / p.S);
+    if (p.nb > 1) {                      // batched: no k-splits
+      b = s; kb0 = 0; kb1 = p.nkb;
+    } else {
+      b = 0;
+      kb0 = (int)((long long)p.nkb * s / p.S);
+      kb1 = (int)((long long)p.nkb * (s + 1) / p.S);
+    }
   }
 };
 
@@ -212,7 +225,7 @@ acc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int ncl = gridDim.x >> 1, cl = blockIdx.x >> 1;
-  const int nunits = p.MT * p.NN * p.S;
+  const int nunits = p.MT * p.NN * p.S * p.nb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::NA; ++s) { mbar_init(bar(L::AFULL + s), 1); mbar_init(bar(L::AEMPTY + s), MODE == TS_AK ? 4 : 1); }
@@ -247,7 +260,7 @@ acc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           const uint32_t phb = (nb / C::NB) & 1u;
           ++nb;
           const uint32_t full_leader = mapa(bar(L::BFULL + sb), 0);
-          if (p.pf > 0 && kb + p.pf < un.kb1) {                 // pull the tiles of k-block kb + pf into L2 now
+          if (p.pf > 0 && p.nterms <= 1 && p.nb <= 1 && kb + p.pf < un.kb1) {                 // pull the tiles of k-block kb + pf into L2 now
             const int kp = (kb + p.pf) * BK;
             tma_prefetch_2d(&tm_b, n0, kp);
             tma_prefetch_2d(&tm_b, n0 + 64, kp);
@@ -256,18 +269,28 @@ acc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
           GTIMED(pw_b, mbar_wait(bar(L::BEMPTY + sb), phb ^ 1));
           if (leader) mbar_expect_tx(bar(L::BFULL + sb), SCALED ? 2 * B_TILE : 2 * (A_TILE + B_TILE));
+          // k-block -> (term, k-block inside the term) and the tensor-map rows of this batch's planes
+          int kk = kb, aoff = 0, boff = 0;
           if (!SCALED) {
+            if (p.nterms > 1) {
+              const int t = kb / p.nkb_t;
+              kk = kb - t * p.nkb_t;
+              aoff = (int)p.pa[t] * p.a_prows;
+              boff = (int)p.pb[t] * p.b_prows;
+            }
+            aoff += un.b * p.a_brows;
+            boff += un.b * p.b_brows;
             const uint32_t adst = base + L::OFF_A + sb * A_TILE;
             if (MODE == SS_AK) {
-              tma_load_2d_pair(adst, &tm_a, kb * BK, m0, full_leader);
+              tma_load_2d_pair(adst, &tm_a, kk * BK, m0 + aoff, full_leader);
             } else {                         // A^T in memory: two [64 k x 64 m] boxes -> M-major tile
-              tma_load_2d_pair(adst, &tm_a, m0, kb * BK, full_leader);
-              tma_load_2d_pair(adst + A_TILE / 2, &tm_a, m0 + 64, kb * BK, full_leader);
+              tma_load_2d_pair(adst, &tm_a, m0, kk * BK + aoff, full_leader);
+              tma_load_2d_pair(adst + A_TILE / 2, &tm_a, m0 + 64, kk * BK + aoff, full_leader);
             }
           }
           const uint32_t bdst = base + L::OFF_B + sb * B_TILE;
-          tma_load_2d_pair(bdst, &tm_b, n0, kb * BK, full_leader);
-          tma_load_2d_pair(bdst + B_TILE / 2, &tm_b, n0 + 64, kb * BK, full_leader);
+          tma_load_2d_pair(bdst, &tm_b, n0, kk * BK + boff, full_leader);
+          tma_load_2d_pair(bdst + B_TILE / 2, &tm_b, n0 + 64, kk * BK + boff, full_leader);
         }
       }
 #ifdef GLORIA_PHASE_CLOCKS
@@ -500,7 +523,7 @@ acc_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       __syncwarp();
       tc_fence_after();
       const int ncol0 = un.n * BN + grp * BNH;
-      float* crow = p.C + (size_t)m_glob * p.ldc + ncol0;
+      float* crow = p.C + (size_t)un.b * p.c_bstride + (size_t)m_glob * p.ldc + ncol0;
 #pragma unroll 1
       for (int c = 0; c < BNH / 16; ++c) {
         float v[16];
@@ -549,7 +572,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const Params& p, cudaSt
   int dev = 0, sms = 0;
   GLORIA_CUDA(cudaGetDevice(&dev));
   GLORIA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int nunits = p.MT * p.NN * p.S;
+  const int nunits = p.MT * p.NN * p.S * p.nb;
   int ncl = sms / 2;
   if (ncl > nunits) ncl = nunits;
   GLORIA_CUDA(cudaFuncSetAttribute(acc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<MODE>::BYTES));
@@ -574,49 +597,84 @@ int pick_splits(int tiles, int ncl, int nkb, int smax) {
 
 }  // namespace ag
 
-// C[M, N] (fp32, row pitch ldc) = or += A B with bf16 operands in HBM.
-//   a_kmajor: A is [M, K] (K contiguous); otherwise A^T is given, [K, M] (M contiguous).   B is [K, N] (N contiguous).
+// C[b] [M, N] (fp32, row pitch ldc) = or += sum_t A[b, pa[t]] B[b, pb[t]] with bf16 operands in HBM.
+//   a_kmajor: A planes are [M, K] (K contiguous); otherwise A^T is given, [K, M] (M contiguous).   B planes are [K, N].
 //   g != null: A[m, k] is multiplied by g[(m / m_div) * g_sm + (k / k_div) * g_sk] in fp32 and rounded to bf16 on the way to
 //   the tensor cores.  The divisor along the CONTIGUOUS axis of A must be a multiple of 8 (16-byte chunks carry one weight).
 //   ksplit: 0 = choose; > 1 or accumulate: tiles are added with red.global.add (C must hold the value to add to).
-int acc_gemm(const void* A, const void* B, float* C, int M, int N, int K, int ldc, bool a_kmajor, int ksplit,
-             bool accumulate, const float* g, int g_sm, int g_sk, int m_div, int k_div, bool force_scaled_path,
-             cudaStream_t st) {
-  if (M <= 0 || N <= 0 || K <= 0 || (N & 15) || (K & 7) || (!a_kmajor && (M & 7)))
+//   Batches / planes (plain modes): see GemmEx in tc_common.cuh.  Every element inside the tensor-map extents must be
+//   finite (rows read past a batch's K are multiplied by zero-filled columns); for transposed A with batches or planes
+//   K must be a multiple of 64.
+int acc_gemm_ex(const GemmEx& e, cudaStream_t st) {
+  const int M = e.M, N = e.N, K = e.K;
+  if (M <= 0 || N <= 0 || K <= 0 || (N & 15) || (K & 7) || (!e.a_kmajor && (M & 7)))
     return fail(GLORIA_ERR_BAD_ARG, "acc_gemm: bad shape M=%d N=%d K=%d", M, N, K);
-  if (g && (m_div <= 0 || k_div <= 0 || ((a_kmajor ? k_div : m_div) & 7)))
-    return fail(GLORIA_ERR_BAD_ARG, "acc_gemm: bad weight blocks m_div=%d k_div=%d", m_div, k_div);
+  if (e.g && (e.m_div <= 0 || e.k_div <= 0 || ((e.a_kmajor ? e.k_div : e.m_div) & 7)))
+    return fail(GLORIA_ERR_BAD_ARG, "acc_gemm: bad weight blocks m_div=%d k_div=%d", e.m_div, e.k_div);
+  const int nb = e.nb > 0 ? e.nb : 1, nterms = e.nterms > 0 ? e.nterms : 1;
+  const bool scaled = e.g != nullptr || e.force_scaled_path;
+  const bool ext = nb > 1 || nterms > 1;
+  if (ext && scaled) return fail(GLORIA_ERR_BAD_ARG, "acc_gemm: batches / planes only in the plain modes");
+  if (nterms != 1 && nterms != 3 && nterms != 6) return fail(GLORIA_ERR_BAD_ARG, "acc_gemm: nterms %d", nterms);
+  if (ext && !e.a_kmajor && (K & 63)) return fail(GLORIA_ERR_BAD_ARG, "acc_gemm: transposed A with batches / planes needs K %% 64 == 0");
   ag::Params p{};
   p.M = M; p.N = N; p.K = K;
   p.MT = (M + 2 * ag::BM - 1) / (2 * ag::BM);
   p.NN = (N + ag::BN - 1) / ag::BN;
-  p.nkb = (K + ag::BK - 1) / ag::BK;
+  p.nkb_t = (K + ag::BK - 1) / ag::BK;
+  p.nkb = p.nkb_t * nterms;
+  p.nb = nb; p.nterms = nterms;
+  p.a_brows = (int)e.a_brows; p.b_brows = (int)e.b_brows; p.c_bstride = e.c_bstride;
+  p.a_prows = (int)e.a_prows; p.b_prows = (int)e.b_prows;
+  // split-precision terms, smallest first (tensor memory accumulates round-toward-zero: the large term goes last).
+  // planes: 0 = leading bf16 piece, 1 = first residual, 2 = second residual
+  static const unsigned char T6A[6] = {2, 1, 0, 1, 0, 0}, T6B[6] = {0, 1, 2, 0, 1, 0};
+  static const unsigned char T3A[3] = {1, 0, 0}, T3B[3] = {0, 1, 0};
+  for (int t = 0; t < nterms; ++t) {
+    p.pa[t] = nterms == 6 ? T6A[t] : nterms == 3 ? T3A[t] : 0;
+    p.pb[t] = nterms == 6 ? T6B[t] : nterms == 3 ? T3B[t] : 0;
+  }
   int dev = 0, sms = 0;
   GLORIA_CUDA(cudaGetDevice(&dev));
   GLORIA_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  p.S = ksplit > 0 ? ksplit : ag::pick_splits(p.MT * p.NN, sms / 2, p.nkb, 8);
+  p.S = nb > 1 ? 1 : e.ksplit > 0 ? e.ksplit : ag::pick_splits(p.MT * p.NN, sms / 2, p.nkb, 8);
   if (p.S > p.nkb) p.S = p.nkb;
-  p.C = C; p.ldc = ldc;
-  p.epi = (p.S > 1 || accumulate) ? 1 : 0;
-  p.g = g; p.g_sm = g_sm; p.g_sk = g_sk; p.m_div = m_div > 0 ? m_div : 1; p.k_div = k_div > 0 ? k_div : 1;
+  p.C = e.C; p.ldc = e.ldc;
+  p.epi = (p.S > 1 || e.accumulate) ? 1 : 0;
+  p.g = e.g; p.g_sm = e.g_sm; p.g_sk = e.g_sk; p.m_div = e.m_div > 0 ? e.m_div : 1; p.k_div = e.k_div > 0 ? e.k_div : 1;
   p.inv_m_div = 1.0f / (float)p.m_div; p.inv_k_div = 1.0f / (float)p.k_div;
-  static const int exp_mode = [] { const char* e = getenv("GLORIA_B200_GEMM_EXP"); return e ? atoi(e) : 0; }();
-  static const int pf_dist = [] { const char* e = getenv("GLORIA_B200_GEMM_PREFETCH"); return e ? atoi(e) : 0; }();
+  static const int exp_mode = [] { const char* x = getenv("GLORIA_B200_GEMM_EXP"); return x ? atoi(x) : 0; }();
+  static const int pf_dist = [] { const char* x = getenv("GLORIA_B200_GEMM_PREFETCH"); return x ? atoi(x) : 0; }();
   p.exp = exp_mode; p.pf = pf_dist;
   if (M >= (1 << 24) || K >= (1 << 24)) return fail(GLORIA_ERR_BAD_ARG, "acc_gemm: M, K must be below 2^24");
   p.dbg = (long long*)g_phase_clock_buffer;
-  if (p.S > 1 && !accumulate) GLORIA_CUDA(cudaMemsetAsync(C, 0, (size_t)M * ldc * sizeof(float), st));
+  if (p.S > 1 && !e.accumulate) {
+    if (e.ldc == N) GLORIA_CUDA(cudaMemsetAsync(e.C, 0, (size_t)M * e.ldc * sizeof(float), st));
+    else GLORIA_CUDA(cudaMemset2DAsync(e.C, (size_t)e.ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
+  }
+  // tensor-map extents in rows: all planes and batches of the operand
+  const uint64_t a_unit = e.a_kmajor ? (uint64_t)M : (uint64_t)K, b_unit = (uint64_t)K;
+  const uint64_t a_rows = e.a_rows > 0 ? (uint64_t)e.a_rows : a_unit, b_rows = e.b_rows > 0 ? (uint64_t)e.b_rows : b_unit;
   CUtensorMap ma, mb;
   int rc;
-  if (a_kmajor) {
-    if ((rc = make_map(&ma, A, (uint64_t)K, (uint64_t)M, ag::BM))) return rc;
+  if (e.a_kmajor) {
+    if ((rc = make_map(&ma, e.A, (uint64_t)K, a_rows, ag::BM))) return rc;
   } else {
-    if ((rc = make_map(&ma, A, (uint64_t)M, (uint64_t)K, ag::BK))) return rc;
+    if ((rc = make_map(&ma, e.A, (uint64_t)M, a_rows, ag::BK))) return rc;
   }
-  if ((rc = make_map(&mb, B, (uint64_t)N, (uint64_t)K, ag::BK))) return rc;
-  const bool scaled = g != nullptr || force_scaled_path;
-  if (a_kmajor) return scaled ? ag::launch<ag::TS_AK>(ma, mb, p, st) : ag::launch<ag::SS_AK>(ma, mb, p, st);
+  if ((rc = make_map(&mb, e.B, (uint64_t)N, b_rows, ag::BK))) return rc;
+  if (e.a_kmajor) return scaled ? ag::launch<ag::TS_AK>(ma, mb, p, st) : ag::launch<ag::SS_AK>(ma, mb, p, st);
   return scaled ? ag::launch<ag::SC_AM>(ma, mb, p, st) : ag::launch<ag::SS_AM>(ma, mb, p, st);
+}
+
+int acc_gemm(const void* A, const void* B, float* C, int M, int N, int K, int ldc, bool a_kmajor, int ksplit,
+             bool accumulate, const float* g, int g_sm, int g_sk, int m_div, int k_div, bool force_scaled_path,
+             cudaStream_t st) {
+  GemmEx e{};
+  e.A = A; e.B = B; e.C = C; e.M = M; e.N = N; e.K = K; e.ldc = ldc; e.a_kmajor = a_kmajor; e.ksplit = ksplit;
+  e.accumulate = accumulate; e.g = g; e.g_sm = g_sm; e.g_sk = g_sk; e.m_div = m_div; e.k_div = k_div;
+  e.force_scaled_path = force_scaled_path;
+  return acc_gemm_ex(e, st);
 }
 
 }  // namespace tc
@@ -631,4 +689,20 @@ extern "C" int gloria_b200_acc_gemm(const void* A, const void* B, float* C, int 
   GLORIA_CHECK_ARG(A && B && C, "null pointer");
   return tc::acc_gemm(A, B, C, M, N, K, N, a_kmajor != 0, ksplit, accumulate != 0, g, g_sm, g_sk, m_div, k_div,
                       force_scaled_path != 0, (cudaStream_t)stream);
+}
+
+// Split-precision form for the parity tests of the fp32 tensor-core mode (tc_f32.cu): dense operand planes
+//   A [3][nb * (a_kmajor ? M : K), a_kmajor ? K : M],  B [3][nb * K, N]  (bf16 pieces of fp32 matrices),  C [nb][M, N];
+//   nterms = 3 or 6 piece products, smallest first.
+extern "C" int gloria_b200_acc_gemm_planes(const void* A, const void* B, float* C, int M, int N, int K, int a_kmajor, int nterms,
+                                           int nb, int ksplit, int accumulate, void* stream) {
+  GLORIA_CHECK_ARG(A && B && C && nb > 0, "null pointer / bad batch count");
+  tc::GemmEx e{};
+  const long long arows = a_kmajor ? M : K;
+  e.A = A; e.B = B; e.C = C; e.M = M; e.N = N; e.K = K; e.ldc = N; e.a_kmajor = a_kmajor != 0; e.ksplit = ksplit;
+  e.accumulate = accumulate != 0;
+  e.nb = nb; e.a_brows = arows; e.b_brows = K; e.c_bstride = (long long)M * N;
+  e.nterms = nterms; e.a_prows = arows * nb; e.b_prows = (long long)K * nb;
+  e.a_rows = 3 * arows * nb; e.b_rows = 3LL * K * nb;
+  return tc::acc_gemm_ex(e, (cudaStream_t)stream);
 }

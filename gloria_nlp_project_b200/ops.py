@@ -23,6 +23,18 @@ MODE_FP32, MODE_BF16 = 0, 1
 
 _WS_BUDGET = int(os.environ.get("GLORIA_B200_WS_BYTES", str(4 << 30)))            # fp32 kernels
 _TC_WS_BUDGET = int(os.environ.get("GLORIA_B200_TC_WS_BYTES", str(96 << 30)))     # bf16 backward operand matrices
+_F32_TC = os.environ.get("GLORIA_B200_F32_TC", "1") != "0"                         # fp32 mode on the tensor cores (tc_f32.cu)
+_F32_TC_WS_BUDGET = int(os.environ.get("GLORIA_B200_F32_TC_WS_BYTES", str(16 << 30)))
+
+
+def _f32_entries(L, D: int, S: int, lcap: int, backward: bool):
+    """(workspace bytes function, kernel entry, name) of the fp32 mode for this shape: the split-precision tensor-core path
+    where it applies (D % 64 == 0, captions of <= 128 words), else the CUDA-core kernels."""
+    if _F32_TC and L.gloria_b200_f32tc_supported(D, S, lcap) == 0:
+        ws = lambda Bi, Bc, Lw: L.gloria_b200_local_f32tc_workspace(Bi, Bc, D, S, Lw, lcap, _F32_TC_WS_BUDGET, 1 if backward else 0)
+        return ws, (L.gloria_b200_local_sim_bwd_f32tc if backward else L.gloria_b200_local_sim_fwd_f32tc), "f32tc"
+    ws = lambda Bi, Bc, Lw: L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
+    return ws, (L.gloria_b200_local_sim_bwd_f32 if backward else L.gloria_b200_local_sim_fwd_f32), "f32"
 _PACKED_PROMPTS = os.environ.get("GLORIA_B200_PACKED_PROMPTS", "1") != "0"           # packed short-caption inference kernel
 _FUSED_TRAIN = os.environ.get("GLORIA_B200_FUSED_TRAIN", "1") != "0"               # fused forward+backward-operand kernel
 _FUSED_DIAG = os.environ.get("GLORIA_B200_FUSED_DIAG", "1") != "0"                 # ... which also emits the diagonal attention maps
@@ -166,12 +178,13 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
     stats = torch.empty((0,), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         if mode == MODE_FP32:
-            nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
+            ws_fn, entry, tag = _f32_entries(L, D, S, lcap, False)
+            nbytes = ws_fn(Bi, Bc, Lw)
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-            rc = L.gloria_b200_local_sim_fwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S,
-                                                 Lw, lcap, word_off, temp1, temp2, agg, eps, sim.data_ptr(),
-                                                 _ptr(diag), _ptr(mean), ws.data_ptr(), nbytes, _stream(ctx))
-            _lib.check(rc, "local_sim_fwd_f32")
+            rc = entry(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S,
+                       Lw, lcap, word_off, temp1, temp2, agg, eps, sim.data_ptr(),
+                       _ptr(diag), _ptr(mean), ws.data_ptr(), nbytes, _stream(ctx))
+            _lib.check(rc, "local_sim_fwd_" + tag)
         else:
             if want_mean and agg == AGG["max"]:
                 raise RuntimeError("word-mean attention output is not available with agg='max'")
@@ -329,13 +342,14 @@ def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                 if ev_done:
                     dctx_event = 0
             else:
-                nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
+                ws_fn, entry, tag = _f32_entries(L, D, S, lcap, True)
+                nbytes = ws_fn(Bi, Bc, Lw)
                 ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-                rc = L.gloria_b200_local_sim_bwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D,
-                                                     S, Lw, lcap, word_off, temp1, temp2, agg, eps, dsim.data_ptr(),
-                                                     None if diag_separately else _ptr(d_diag), _ptr(d_mean),
-                                                     d_ctx.data_ptr(), d_words.data_ptr(), ws.data_ptr(), nbytes, st)
-                _lib.check(rc, "local_sim_bwd_f32")
+                rc = entry(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D,
+                           S, Lw, lcap, word_off, temp1, temp2, agg, eps, dsim.data_ptr(),
+                           None if diag_separately else _ptr(d_diag), _ptr(d_mean),
+                           d_ctx.data_ptr(), d_words.data_ptr(), ws.data_ptr(), nbytes, st)
+                _lib.check(rc, "local_sim_bwd_" + tag)
         if diag_separately:
             nbytes = L.gloria_b200_diag_attn_workspace(Bc, D, S, Lw, lcap)
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)

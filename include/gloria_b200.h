@@ -96,6 +96,28 @@ int gloria_b200_local_sim_bwd_f32(const float* ctx, const float* words, const in
                                   float* d_ctx, float* d_words,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * fp32 mode on the tensor cores (tc_f32.cu): the same two entry points with every bmm of gloria_loss.py:40,59 (and of
+ * their autograd) on the hand-written tcgen05 GEMM with split-precision operands (three bf16 pieces per fp32 value,
+ * six piece products per GEMM in the forward: everything down to 2^-24, fp32 accumulation in tensor memory), softmaxes /
+ * cosine / aggregation as streaming fp32 kernels.  Same arguments, results and gates as the _f32 entries above
+ * (logits within 1e-5 relative).  `backward` selects the workspace layout of the backward (it holds more buffers).
+ * gloria_b200_f32tc_supported: 0 when the shape is covered (D % 64 == 0, cap_len <= 128), else the _f32 entries serve it.
+ * ---------------------------------------------------------------------------------------------------------- */
+int gloria_b200_f32tc_supported(int D, int S, int Lcap);
+size_t gloria_b200_local_f32tc_workspace(int Bi, int Bc, int D, int S, int Lw, int Lcap, size_t budget, int backward);
+int gloria_b200_local_sim_fwd_f32tc(const float* ctx, const float* words, const int32_t* cap_lens,
+                                    int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                    float temp1, float temp2, int agg, float eps,
+                                    float* sim, float* attn_diag, float* attn_mean,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+int gloria_b200_local_sim_bwd_f32tc(const float* ctx, const float* words, const int32_t* cap_lens,
+                                    int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                    float temp1, float temp2, int agg, float eps,
+                                    const float* dsim, const float* d_attn_diag, const float* d_attn_mean,
+                                    float* d_ctx, float* d_words,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+
 /* Diagonal pairs only (B pairs instead of B^2): the attention maps A_ii that local_loss returns (att_maps,
  * gloria_loss.py:141-143; consumed by get_attn_maps, gloria_model.py:209-211) and the gradient flowing back through
  * them (supervised-attention term of GLoRIA.calc_loss, gloria_model.py:143-147).  attn_diag / d_attn_diag are
@@ -291,6 +313,12 @@ int gloria_b200_tc_local_sim_bwd_train_ev(const void* ctx_t, const void* words_t
 int gloria_b200_acc_gemm(const void* A, const void* B, float* C, int M, int N, int K, int a_kmajor, int ksplit,
                          int accumulate, const float* g, int g_sm, int g_sk, int m_div, int k_div,
                          int force_scaled_path, void* stream);
+/* The same GEMM with split-precision operands (the fp32 tensor-core mode): A and B are given as three dense planes of bf16
+ * pieces of fp32 matrices (plane 0 = bf16(x), 1 = bf16(x - p0), 2 = bf16(x - p0 - p1)); nterms = 6 sums every piece
+ * product down to 2^-24, nterms = 3 the three leading ones; nb independent problems are stacked along the rows of every
+ * plane (A [3][nb*M, K] or, transposed, [3][nb*K, M]; B [3][nb*K, N]; C [nb][M, N]). */
+int gloria_b200_acc_gemm_planes(const void* A, const void* B, float* C, int M, int N, int K, int a_kmajor, int nterms,
+                                int nb, int ksplit, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Global similarity (global_loss, gloria_loss.py:75-80; get_global_similarities, gloria_model.py:164-169):
