@@ -34,8 +34,10 @@ PROTOTYPES = {
     "gloria_b200_local_f32tc_workspace": (_z, [_i, _i, _i, _i, _i, _i, _z, _i]),
     "gloria_b200_local_sim_fwd_f32tc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p, _z,
                                              _p]),
+    "gloria_b200_local_sim_fwd_f32tc_train": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p,
+                                                   _z, _p]),
     "gloria_b200_local_sim_bwd_f32tc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p, _p,
-                                             _p, _z, _p]),
+                                             _p, _z, _i, _p]),
     "gloria_b200_diag_attn_workspace": (_z, [_i, _i, _i, _i, _i]),
     "gloria_b200_diag_attn_fwd_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p, _z, _p]),
     "gloria_b200_diag_attn_bwd_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p, _z, _p]),

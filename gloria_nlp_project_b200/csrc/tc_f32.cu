@@ -133,80 +133,124 @@ __global__ void split_words(const float* __restrict__ wt32, const int* __restric
 }
 
 // Double softmax of one (image, caption) block (gloria_loss.py:42-53).  SC block: scores on entry, P (word softmax) on exit.
-// AT_p block: A = softmax_s(temp1 P) as bf16 pieces, zero in padded rows / columns.  dynamic smem: S * (Lp + 1) + 3 * 128 floats
-__global__ void __launch_bounds__(256) softmax_fwd(float* __restrict__ sc, bf16* __restrict__ atp, const int* __restrict__ cap_lens,
-                                                   int i0, int nc, int Bi, int Bc, int S, int Sq, int Lcap, int Lp, int NC,
-                                                   float temp1, float* __restrict__ attn_diag, float* __restrict__ attn_mean) {
+// AT_p block: A = softmax_s(temp1 P) as bf16 pieces, zero in padded rows / columns.  512 threads;
+// dynamic smem: S * (Lp + 1) + 5 * 128 floats
+constexpr int SM_THREADS = 512;
+constexpr int SM_PARTS = SM_THREADS / 128;      // threads per word in the column passes
+constexpr int RB = 4;                           // region rows a warp keeps in flight
+__global__ void __launch_bounds__(SM_THREADS) softmax_fwd(float* __restrict__ sc, bf16* __restrict__ atp,
+                                                          const int* __restrict__ cap_lens, int i0, int nc, int Bi, int Bc, int S,
+                                                          int Sq, int Lcap, int Lp, int NC, float temp1,
+                                                          float* __restrict__ attn_diag, float* __restrict__ attn_mean) {
   extern __shared__ float sm[];
   const int LP1 = Lp + 1;
   float* tile = sm;                          // E[s][l]
-  float* zpart = sm + (size_t)S * LP1;       // [2][128]
-  float* invz = zpart + 256;                 // [128]
+  float* zpart = sm + (size_t)S * LP1;       // [SM_PARTS][128]
+  float* invz = zpart + SM_PARTS * 128;      // [128]
   const int p = blockIdx.x, j = p / nc, ii = p - j * nc, i = i0 + ii;
   const int L = min(max(cap_lens[i], 0), Lcap);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SM_THREADS >> 5;
   float* scb = sc + (size_t)j * Sq * NC + (size_t)ii * Lp;
-  // softmax #1 over the caption's words, warp per region row (coalesced along l)
-  for (int s = warp; s < S; s += nwarps) {
-    float* row = scb + (size_t)s * NC;
-    float m = -INFINITY;
-    for (int l = lane; l < L; l += 32) m = fmaxf(m, row[l]);
-    m = warp_max(m);
-    float den = 0.f;
-    for (int l = lane; l < L; l += 32) den += expf(row[l] - m);
-    den = warp_sum(den);
-    const float inv = 1.f / den;
-    for (int l = lane; l < Lp; l += 32) {
-      const float P = (l < L) ? expf(row[l] - m) * inv : 0.f;
-      row[l] = P;
-      tile[(size_t)s * LP1 + l] = (l < L) ? expf(temp1 * P) : 0.f;
+  // softmax #1 over the caption's words: a warp owns RB region rows at a time (coalesced along l, <= 4 words per lane)
+  for (int s0 = warp * RB; s0 < S; s0 += nwarps * RB) {
+    float v[RB][4], m[RB], den[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const float* row = scb + (size_t)(s0 + r) * NC;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int l = lane + 32 * k;
+        v[r][k] = (s0 + r < S && l < L) ? row[l] : -INFINITY;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) m[r] = warp_max(fmaxf(fmaxf(v[r][0], v[r][1]), fmaxf(v[r][2], v[r][3])));
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float e = (v[r][k] == -INFINITY) ? 0.f : expf(v[r][k] - m[r]);
+        v[r][k] = e;
+        d += e;
+      }
+      den[r] = warp_sum(d);
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      if (s0 + r < S) {
+        float* row = scb + (size_t)(s0 + r) * NC;
+        const float inv = 1.f / den[r];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int l = lane + 32 * k;
+          if (l < Lp) {
+            const float P = (l < L) ? v[r][k] * inv : 0.f;
+            row[l] = P;
+            tile[(size_t)(s0 + r) * LP1 + l] = (l < L) ? expf(temp1 * P) : 0.f;
+          }
+        }
+      }
     }
   }
   __syncthreads();
-  // softmax #2 over the regions: Z_l (two threads per word, rows interleaved)
+  // softmax #2 over the regions: Z_l (SM_PARTS threads per word, rows interleaved)
   {
-    const int l = tid & 127, half = tid >> 7;
-    float z = 0.f;
-    if (l < Lp)
-      for (int s = half; s < S; s += 2) z += tile[(size_t)s * LP1 + l];
-    zpart[half * 128 + l] = z;
+    const int l = tid & 127, part = tid >> 7;
+    float z0 = 0.f, z1 = 0.f;
+    if (l < L) {
+      int s = part;
+      for (; s + SM_PARTS < S; s += 2 * SM_PARTS) {
+        z0 += tile[(size_t)s * LP1 + l];
+        z1 += tile[(size_t)(s + SM_PARTS) * LP1 + l];
+      }
+      if (s < S) z0 += tile[(size_t)s * LP1 + l];
+    }
+    zpart[part * 128 + l] = z0 + z1;
   }
   __syncthreads();
-  if (tid < 128) invz[tid] = (tid < L) ? 1.f / (zpart[tid] + zpart[128 + tid]) : 0.f;
+  if (tid < 128) {
+    float z = 0.f;
+#pragma unroll
+    for (int q = 0; q < SM_PARTS; ++q) z += zpart[q * 128 + tid];
+    invz[tid] = (tid < L) ? 1.f / z : 0.f;
+  }
   __syncthreads();
   // A as bf16 pieces, two words per thread
   const size_t plane = (size_t)Bi * Sq * NC;
   const int half_lp = Lp >> 1;
   bf16* ab = atp + (size_t)j * Sq * NC + (size_t)ii * Lp;
-  for (int idx = tid; idx < Sq * half_lp; idx += blockDim.x) {
-    const int s = idx / half_lp, l = (idx - s * half_lp) * 2;
-    float a0 = 0.f, a1 = 0.f;
-    if (s < S) {
-      a0 = tile[(size_t)s * LP1 + l] * invz[l];
-      a1 = tile[(size_t)s * LP1 + l + 1] * invz[l + 1];
+  for (int s = warp; s < Sq; s += nwarps) {
+    for (int h = lane; h < half_lp; h += 32) {
+      const int l = 2 * h;
+      float a0 = 0.f, a1 = 0.f;
+      if (s < S) {
+        a0 = tile[(size_t)s * LP1 + l] * invz[l];
+        a1 = tile[(size_t)s * LP1 + l + 1] * invz[l + 1];
+      }
+      bf16 x0, x1, x2, y0, y1, y2;
+      split3(a0, x0, x1, x2);
+      split3(a1, y0, y1, y2);
+      const size_t o = (size_t)s * NC + l;
+      *reinterpret_cast<__nv_bfloat162*>(ab + o) = __nv_bfloat162(x0, y0);
+      *reinterpret_cast<__nv_bfloat162*>(ab + plane + o) = __nv_bfloat162(x1, y1);
+      *reinterpret_cast<__nv_bfloat162*>(ab + 2 * plane + o) = __nv_bfloat162(x2, y2);
     }
-    bf16 x0, x1, x2, y0, y1, y2;
-    split3(a0, x0, x1, x2);
-    split3(a1, y0, y1, y2);
-    const size_t o = (size_t)s * NC + l;
-    *reinterpret_cast<__nv_bfloat162*>(ab + o) = __nv_bfloat162(x0, y0);
-    *reinterpret_cast<__nv_bfloat162*>(ab + plane + o) = __nv_bfloat162(x1, y1);
-    *reinterpret_cast<__nv_bfloat162*>(ab + 2 * plane + o) = __nv_bfloat162(x2, y2);
   }
   if (attn_diag != nullptr && j == i) {       // att_maps of the diagonal pair, [Bc, Lcap, S] (gloria_loss.py:141-143)
     float* dg = attn_diag + (size_t)i * Lcap * S;
-    for (int idx = tid; idx < Lcap * S; idx += blockDim.x) {
-      const int l = idx / S, s = idx - l * S;
-      dg[idx] = (l < L) ? tile[(size_t)s * LP1 + l] * invz[l] : 0.f;
+    for (int l = warp; l < Lcap; l += nwarps) {
+      const float iz = (l < L) ? invz[l] : 0.f;
+      for (int x = lane; x < S; x += 32) dg[(size_t)l * S + x] = (l < L) ? tile[(size_t)x * LP1 + l] * iz : 0.f;
     }
   }
   if (attn_mean != nullptr) {                 // word-mean attention (gloria_loss.py:132), [Bi, Bc, S]
     float* mo = attn_mean + ((size_t)j * Bc + i) * S;
     const float invL = L > 0 ? 1.f / (float)L : 0.f;
-    for (int s = tid; s < S; s += blockDim.x) {
+    for (int x = tid; x < S; x += SM_THREADS) {
       float acc = 0.f;
-      for (int l = 0; l < L; ++l) acc += tile[(size_t)s * LP1 + l] * invz[l];
-      mo[s] = acc * invL;
+      for (int l = 0; l < L; ++l) acc += tile[(size_t)x * LP1 + l] * invz[l];
+      mo[x] = acc * invL;
     }
   }
 }
@@ -226,13 +270,14 @@ __global__ void __launch_bounds__(256) cosine_agg(const float* __restrict__ cx, 
   const int L = min(max(cap_lens[i], 0), Lcap);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   for (int l = warp; l < L; l += nwarps) {
-    const float* w = wt32 + ((size_t)i * Lw + off + l) * D;
-    const float* c = cx + ((size_t)j * NC + (size_t)ii * Lp + l) * D;
+    const float4* w = reinterpret_cast<const float4*>(wt32 + ((size_t)i * Lw + off + l) * D);
+    const float4* c = reinterpret_cast<const float4*>(cx + ((size_t)j * NC + (size_t)ii * Lp + l) * D);
     float dot = 0.f, c2 = 0.f;
-    for (int d = lane; d < D; d += 32) {
-      const float cv = c[d];
-      dot = fmaf(w[d], cv, dot);
-      c2 = fmaf(cv, cv, c2);
+#pragma unroll 6
+    for (int d = lane; d < (D >> 2); d += 32) {        // D % 64 == 0: rows are 16-byte aligned
+      const float4 cv = c[d], wv = w[d];
+      dot = fmaf(wv.x, cv.x, dot); dot = fmaf(wv.y, cv.y, dot); dot = fmaf(wv.z, cv.z, dot); dot = fmaf(wv.w, cv.w, dot);
+      c2 = fmaf(cv.x, cv.x, c2); c2 = fmaf(cv.y, cv.y, c2); c2 = fmaf(cv.z, cv.z, c2); c2 = fmaf(cv.w, cv.w, c2);
     }
     dot = warp_sum(dot);
     c2 = warp_sum(c2);
@@ -284,86 +329,121 @@ __global__ void __launch_bounds__(256) cosine_agg(const float* __restrict__ cx, 
 }
 
 // dC = ddot W + beta C as bf16 pieces (zero rows beyond the caption), and the direct word gradient
-// dWt32[i][off+l][:] = sum_j ddot C + gamma W.   grid (Lp, nc): one CTA owns word l of caption i0 + ii.
-__global__ void __launch_bounds__(256) context_grad(const float* __restrict__ cx, const float* __restrict__ wt32,
-                                                    float* __restrict__ dwt32, const float* __restrict__ coef,
-                                                    const int* __restrict__ cap_lens, bf16* __restrict__ dcp, int i0, int nc,
-                                                    int Bi, int Lcap, int Lp, int NC, int Lw, int off, int D) {
+// dWt32[i][off+l][:] = sum_j ddot C + gamma W.   grid (Lp, nc): one CTA owns word l of caption i0 + ii; a thread owns four
+// channels and every ngroups-th image, the groups' partial sums meet in shared memory.  dynamic smem: blockDim float4.
+constexpr int CG_THREADS = 512;
+__global__ void __launch_bounds__(CG_THREADS) context_grad(const float* __restrict__ cx, const float* __restrict__ wt32,
+                                                           float* __restrict__ dwt32, const float* __restrict__ coef,
+                                                           const int* __restrict__ cap_lens, bf16* __restrict__ dcp, int i0, int nc,
+                                                           int Bi, int Lcap, int Lp, int NC, int Lw, int off, int D) {
+  extern __shared__ float4 part[];
   const int l = blockIdx.x, ii = blockIdx.y, i = i0 + ii;
   const int L = min(max(cap_lens[i], 0), Lcap);
   const bool live = l < L;
-  const float* w = wt32 + ((size_t)i * Lw + off + l) * D;
-  float* dw = dwt32 + ((size_t)i * Lw + off + l) * D;
+  const int nq = D >> 2;                                   // float4 chunks per row
+  const int ngroups = max(1, min(CG_THREADS / nq, Bi));
+  const int dq = threadIdx.x % nq, jg = threadIdx.x / nq;
   const size_t plane = (size_t)Bi * NC * D;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    const float wv = live ? w[d] : 0.f;
-    float acc = 0.f;
-    for (int j = 0; j < Bi; ++j) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (jg < ngroups) {
+    float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) wv = reinterpret_cast<const float4*>(wt32 + ((size_t)i * Lw + off + l) * D)[dq];
+#pragma unroll 4
+    for (int j = jg; j < Bi; j += ngroups) {
       const size_t row = (size_t)j * NC + (size_t)ii * Lp + l;
-      float dc = 0.f;
+      float4 dc = make_float4(0.f, 0.f, 0.f, 0.f);
       if (live) {
         const float* cf = coef + ((size_t)j * nc + ii) * 3 * Lp;
         const float ddot = cf[l], beta = cf[Lp + l], gamma = cf[2 * Lp + l];
-        const float cv = cx[row * D + d];
-        dc = fmaf(ddot, wv, beta * cv);
-        acc += fmaf(ddot, cv, gamma * wv);
+        const float4 cv = reinterpret_cast<const float4*>(cx + row * D)[dq];
+        dc.x = fmaf(ddot, wv.x, beta * cv.x); dc.y = fmaf(ddot, wv.y, beta * cv.y);
+        dc.z = fmaf(ddot, wv.z, beta * cv.z); dc.w = fmaf(ddot, wv.w, beta * cv.w);
+        acc.x += fmaf(ddot, cv.x, gamma * wv.x); acc.y += fmaf(ddot, cv.y, gamma * wv.y);
+        acc.z += fmaf(ddot, cv.z, gamma * wv.z); acc.w += fmaf(ddot, cv.w, gamma * wv.w);
       }
-      bf16 p0, p1, p2;
-      split3(dc, p0, p1, p2);
-      const size_t o = row * D + d;
-      dcp[o] = p0; dcp[plane + o] = p1; dcp[2 * plane + o] = p2;
+      bf16 a0, a1, a2, b0, b1, b2, c0, c1, c2, d0, d1, d2;
+      split3(dc.x, a0, a1, a2); split3(dc.y, b0, b1, b2); split3(dc.z, c0, c1, c2); split3(dc.w, d0, d1, d2);
+      const size_t o = row * D + 4 * (size_t)dq;
+      __nv_bfloat162 q0[2] = {__nv_bfloat162(a0, b0), __nv_bfloat162(c0, d0)};
+      __nv_bfloat162 q1[2] = {__nv_bfloat162(a1, b1), __nv_bfloat162(c1, d1)};
+      __nv_bfloat162 q2[2] = {__nv_bfloat162(a2, b2), __nv_bfloat162(c2, d2)};
+      *reinterpret_cast<uint2*>(dcp + o) = *reinterpret_cast<uint2*>(q0);
+      *reinterpret_cast<uint2*>(dcp + plane + o) = *reinterpret_cast<uint2*>(q1);
+      *reinterpret_cast<uint2*>(dcp + 2 * plane + o) = *reinterpret_cast<uint2*>(q2);
     }
-    if (live) dw[d] = acc;
+  }
+  if (!live) return;                                       // (uniform over the CTA)
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  if (jg == 0) {
+    for (int q = 1; q < ngroups; ++q) {
+      const float4 o = part[q * nq + dq];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    reinterpret_cast<float4*>(dwt32 + ((size_t)i * Lw + off + l) * D)[dq] = acc;
   }
 }
 
 // Backward of the two softmaxes for one (image, caption) block.  DAt block [Lp, Sq]: dL/dA (transposed); AT_p: A;
-// SC block: P.  Output DS_p block: dL/dscores as bf16 pieces (zero in padded rows / columns).
-// dynamic smem: S * (Lp + 1) + 3 * 128 floats
-__global__ void __launch_bounds__(256) softmax_bwd(const float* __restrict__ dat, const bf16* __restrict__ atp,
-                                                   const float* __restrict__ sc, bf16* __restrict__ dsp,
-                                                   const int* __restrict__ cap_lens, int i0, int nc, int Bi, int Bc, int S, int Sq,
-                                                   int Lcap, int Lp, int NC, float temp1, const float* __restrict__ d_attn_diag,
-                                                   const float* __restrict__ d_attn_mean) {
+// SC block: P.  Output DS_p block: dL/dscores as bf16 pieces (zero in padded rows / columns).  512 threads;
+// dynamic smem: S * (Lp + 1) + 5 * 128 floats
+__global__ void __launch_bounds__(SM_THREADS) softmax_bwd(const float* __restrict__ dat, const bf16* __restrict__ atp,
+                                                          const float* __restrict__ sc, bf16* __restrict__ dsp,
+                                                          const int* __restrict__ cap_lens, int i0, int nc, int Bi, int Bc, int S,
+                                                          int Sq, int Lcap, int Lp, int NC, float temp1,
+                                                          const float* __restrict__ d_attn_diag,
+                                                          const float* __restrict__ d_attn_mean) {
   extern __shared__ float sm[];
   const int LP1 = Lp + 1;
   float* tile = sm;                          // g[s][l]
-  float* zpart = sm + (size_t)S * LP1;       // [2][128]
-  float* rs = zpart + 256;                   // [128]
+  float* zpart = sm + (size_t)S * LP1;       // [SM_PARTS][128]
+  float* rs = zpart + SM_PARTS * 128;        // [128]
   const int p = blockIdx.x, j = p / nc, ii = p - j * nc, i = i0 + ii;
   const int L = min(max(cap_lens[i], 0), Lcap);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = SM_THREADS >> 5;
   const float* db = dat + ((size_t)j * NC + (size_t)ii * Lp) * Sq;
   const float* ed = (d_attn_diag != nullptr && j == i) ? d_attn_diag + (size_t)i * Lcap * S : nullptr;
   const float* em = (d_attn_mean != nullptr) ? d_attn_mean + ((size_t)j * Bc + i) * S : nullptr;
   const float invL = L > 0 ? 1.f / (float)L : 0.f;
-  for (int idx = tid; idx < L * S; idx += blockDim.x) {
-    const int l = idx / S, s = idx - l * S;
-    float v = db[(size_t)l * Sq + s];
-    if (ed) v += ed[idx];
-    if (em) v += em[s] * invL;
-    tile[(size_t)s * LP1 + l] = v;
+  // dL/dA of the block, transposed into g[s][l]: a warp owns a word row of DAt (coalesced along s)
+  for (int l = warp; l < L; l += nwarps) {
+    const float* src = db + (size_t)l * Sq;
+#pragma unroll 4
+    for (int x = lane; x < S; x += 32) {
+      float v = src[x];
+      if (ed) v += ed[(size_t)l * S + x];
+      if (em) v += em[x] * invL;
+      tile[(size_t)x * LP1 + l] = v;
+    }
   }
   __syncthreads();
-  // softmax #2 backward: dZ = A (dA - sum_s A dA);  dP = temp1 dZ      (two threads per word, rows interleaved)
+  // softmax #2 backward: dZ = A (dA - sum_s A dA);  dP = temp1 dZ      (SM_PARTS threads per word, rows interleaved)
   const size_t plane = (size_t)Bi * Sq * NC;
   const bf16* ab = atp + (size_t)j * Sq * NC + (size_t)ii * Lp;
-  const int lc = tid & 127, half = tid >> 7;
+  const int lc = tid & 127, part = tid >> 7;
   {
     float acc = 0.f;
-    if (lc < L)
-      for (int s = half; s < S; s += 2) {
+    if (lc < L) {
+#pragma unroll 4
+      for (int s = part; s < S; s += SM_PARTS) {
         const size_t o = (size_t)s * NC + lc;
         acc = fmaf(join3(ab[o], ab[plane + o], ab[2 * plane + o]), tile[(size_t)s * LP1 + lc], acc);
       }
-    zpart[half * 128 + lc] = acc;
+    }
+    zpart[part * 128 + lc] = acc;
   }
   __syncthreads();
-  if (tid < 128) rs[tid] = zpart[tid] + zpart[128 + tid];
+  if (tid < 128) {
+    float z = 0.f;
+#pragma unroll
+    for (int q = 0; q < SM_PARTS; ++q) z += zpart[q * 128 + tid];
+    rs[tid] = z;
+  }
   __syncthreads();
   if (lc < L) {
     const float r = rs[lc];
-    for (int s = half; s < S; s += 2) {
+#pragma unroll 4
+    for (int s = part; s < S; s += SM_PARTS) {
       const size_t o = (size_t)s * NC + lc;
       const float a = join3(ab[o], ab[plane + o], ab[2 * plane + o]);
       float* t = tile + (size_t)s * LP1 + lc;
@@ -371,22 +451,42 @@ __global__ void __launch_bounds__(256) softmax_bwd(const float* __restrict__ dat
     }
   }
   __syncthreads();
-  // softmax #1 backward: dS = P (dP - sum_l P dP), warp per region row; bf16 pieces out
+  // softmax #1 backward: dS = P (dP - sum_l P dP): a warp owns RB region rows at a time; bf16 pieces out
   const float* pb = sc + (size_t)j * Sq * NC + (size_t)ii * Lp;
   bf16* ob = dsp + (size_t)j * Sq * NC + (size_t)ii * Lp;
-  for (int s = warp; s < Sq; s += nwarps) {
-    const size_t ro = (size_t)s * NC;
-    float t = 0.f;
-    if (s < S) {
-      for (int l = lane; l < L; l += 32) t = fmaf(pb[ro + l], tile[(size_t)s * LP1 + l], t);
-      t = warp_sum(t);
+  for (int s0 = warp * RB; s0 < Sq; s0 += nwarps * RB) {
+    float P[RB][4], g[RB][4], t[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int s = s0 + r;
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int l = lane + 32 * k;
+        const bool in = s < S && l < L;
+        P[r][k] = in ? pb[(size_t)s * NC + l] : 0.f;
+        g[r][k] = in ? tile[(size_t)s * LP1 + l] : 0.f;
+        d = fmaf(P[r][k], g[r][k], d);
+      }
+      t[r] = d;
     }
-    for (int l = lane; l < Lp; l += 32) {
-      float v = 0.f;
-      if (s < S && l < L) v = pb[ro + l] * (tile[(size_t)s * LP1 + l] - t);
-      bf16 p0, p1, p2;
-      split3(v, p0, p1, p2);
-      ob[ro + l] = p0; ob[plane + ro + l] = p1; ob[2 * plane + ro + l] = p2;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) t[r] = warp_sum(t[r]);
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      const int s = s0 + r;
+      if (s < Sq) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int l = lane + 32 * k;
+          if (l < Lp) {
+            bf16 p0, p1, p2;
+            split3(P[r][k] * (g[r][k] - t[r]), p0, p1, p2);
+            const size_t o = (size_t)s * NC + l;
+            ob[o] = p0; ob[plane + o] = p1; ob[2 * plane + o] = p2;
+          }
+        }
+      }
     }
   }
 }
@@ -448,7 +548,7 @@ struct Plan {
 
 static int round_up(int x, int a) { return (x + a - 1) / a * a; }
 
-static size_t softmax_smem(int S, int Lp) { return ((size_t)S * (Lp + 1) + 3 * 128) * sizeof(float); }
+static size_t softmax_smem(int S, int Lp) { return ((size_t)S * (Lp + 1) + (SM_PARTS + 1) * 128) * sizeof(float); }
 
 static size_t fixed_bytes(const Dims& d, bool bwd) {
   size_t f = align_up((size_t)3 * d.Bi * d.Sq * d.D * 2, 256) + align_up((size_t)d.Bc * d.Lw * d.D * 4, 256) +
@@ -503,7 +603,7 @@ static Plan make_plan(const Dims& d, size_t bytes, bool bwd) {
 
 static int supported(int D, int S, int Lcap) {
   if (D <= 0 || S <= 0 || Lcap <= 0) return 1;
-  if (D % 64) return 1;
+  if (D % 64 || D > 2048) return 1;
   const int Lp = round_up(Lcap, 8);
   if (Lp > 128) return 1;
   if (softmax_smem(S, Lp) > 220 * 1024) return 1;
@@ -559,7 +659,7 @@ static int chunk_forward(const Dims& d, const Plan& pl, char* ws, const int32_t*
     e.a_rows = 3LL * d.Bi * d.Sq; e.b_rows = 3LL * d.D;
     if ((rc = tc::acc_gemm_ex(e, st))) return rc;
   }
-  softmax_fwd<<<(unsigned)(d.Bi * nc), 256, softmax_smem(d.S, d.Lp), st>>>(sc, atp, cap_lens, i0, nc, d.Bi, d.Bc, d.S, d.Sq, d.Lcap,
+  softmax_fwd<<<(unsigned)(d.Bi * nc), SM_THREADS, softmax_smem(d.S, d.Lp), st>>>(sc, atp, cap_lens, i0, nc, d.Bi, d.Bc, d.S, d.Sq, d.Lcap,
                                                                           d.Lp, NC, temp1, attn_diag, attn_mean);
   GLORIA_LAUNCHED("f32tc::softmax_fwd");
   if (NC > nc * d.Lp) {      // padding columns of A: exact zeros in every plane
@@ -602,25 +702,28 @@ static int set_smem(const void* fn, size_t bytes) {
   return GLORIA_OK;
 }
 
-extern "C" int gloria_b200_local_sim_fwd_f32tc(const float* ctx, const float* words, const int32_t* cap_lens, int Bi, int Bc, int D,
-                                               int S, int Lw, int Lcap, int word_off, float temp1, float temp2, int agg, float eps,
-                                               float* sim, float* attn_diag, float* attn_mean, void* workspace,
-                                               size_t workspace_bytes, void* stream) {
+// keep = true: the workspace is laid out for the backward, must hold all captions in one chunk, and is left holding the
+// forward's state (operand pieces, P, A, C) for gloria_b200_local_sim_bwd_f32tc(..., state_from_forward = 1)
+static int forward_impl(const float* ctx, const float* words, const int32_t* cap_lens, int Bi, int Bc, int D, int S, int Lw,
+                        int Lcap, int word_off, float temp1, float temp2, int agg, float eps, float* sim, float* attn_diag,
+                        float* attn_mean, void* workspace, size_t workspace_bytes, bool keep, cudaStream_t st) {
   int rc = check_common(ctx, words, cap_lens, Bi, Bc, D, S, Lw, Lcap, word_off, agg);
   if (rc) return rc;
   GLORIA_CHECK_ARG(sim != nullptr && workspace != nullptr, "null output / workspace");
   GLORIA_CHECK_ARG(attn_diag == nullptr || Bi == Bc, "attn_diag needs Bi == Bc (got %d x %d)", Bi, Bc);
-  cudaStream_t st = (cudaStream_t)stream;
   Dims d{Bi, Bc, D, S, round_up(S, 64), Lw, Lcap, round_up(Lcap, 8), word_off};
-  const Plan pl = make_plan(d, workspace_bytes, false);
-  if (pl.nc < 1) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B too small", workspace_bytes);
+  const Plan pl = make_plan(d, workspace_bytes, keep);
+  if (pl.nc < 1 || (keep && pl.nc < Bc))
+    return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B too small%s", workspace_bytes, keep ? " to keep the forward's state" : "");
   if ((rc = set_smem((const void*)softmax_fwd, softmax_smem(S, d.Lp)))) return rc;
   char* ws = (char*)workspace;
-  if ((rc = prepare(ctx, words, d, pl, ws, false, st))) return rc;
+  if ((rc = prepare(ctx, words, d, pl, ws, keep, st))) return rc;
   for (int i0 = 0; i0 < Bc; i0 += pl.nc) {
     const int nc = min(pl.nc, Bc - i0);
     const int NC = round_up(nc * d.Lp, 64);
-    if ((rc = chunk_forward(d, pl, ws, cap_lens, i0, nc, NC, temp1, 6, 6, false, attn_diag, attn_mean, st))) return rc;
+    // scores with all six piece products (they pass through two softmaxes); the context GEMM with three: its 2^-17
+    // relative error per product averages out over the D channels of the cosine
+    if ((rc = chunk_forward(d, pl, ws, cap_lens, i0, nc, NC, temp1, 6, 3, keep, attn_diag, attn_mean, st))) return rc;
     cosine_agg<<<(unsigned)(Bi * nc), 256, 3 * d.Lp * sizeof(float), st>>>(
         (const float*)(ws + pl.cx), (const float*)(ws + pl.wt32), (const float*)(ws + pl.wn), cap_lens, i0, nc, Bc, Lcap, d.Lp, NC, Lw,
         word_off, D, temp2, agg, eps, sim, nullptr, nullptr);
@@ -629,10 +732,27 @@ extern "C" int gloria_b200_local_sim_fwd_f32tc(const float* ctx, const float* wo
   return GLORIA_OK;
 }
 
+extern "C" int gloria_b200_local_sim_fwd_f32tc(const float* ctx, const float* words, const int32_t* cap_lens, int Bi, int Bc, int D,
+                                               int S, int Lw, int Lcap, int word_off, float temp1, float temp2, int agg, float eps,
+                                               float* sim, float* attn_diag, float* attn_mean, void* workspace,
+                                               size_t workspace_bytes, void* stream) {
+  return forward_impl(ctx, words, cap_lens, Bi, Bc, D, S, Lw, Lcap, word_off, temp1, temp2, agg, eps, sim, attn_diag, attn_mean,
+                      workspace, workspace_bytes, false, (cudaStream_t)stream);
+}
+
+extern "C" int gloria_b200_local_sim_fwd_f32tc_train(const float* ctx, const float* words, const int32_t* cap_lens, int Bi, int Bc,
+                                                     int D, int S, int Lw, int Lcap, int word_off, float temp1, float temp2, int agg,
+                                                     float eps, float* sim, float* attn_diag, float* attn_mean, void* workspace,
+                                                     size_t workspace_bytes, void* stream) {
+  return forward_impl(ctx, words, cap_lens, Bi, Bc, D, S, Lw, Lcap, word_off, temp1, temp2, agg, eps, sim, attn_diag, attn_mean,
+                      workspace, workspace_bytes, true, (cudaStream_t)stream);
+}
+
 extern "C" int gloria_b200_local_sim_bwd_f32tc(const float* ctx, const float* words, const int32_t* cap_lens, int Bi, int Bc, int D,
                                                int S, int Lw, int Lcap, int word_off, float temp1, float temp2, int agg, float eps,
                                                const float* dsim, const float* d_attn_diag, const float* d_attn_mean, float* d_ctx,
-                                               float* d_words, void* workspace, size_t workspace_bytes, void* stream) {
+                                               float* d_words, void* workspace, size_t workspace_bytes, int state_from_forward,
+                                               void* stream) {
   int rc = check_common(ctx, words, cap_lens, Bi, Bc, D, S, Lw, Lcap, word_off, agg);
   if (rc) return rc;
   GLORIA_CHECK_ARG(dsim && d_ctx && d_words && workspace, "null gradient / workspace pointer");
@@ -642,6 +762,8 @@ extern "C" int gloria_b200_local_sim_bwd_f32tc(const float* ctx, const float* wo
   Dims d{Bi, Bc, D, S, round_up(S, 64), Lw, Lcap, round_up(Lcap, 8), word_off};
   const Plan pl = make_plan(d, workspace_bytes, true);
   if (pl.nc < 1) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B too small", workspace_bytes);
+  const bool have_state = state_from_forward != 0;
+  if (have_state && pl.nc < Bc) return fail(GLORIA_ERR_WORKSPACE, "workspace %zu B cannot be a kept forward state", workspace_bytes);
   if ((rc = set_smem((const void*)softmax_fwd, softmax_smem(S, d.Lp)))) return rc;
   if ((rc = set_smem((const void*)softmax_bwd, softmax_smem(S, d.Lp)))) return rc;
   char* ws = (char*)workspace;
@@ -660,19 +782,19 @@ extern "C" int gloria_b200_local_sim_bwd_f32tc(const float* ctx, const float* wo
   float* dat = (float*)(ws + pl.dat);
   bf16* dsp = (bf16*)(ws + pl.dsp);
   float* dwc = (float*)(ws + pl.dwc);
-  if ((rc = prepare(ctx, words, d, pl, ws, true, st))) return rc;
+  if (!have_state && (rc = prepare(ctx, words, d, pl, ws, true, st))) return rc;
   GLORIA_CUDA(cudaMemsetAsync(drt, 0, (size_t)Bi * d.Sq * D * sizeof(float), st));
   GLORIA_CUDA(cudaMemsetAsync(dwt32, 0, (size_t)Bc * Lw * D * sizeof(float), st));
   for (int i0 = 0; i0 < Bc; i0 += pl.nc) {
     const int nc = min(pl.nc, Bc - i0);
     const int NC = round_up(nc * d.Lp, 64);
     const int tail = NC - nc * d.Lp;
-    // recompute the forward intermediates of the chunk (scores with all six terms: they pass through two softmaxes)
-    if ((rc = chunk_forward(d, pl, ws, cap_lens, i0, nc, NC, temp1, 6, 3, true, nullptr, nullptr, st))) return rc;
+    // recompute the forward intermediates of the chunk unless the forward left them here
+    if (!have_state && (rc = chunk_forward(d, pl, ws, cap_lens, i0, nc, NC, temp1, 6, 3, true, nullptr, nullptr, st))) return rc;
     cosine_agg<<<(unsigned)(Bi * nc), 256, 3 * d.Lp * sizeof(float), st>>>(cx, wt32, wn, cap_lens, i0, nc, Bc, Lcap, d.Lp, NC, Lw,
                                                                           word_off, D, temp2, agg, eps, nullptr, dsim, coef);
     GLORIA_LAUNCHED("f32tc::cosine_agg(bwd)");
-    context_grad<<<dim3((unsigned)d.Lp, (unsigned)nc), 256, 0, st>>>(cx, wt32, dwt32, coef, cap_lens, dcp, i0, nc, Bi, Lcap, d.Lp, NC,
+    context_grad<<<dim3((unsigned)d.Lp, (unsigned)nc), CG_THREADS, CG_THREADS * sizeof(float4), st>>>(cx, wt32, dwt32, coef, cap_lens, dcp, i0, nc, Bi, Lcap, d.Lp, NC,
                                                                      Lw, word_off, D);
     GLORIA_LAUNCHED("f32tc::context_grad");
     if (tail > 0)            // padding rows of dC: exact zeros in every plane
@@ -697,7 +819,7 @@ extern "C" int gloria_b200_local_sim_bwd_f32tc(const float* ctx, const float* wo
       e.a_rows = 3LL * Bi * d.Sq; e.b_rows = 3LL * Bi * NC;
       if ((rc = tc::acc_gemm_ex(e, st))) return rc;
     }
-    softmax_bwd<<<(unsigned)(Bi * nc), 256, softmax_smem(S, d.Lp), st>>>(dat, atp, sc, dsp, cap_lens, i0, nc, Bi, Bc, S, d.Sq, Lcap, d.Lp,
+    softmax_bwd<<<(unsigned)(Bi * nc), SM_THREADS, softmax_smem(S, d.Lp), st>>>(dat, atp, sc, dsp, cap_lens, i0, nc, Bi, Bc, S, d.Sq, Lcap, d.Lp,
                                                                         NC, temp1, d_attn_diag, d_attn_mean);
     GLORIA_LAUNCHED("f32tc::softmax_bwd");
     if (tail > 0)

@@ -27,17 +27,74 @@ _F32_TC = os.environ.get("GLORIA_B200_F32_TC", "1") != "0"                      
 _F32_TC_WS_BUDGET = int(os.environ.get("GLORIA_B200_F32_TC_WS_BYTES", str(16 << 30)))
 
 
-def _f32_entries(L, D: int, S: int, lcap: int, backward: bool):
-    """(workspace bytes function, kernel entry, name) of the fp32 mode for this shape: the split-precision tensor-core path
-    where it applies (D % 64 == 0, captions of <= 128 words), else the CUDA-core kernels."""
-    if _F32_TC and L.gloria_b200_f32tc_supported(D, S, lcap) == 0:
-        ws = lambda Bi, Bc, Lw: L.gloria_b200_local_f32tc_workspace(Bi, Bc, D, S, Lw, lcap, _F32_TC_WS_BUDGET, 1 if backward else 0)
-        return ws, (L.gloria_b200_local_sim_bwd_f32tc if backward else L.gloria_b200_local_sim_fwd_f32tc), "f32tc"
-    ws = lambda Bi, Bc, Lw: L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
-    return ws, (L.gloria_b200_local_sim_bwd_f32 if backward else L.gloria_b200_local_sim_fwd_f32), "f32"
-_PACKED_PROMPTS = os.environ.get("GLORIA_B200_PACKED_PROMPTS", "1") != "0"           # packed short-caption inference kernel
-_FUSED_TRAIN = os.environ.get("GLORIA_B200_FUSED_TRAIN", "1") != "0"               # fused forward+backward-operand kernel
-_FUSED_DIAG = os.environ.get("GLORIA_B200_FUSED_DIAG", "1") != "0"                 # ... which also emits the diagonal attention maps
+def _f32_tc(L, D: int, S: int, lcap: int) -> bool:
+    """fp32 mode on the tensor cores (split-precision tcgen05 GEMMs, tc_f32.cu) where the shape allows it
+    (D % 64 == 0, captions of <= 128 words), else the CUDA-core kernels (simt_f32.cu)."""
+    return _F32_TC and L.gloria_b200_f32tc_supported(D, S, lcap) == 0
+
+
+def _f32_forward(L, ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, sim, diag, mean, need_grad) -> Tensor:
+    """fp32-mode forward; returns the state for the backward (uint8; empty = the backward recomputes)."""
+    Bi, D, S = ctx.shape
+    Bc, _, Lw = words.shape
+    dev, st = ctx.device, _stream(ctx)
+    empty = torch.empty((0,), dtype=torch.uint8, device=dev)
+    args = (Bc, D, S, Lw, lcap, word_off, temp1, temp2, agg, eps)
+    if not _f32_tc(L, D, S, lcap):
+        nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        rc = L.gloria_b200_local_sim_fwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, *args, sim.data_ptr(),
+                                             _ptr(diag), _ptr(mean), ws.data_ptr(), nbytes, st)
+        _lib.check(rc, "local_sim_fwd_f32")
+        return empty
+    if need_grad and agg != AGG["max"]:
+        # training: keep the forward's operand pieces, P, A and contexts for the backward when they fit in one chunk
+        nbytes = L.gloria_b200_local_f32tc_workspace(Bi, Bc, D, S, Lw, lcap, 0, 1)
+        if nbytes <= min(_F32_TC_WS_BUDGET, int(_available_bytes(dev, nbytes) * 0.9)):
+            state = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+            rc = L.gloria_b200_local_sim_fwd_f32tc_train(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, *args,
+                                                         sim.data_ptr(), _ptr(diag), _ptr(mean), state.data_ptr(), nbytes, st)
+            _lib.check(rc, "local_sim_fwd_f32tc_train")
+            return state
+    # forward only (or a state too large to keep): captions are chunked inside the library; many images against few
+    # captions (zero-shot scoring) are cut into image blocks here so that every block's buffers fit the budget
+    nj = Bi
+    if diag.numel() == 0:
+        while nj > 64 and L.gloria_b200_local_f32tc_workspace(nj, Bc, D, S, Lw, lcap, 0, 0) > _F32_TC_WS_BUDGET:
+            nj = (nj + 1) // 2
+    nbytes = L.gloria_b200_local_f32tc_workspace(nj, Bc, D, S, Lw, lcap, _F32_TC_WS_BUDGET, 0)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    for j0 in range(0, Bi, nj):
+        j1 = min(Bi, j0 + nj)
+        rc = L.gloria_b200_local_sim_fwd_f32tc(ctx[j0:j1].data_ptr(), words.data_ptr(), cap_lens.data_ptr(), j1 - j0, *args,
+                                               sim[j0:j1].data_ptr(), _ptr(diag), _ptr(mean[j0:j1]) if mean.numel() else None,
+                                               ws.data_ptr(), nbytes, st)
+        _lib.check(rc, "local_sim_fwd_f32tc")
+    return empty
+
+
+def _f32_backward(L, ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim, d_diag, d_mean, d_ctx, d_words,
+                  state) -> None:
+    Bi, D, S = ctx.shape
+    Bc, _, Lw = words.shape
+    dev, st = ctx.device, _stream(ctx)
+    args = (Bi, Bc, D, S, Lw, lcap, word_off, temp1, temp2, agg, eps, dsim.data_ptr(), _ptr(d_diag), _ptr(d_mean),
+            d_ctx.data_ptr(), d_words.data_ptr())
+    if not _f32_tc(L, D, S, lcap):
+        nbytes = L.gloria_b200_local_f32_workspace(Bi, Bc, D, S, Lw, lcap, _WS_BUDGET)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        rc = L.gloria_b200_local_sim_bwd_f32(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), *args, ws.data_ptr(), nbytes, st)
+        _lib.check(rc, "local_sim_bwd_f32")
+        return
+    if state is not None and state.numel() > 0:
+        rc = L.gloria_b200_local_sim_bwd_f32tc(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), *args, state.data_ptr(),
+                                               state.numel(), 1, st)
+    else:
+        nbytes = L.gloria_b200_local_f32tc_workspace(Bi, Bc, D, S, Lw, lcap, _F32_TC_WS_BUDGET, 1)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        rc = L.gloria_b200_local_sim_bwd_f32tc(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), *args, ws.data_ptr(), nbytes,
+                                               0, st)
+    _lib.check(rc, "local_sim_bwd_f32tc")
 
 
 class Packed:
@@ -178,13 +235,7 @@ def local_sim_fwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
     stats = torch.empty((0,), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         if mode == MODE_FP32:
-            ws_fn, entry, tag = _f32_entries(L, D, S, lcap, False)
-            nbytes = ws_fn(Bi, Bc, Lw)
-            ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-            rc = entry(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D, S,
-                       Lw, lcap, word_off, temp1, temp2, agg, eps, sim.data_ptr(),
-                       _ptr(diag), _ptr(mean), ws.data_ptr(), nbytes, _stream(ctx))
-            _lib.check(rc, "local_sim_fwd_" + tag)
+            stats = _f32_forward(L, ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, sim, diag, mean, need_grad)
         else:
             if want_mean and agg == AGG["max"]:
                 raise RuntimeError("word-mean attention output is not available with agg='max'")
@@ -294,9 +345,9 @@ def _tc_packed_fwd(L, ctx, words, cap_lens, word_off, temp1, temp2, agg, eps, si
 def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, want_mean, mode, need_grad=True):
     Bi, D, S = ctx.shape
     Bc = words.shape[0]
-    if mode == MODE_BF16 and need_grad and agg != AGG["max"]:
-        # fused-training workspace or recompute statistics: which one is decided from free memory at run time, so the
-        # length of the byte state is a data-dependent size
+    if (mode == MODE_BF16 or _F32_TC) and need_grad and agg != AGG["max"]:
+        # fused-training workspace / recompute statistics (bf16), kept forward state or none (fp32): which one is decided
+        # from free memory at run time, so the length of the byte state is a data-dependent size
         n = torch.library.get_ctx().new_dynamic_size()
         state = ctx.new_empty((n,), dtype=torch.uint8)
     else:
@@ -342,14 +393,8 @@ def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_
                 if ev_done:
                     dctx_event = 0
             else:
-                ws_fn, entry, tag = _f32_entries(L, D, S, lcap, True)
-                nbytes = ws_fn(Bi, Bc, Lw)
-                ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-                rc = entry(ctx.data_ptr(), words.data_ptr(), cap_lens.data_ptr(), Bi, Bc, D,
-                           S, Lw, lcap, word_off, temp1, temp2, agg, eps, dsim.data_ptr(),
-                           None if diag_separately else _ptr(d_diag), _ptr(d_mean),
-                           d_ctx.data_ptr(), d_words.data_ptr(), ws.data_ptr(), nbytes, st)
-                _lib.check(rc, "local_sim_bwd_" + tag)
+                _f32_backward(L, ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, dsim,
+                              None if diag_separately else d_diag, d_mean, d_ctx, d_words, stats)
         if diag_separately:
             nbytes = L.gloria_b200_diag_attn_workspace(Bc, D, S, Lw, lcap)
             ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)

@@ -111,12 +111,22 @@ int gloria_b200_local_sim_fwd_f32tc(const float* ctx, const float* words, const 
                                     float temp1, float temp2, int agg, float eps,
                                     float* sim, float* attn_diag, float* attn_mean,
                                     void* workspace, size_t workspace_bytes, void* stream);
+/* Training forward: the workspace is laid out for the backward (gloria_b200_local_f32tc_workspace(..., backward = 1) with
+ * budget 0 = all captions in one chunk; GLORIA_ERR_WORKSPACE otherwise) and is left holding the forward's state -- operand
+ * pieces, P, A and the contexts.  The backward below then takes the same buffer with state_from_forward = 1 and recomputes
+ * nothing; it only reads that state, so a forward can be differentiated more than once.  With state_from_forward = 0 the
+ * backward recomputes the forward chunk by chunk inside any workspace (no activations kept). */
+int gloria_b200_local_sim_fwd_f32tc_train(const float* ctx, const float* words, const int32_t* cap_lens,
+                                          int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
+                                          float temp1, float temp2, int agg, float eps,
+                                          float* sim, float* attn_diag, float* attn_mean,
+                                          void* workspace, size_t workspace_bytes, void* stream);
 int gloria_b200_local_sim_bwd_f32tc(const float* ctx, const float* words, const int32_t* cap_lens,
                                     int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
                                     float temp1, float temp2, int agg, float eps,
                                     const float* dsim, const float* d_attn_diag, const float* d_attn_mean,
                                     float* d_ctx, float* d_words,
-                                    void* workspace, size_t workspace_bytes, void* stream);
+                                    void* workspace, size_t workspace_bytes, int state_from_forward, void* stream);
 
 /* Diagonal pairs only (B pairs instead of B^2): the attention maps A_ii that local_loss returns (att_maps,
  * gloria_loss.py:141-143; consumed by get_attn_maps, gloria_model.py:209-211) and the gradient flowing back through

@@ -146,3 +146,41 @@ def test_word_window_and_max(gl, monkeypatch):
     sim, _, _, _ = gl.local_similarities(cu(img_l), cu(txt_l[:4]), lens, 4.0, 5.0, "max", word_offset=1)
     ref = O.local_similarities(img_l.astype(np.float64), txt_l[:4].astype(np.float64), lens, 4.0, 5.0, "max", word_offset=1)
     assert relerr(sim, ref) < LOGIT_TOL
+
+
+def test_image_blocks_forward_only(gl, monkeypatch):
+    """Zero-shot call shape (many images, few short prompts, no gradient): the images are cut into blocks that fit the
+    workspace budget; the result does not depend on the cut."""
+    from gloria_nlp_project_b200 import ops
+    monkeypatch.setattr(ops, "_F32_TC", True)
+    img_l, txt_l, _, _, _ = gen_inputs(17, 300, 768, 19, 19, 18, dtype=np.float32)
+    lens = [4, 16, 9, 12, 7]
+    img, txt = cu(img_l), cu(txt_l[:5])
+    with torch.no_grad():
+        whole, _, _, _ = gl.local_similarities(img, txt, lens, 4.0, 5.0, "max", word_offset=1)
+        monkeypatch.setattr(ops, "_F32_TC_WS_BUDGET", 160 << 20)
+        cut, _, mean, _ = gl.local_similarities(img, txt, lens, 4.0, 5.0, "max", word_offset=1, want_mean_attn=True)
+    assert torch.equal(whole, cut)
+    assert torch.allclose(mean.sum(-1), torch.ones_like(mean[..., 0]), atol=1e-5)
+    ref = O.local_similarities(img_l[:40].astype(np.float64), txt_l[:5].astype(np.float64), lens, 4.0, 5.0, "max", word_offset=1)
+    assert relerr(cut[:40], ref) < LOGIT_TOL
+
+
+def test_kept_state_can_be_differentiated_twice(gl, monkeypatch):
+    """The training forward keeps its state for the backward, which only reads it: retain_graph works, and the gradients
+    equal those of the recompute backward."""
+    from gloria_nlp_project_b200 import ops
+    monkeypatch.setattr(ops, "_F32_TC", True)
+    img_l, txt_l, _, _, cl = gen_inputs(19, 5, 768, 19, 19, 40, dtype=np.float32)
+    img, txt = cu(img_l, True), cu(txt_l, True)
+    l0, l1, *_ = gl.local_loss(img, txt, cl)
+    (l0 + l1).backward(retain_graph=True)
+    g1i, g1t = img.grad.clone(), txt.grad.clone()
+    img.grad = txt.grad = None
+    (l0 + l1).backward()
+    assert torch.equal(g1i, img.grad) and torch.equal(g1t, txt.grad)
+    monkeypatch.setattr(ops, "_F32_TC_WS_BUDGET", 64 << 20)          # too small to keep a state: recompute backward
+    img2, txt2 = cu(img_l, True), cu(txt_l, True)
+    m0, m1, *_ = gl.local_loss(img2, txt2, cl)
+    (m0 + m1).backward()
+    assert relerr(img2.grad, g1i) < 1e-5 and relerr(txt2.grad, g1t) < 1e-5
