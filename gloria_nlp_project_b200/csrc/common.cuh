@@ -17,6 +17,11 @@ void timer_record(int slot, int which, cudaStream_t st);   // which: 0 = before,
 // so that only the translation units that call cuBLAS include its header
 void* cublas_handle_opaque();
 
+// tc_f32.cu: scores of the diagonal pairs on the split-precision tensor-core GEMM (0 bytes = shape not covered)
+size_t f32tc_diag_scores_workspace(int B, int D, int S, int Lcap);
+int f32tc_diag_scores(const float* ctx, const float* wt32, const int32_t* cap_lens, int B, int D, int S, int Lw, int Lcap, int off,
+                      float* sc, void* ws, size_t ws_bytes, cudaStream_t st);
+
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 

@@ -7,7 +7,6 @@
 // the backward recomputes scores / P / A / C per chunk and applies the closed-form gradients.
 //
 // Pair index inside a chunk of `nc` captions starting at i0:  p = j * nc + (i - i0)   (image-major).
-#include <cublas_v2.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -618,7 +617,7 @@ extern "C" int gloria_b200_local_sim_bwd_f32(const float* ctx, const float* word
 // ---------------------------------------------------------------------------------------------------------------
 namespace gloria {
 namespace {
-struct DiagPlan { size_t off_wt, off_dwt, off_wn, off_sc, off_at, off_da, total; };
+struct DiagPlan { size_t off_wt, off_dwt, off_wn, off_sc, off_at, off_da, off_tc, tc_bytes, total; };
 DiagPlan diag_plan(int B, int D, int S, int Lw, int Lcap) {
   DiagPlan pl{};
   size_t o = 0;
@@ -629,27 +628,30 @@ DiagPlan diag_plan(int B, int D, int S, int Lw, int Lcap) {
   pl.off_sc = take((size_t)B * Lcap * S * sizeof(float));
   pl.off_at = take((size_t)B * Lcap * S * sizeof(float));
   pl.off_da = take((size_t)B * Lcap * S * sizeof(float));
+  pl.tc_bytes = gloria::f32tc_diag_scores_workspace(B, D, S, Lcap);      // operand pieces of the tensor-core score GEMM
+  pl.off_tc = take(pl.tc_bytes);
   pl.total = o;
   return pl;
 }
 
 // scores + double softmax of the pairs (i, i); leaves P in sc and A in at (and attn_diag if given)
 int diag_forward(const float* ctx, const float* Wt, const int32_t* cap_lens, int B, int D, int S, int Lw, int Lcap,
-                 int off, float temp1, float* sc, float* at, float* attn_diag, cudaStream_t st) {
-  // S_[i][l][s] = sum_d Wt[i][off+l][d] ctx[i][d][s]: a plain strided-batched fp32 GEMM (cuBLAS SGEMM, no TF32);
-  // row-major [Lcap, S] = [Lcap, D] [D, S]  ==  column-major [S, Lcap] = ctx_i [S, D] . Wt_i^T [D, Lcap]
-  cublasHandle_t h = (cublasHandle_t)cublas_handle_opaque();
-  if (!h) return fail(GLORIA_ERR_DRIVER, "cublasCreate failed");
-  const float one = 1.f, zero = 0.f;
-  cublasStatus_t cs = cublasSetStream(h, st);
-  if (cs == CUBLAS_STATUS_SUCCESS) cs = cublasSetWorkspace(h, nullptr, 0);       // default pool (never a stale caller buffer)
-  if (cs == CUBLAS_STATUS_SUCCESS) cs = cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
-  if (cs == CUBLAS_STATUS_SUCCESS)
-    cs = cublasSgemmStridedBatched(h, CUBLAS_OP_N, CUBLAS_OP_N, S, Lcap, D, &one, ctx, S, (long long)D * S,
-                                   Wt + (long long)off * D, D, (long long)Lw * D, &zero, sc, S, (long long)Lcap * S, B);
-  if (cs == CUBLAS_STATUS_SUCCESS) cs = cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);
-  if (cs != CUBLAS_STATUS_SUCCESS) return fail(GLORIA_ERR_DRIVER, "cublasSgemmStridedBatched -> status %d", (int)cs);
-  ++launch_counter();
+                 int off, float temp1, float* sc, float* at, float* attn_diag, void* tc_ws, size_t tc_bytes, cudaStream_t st) {
+  // S_[i][l][s] = sum_d Wt[i][off+l][d] ctx[i][d][s]: one batch per pair on the split-precision tensor-core GEMM
+  // (tc_f32.cu; fp32 accuracy) where the shape is covered, else on the CUDA-core GEMM above
+  int rc;
+  if (tc_bytes > 0) {
+    if ((rc = f32tc_diag_scores(ctx, Wt, cap_lens, B, D, S, Lw, Lcap, off, sc, tc_ws, tc_bytes, st))) return rc;
+  } else {
+    GemmArgs g{};
+    g.A = Wt + (long long)off * D; g.B = ctx; g.C = sc;
+    g.M = Lcap; g.N = S; g.K = D; g.R = 1;
+    g.sAm = D; g.sAk = 1; g.sAb0 = 0; g.sAb1 = (long long)Lw * D; g.sAr = 0;
+    g.sBk = S; g.sBn = 1; g.sBb0 = 0; g.sBb1 = (long long)D * S; g.sBr = 0;
+    g.sCm = S; g.sCn = 1; g.sCb0 = 0; g.sCb1 = (long long)Lcap * S;
+    g.nb0 = 1; g.nb1 = B; g.beta = 0.f; g.mlim = cap_lens; g.mlim_off = 0;
+    if ((rc = launch_gemm(g, st))) return rc;
+  }
   double_softmax_fwd<<<(unsigned)B, 256, 0, st>>>(sc, at, cap_lens, 0, B, B, Lcap, S, temp1, attn_diag, nullptr, 1);
   GLORIA_LAUNCHED("double_softmax_fwd(diag)");
   return GLORIA_OK;
@@ -675,7 +677,7 @@ extern "C" int gloria_b200_diag_attn_fwd_f32(const float* ctx, const float* word
   float* Wt = (float*)(ws + pl.off_wt);
   if ((rc = prepack_words(words, Wt, (float*)(ws + pl.off_wn), B, D, Lw, st))) return rc;
   return diag_forward(ctx, Wt, cap_lens, B, D, S, Lw, Lcap, word_off, temp1, (float*)(ws + pl.off_sc),
-                      (float*)(ws + pl.off_at), attn_diag, st);
+                      (float*)(ws + pl.off_at), attn_diag, ws + pl.off_tc, pl.tc_bytes, st);
 }
 
 extern "C" int gloria_b200_diag_attn_bwd_f32(const float* ctx, const float* words, const int32_t* cap_lens, int B,
@@ -695,7 +697,8 @@ extern "C" int gloria_b200_diag_attn_bwd_f32(const float* ctx, const float* word
   float* at = (float*)(ws + pl.off_at);
   float* da = (float*)(ws + pl.off_da);
   if ((rc = prepack_words(words, Wt, (float*)(ws + pl.off_wn), B, D, Lw, st))) return rc;
-  if ((rc = diag_forward(ctx, Wt, cap_lens, B, D, S, Lw, Lcap, word_off, temp1, sc, at, nullptr, st))) return rc;
+  if ((rc = diag_forward(ctx, Wt, cap_lens, B, D, S, Lw, Lcap, word_off, temp1, sc, at, nullptr, ws + pl.off_tc, pl.tc_bytes, st)))
+    return rc;
   GLORIA_CUDA(cudaMemsetAsync(da, 0, (size_t)B * Lcap * S * sizeof(float), st));
   GLORIA_CUDA(cudaMemsetAsync(dWt, 0, (size_t)B * Lw * D * sizeof(float), st));
   double_softmax_bwd<<<(unsigned)B, 256, 0, st>>>(da, at, sc, cap_lens, 0, B, B, Lcap, S, temp1, d_attn_diag, nullptr, 1);
@@ -737,7 +740,7 @@ extern "C" int gloria_b200_diag_attn_bwd_f32(const float* ctx, const float* word
 // ---------------------------------------------------------------------------------------------------------------
 namespace gloria {
 namespace {
-struct AttnPlan { size_t off_wt, off_dwt, off_wn, off_sc, off_at, off_da, off_cx, off_lens, total; };
+struct AttnPlan { size_t off_wt, off_dwt, off_wn, off_sc, off_at, off_da, off_cx, off_lens, off_tc, tc_bytes, total; };
 AttnPlan attn_plan(int B, int D, int S, int L) {
   AttnPlan pl{};
   size_t o = 0;
@@ -750,6 +753,8 @@ AttnPlan attn_plan(int B, int D, int S, int L) {
   pl.off_da = take((size_t)B * L * S * 4);
   pl.off_cx = take((size_t)B * L * D * 4);
   pl.off_lens = take((size_t)B * 4);
+  pl.tc_bytes = gloria::f32tc_diag_scores_workspace(B, D, S, L);
+  pl.off_tc = take(pl.tc_bytes);
   pl.total = o;
   return pl;
 }
@@ -809,7 +814,7 @@ extern "C" int gloria_b200_attention_fwd_f32(const float* query, const float* ct
   GLORIA_LAUNCHED("fill_int");
   if ((rc = prepack_words(query, Wt, (float*)(ws + pl.off_wn), B, D, L, st))) return rc;
   if ((rc = diag_forward(ctx, Wt, lens, B, D, S, L, L, 0, temp1, (float*)(ws + pl.off_sc), (float*)(ws + pl.off_at),
-                         attn, st)))
+                         attn, ws + pl.off_tc, pl.tc_bytes, st)))
     return rc;
   if ((rc = paired_context((float*)(ws + pl.off_at), ctx, cx, B, D, S, L, st))) return rc;
   dim3 grid((L + 31) / 32, (D + 31) / 32, B), block(32, 8);
@@ -838,7 +843,7 @@ extern "C" int gloria_b200_attention_bwd_f32(const float* query, const float* ct
   fill_int<<<(B + 255) / 256, 256, 0, st>>>(lens, B, L);
   GLORIA_LAUNCHED("fill_int");
   if ((rc = prepack_words(query, Wt, (float*)(ws + pl.off_wn), B, D, L, st))) return rc;
-  if ((rc = diag_forward(ctx, Wt, lens, B, D, S, L, L, 0, temp1, sc, at, nullptr, st))) return rc;
+  if ((rc = diag_forward(ctx, Wt, lens, B, D, S, L, L, 0, temp1, sc, at, nullptr, ws + pl.off_tc, pl.tc_bytes, st))) return rc;
   GLORIA_CUDA(cudaMemsetAsync(da, 0, (size_t)B * L * S * sizeof(float), st));
   GLORIA_CUDA(cudaMemsetAsync(d_ctx, 0, (size_t)B * D * S * sizeof(float), st));
   if (d_wctx) {

@@ -63,6 +63,7 @@ __global__ void split_ctx(const float* __restrict__ ctx, bf16* __restrict__ rt, 
       rn[o] = p0; rn[rn_plane + o] = p1; rn[2 * rn_plane + o] = p2;
     }
   }
+  if (rt == nullptr) return;
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int s = s0 + r, d = d0 + threadIdx.x;
@@ -122,6 +123,7 @@ __global__ void split_words(const float* __restrict__ wt32, const int* __restric
       wtp[o] = p0; wtp[plane + o] = p1; wtp[2 * plane + o] = p2;
     }
   }
+  if (wnp == nullptr) return;
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int d = d0 + r, c = c0 + threadIdx.x;
@@ -130,6 +132,14 @@ __global__ void split_words(const float* __restrict__ wt32, const int* __restric
     const size_t o = (size_t)d * NC + c;
     wnp[o] = p0; wnp[plane + o] = p1; wnp[2 * plane + o] = p2;
   }
+}
+
+// tmp [B][Lp][Sq] -> sc [B][Lcap][S]  (scores of the diagonal pairs in the layout of simt_f32.cu's diagonal kernels)
+__global__ void repack_diag_scores(const float* __restrict__ tmp, float* __restrict__ sc, int Lcap, int Lp, int S, int Sq) {
+  const int l = blockIdx.x, i = blockIdx.y;
+  const float* src = tmp + ((size_t)i * Lp + l) * Sq;
+  float* dst = sc + ((size_t)i * Lcap + l) * S;
+  for (int x = threadIdx.x; x < S; x += blockDim.x) dst[x] = src[x];
 }
 
 // Double softmax of one (image, caption) block (gloria_loss.py:42-53).  SC block: scores on entry, P (word softmax) on exit.
@@ -679,6 +689,44 @@ static int chunk_forward(const Dims& d, const Plan& pl, char* ws, const int32_t*
 }
 
 }  // namespace f32tc
+
+// Scores of the B diagonal pairs, sc[i][l][s] = sum_d Wt32[i][off+l][d] ctx[i][d][s] ([B, Lcap, S], fp32 accuracy), on the
+// split-precision tensor-core GEMM: one batch per pair (att_maps of local_loss, gloria_loss.py:141-143; get_attn_maps,
+// gloria_model.py:209-211).  Returns 0 bytes when the shape is not covered (the caller then uses its CUDA-core GEMM).
+size_t f32tc_diag_scores_workspace(int B, int D, int S, int Lcap) {
+  using namespace f32tc;
+  if (supported(D, S, Lcap)) return 0;
+  const int Lp = round_up(Lcap, 8), Sq = round_up(S, 64), NC = round_up(B * Lp, 64);
+  return align_up((size_t)3 * NC * D * 2, 256) + align_up((size_t)3 * B * D * Sq * 2, 256) + align_up((size_t)B * Lp * Sq * 4, 256);
+}
+int f32tc_diag_scores(const float* ctx, const float* wt32, const int32_t* cap_lens, int B, int D, int S, int Lw, int Lcap, int off,
+                      float* sc, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace f32tc;
+  const size_t need = f32tc_diag_scores_workspace(B, D, S, Lcap);
+  if (need == 0 || ws == nullptr || ws_bytes < need) return fail(GLORIA_ERR_WORKSPACE, "diag scores: workspace %zu B < %zu B", ws_bytes, need);
+  const int Lp = round_up(Lcap, 8), Sq = round_up(S, 64), NC = round_up(B * Lp, 64);
+  char* w = (char*)ws;
+  bf16* wtp = (bf16*)w;
+  bf16* rn = (bf16*)(w + align_up((size_t)3 * NC * D * 2, 256));
+  float* tmp = (float*)((char*)rn + align_up((size_t)3 * B * D * Sq * 2, 256));
+  split_ctx<<<dim3(Sq / 32, D / 32, B), dim3(32, 8), 0, st>>>(ctx, nullptr, rn, B, D, S, Sq);
+  GLORIA_LAUNCHED("f32tc::split_ctx(diag)");
+  split_words<<<dim3(NC / 32, D / 32), dim3(32, 8), 0, st>>>(wt32, cap_lens, nullptr, wtp, 0, B, Lw, Lcap, Lp, off, D, NC);
+  GLORIA_LAUNCHED("f32tc::split_words(diag)");
+  tc::GemmEx e{};
+  e.A = wtp; e.B = rn; e.C = tmp;
+  e.M = Lp; e.N = Sq; e.K = D; e.ldc = Sq; e.a_kmajor = true; e.ksplit = 1;
+  e.nb = B; e.a_brows = Lp; e.b_brows = D; e.c_bstride = (long long)Lp * Sq;
+  e.nterms = 6;
+  e.a_prows = NC; e.b_prows = (long long)B * D;
+  e.a_rows = 3LL * NC; e.b_rows = 3LL * B * D;
+  int rc = tc::acc_gemm_ex(e, st);
+  if (rc) return rc;
+  repack_diag_scores<<<dim3((unsigned)Lcap, (unsigned)B), 128, 0, st>>>(tmp, sc, Lcap, Lp, S, Sq);
+  GLORIA_LAUNCHED("f32tc::repack_diag_scores");
+  return GLORIA_OK;
+}
+
 }  // namespace gloria
 
 using namespace gloria;

@@ -25,6 +25,9 @@ _WS_BUDGET = int(os.environ.get("GLORIA_B200_WS_BYTES", str(4 << 30)))          
 _TC_WS_BUDGET = int(os.environ.get("GLORIA_B200_TC_WS_BYTES", str(96 << 30)))     # bf16 backward operand matrices
 _F32_TC = os.environ.get("GLORIA_B200_F32_TC", "1") != "0"                         # fp32 mode on the tensor cores (tc_f32.cu)
 _F32_TC_WS_BUDGET = int(os.environ.get("GLORIA_B200_F32_TC_WS_BYTES", str(16 << 30)))
+_PACKED_PROMPTS = os.environ.get("GLORIA_B200_PACKED_PROMPTS", "1") != "0"           # packed short-caption inference kernel
+_FUSED_TRAIN = os.environ.get("GLORIA_B200_FUSED_TRAIN", "1") != "0"               # fused forward+backward-operand kernel
+_FUSED_DIAG = os.environ.get("GLORIA_B200_FUSED_DIAG", "1") != "0"                 # ... which also emits the diagonal attention maps
 
 
 def _f32_tc(L, D: int, S: int, lcap: int) -> bool:
