@@ -404,27 +404,48 @@ tc_fwd_kernel(const __grid_constant__ CUtensorMap tm_rt, const __grid_constant__
 // prepack: fp32 native layouts -> padded bf16 TMA-legal layouts
 // ---------------------------------------------------------------------------------------------------------------
 // ctx [Bi, D, S] -> Rn [Bi, D, Spad] (bf16), Rt [Bi, Spad, D] (bf16) and Rh [Bi, Spad, D] (fp16)
-// grid (Spad/32, D/64, Bi), block (32, 8).  The score GEMM runs on the fp16 copies: the word softmax amplifies operand
+// grid (Spad/64, D/64, Bi), block (32, 8).  The score GEMM runs on the fp16 copies: the word softmax amplifies operand
 // rounding (scores of unit-variance 768-d features have std 27.7) and fp16 carries 3 more mantissa bits than bf16 at
 // the same tensor rate -- it is also the dtype the reference's AMP runs this bmm in.
-__global__ void pack_ctx(const float* __restrict__ ctx, __nv_bfloat16* __restrict__ Rn, __nv_bfloat16* __restrict__ Rt,
-                         __half* __restrict__ Rh, int D, int S, int Spad, int sp) {
-  // one 32 (regions) x 64 (channels) tile per block: 128-byte reads along s, 128-byte (2 channels per thread) writes
-  // along d of both transposed copies
-  __shared__ float t[64][33];
-  const int b = blockIdx.z, s0 = blockIdx.x * 32, d0 = blockIdx.y * 64;
-  const int s = s0 + threadIdx.x;
-  for (int r = threadIdx.y; r < 64; r += 8) {
-    const int d = d0 + r;
-    const float v = (s < S) ? ctx[((size_t)b * D + d) * S + s] : 0.f;
-    if (Rn != nullptr) Rn[((size_t)b * D + d) * Spad + s] = __float2bfloat16_rn(v);
-    t[r][threadIdx.x] = v;
+__global__ void __launch_bounds__(256) pack_ctx(const float* __restrict__ ctx, __nv_bfloat16* __restrict__ Rn,
+                                                 __nv_bfloat16* __restrict__ Rt, __half* __restrict__ Rh, int D, int S, int Spad,
+                                                 int sp) {
+  // one 64 (regions) x 64 (channels) tile per block: every thread first issues its 16 loads (two 128-byte rows per warp
+  // and channel), then writes the s-major copy (bf16 pairs exchanged by shuffle: 128-byte rows) and, through shared
+  // memory, 128-byte rows (2 channels per thread) along d of both transposed copies
+  __shared__ float t[64][65];
+  const int b = blockIdx.z, s0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  float v[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float* row = ctx + ((size_t)b * D + d0 + ty + 8 * k) * S;
+    v[k][0] = (s0 + tx < S) ? __ldg(row + s0 + tx) : 0.f;
+    v[k][1] = (s0 + 32 + tx < S) ? __ldg(row + s0 + 32 + tx) : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = ty + 8 * k;
+    t[r][tx] = v[k][0];
+    t[r][tx + 32] = v[k][1];
+    if (Rn != nullptr) {
+      // lane pairs trade halves so that every lane stores one bf16 pair: even lanes write columns (tx, tx+1) of the first
+      // 32, odd lanes columns (tx-1+32, tx+32) of the second
+      const float mine = (tx & 1) ? v[k][1] : v[k][0];
+      const float send = (tx & 1) ? v[k][0] : v[k][1];
+      const float got = __shfl_xor_sync(0xffffffffu, send, 1);
+      const int col = (tx & 1) ? s0 + 32 + tx - 1 : s0 + tx;
+      const __nv_bfloat162 pr = (tx & 1) ? __floats2bfloat162_rn(got, mine) : __floats2bfloat162_rn(mine, got);
+      *reinterpret_cast<__nv_bfloat162*>(Rn + ((size_t)b * D + d0 + r) * Spad + col) = pr;
+    }
   }
   __syncthreads();
-  const int d = d0 + 2 * threadIdx.x;
-  for (int r = threadIdx.y; r < 32; r += 8) {
+  const int d = d0 + 2 * tx;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = ty + 8 * k;
     const int so = s0 + r;
-    const float v0 = t[2 * threadIdx.x][r], v1 = t[2 * threadIdx.x + 1][r];
+    const float v0 = t[2 * tx][r], v1 = t[2 * tx + 1][r];
     if (Rt != nullptr && so < sp)
       *reinterpret_cast<__nv_bfloat162*>(Rt + ((size_t)b * sp + so) * D + d) = __floats2bfloat162_rn(v0, v1);
     *reinterpret_cast<__half2*>(Rh + ((size_t)b * Spad + so) * D + d) = __floats2half2_rn(v0, v1);
@@ -582,7 +603,7 @@ extern "C" int gloria_b200_tc_prepack_ctx(const float* ctx, int Bi, int D, int S
   if (gloria_b200_tc_supported(D, S, 1)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d", D, S);
   cudaStream_t st = (cudaStream_t)stream;
   const int Spad = gloria_b200_tc_spad(S);
-  pack_ctx<<<dim3(Spad / 32, D / 64, Bi), dim3(32, 8), 0, st>>>(ctx, (__nv_bfloat16*)ctx_n, (__nv_bfloat16*)ctx_t,
+  pack_ctx<<<dim3(Spad / 64, D / 64, Bi), dim3(32, 8), 0, st>>>(ctx, (__nv_bfloat16*)ctx_n, (__nv_bfloat16*)ctx_t,
                                                                (__half*)ctx_h, D, S, Spad, gloria_b200_tc_sp(S));
   GLORIA_LAUNCHED("pack_ctx");
   return GLORIA_OK;

@@ -69,10 +69,24 @@ class LazyAttnMaps(Sequence):
         return self.stacked[i:i + 1, :L, self._s0:].reshape(1, L, *self._hw)
 
 
-def _att_maps(diag, lens, dev_lens_obj, s0, ih, iw, n):
+class AttnMapList(list):
+    """The reference's plain list of [1, L_i, H, W] maps (host-side caption lengths), which also remembers the padded
+    [B, Lcap, S] tensor it views and the lengths on the device: consumers that reduce over all maps
+    (`supervised_attention_loss`) then run a handful of batched launches instead of B small ones."""
+    stacked = None
+    lens_tensor = None
+    _s0 = 0
+    _hw = (0, 0)
+
+
+def _att_maps(diag, lens, dev_lens_obj, s0, ih, iw, n, dev_lens=None):
     if lens is None:
         return LazyAttnMaps(diag, dev_lens_obj, s0, ih, iw)
-    return [diag[i:i + 1, :lens[i], s0:].reshape(1, lens[i], ih, iw) for i in range(n)]
+    out = AttnMapList(diag[i:i + 1, :lens[i], s0:].reshape(1, lens[i], ih, iw) for i in range(n))
+    if dev_lens is None:
+        dev_lens = torch.tensor(lens[:n], dtype=torch.int32).to(diag.device, non_blocking=True)
+    out.stacked, out.lens_tensor, out._s0, out._hw = diag, dev_lens, s0, (ih, iw)
+    return out
 
 
 def _cap_lens(cap_lens: Union[Sequence[int], torch.Tensor, "DeviceCapLens"], n: int, word_off: int, Lw: int,
@@ -194,7 +208,7 @@ def diagonal_attention_maps(img_features, words_emb, cap_lens, temp1=4.0, no_att
     lcap = max(lens) if lens is not None else Lw - word_offset
     diag = ops.diag_attn_fwd(ctx, words_emb.float(), dev_lens, lcap, word_offset, float(temp1))
     s0 = 1 if no_attn_vec is not None else 0
-    return _att_maps(diag, lens, cap_lens, s0, ih, iw, Bc)
+    return _att_maps(diag, lens, cap_lens, s0, ih, iw, Bc, dev_lens)
 
 
 _CELL_INDEX = {}
@@ -215,11 +229,12 @@ def supervised_attention_loss(att_maps, segmentation_labels):
     nearest upsampling repeats each grid cell over a fixed set of pixels, so  sum(label * up) / sum(up)  is
     sum_c map[c] * (#labelled pixels of cell c) / sum_c map[c] * (#pixels of cell c).  Returns the batch mean of
     -log of that ratio (the caller applies segmentation_loss_weight)."""
-    if isinstance(att_maps, LazyAttnMaps):
+    lens_t = att_maps._lens.tensor if isinstance(att_maps, LazyAttnMaps) else getattr(att_maps, "lens_tensor", None)
+    if lens_t is not None and getattr(att_maps, "stacked", None) is not None:
         # word-mean of each map from the padded tensor (rows beyond a caption's length are zero): sum / length, no sync
         ih, iw = att_maps._hw
         d = att_maps.stacked[:, :, att_maps._s0:]
-        n = att_maps._lens.tensor[:d.shape[0]].clamp(1, d.shape[1]).to(d.dtype)
+        n = lens_t[:d.shape[0]].clamp(1, d.shape[1]).to(d.dtype)
         mean_maps = (d.sum(1) / n[:, None]).reshape(d.shape[0], ih, iw)
     else:
         mean_maps = torch.cat([m.mean(1) for m in att_maps], 0)              # [B, h, w]  (:144)
