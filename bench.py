@@ -35,7 +35,7 @@ CPU_SAMPLE = 16          # the CPU arm times a CPU_SAMPLE x CPU_SAMPLE block of 
 # DRAM bytes per launch (read + write) of the dominant kernels at B=512, N=1, from the ncu captures under profiles/
 TRAFFIC_B512 = {("tc_fwd_kernel", False): 2511333120 + 237689344,            # r01_traffic_B512_ncu.csv
                 ("tc_bwd_pair_kernel", False): 5648215808 + 45244279296,
-                ("tc_fwd_kernel", True): 21674893000 + 42595012000}           # r01_end_fused_train_B512_ncu_summary.txt
+                ("tc_fwd_kernel", True): 3192498000 + 40386191000}            # r02_fused_train_B512_ncu_summary.txt
 
 
 def parse():
@@ -289,7 +289,9 @@ def run_b200(args):
         full = torch.randn(shape, generator=gen)
         host[name] = full[rank * n:(rank + 1) * n].contiguous().pin_memory()
         del full
-    cap_lens = [LW] * n
+    # caption lengths as the drop-in text encoder hands them over (text_model.aggregate_tokens -> sents.cap_lens): a device
+    # tensor, so the step has no host round trip for them (gloria_loss.DeviceCapLens)
+    cap_lens = gloria_loss.DeviceCapLens(torch.full((n,), LW, dtype=torch.int32, device=dev))
     names = ("img_l", "txt_l", "img_g", "txt_g")
     h2d = sum(host[k].numel() * host[k].element_size() for k in names)
 
@@ -453,12 +455,17 @@ def run_b200(args):
     dom = max(cand, key=lambda k: kt[k]) if cand else None
     roofline = None
     if not timed:
-        # whole step against the fp32 FFMA peak of the part (148 SMs x 128 FMA x 2 x max SM clock), no per-kernel split
-        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-        roofline = {"bound": "fp32 FFMA (SIMT)", "kernel": "fp32 mode: strided SIMT GEMMs + fused softmax/cosine kernels (whole step)",
-                    "achieved": f_step / (ms * 1e-3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": f_step / (ms * 1e-3) / 1e12 / fp32_peak, "traffic": None,
-                    "peak_source": "nominal fp32 FFMA rate (no measured fp32 peak in MEASURED_PEAKS.json)"}
+        # fp32 mode (tensor-core path, tc_f32.cu): the whole step against the sustained bf16 tensor peak.  Every fp32 product
+        # is executed as 6 (scores) or 3 (all other GEMMs) bf16 piece products: 9 piece GEMMs forward + 12 backward, each
+        # 2 S D L per pair, against the 6 algorithmic GEMMs -- `frac` counts algorithmic FLOPs, `frac_executed` what ran
+        f_exec = 21.0 * f_fwd / 2.0
+        roofline = {"bound": "tensor",
+                    "kernel": "fp32 mode: split-precision acc_gemm_kernel (6 / 3 bf16 piece products per fp32 product) + "
+                              "streaming softmax / cosine kernels (whole step)",
+                    "achieved": f_step / (ms * 1e-3) / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
+                    "frac": f_step / (ms * 1e-3) / 1e12 / pk["tflops"], "traffic": None, "peak_source": pk["src"],
+                    "executed_piece_flops_per_step": f_exec,
+                    "frac_executed": f_exec / (ms * 1e-3) / 1e12 / pk["tflops"]}
     elif dom:
         ach = kflops[dom] / (kt[dom] * 1e-3) / 1e12
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/ (B=512, N=1 captures), else null
@@ -487,6 +494,7 @@ def run_b200(args):
                        "l2": "inputs larger than L2 (region features %.0f MB per rank)" % (B * D * S * 4 / 1e6)
                              if B * D * S * 4 > 126e6 else "inputs smaller than L2: a 256 MB buffer is written between "
                                                            "timed iterations (outside the per-step events)",
+                       "cap_lens": "device tensor (DeviceCapLens), all captions 97 words",
                        "loss": loss_val},
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,

@@ -25,6 +25,7 @@ PROTOTYPES = {
     "gloria_b200_set_timer_events": (_i, [_i, _p, _p]),
     "gloria_b200_record_event": (_i, [_p, _p]),
     "gloria_b200_debug_phase_clocks": (None, [_p]),
+    "gloria_b200_upload_ints": (_i, [_p, _i, _p, _p]),
     "gloria_b200_local_f32_workspace": (_z, [_i, _i, _i, _i, _i, _i, _z]),
     "gloria_b200_local_sim_fwd_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _i, _f, _p, _p, _p, _p, _z,
                                            _p]),

@@ -84,7 +84,7 @@ def _att_maps(diag, lens, dev_lens_obj, s0, ih, iw, n, dev_lens=None):
         return LazyAttnMaps(diag, dev_lens_obj, s0, ih, iw)
     out = AttnMapList(diag[i:i + 1, :lens[i], s0:].reshape(1, lens[i], ih, iw) for i in range(n))
     if dev_lens is None:
-        dev_lens = torch.tensor(lens[:n], dtype=torch.int32).to(diag.device, non_blocking=True)
+        dev_lens = ops.upload_ints(lens[:n], diag.device)
     out.stacked, out.lens_tensor, out._s0, out._hw = diag, dev_lens, s0, (ih, iw)
     return out
 
@@ -108,8 +108,7 @@ def _cap_lens(cap_lens: Union[Sequence[int], torch.Tensor, "DeviceCapLens"], n: 
     if min(lens) < 1 or max(lens) + word_off > Lw:
         raise RuntimeError(f"cap_lens out of range: need 1 <= len and len + {word_off} <= {Lw}, got "
                            f"[{min(lens)}, {max(lens)}]")
-    dev_lens = torch.tensor(lens, dtype=torch.int32).to(device, non_blocking=True)
-    return dev_lens, lens
+    return ops.upload_ints(lens, device), lens
 
 
 def _context(img_features: torch.Tensor, no_attn_vec: Optional[torch.Tensor]) -> torch.Tensor:

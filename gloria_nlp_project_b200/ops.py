@@ -9,6 +9,7 @@ op with CPU tensors raises RuntimeError.
 from __future__ import annotations
 
 import contextlib
+import ctypes as C
 import os
 import threading
 from typing import Optional, Tuple
@@ -184,6 +185,19 @@ def _available_bytes(dev: torch.device, want: int) -> int:
         return optimistic
     free, _ = torch.cuda.mem_get_info(idx)
     return free + torch.cuda.memory_reserved(idx) - torch.cuda.memory_allocated(idx)
+
+
+def upload_ints(values, device: torch.device) -> Tensor:
+    """int32 device tensor from a short host list (caption lengths) through the kernel parameter buffer: asynchronous, no
+    copy engine (a pageable H2D copy blocks the host and queues behind the next batch's prefetch on the copy engine)."""
+    n = len(values)
+    out = torch.empty((n,), dtype=torch.int32, device=device)
+    if n:
+        arr = (C.c_int32 * n)(*values)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().gloria_b200_upload_ints(arr, n, out.data_ptr(), torch.cuda.current_stream(device).cuda_stream),
+                       "upload_ints")
+    return out
 
 
 def _need_cuda(*ts: Tensor) -> None:

@@ -63,6 +63,9 @@ long long gloria_b200_launch_count(int reset);
 int gloria_b200_set_timer_events(int slot, void* start_event, void* stop_event);
 /* cudaEventRecord(event, stream) for callers that hold only raw handles (see gloria_b200_tc_local_sim_bwd_train_ev). */
 int gloria_b200_record_event(void* event, void* stream);
+/* n host int32 values (caption lengths) -> device array, passed through the kernel parameter buffer (960 per launch):
+ * asynchronous on `stream`, no copy engine, the host array may be reused as soon as the call returns. */
+int gloria_b200_upload_ints(const int32_t* host, int n, int32_t* dev, void* stream);
 /* Development aid (builds with -DGLORIA_PHASE_CLOCKS only): device buffer receiving 8 int64 phase clocks per CTA. */
 void gloria_b200_debug_phase_clocks(void* device_buffer);
 

@@ -1,5 +1,5 @@
 """ncu per-launch CSV (gpu__time_duration.sum + DRAM bytes) -> the launch list of ONE step with each kernel's share.
-usage: python scripts/launch_list.py launches.csv "header text" > profiles/rNN_..._launch_list.txt
+usage: python scripts/launch_list.py launches.csv "header text" [first-kernel name fragment] > profiles/rNN_..._launch_list.txt
 The step is delimited by the fused training kernel (tc_bwd_pair_kernel): the last complete step of the capture is used."""
 import csv
 import re
@@ -26,7 +26,8 @@ seq = [launches[k] for k in order]
 fused = [i for i, l in enumerate(seq) if "tc_bwd_pair_kernel" in l["name"]]
 # one step = from the first kernel after the previous step's last kernel to the last kernel before the next step's first
 # prepack: cut at the pack_ctx launches that precede each fused kernel
-packs = [i for i, l in enumerate(seq) if "pack_ctx" in l["name"] and "unpack" not in l["name"]]
+first = sys.argv[3] if len(sys.argv) > 3 else "pack_ctx"          # name fragment of the first kernel of a step
+packs = [i for i, l in enumerate(seq) if first in l["name"] and "unpack" not in l["name"]]
 start = packs[-1]
 end = len(seq)
 prev_start = packs[-2] if len(packs) > 1 else 0
