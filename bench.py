@@ -307,13 +307,16 @@ def run_b200(args):
         return loss
 
     copy_stream = torch.cuda.Stream(device=dev)
+    h2d_events = []                                         # (start, end) of every step's input copy on the copy stream
 
     def issue_h2d():
         """Issue this step's host->device copies on the copy stream (pinned memory, asynchronous)."""
         with torch.cuda.stream(copy_stream):
+            e_a, ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_a.record(copy_stream)
             t = {k: host[k].to(dev, non_blocking=True) for k in names}
-            ev = torch.cuda.Event()
             ev.record(copy_stream)
+        h2d_events.append((e_a, ev))
         return t, ev
 
     readback = {"n": 0, "buf": [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)],
@@ -423,6 +426,10 @@ def run_b200(args):
     e1.record()
     sync()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    # how long the input copies themselves took (copy-stream events of the timed steps, max over ranks): when this is close
+    # to the e2e step time, the end-to-end number is bound by the host's H2D bandwidth, not by the kernels
+    cp = [a.elapsed_time(b) for a, b in h2d_events[-args.steps - 1:-1]] or [0.0]
+    ms_h2d = max_over_ranks(sum(cp) / len(cp))
 
     if rank != 0:
         if world > 1:
@@ -498,6 +505,7 @@ def run_b200(args):
                        "loss": loss_val},
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
+                    "h2d_copy_ms_per_step": ms_h2d, "h2d_GBps_per_rank": h2d / max(ms_h2d, 1e-9) / 1e6,
                     "readback": "loss copied to pinned host memory every step (asynchronous), read by the host one step later"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "parity_check": parity}

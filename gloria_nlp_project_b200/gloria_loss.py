@@ -176,15 +176,16 @@ def local_similarities(img_features, words_emb, cap_lens, temp1=4.0, temp2=5.0, 
         parts, order = [], []
         with ops.shared_ctx_pack(ctx):                               # the images are packed once for all groups
             for idx, lcap_b in buckets:
-                sel = torch.tensor(idx, dtype=torch.long).to(ctx.device, non_blocking=True)
+                sel = ops.upload_ints(idx, ctx.device)               # (through the kernel parameter buffer: no H2D copy)
                 sim_b, _, _, _ = ops.local_sim_fwd(ctx, words.index_select(0, sel), dev_lens.index_select(0, sel),
                                                    lcap_b, word_offset, float(temp1), float(temp2), ops.AGG[agg],
                                                    float(eps), False, False, mode, need_grad)
                 parts.append(sim_b)
                 order += idx
-        inv = torch.empty(Bc, dtype=torch.long)
-        inv[torch.tensor(order)] = torch.arange(Bc)
-        sim = torch.cat(parts, 1).index_select(1, inv.to(ctx.device, non_blocking=True))
+        inv = [0] * Bc
+        for k, i in enumerate(order):
+            inv[i] = k
+        sim = torch.cat(parts, 1).index_select(1, ops.upload_ints(inv, ctx.device))
         diag = None
         if want_attn_maps:                                           # B diagonal pairs through the exact fp32 kernels
             diag = ops.diag_attn_fwd(ctx, words, dev_lens, max(lens), word_offset, float(temp1))
