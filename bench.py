@@ -326,12 +326,14 @@ def run_b200(args):
         """One end-to-end step: inputs come from pinned host memory (their copy was issued one step earlier and
         overlaps the previous step's kernels), the loss value is read back to the host."""
         t, ev = cur
-        nxt = issue_h2d() if prefetch_next else None
         torch.cuda.current_stream().wait_event(ev)
         for v in t.values():
             v.record_stream(torch.cuda.current_stream())
             v.requires_grad_(True)
         loss = loss_of(t)
+        # the next step's input copy is enqueued between forward and backward: under the forward's gather phase (8 ranks)
+        # the same copy costs 2.9 ms per step, under the backward 0.5 ms (scripts/profile_e2e_sharded.py)
+        nxt = issue_h2d() if prefetch_next else None
         loss.backward()
         # device->host read of the step's result: an asynchronous copy into pinned memory, issued every step and consumed
         # one step later (a blocking float(loss) here would expose the host's launch latency of the NEXT step, which at
