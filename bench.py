@@ -319,6 +319,11 @@ def run_b200(args):
         h2d_events.append((e_a, ev))
         return t, ev
 
+    # Where the next step's input copy is enqueued.  Sharded over many ranks the step is short and starts with the gather
+    # phase, under which a concurrent 90 MB copy per rank costs 2.9 ms per step (8 ranks; 0.5 ms between forward and
+    # backward: scripts/profile_e2e_sharded.py); on one GPU the copy is 724 MB and is cheapest under the fused kernel at
+    # the top of the step (0.75 ms against 2.0 ms under the HBM-bound backward).
+    prefetch_mid = world >= 4
     readback = {"n": 0, "buf": [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)],
                 "ev": [torch.cuda.Event(), torch.cuda.Event()]}
 
@@ -326,14 +331,14 @@ def run_b200(args):
         """One end-to-end step: inputs come from pinned host memory (their copy was issued one step earlier and
         overlaps the previous step's kernels), the loss value is read back to the host."""
         t, ev = cur
+        nxt = issue_h2d() if (prefetch_next and not prefetch_mid) else None
         torch.cuda.current_stream().wait_event(ev)
         for v in t.values():
             v.record_stream(torch.cuda.current_stream())
             v.requires_grad_(True)
         loss = loss_of(t)
-        # the next step's input copy is enqueued between forward and backward: under the forward's gather phase (8 ranks)
-        # the same copy costs 2.9 ms per step, under the backward 0.5 ms (scripts/profile_e2e_sharded.py)
-        nxt = issue_h2d() if prefetch_next else None
+        if prefetch_next and prefetch_mid:
+            nxt = issue_h2d()
         loss.backward()
         # device->host read of the step's result: an asynchronous copy into pinned memory, issued every step and consumed
         # one step later (a blocking float(loss) here would expose the host's launch latency of the NEXT step, which at
@@ -508,7 +513,9 @@ def run_b200(args):
             "e2e": {"value": B / (ms_e2e * 1e-3), "unit": "pairs/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * world,
                     "h2d_copy_ms_per_step": ms_h2d, "h2d_GBps_per_rank": h2d / max(ms_h2d, 1e-9) / 1e6,
-                    "readback": "loss copied to pinned host memory every step (asynchronous), read by the host one step later"},
+                    "readback": "loss copied to pinned host memory every step (asynchronous), read by the host one step later",
+                    "prefetch": "next step's inputs enqueued " + ("between forward and backward" if prefetch_mid
+                                                                   else "at the top of the step") + " on a copy stream"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "parity_check": parity}
     print(json.dumps(line), flush=True)
