@@ -20,6 +20,8 @@ from __future__ import annotations
 
 from typing import Callable, Optional, Sequence
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -128,7 +130,7 @@ class _ShardedLocalSim(torch.autograd.Function):
                 None, None)
 
 
-_N_PARTS = 2          # image parts per rank shard: gather / reduce_scatter of one part overlap the kernels of the other
+_N_PARTS = int(os.environ.get("GLORIA_B200_SHARD_PARTS", "2"))   # image parts per rank shard: gather / reduce_scatter of one part overlap the kernels of the other
 
 
 def part_major_rows(n_per_rank: int, world: int, parts: int) -> torch.Tensor:
@@ -371,12 +373,14 @@ def sharded_loss(img_emb_l: torch.Tensor, text_emb_l: torch.Tensor, img_emb_g: t
         sim = local_sim_fn(img_emb_l, text_emb_l, cap_lens, temp1, temp2, agg)
         cosm = global_cos_fn(img_emb_g, text_emb_g, eps)
         return (*ce_fn(sim, temp3), *ce_fn(cosm, temp3))
-    img_g_all = gather_reduce_scatter(img_emb_g, group)              # [B, D]
     if local_sim_fn is _default_local_sim:
         sim_blk = _sharded_local_sim(img_emb_l, text_emb_l, cap_lens, temp1, temp2, agg, group, eps)   # [B, B/G]
     else:
         img_all = gather_reduce_scatter(img_emb_l, group)            # [B, D, H, W]
         sim_blk = local_sim_fn(img_all, text_emb_l, cap_lens, temp1, temp2, agg)      # [B, B/G]
+    # (gathered AFTER the local term was built: autograd runs backward nodes in reverse creation order, so the small
+    # reduce_scatter of d_img_g then precedes the local backward instead of trailing the whole step by a launch latency)
+    img_g_all = gather_reduce_scatter(img_emb_g, group)              # [B, D]
     cos_blk = global_cos_fn(img_g_all, text_emb_g, eps)                                # [B, B/G]
     # one small collective for both logit blocks: rows = captions of every rank after the transpose
     both = torch.stack([sim_blk.t(), cos_blk.t()], 1)                # [B/G, 2, B]
