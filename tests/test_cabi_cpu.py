@@ -179,3 +179,32 @@ def test_lazy_containers_host_logic():
     assert len(maps) == 2 and maps[0].shape == (1, 4, 2, 2) and maps[-1].shape == (1, 2, 2, 2)
     assert torch.equal(maps[1], diag[1:2, :2, 1:].reshape(1, 2, 2, 2))
     assert [m.shape[1] for m in maps] == [4, 2]
+
+
+def test_f32_tensor_core_host_side(libpath):
+    """fp32 mode on the tensor cores (tc_f32.cu): shape coverage, workspace arithmetic and argument checks are host code."""
+    from gloria_nlp_project_b200 import _lib
+    L = _lib.lib()
+    assert L.gloria_b200_f32tc_supported(768, 361, 97) == 0          # the path's own shape
+    assert L.gloria_b200_f32tc_supported(768, 362, 128) == 0         # + the no-attention column, longest caption covered
+    assert L.gloria_b200_f32tc_supported(48, 361, 97) != 0           # D % 64: stays on the CUDA-core kernels
+    assert L.gloria_b200_f32tc_supported(768, 361, 129) != 0         # captions beyond 128 words
+    assert L.gloria_b200_f32tc_supported(4096, 361, 97) != 0
+    fwd = L.gloria_b200_local_f32tc_workspace(48, 48, 768, 361, 97, 97, 0, 0)
+    bwd = L.gloria_b200_local_f32tc_workspace(48, 48, 768, 361, 97, 97, 0, 1)
+    assert 0 < fwd < bwd < 8 << 30                                   # the backward layout holds more buffers; 3.9 GB at B = 48
+    capped = L.gloria_b200_local_f32tc_workspace(512, 512, 768, 361, 97, 97, 4 << 30, 1)
+    least = L.gloria_b200_local_f32tc_workspace(512, 1, 768, 361, 97, 97, 0, 1)
+    assert capped == max(4 << 30, capped) and capped >= least > 0    # a budget below one caption's chunk is raised to it
+    assert L.gloria_b200_local_f32tc_workspace(48, 48, 768, 361, 97, 97, 1 << 30, 0) <= max(1 << 30, fwd)
+    assert L.gloria_b200_local_f32tc_workspace(0, 48, 768, 361, 97, 97, 0, 0) == 0
+    rc = L.gloria_b200_local_sim_fwd_f32tc(None, None, None, 1, 1, 64, 1, 1, 1, 0, 4.0, 5.0, 0, 1e-8, None, None, None, None, 0,
+                                           None)
+    assert rc == 1 and b"null" in L.gloria_b200_last_error()
+    # split-precision GEMM: bad term counts / shapes are refused before any launch
+    one = ctypes.c_void_p(16)
+    assert L.gloria_b200_acc_gemm_planes(one, one, one, 128, 128, 64, 1, 4, 1, 1, 0, None) == 1
+    assert b"nterms" in L.gloria_b200_last_error()
+    assert L.gloria_b200_acc_gemm_planes(one, one, one, 128, 100, 64, 1, 6, 1, 1, 0, None) == 1       # N % 16
+    assert L.gloria_b200_acc_gemm_planes(one, one, one, 128, 128, 72, 0, 3, 2, 1, 0, None) == 1       # transposed A: K % 64
+    assert L.gloria_b200_upload_ints(None, 4, None, None) == 1
