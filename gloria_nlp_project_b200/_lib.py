@@ -77,6 +77,8 @@ PROTOTYPES = {
                                                      _p, _i, _p]),
     "gloria_b200_tc_local_sim_bwd_train_parts": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _i,
                                                       _p, _p]),
+    "gloria_b200_tc_train_drt_offset": (_z, [_i, _i, _i, _i, _i]),
+    "gloria_b200_tc_unpack_dctx": (_i, [_p, _p, _i, _i, _i, _p]),
     "gloria_b200_tc_local_sim_bwd_train_ev": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _z, _p, _p]),
     "gloria_b200_acc_gemm": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p]),
     "gloria_b200_acc_gemm_planes": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),

@@ -39,6 +39,11 @@ __global__ void __launch_bounds__(256) global_cos_fwd(const float* __restrict__ 
 
 // Gradient w.r.t. the "row side" of cos[a,b] = <x_a, y_b> / max(|x_a||y_b|, eps); dcos is addressed through
 // (rs, cs) so the same kernel serves both sides.  dynamic smem: (D + Bc) floats.
+// Both phases are sums over the other side's rows b and are latency-bound (every operand is an L2 hit), so each warp
+// keeps 16 / 32 independent loads in flight: phase 1 takes two rows b per step in 256-channel pieces, phase 2 gives each
+// warp one eighth of the rows b and 256 channels at a time, four rows per step, and the eight partial sums are added in
+// a fixed order through shared memory (deterministic).  Before, phase 2 was one dependent chain of Bc loads per thread:
+// 171 us for a [512 x 64] caption shard, whose 64 column-side blocks each walk 512 rows.
 __global__ void __launch_bounds__(256) global_cos_bwd_side(const float* __restrict__ x_, const float* __restrict__ y_,
                                                            const float* __restrict__ xn_,
                                                            const float* __restrict__ yn_,
@@ -58,42 +63,107 @@ __global__ void __launch_bounds__(256) global_cos_bwd_side(const float* __restri
   float* xs = smem;
   float* dd = smem + D;
   __shared__ float red[8];
+  __shared__ float part[8][256];
   const int a = side_y ? (int)blockIdx.x - Bi : (int)blockIdx.x;
   for (int d = threadIdx.x; d < D; d += blockDim.x) xs[d] = x[(long long)a * D + d];
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = 8;
   const float na = xn[a];
   float esum = 0.f;   // sum_b (dL/d(|x_a||y_b|)) * |y_b|   (lane 0 of each warp)
-  for (int b = warp; b < Bc; b += nwarps) {
-    const float* yr = y + (long long)b * D;
-    float dot = 0.f;
-    for (int d = lane; d < D; d += 32) dot = fmaf(xs[d], yr[d], dot);
-    dot = warp_sum(dot);
+  // ---- phase 1: dd[b] = g / den, esum; rows b = warp, warp + 8, ... two at a time
+  for (int b = warp; b < Bc; b += 2 * NW) {
+    const int b1 = b + NW;
+    const bool has1 = b1 < Bc;
+    const float* y0 = y + (long long)b * D;
+    const float* y1 = y + (long long)(has1 ? b1 : b) * D;
+    float dot0 = 0.f, dot1 = 0.f;
+    for (int d0 = 0; d0 < D; d0 += 256) {
+      float v0[8], v1[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int d = d0 + k * 32 + lane;
+        v0[k] = d < D ? __ldg(y0 + d) : 0.f;
+        v1[k] = d < D ? __ldg(y1 + d) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int d = d0 + k * 32 + lane;
+        const float xv = d < D ? xs[d] : 0.f;
+        dot0 = fmaf(xv, v0[k], dot0);
+        dot1 = fmaf(xv, v1[k], dot1);
+      }
+    }
+    dot0 = warp_sum(dot0);
+    dot1 = warp_sum(dot1);
     if (lane == 0) {
-      const float g = dcos[a * rs + b * cs];
-      const float prod = na * yn[b];
-      const float den = fmaxf(prod, eps);
-      dd[b] = g / den;
-      if (prod >= eps) esum += -g * dot / (den * den) * yn[b];
+      {
+        const float g = dcos[a * rs + b * cs];
+        const float prod = na * yn[b];
+        const float den = fmaxf(prod, eps);
+        dd[b] = g / den;
+        if (prod >= eps) esum += -g * dot0 / (den * den) * yn[b];
+      }
+      if (has1) {
+        const float g = dcos[a * rs + b1 * cs];
+        const float prod = na * yn[b1];
+        const float den = fmaxf(prod, eps);
+        dd[b1] = g / den;
+        if (prod >= eps) esum += -g * dot1 / (den * den) * yn[b1];
+      }
     }
   }
   if (lane == 0) red[warp] = esum;
   __syncthreads();
   float tot = 0.f;
-  for (int w = 0; w < nwarps; ++w) tot += red[w];
+#pragma unroll
+  for (int w = 0; w < NW; ++w) tot += red[w];
   const float coef = na > 0.f ? tot / na : 0.f;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    // four independent chains: with few rows per launch (a caption shard of a large batch) this loop is latency-bound
-    float acc0 = coef * xs[d], acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-    int b = 0;
-    for (; b + 4 <= Bc; b += 4) {
-      acc0 = fmaf(dd[b], __ldg(y + (long long)b * D + d), acc0);
-      acc1 = fmaf(dd[b + 1], __ldg(y + (long long)(b + 1) * D + d), acc1);
-      acc2 = fmaf(dd[b + 2], __ldg(y + (long long)(b + 2) * D + d), acc2);
-      acc3 = fmaf(dd[b + 3], __ldg(y + (long long)(b + 3) * D + d), acc3);
+  // ---- phase 2: dx[a, d] = coef x[a, d] + sum_b dd[b] y[b, d]
+  const int per = (Bc + NW - 1) / NW;
+  const int bs = warp * per, be = min(Bc, bs + per);
+  for (int d0 = 0; d0 < D; d0 += 256) {
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    int b = bs;
+    for (; b + 4 <= be; b += 4) {
+      float v[4][8];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int d = d0 + k * 32 + lane;
+          v[r][k] = d < D ? __ldg(y + (long long)(b + r) * D + d) : 0.f;
+        }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float w = dd[b + r];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, v[r][k], acc[k]);
+      }
     }
-    for (; b < Bc; ++b) acc0 = fmaf(dd[b], __ldg(y + (long long)b * D + d), acc0);
-    dx[(long long)a * D + d] = (acc0 + acc1) + (acc2 + acc3);
+    for (; b < be; ++b) {
+      const float w = dd[b];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int d = d0 + k * 32 + lane;
+        if (d < D) acc[k] = fmaf(w, __ldg(y + (long long)b * D + d), acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) part[warp][k * 32 + lane] = acc[k];
+    __syncthreads();
+    {
+      const int d = d0 + (int)threadIdx.x;
+      if (d < D) {
+        float s = coef * xs[d];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += part[w][threadIdx.x];
+        dx[(long long)a * D + d] = s;
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -172,8 +242,9 @@ extern "C" int gloria_b200_global_sim_bwd(const float* x, const float* y, const 
                                           void* stream) {
   GLORIA_CHECK_ARG(x && y && xn && yn && dcos && dx && dy, "null pointer");
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && D > 0, "bad sizes Bi=%d Bc=%d D=%d", Bi, Bc, D);
-  GLORIA_CHECK_ARG((size_t)(D + (Bi > Bc ? Bi : Bc)) * sizeof(float) <= 48 * 1024,
-                   "global_sim_bwd: D + B = %d exceeds the 48 KB shared-memory tile", D + (Bi > Bc ? Bi : Bc));
+  // (the kernel also holds 8.2 KB of static shared memory for its partial sums)
+  GLORIA_CHECK_ARG((size_t)(D + (Bi > Bc ? Bi : Bc)) * sizeof(float) <= 39 * 1024,
+                   "global_sim_bwd: D + B = %d exceeds the 39 KB shared-memory tile", D + (Bi > Bc ? Bi : Bc));
   cudaStream_t st = (cudaStream_t)stream;
   global_cos_bwd_side<<<Bi + Bc, 256, (D + (Bi > Bc ? Bi : Bc)) * sizeof(float), st>>>(x, y, xn, yn, dcos, Bi, Bc, D, eps,
                                                                                         dx, dy);

@@ -908,15 +908,42 @@ __global__ void normalise_diag(float* __restrict__ a, const int* __restrict__ ca
   for (int s = lane; s < S; s += 32) r[s] *= z;
 }
 
-// gamma[i, l] = sum_j g[j, i] * go[j, (i,l)]   (fused training path);  one thread per column
-__global__ void gamma_sum(const float* __restrict__ go, const float* __restrict__ g, float* __restrict__ gamma, int Bi,
-                          int R1, int Bc, int i0, int lpad) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= R1) return;
-  const int i = i0 + c / lpad;
+// gamma[i, l] = sum_j g[j, i] * go[j, (i,l)]   (fused training path).  Block = 32 columns x 8 slices of the image axis
+// (one 128-byte row segment per warp-load, 8 loads in flight per thread), slices summed in a fixed order through shared
+// memory: deterministic, and R1 / 32 blocks instead of R1 / 256 (a caption shard of 64 captions used 26 SMs for 140 us).
+__global__ void __launch_bounds__(256) gamma_sum(const float* __restrict__ go, const float* __restrict__ g,
+                                                 float* __restrict__ gamma, int Bi, int R1, int Bc, int i0, int lpad) {
+  __shared__ float part[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  for (int j = 0; j < Bi; ++j) acc = fmaf(g[(size_t)j * Bc + i], go[(size_t)j * R1 + c], acc);
-  gamma[(size_t)i0 * lpad + c] = acc;
+  if (c < R1) {
+    const int i = i0 + c / lpad;
+    const int per = (Bi + 7) / 8;
+    const int j0 = slice * per, j1 = min(Bi, j0 + per);
+    const float* gp = g + i;
+    const float* op = go + c;
+    int j = j0;
+    for (; j + 8 <= j1; j += 8) {
+      float a[8], b[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a[k] = __ldg(gp + (size_t)(j + k) * Bc);
+        b[k] = __ldg(op + (size_t)(j + k) * R1);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = fmaf(a[k], b[k], acc);
+    }
+    for (; j < j1; ++j) acc = fmaf(__ldg(gp + (size_t)j * Bc), __ldg(op + (size_t)j * R1), acc);
+  }
+  part[slice][lane] = acc;
+  __syncthreads();
+  if (slice == 0 && c < R1) {
+    float tot = part[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) tot += part[k][lane];
+    gamma[(size_t)i0 * lpad + c] = tot;
+  }
 }
 
 __global__ void f32_to_bf16(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
@@ -1437,7 +1464,9 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const
                                                         size_t workspace_bytes, int n_parts, void* const* part_events,
                                                         void* stream) {
   GLORIA_CHECK_ARG(n_parts >= 1 && Bi % n_parts == 0, "n_parts=%d must divide Bi=%d", n_parts, Bi);
-  GLORIA_CHECK_ARG(ctx_t && words_t && cap_lens && dsim && d_ctx && d_words && workspace, "null pointer");
+  // d_ctx may be NULL: the image-side gradient then stays in the workspace as dRt [Bi, sp, D] fp32
+  // (gloria_b200_tc_train_drt_offset) -- see gloria_b200_tc_unpack_dctx
+  GLORIA_CHECK_ARG(ctx_t && words_t && cap_lens && dsim && d_words && workspace, "null pointer");
   GLORIA_CHECK_ARG(Bi > 0 && Bc > 0 && word_off >= 0 && word_off + Lcap <= Lw, "bad sizes");
   if (gloria_b200_tc_supported(D, S, Lcap)) return fail(GLORIA_ERR_UNSUPPORTED, "shape D=%d S=%d Lcap=%d", D, S, Lcap);
   cudaStream_t st = (cudaStream_t)stream;
@@ -1501,8 +1530,10 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const
                                              (long long)sp * D, Mbp, CUDA_R_16BF, sp, (long long)sp * sp, &one, dRp,
                                              CUDA_R_32F, D, (long long)sp * D, nj, CUBLAS_COMPUTE_32F,
                                              CUBLAS_GEMM_DEFAULT));
-    bw::unpack_dctx<<<dim3((S + 31) / 32, D / 32, nj), dim3(32, 8), 0, st>>>(dRp, d_ctx + j0 * D * S, D, S, sp);
-    GLORIA_LAUNCHED("unpack_dctx");
+    if (d_ctx != nullptr) {
+      bw::unpack_dctx<<<dim3((S + 31) / 32, D / 32, nj), dim3(32, 8), 0, st>>>(dRp, d_ctx + j0 * D * S, D, S, sp);
+      GLORIA_LAUNCHED("unpack_dctx");
+    }
     if (part_events && part_events[part]) GLORIA_CUDA(cudaEventRecord((cudaEvent_t)part_events[part], st));
   }
   // ---- caption side.  dWt[(i,l), d] = sum_(j,s) g[j,i] X^T[(j,s),(i,l)] Rt[(j,s), d]   (A^T = X^T in memory)
@@ -1518,11 +1549,29 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const
     }
   }
   timer_record(GLORIA_TIMER_TC_BWD_GEMM, 1, st);
-  bw::gamma_sum<<<(R1 + 255) / 256, 256, 0, st>>>((const float*)(ws + pl.off_go), dsim, gamma, Bi, R1, Bc, 0, lp);
+  bw::gamma_sum<<<(R1 + 31) / 32, 256, 0, st>>>((const float*)(ws + pl.off_go), dsim, gamma, Bi, R1, Bc, 0, lp);
   GLORIA_LAUNCHED("gamma_sum");
   bw::unpack_dwords_tc<<<dim3((Lw + 31) / 32, D / 32, Bc), dim3(32, 8), 0, st>>>(dWt, gamma, Wt, cap_lens, d_words, D,
                                                                                Lw, lp, Lcap, word_off);
   GLORIA_LAUNCHED("unpack_dwords_tc");
+  return GLORIA_OK;
+}
+
+// Where the packed image-side gradient dRt [Bi, sp, D] fp32 (sp = gloria_b200_tc_sp(S) rows per image, rows >= S are
+// padding) sits in the training workspace; 0 = unsupported shape.
+extern "C" size_t gloria_b200_tc_train_drt_offset(int Bi, int Bc, int D, int S, int Lcap) {
+  if (Bi <= 0 || Bc <= 0 || gloria_b200_tc_supported(D, S, Lcap)) return 0;
+  return bw::train_plan(Bi, Bc, D, gloria_b200_tc_spad(S), gloria_b200_tc_sp(S), gloria_b200_tc_lp(Lcap)).off_drt;
+}
+
+// dRt [n, sp, D] fp32 (packed, as the backward leaves it) -> d_ctx [n, D, S] (the caller's layout).  A caption-sharded
+// caller reduce_scatters the PACKED rows and unpacks only the images it owns (1 / world of the transposes).
+extern "C" int gloria_b200_tc_unpack_dctx(const float* drt, float* d_ctx, int n, int D, int S, void* stream) {
+  GLORIA_CHECK_ARG(drt && d_ctx, "null pointer");
+  GLORIA_CHECK_ARG(n > 0 && n <= 65535 && D > 0 && D % 32 == 0 && S > 0, "bad sizes n=%d D=%d S=%d", n, D, S);
+  bw::unpack_dctx<<<dim3((S + 31) / 32, D / 32, n), dim3(32, 8), 0, (cudaStream_t)stream>>>(drt, d_ctx, D, S,
+                                                                                           gloria_b200_tc_sp(S));
+  GLORIA_LAUNCHED("unpack_dctx");
   return GLORIA_OK;
 }
 

@@ -130,6 +130,7 @@ class _ShardedLocalSim(torch.autograd.Function):
                 None, None)
 
 
+_PACKED_RS = os.environ.get("GLORIA_B200_SHARD_PACKED_RS", "1") != "0"   # reduce_scatter the packed gradient rows, unpack own images only
 _N_PARTS = int(os.environ.get("GLORIA_B200_SHARD_PARTS", "2"))   # image parts per rank shard: gather / reduce_scatter of one part overlap the kernels of the other
 
 
@@ -257,7 +258,6 @@ class _ShardedLocalSimParts(torch.autograd.Function):
         with torch.cuda.device(dev):
             dsim_pm = torch.empty((B, Bc), dtype=torch.float32, device=dev)
             dsim_pm.index_copy_(0, perm, dsim.float().contiguous())
-            d_ctx_all = torch.empty((B, D, S), dtype=torch.float32, device=dev)       # part-major
             d_words = torch.empty((Bc, D, Lw), dtype=torch.float32, device=dev)
             d_ctx = torch.empty((n, D, S), dtype=torch.float32, device=dev)
             events = []
@@ -266,15 +266,31 @@ class _ShardedLocalSimParts(torch.autograd.Function):
                 e.record(main)                                    # materialise the handle; the library re-records it
                 events.append(e)
             handles = (ctypes.c_void_p * P)(*[e.cuda_event for e in events])
+            if _PACKED_RS:
+                # the image-side gradient is reduce_scattered in the library's packed layout ([image, region row, D], straight
+                # out of the workspace) and only this rank's n images are transposed into [n, D, S] afterwards: before,
+                # every rank transposed all B images (0.4 ms of an 8-rank step) ahead of the collective
+                sp = L.gloria_b200_tc_sp(S)
+                off = L.gloria_b200_tc_train_drt_offset(B, Bc, D, S, lcap)
+                grad_all = ws[off:off + B * sp * D * 4].view(torch.float32).view(B, sp, D)          # part-major
+                own = torch.empty((n, sp, D), dtype=torch.float32, device=dev)
+                out_ptr = None
+            else:
+                grad_all = torch.empty((B, D, S), dtype=torch.float32, device=dev)                  # part-major
+                own = d_ctx
+                out_ptr = grad_all.data_ptr()
             _lib.check(L.gloria_b200_tc_local_sim_bwd_train_parts(
                 ctx_t.data_ptr(), words_t.data_ptr(), dev_lens.data_ptr(), B, Bc, D, S, Lw, lcap, 0, dsim_pm.data_ptr(),
-                d_ctx_all.data_ptr(), d_words.data_ptr(), ws.data_ptr(), ws.numel(), P,
+                out_ptr, d_words.data_ptr(), ws.data_ptr(), ws.numel(), P,
                 ctypes.cast(handles, ctypes.c_void_p), _stream(ctx_t)), "tc_local_sim_bwd_train_parts")
             for p in range(P):
                 side.wait_event(events[p])                        # rows of part p are final; later parts still compute
                 with torch.cuda.stream(side):
-                    dist.reduce_scatter_tensor(d_ctx[p * m:(p + 1) * m], d_ctx_all[p * world * m:(p + 1) * world * m],
+                    dist.reduce_scatter_tensor(own[p * m:(p + 1) * m], grad_all[p * world * m:(p + 1) * world * m],
                                                op=dist.ReduceOp.SUM, group=group)
+                    if _PACKED_RS:
+                        _lib.check(L.gloria_b200_tc_unpack_dctx(own[p * m:].data_ptr(), d_ctx[p * m:].data_ptr(), m, D, S,
+                                                                side.cuda_stream), "tc_unpack_dctx")
             main.wait_stream(side)
         return (d_ctx.reshape(img_shape).to(img_dtype), d_words.to(txt_dtype), None, None, None, None, None, None,
                 None, None)

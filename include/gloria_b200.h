@@ -294,12 +294,18 @@ int gloria_b200_tc_local_sim_fwd_train_diag(const void* ctx_h, const void* ctx_t
                                             void* stream);
 /* Backward with the image side done in n_parts equal image ranges (n_parts divides Bi); part_events[k] (cudaEvent_t or
  * NULL; the array itself may be NULL) is recorded on `stream` once the d_ctx rows of part k are final.  The
- * caption-side GEMM runs last. */
+ * caption-side GEMM runs last.  d_ctx may be NULL: the image-side gradient is then left in the workspace in its packed
+ * form dRt [Bi, sp, D] fp32 at gloria_b200_tc_train_drt_offset (final for part k at part_events[k]) and the caller
+ * unpacks the images it wants with gloria_b200_tc_unpack_dctx -- a caption-sharded caller reduce_scatters the packed
+ * rows and transposes only its own images (autograd of the all_gather in SURVEY 8e). */
 int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const void* words_t, const int32_t* cap_lens,
                                              int Bi, int Bc, int D, int S, int Lw, int Lcap, int word_off,
                                              const float* dsim, float* d_ctx, float* d_words,
                                              void* workspace, size_t workspace_bytes, int n_parts,
                                              void* const* part_events, void* stream);
+size_t gloria_b200_tc_train_drt_offset(int Bi, int Bc, int D, int S, int Lcap);
+/* dRt [n, sp, D] fp32 -> d_ctx [n, D, S] (the layout of img_emb_l's gradient); D % 32 == 0. */
+int gloria_b200_tc_unpack_dctx(const float* drt, float* d_ctx, int n, int D, int S, void* stream);
 /* Same, with a caller-owned cudaEvent_t (or NULL) that is recorded on `stream` as soon as d_ctx is final -- before the
  * caption-side GEMM.  A caption-sharded caller waits on it to start the reduce_scatter of d_ctx while the
  * rest of the backward still runs. */

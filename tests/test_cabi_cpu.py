@@ -208,3 +208,19 @@ def test_f32_tensor_core_host_side(libpath):
     assert L.gloria_b200_acc_gemm_planes(one, one, one, 128, 100, 64, 1, 6, 1, 1, 0, None) == 1       # N % 16
     assert L.gloria_b200_acc_gemm_planes(one, one, one, 128, 128, 72, 0, 3, 2, 1, 0, None) == 1       # transposed A: K % 64
     assert L.gloria_b200_upload_ints(None, 4, None, None) == 1
+
+
+def test_packed_image_gradient_entry_points(libpath):
+    """Packed reduce_scatter of the sharded backward: where dRt sits in the training workspace, and the unpack's checks."""
+    from gloria_nlp_project_b200 import _lib
+    L = _lib.lib()
+    total = L.gloria_b200_tc_train_workspace(512, 64, 768, 361, 97)
+    off = L.gloria_b200_tc_train_drt_offset(512, 64, 768, 361, 97)
+    sp = L.gloria_b200_tc_sp(361)
+    assert off > 0 and off % 1024 == 0 and off + 512 * sp * 768 * 4 <= total     # dRt [Bi, sp, D] fp32 lies inside
+    assert L.gloria_b200_tc_train_drt_offset(512, 64, 48, 361, 97) == 0          # unsupported shape
+    assert L.gloria_b200_tc_train_drt_offset(0, 64, 768, 361, 97) == 0
+    one = ctypes.c_void_p(16)
+    assert L.gloria_b200_tc_unpack_dctx(None, one, 4, 768, 361, None) == 1 and b"null" in L.gloria_b200_last_error()
+    assert L.gloria_b200_tc_unpack_dctx(one, one, 4, 100, 361, None) == 1         # D % 32
+    assert L.gloria_b200_tc_unpack_dctx(one, one, 0, 768, 361, None) == 1

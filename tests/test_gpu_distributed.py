@@ -152,3 +152,44 @@ def test_sharded_calc_loss_two_gpus():
         for got, leaf in zip(grads, leaves):
             ref = leaf.grad.cpu().numpy()[rank * n:(rank + 1) * n]
             assert float(np.abs(got - ref).max() / np.abs(ref).max()) < 2e-3
+
+
+def test_part_pipelined_path_one_rank_packed_gradient():
+    """The part-pipelined sharded path on ONE GPU (a world of one rank: every collective is a copy): its image-side
+    gradient travels in the library's packed layout and only the rank's own images are unpacked
+    (gloria_b200_tc_unpack_dctx).  Packed and unpacked routes must agree bit for bit, and both with the oracle."""
+    import gloria_nlp_project_b200 as G
+    from gloria_nlp_project_b200 import distributed as D, gloria_loss, ops
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()))
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        B, img_l, txt_l, img_g, txt_g, cl = _inputs()
+        dev_lens, _ = gloria_loss._cap_lens(cl, B, 0, txt_l.shape[2], torch.device("cuda", 0))
+        gsim = torch.tensor(np.random.default_rng(3).standard_normal((B, B)).astype(np.float32), device="cuda")
+        outs = []
+        for packed in (True, False):
+            D._PACKED_RS = packed
+            leaves = [torch.tensor(a, device="cuda").requires_grad_(True) for a in (img_l, txt_l)]
+            sim = D._ShardedLocalSimParts.apply(leaves[0], leaves[1], dev_lens, txt_l.shape[2], 4.0, 5.0, ops.AGG["sum"],
+                                                1e-8, None, 2)
+            (sim * gsim).sum().backward()
+            torch.cuda.synchronize()
+            outs.append((sim.detach().cpu().numpy(), leaves[0].grad.cpu().numpy(), leaves[1].grad.cpu().numpy()))
+    finally:
+        D._PACKED_RS = True
+        dist.destroy_process_group()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    i64, t64 = img_l.astype(np.float64), txt_l.astype(np.float64)
+    want = O.local_similarities(i64, t64, cl)
+    assert float(np.abs(outs[0][0] - want).max() / np.abs(want).max()) < 2e-3
+    g64 = gsim.cpu().numpy().astype(np.float64)
+    ctx = i64.reshape(B, 768, -1)
+    d_img, d_txt = np.zeros_like(ctx), np.zeros_like(t64)
+    for i in range(B):
+        dc, dw = O.local_sim_pair_bwd(ctx, t64[i, :, :cl[i]], 4.0, 5.0, g64[:, i])
+        d_img += dc
+        d_txt[i, :, :cl[i]] = dw
+    assert float(np.abs(outs[0][1].reshape(B, 768, -1) - d_img).max() / np.abs(d_img).max()) < 1e-2
+    assert float(np.abs(outs[0][2] - d_txt).max() / np.abs(d_txt).max()) < 1e-2
