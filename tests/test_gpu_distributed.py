@@ -157,7 +157,7 @@ def test_sharded_calc_loss_two_gpus():
 def test_part_pipelined_path_one_rank_packed_gradient():
     """The part-pipelined sharded path on ONE GPU (a world of one rank: every collective is a copy): its image-side
     gradient travels in the library's packed layout and only the rank's own images are unpacked
-    (gloria_b200_tc_unpack_dctx).  Packed and unpacked routes must agree bit for bit, and both with the oracle."""
+    (gloria_b200_tc_unpack_dctx).  Packed and unpacked routes must agree, and both with the oracle."""
     import gloria_nlp_project_b200 as G
     from gloria_nlp_project_b200 import distributed as D, gloria_loss, ops
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()))
@@ -179,8 +179,8 @@ def test_part_pipelined_path_one_rank_packed_gradient():
     finally:
         D._PACKED_RS = True
         dist.destroy_process_group()
-    for a, b in zip(outs[0], outs[1]):
-        assert np.array_equal(a, b)
+    for a, b in zip(outs[0], outs[1]):      # (not bit for bit: the fused kernel's column sums use shared-memory atomics)
+        assert float(np.abs(a - b).max() / np.abs(b).max()) < 1e-4
     i64, t64 = img_l.astype(np.float64), txt_l.astype(np.float64)
     want = O.local_similarities(i64, t64, cl)
     assert float(np.abs(outs[0][0] - want).max() / np.abs(want).max()) < 2e-3
