@@ -1078,6 +1078,30 @@ int bwd_gemm_mode() {
   return mode;
 }
 
+// GLORIA_B200_BWD_OVERLAP=1: the M-term kernel (reads E^T, never X) runs on a library-owned side stream beside the
+// streaming pass X *= g and the dR GEMM instead of between the GEMMs.  Per device and thread: one non-blocking stream and
+// two events (fork / join), created on first use; the fork-join is expressed with events only, so it is capturable.
+int bwd_overlap_mode() {
+  static const int mode = [] {
+    const char* e = getenv("GLORIA_B200_BWD_OVERLAP");
+    return e ? atoi(e) : 0;
+  }();
+  return mode;
+}
+struct SideStream { cudaStream_t st = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+SideStream* side_stream() {
+  static thread_local SideStream s[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!s[dev].st) {
+    if (cudaStreamCreateWithFlags(&s[dev].st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s[dev].fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s[dev].join, cudaEventDisableTiming) != cudaSuccess)
+      return nullptr;
+  }
+  return &s[dev];
+}
+
 #define GLORIA_CUBLAS(expr)                                                                       \
   do {                                                                                            \
     cublasStatus_t _s = (expr);                                                                   \
@@ -1495,6 +1519,21 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const
   const int gmode = bw::bwd_gemm_mode();
   // everything the forward stored is for g = 1 and linear in g = dsim[j, i]: the own GEMMs apply it to their A operand in
   // flight (mode 0); otherwise one streaming pass scales X in place first
+  const int nj = Bi / n_parts;
+  bw::SideStream* side = (gmode != 0 && bw::bwd_overlap_mode() != 0) ? bw::side_stream() : nullptr;
+  if (side) {
+    // fork: the M-term of every part goes to the side stream first (it depends on nothing the main stream does below)
+    GLORIA_CUDA(cudaEventRecord(side->fork, st));
+    GLORIA_CUDA(cudaStreamWaitEvent(side->st, side->fork, 0));
+    for (int part = 0; part < n_parts; ++part) {
+      const size_t j0 = (size_t)part * nj;
+      int rc;
+      if ((rc = launch_mterm(E + j0 * sp * R1, (const float*)(ws + pl.off_fo) + j0 * R1, dsim + j0 * Bc, Mf + j0 * sp * sp,
+                             Mb + j0 * sp * sp, nj, Bc, 0, R1, lp, sp, false, side->st)))
+        return rc;
+    }
+    GLORIA_CUDA(cudaEventRecord(side->join, side->st));
+  }
   if (gmode != 0) {
     bw::scale_x<<<sgrid, 256, 0, st>>>(X, dsim, R1, sp, Bc, 0, lp, (const int*)(ws + pl.off_flag));
     GLORIA_LAUNCHED("scale_x");
@@ -1502,7 +1541,6 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const
     GLORIA_LAUNCHED("mark_consumed");
   }
   // ---- image side, part by part
-  const int nj = Bi / n_parts;
   for (int part = 0; part < n_parts; ++part) {
     const size_t j0 = (size_t)part * nj;
     const __nv_bfloat16* Xp = X + j0 * sp * R1;
@@ -1522,9 +1560,12 @@ extern "C" int gloria_b200_tc_local_sim_bwd_train_parts(const void* ctx_t, const
     }
     // M_j[a, b] = sum_(i,l) E^T[(j,a),(i,l)] g[j,i] f[j,(i,l)] E^T[(j,b),(i,l)]   (own tcgen05 kernel, tc_mterm.cu)
     // (the epilogue writes the bf16 operand of the M.R GEMM directly: no fp32 M, no conversion pass)
-    if ((rc = launch_mterm(E + j0 * sp * R1, (const float*)(ws + pl.off_fo) + j0 * R1, dsim + j0 * Bc, Mp, Mbp, nj, Bc, 0,
-                           R1, lp, sp, false, st)))
+    if (side) {
+      if (part == 0) GLORIA_CUDA(cudaStreamWaitEvent(st, side->join, 0));      // join: every M_j is final
+    } else if ((rc = launch_mterm(E + j0 * sp * R1, (const float*)(ws + pl.off_fo) + j0 * R1, dsim + j0 * Bc, Mp, Mbp, nj,
+                                  Bc, 0, R1, lp, sp, false, st))) {
       return rc;
+    }
     // dRt_j += M_j Rt_j   (M_j symmetric up to rounding; column-major: [D, sp] = Rt_j^T . M_j)
     GLORIA_CUBLAS(cublasGemmStridedBatchedEx(h, CUBLAS_OP_N, CUBLAS_OP_N, D, sp, sp, &one, Rp, CUDA_R_16BF, D,
                                              (long long)sp * D, Mbp, CUDA_R_16BF, sp, (long long)sp * sp, &one, dRp,
