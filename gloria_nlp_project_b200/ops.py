@@ -375,6 +375,10 @@ def _(ctx, words, cap_lens, lcap, word_off, temp1, temp2, agg, eps, want_diag, w
             ctx.new_empty((Bi, Bc, S) if want_mean else (0,)), state)
 
 
+# (`stats` is the forward's opaque byte state.  On the fused bf16 path the library scales the operand rows inside it by dsim
+# in place -- it is produced by one forward and consumed by one backward, `check_state_unconsumed` and a device-side flag
+# refuse a second use -- so no caller-visible tensor value changes; it is therefore not listed in mutates_args, which
+# would make the functionaliser clone 41.7 GB at B = 512.)
 @torch.library.custom_op("gloria_b200::local_sim_bwd", mutates_args=())
 def local_sim_bwd(ctx: Tensor, words: Tensor, cap_lens: Tensor, lcap: int, word_off: int, temp1: float,
                   temp2: float, agg: int, eps: float, dsim: Optional[Tensor], d_diag: Optional[Tensor],
