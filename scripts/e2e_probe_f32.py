@@ -1,3 +1,4 @@
+"""Development probe: end-to-end B = 48 fp32-mode step with and without the per-step pageable copies (found the 10 ms copy-engine stall fixed by gloria_b200_upload_ints)."""
 import os, sys, time
 sys.path.insert(0, ".")
 import torch
